@@ -1,0 +1,159 @@
+/* megb200 — C-ABI of the B200-native BrainEncoder + CLIPLoss training hot path.
+ *
+ * The reference (arayabrain/MEG-decoding) is pure Python/PyTorch and has no FFI; every entry point below
+ * replaces the ATen calls issued by one reference op site (cited per function, paths relative to the
+ * reference tree).  Plain pointers and sizes only; all pointers are DEVICE pointers unless stated.
+ * Return value: 0 = ok, <0 = argument/shape error (MEGB200_ERR_*), >0 = cudaError_t.  No exceptions cross
+ * the boundary; megb200_last_error() returns a thread-local message.  Every kernel is launched on the
+ * `stream` argument (a cudaStream_t passed as void*); the library never synchronises, allocates or frees.
+ *
+ * Activation layout ("PC"): [B][T][Cs] — position-major, channels contiguous, Cs = channel stride (a multiple
+ * of 8, >= the logical channel count C).  `dtype` selects the storage type of activations and packed weights:
+ * MEGB200_F32 (check mode) or MEGB200_BF16.  `backend` selects the contraction engine: MEGB200_SIMT (fp32
+ * CUDA-core FMA, any dtype) or MEGB200_TC (tcgen05.mma kind::f16 + TMA + TMEM accumulators, bf16 only).
+ * Accumulation is always fp32.
+ */
+#ifndef MEGB200_H_
+#define MEGB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MEGB200_VERSION 100
+
+#define MEGB200_F32 0
+#define MEGB200_BF16 1
+
+#define MEGB200_SIMT 0
+#define MEGB200_TC 1
+
+#define MEGB200_ERR_ARG (-1)
+#define MEGB200_ERR_UNSUPPORTED (-2)
+#define MEGB200_ERR_DRIVER (-3)
+
+int megb200_version(void);
+const char* megb200_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------- packing */
+/* X f32 [B][C][T] (NCW, as the collator delivers it: gwilliams2022.py:654-662) -> PC [B][T][Cs]; pad
+ * channels C..Cs-1 are written as zero. */
+int megb200_pack_x(const float* X, void* Xp, int B, int C, int T, int Cs, int dtype, void* stream);
+
+/* Conv weight f32 [G][O][I][Kt] (nn.Conv1d layout, models.py:252-265,284-306,360-361) -> packed operand
+ * [G][Np][Kt*Kp] of `dtype`.
+ *   mode 0 (forward):  out[g][o][j*Kp + i] = w[g][o][i][j]            N = O, K = I
+ *   mode 1 (dgrad):    out[g][i][j*Kp + o] = w[g][o][i][Kt-1-j]       N = I, K = O   (flipped taps)
+ * Everything outside the logical extent is zero. */
+int megb200_pack_weight(const float* w, void* out, int G, int O, int I, int Kt, int Np, int Kp, int mode,
+                        int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------- contractions */
+/* "tap GEMM": out[b][t][n] = sum_j sum_c A[b][t + (j - taps/2)*dil][c] * W[g][n][j*Kp + c]
+ *                            (+ bias[g][n]) (+ Res[b][t][n]),   g = group[b] (0 when group == NULL),
+ * zero outside [0,T) ("same" padding).  One kernel serves: the spatial-attention mix + shared 1x1 + per-subject
+ * 1x1 chain pre-multiplied into one grouped GEMM keyed by subject index (models.py:220,269-272), Conv1d k=3
+ * forward (models.py:310-319), its data gradient (flipped/transposed pack), and the 1x1 head convs
+ * (models.py:373-374).  N = logical output channels; channels N..Cos-1 of Out are written as zero. */
+int megb200_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int N, int Np, int Kp, int taps,
+                    int dil, const float* bias, const void* Res, int Crs, const int32_t* group, int G, void* Out,
+                    int Cos, int dtype, int backend, void* stream);
+
+/* Weight gradient: dW[g][m][c][j] += sum_{b: group[b]==g} sum_t dU[b][t][m] * Xin[b][t + (j - taps/2)*dil][c]
+ * (f32, nn.Conv1d layout [G][M][C][taps]; accumulated — caller zeroes).  Replaces autograd's
+ * convolution_backward weight path for every conv on the path, and the per-subject accumulation for the
+ * grouped subject GEMM.  `order` (grouped mode only) lists the samples sorted by group
+ * (megb200_group_order); `workspace` holds the split-K partial sums of the tensor-core engine (f32, at least
+ * taps*M*C*4 bytes, more = more parallelism); both may be NULL for the SIMT engine. */
+int megb200_wgrad(const void* dU, int M, int Ms, const void* Xin, int C, int Cs, int B, int T, int taps, int dil,
+                  const int32_t* group, const int32_t* order, int G, float* dW, float* workspace, size_t ws_bytes,
+                  int dtype, int backend, void* stream);
+/* order = stable argsort of group[0..B) (values in [0,G)); bit-exact integer work, one CTA. */
+int megb200_group_order(const int32_t* group, int B, int G, int32_t* order, void* stream);
+
+/* out[g][c] += sum_{b: group[b]==g} sum_t U[b][t][c]   (bias gradients; f32 [G][C], accumulated) */
+int megb200_colsum(const void* U, int B, int T, int C, int Cs, const int32_t* group, int G, float* out, int dtype,
+                   void* stream);
+
+/* Row-major f32 batched GEMM for the small per-step matrices of the subject block / spatial attention
+ * (models.py:204-208 and the chain rule of SURVEY appendix A1-A2):
+ *   C[b] = alpha * op(A[b]) * op(B[b]) + beta * C[b],   op = transpose when the flag is set. */
+int megb200_sgemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
+                  long long strideA, const float* Bm, int ldb, long long strideB, float beta, float* C, int ldc,
+                  long long strideC, int batch, void* stream);
+
+/* -------------------------------------------------------------------------------------- spatial attention */
+/* W[o][:] = softmax(a[o][:]) ; Wm = W * mask[None,:]  (models.py:213 and :235-239 folded into the weights).
+ * mask may be NULL (eval mode). a, W, Wm: f32 [D1][C]. */
+int megb200_sa_softmax(const float* a, const float* mask, float* W, float* Wm, int D1, int C, void* stream);
+/* da = W * (g - rowsum(W * g)),  g = dWm * mask   (softmax Jacobian) */
+int megb200_sa_softmax_bwd(const float* W, const float* dWm, const float* mask, float* da, int D1, int C,
+                           void* stream);
+
+/* ---------------------------------------------------------------------------------------------- BatchNorm/GELU/GLU */
+/* sums[0][c] += sum u, sums[1][c] += sum u^2 over all (b,t)   (models.py:291,299 train-mode statistics) */
+int megb200_bn_stats(const void* U, long long rows, int C, int Cs, float* sums, int dtype, void* stream);
+/* training != 0: mean/var from sums (biased var), running stats updated in place (momentum, unbiased var);
+ * training == 0: running stats used.  Writes scale = gamma*rstd, shift = beta - mean*scale, mean, rstd. */
+int megb200_bn_finalize(const float* sums, const float* gamma, const float* beta, float* running_mean,
+                        float* running_var, long long count, float eps, float momentum, int training, float* scale,
+                        float* shift, float* mean, float* rstd, int C, void* stream);
+/* H = gelu(scale*U + shift)   (models.py:314,317) */
+int megb200_bn_gelu(const void* U, const float* scale, const float* shift, void* H, long long rows, int C, int Cs,
+                    int dtype, void* stream);
+/* dY = dH * gelu'(scale*U+shift); sums2[0][c] += sum dY, sums2[1][c] += sum dY*xhat, xhat = (U-mean)*rstd */
+int megb200_bn_gelu_bwd_reduce(const void* dH, const void* U, const float* scale, const float* shift,
+                               const float* mean, const float* rstd, void* dY, float* sums2, long long rows, int C,
+                               int Cs, int dtype, void* stream);
+/* dU = gamma*rstd * (dY - sums2[0]/n - xhat * sums2[1]/n)    */
+int megb200_bn_bwd_apply(const void* dY, const void* U, const float* gamma, const float* mean, const float* rstd,
+                         const float* sums2, long long count, void* dU, long long rows, int C, int Cs, int dtype,
+                         void* stream);
+/* eval-mode backward is never needed (no grad in eval). */
+
+/* Out[.., c] = V[.., c] * sigmoid(V[.., C + c]),  V: [rows][Vs] with 2C logical channels (models.py:320) */
+int megb200_glu(const void* V, void* Out, long long rows, int C, int Vs, int Os, int dtype, void* stream);
+int megb200_glu_bwd(const void* dOut, const void* V, void* dV, long long rows, int C, int Vs, int Os, int dtype,
+                    void* stream);
+/* Q = gelu(P) ; dP = dQ * gelu'(P)   (models.py:373-374) */
+int megb200_gelu(const void* P, void* Q, long long n, int dtype, void* stream);
+int megb200_gelu_bwd(const void* dQ, const void* P, void* dP, long long n, int dtype, void* stream);
+/* seq2static head (models.py:382): Zm[b][f] = mean_t Z[b][t][f] ; backward broadcasts dZm/T */
+int megb200_time_mean(const void* Z, void* Zm, int B, int T, int F, int Fs, int dtype, void* stream);
+int megb200_time_mean_bwd(const void* dZm, void* dZ, int B, int T, int F, int Fs, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------- CLIP loss */
+/* Y f32 [B][F][T] (NCW) -> Yp [B][T][F] of `dtype` and ysq[b] += sum Y^2 (f32, from the unrounded values).
+ * T == 1 handles the static [B][F] targets.  loss.py:88-93 (reshape + norm). */
+int megb200_clip_prep_y(const float* Y, void* Yp, float* ysq, int B, int F, int T, int dtype, void* stream);
+/* sq[b] += sum_d Z[b][d]^2   (loss.py:93) */
+int megb200_rowsumsq(const void* Z, float* sq, int B, long long D, int dtype, void* stream);
+/* raw[i][j] += sum_d Yp[i][d] * Zp[j][d]   f32 [By][Bz]  (loss.py:96, split-K over D with f32 atomics) */
+int megb200_clip_logits(const void* Yp, const void* Zp, float* raw, int By, int Bz, long long D, int dtype,
+                        int backend, void* stream);
+/* L[i][j] = raw * exp(temp) / sqrt(ysq[i]*zsq[j])  (loss.py:92-99); per speech row i the partial
+ * (max, sum exp) over the local brains; per brain column j the complete log-sum-exp over all speech rows. */
+int megb200_clip_ce_partial(const float* raw, const float* ysq, const float* zsq, const float* temp, float* L,
+                            float* row_max, float* row_sumexp, float* col_lse, int By, int Bz, void* stream);
+/* Given the complete row LSEs: out[0] += loss contribution of this shard, out[1] += d loss / d temp;
+ * coef[j][i] = dL[i][j] * exp(temp)/(|y_i||z_j|)  (`dtype`), cvec[j] = sum_i dL[i][j]*L[i][j] / zsq[j].
+ * dL = (exp(L-row_lse[i]) + exp(L-col_lse[j]) - 2*[i == off + j]) * wscale, wscale = 1/(2*Bglob) for
+ * reduction="mean", 1/2 for "sum" (loss.py:60,107).  out2/cvec are accumulated. */
+int megb200_clip_ce_finish(const float* L, const float* row_lse, const float* col_lse, const float* ysq,
+                           const float* zsq, const float* temp, int off, float wscale, float* out2, void* coef,
+                           int ldc, float* cvec, int By, int Bz, int dtype, void* stream);
+/* dZ[j][d] = gscale[0] * ( sum_i coef[j][i]*Yp[i][d] - Z[j][d]*cvec[j] )   (normalisation Jacobian folded).
+ * coef is [Bz][ldc] with ldc >= By a multiple of 8 (ragged batches keep TMA's 16-byte stride rule). */
+int megb200_clip_dz(const void* coef, int ldc, const void* Yp, const void* Z, const float* cvec, const float* gscale,
+                    void* dZ, int By, int Bz, long long D, int dtype, int backend, void* stream);
+
+/* ---------------------------------------------------------------------------------------------- misc */
+/* d[i] = s[i] cast between f32 and the activation dtype (n elements) */
+int megb200_cast(const void* src, void* dst, long long n, int src_dtype, int dst_dtype, void* stream);
+#ifdef __cplusplus
+}
+#endif
+#endif /* MEGB200_H_ */

@@ -1,0 +1,225 @@
+// C-ABI entry points that dispatch between the two contraction engines, plus library-level plumbing
+// (error string, SM count, TMA descriptor encoding through the runtime-resolved driver entry point).
+#include <stdarg.h>
+
+#include "tc_common.cuh"
+
+namespace megb200 {
+
+static thread_local char g_err[512] = "";
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int num_sms() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+namespace tc {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box) {
+  EncodeTiledFn fn = get_encode();
+  if (fn == nullptr) {
+    set_last_error("cuTensorMapEncodeTiled is not available from the driver");
+    return MEGB200_ERR_DRIVER;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) {
+    set_last_error("TMA operand base %p is not 16-byte aligned", base);
+    return MEGB200_ERR_ARG;
+  }
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) {
+      gstr[i - 1] = strides_bytes[i - 1];
+      if (gstr[i - 1] % 16 != 0) {
+        set_last_error("TMA stride %llu (dim %d) is not a multiple of 16 bytes", (unsigned long long)gstr[i - 1], i);
+        return MEGB200_ERR_ARG;
+      }
+    }
+  }
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu box %u,%u)", (int)r, rank,
+                   (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0), box[0],
+                   rank > 1 ? box[1] : 0);
+    return MEGB200_ERR_DRIVER;
+  }
+  return 0;
+}
+
+int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int N, int Np, int Kp, int taps, int dil,
+               const float* bias, const void* Res, int Crs, const int32_t* group, int G, void* Out, int Cos,
+               cudaStream_t st);
+int tc_wgrad(const void* dU, int M, int Ms, const void* Xin, int C, int Cs, int B, int T, int taps, int dil,
+             const int32_t* group, const int32_t* order, int G, float* dW, float* workspace, size_t ws_bytes,
+             cudaStream_t st);
+int tc_clip_logits(const void* Yp, const void* Zp, float* raw, int By, int Bz, long long D, cudaStream_t st);
+int tc_clip_dz(const void* coef, int ldc, const void* Yp, const void* Z, const float* cvec, const float* gscale,
+               void* dZ, int By, int Bz, long long D, cudaStream_t st);
+}  // namespace tc
+
+template <typename T>
+int simt_tapgemm(const void* A, int B, int Tn, int Ca, int Cas, const void* W, int N, int Np, int Kp, int taps,
+                 int dil, const float* bias, const void* Res, int Crs, const int32_t* group, void* Out, int Cos,
+                 cudaStream_t st);
+template <typename T>
+int simt_wgrad(const void* dU, int M, int Ms, const void* Xin, int C, int Cs, int B, int Tn, int taps, int dil,
+               const int32_t* group, float* dW, cudaStream_t st);
+template <typename T>
+int simt_clip_logits(const void* Yp, const void* Zp, float* raw, int By, int Bz, long long D, cudaStream_t st);
+template <typename T>
+int simt_clip_dz(const void* coef, int ldc, const void* Yp, const void* Z, const float* cvec, const float* gscale,
+                 void* dZ, int By, int Bz, long long D, cudaStream_t st);
+
+// stable counting sort of the sample indices by group: one CTA, bit-exact integer work
+__global__ void group_order_kernel(const int32_t* __restrict__ group, int B, int G, int32_t* __restrict__ order) {
+  extern __shared__ int cnt[];  // [G + 1]
+  for (int i = threadIdx.x; i <= G; i += blockDim.x) cnt[i] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < B; i += blockDim.x) atomicAdd(&cnt[group[i] + 1], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int g = 0; g < G; ++g) cnt[g + 1] += cnt[g];  // cnt[g] = first slot of group g
+  }
+  __syncthreads();
+  // stability: thread g walks the samples in order and emits its own group's members
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    int pos = cnt[g];
+    for (int i = 0; i < B; ++i)
+      if (group[i] == g) order[pos++] = i;
+  }
+}
+
+}  // namespace megb200
+
+using namespace megb200;
+
+extern "C" {
+
+int megb200_version(void) { return MEGB200_VERSION; }
+const char* megb200_last_error(void) { return g_err; }
+
+int megb200_group_order(const int32_t* group, int B, int G, int32_t* order, void* stream) {
+  MEGB_CHECK_ARG(group && order && B > 0 && G > 0 && G < 8192, "group_order: bad arguments");
+  group_order_kernel<<<1, 256, (G + 1) * sizeof(int), (cudaStream_t)stream>>>(group, B, G, order);
+  MEGB_LAUNCH_OK();
+  return 0;
+}
+
+int megb200_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int N, int Np, int Kp, int taps,
+                    int dil, const float* bias, const void* Res, int Crs, const int32_t* group, int G, void* Out,
+                    int Cos, int dtype, int backend, void* stream) {
+  MEGB_CHECK_ARG(A && W && Out && B > 0 && T > 0 && Ca > 0 && N > 0 && taps >= 1 && (taps & 1) && dil >= 1 && G >= 1,
+                 "tapgemm: bad arguments");
+  MEGB_CHECK_ARG(Cas >= Ca && Cos >= N && Np >= N && Kp >= Ca, "tapgemm: strides/padding smaller than extents");
+  MEGB_CHECK_ARG(Res == nullptr || Crs >= N, "tapgemm: residual stride smaller than N");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (backend == MEGB200_TC) {
+    if (dtype != MEGB200_BF16) {
+      set_last_error("tapgemm: the tensor-core engine needs bf16 activations");
+      return MEGB200_ERR_UNSUPPORTED;
+    }
+    return tc::tc_tapgemm(A, B, T, Ca, Cas, W, N, Np, Kp, taps, dil, bias, Res, Crs, group, G, Out, Cos, st);
+  }
+  MEGB_CHECK_ARG(backend == MEGB200_SIMT, "tapgemm: unknown backend %d", backend);
+  if (dtype == MEGB200_F32)
+    return simt_tapgemm<float>(A, B, T, Ca, Cas, W, N, Np, Kp, taps, dil, bias, Res, Crs, group, Out, Cos, st);
+  if (dtype == MEGB200_BF16)
+    return simt_tapgemm<__nv_bfloat16>(A, B, T, Ca, Cas, W, N, Np, Kp, taps, dil, bias, Res, Crs, group, Out, Cos, st);
+  MEGB_CHECK_ARG(false, "tapgemm: unknown dtype %d", dtype);
+}
+
+int megb200_wgrad(const void* dU, int M, int Ms, const void* Xin, int C, int Cs, int B, int T, int taps, int dil,
+                  const int32_t* group, const int32_t* order, int G, float* dW, float* workspace, size_t ws_bytes,
+                  int dtype, int backend, void* stream) {
+  MEGB_CHECK_ARG(dU && Xin && dW && M > 0 && C > 0 && B > 0 && T > 0 && taps >= 1 && (taps & 1) && dil >= 1 && G >= 1,
+                 "wgrad: bad arguments");
+  MEGB_CHECK_ARG(Ms >= M && Cs >= C, "wgrad: strides smaller than extents");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (backend == MEGB200_TC) {
+    if (dtype != MEGB200_BF16) {
+      set_last_error("wgrad: the tensor-core engine needs bf16 activations");
+      return MEGB200_ERR_UNSUPPORTED;
+    }
+    return tc::tc_wgrad(dU, M, Ms, Xin, C, Cs, B, T, taps, dil, group, order, G, dW, workspace, ws_bytes, st);
+  }
+  MEGB_CHECK_ARG(backend == MEGB200_SIMT, "wgrad: unknown backend %d", backend);
+  if (dtype == MEGB200_F32) return simt_wgrad<float>(dU, M, Ms, Xin, C, Cs, B, T, taps, dil, group, dW, st);
+  if (dtype == MEGB200_BF16) return simt_wgrad<__nv_bfloat16>(dU, M, Ms, Xin, C, Cs, B, T, taps, dil, group, dW, st);
+  MEGB_CHECK_ARG(false, "wgrad: unknown dtype %d", dtype);
+}
+
+int megb200_clip_logits(const void* Yp, const void* Zp, float* raw, int By, int Bz, long long D, int dtype,
+                        int backend, void* stream) {
+  MEGB_CHECK_ARG(Yp && Zp && raw && By > 0 && Bz > 0 && D > 0, "clip_logits: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (backend == MEGB200_TC) {
+    if (dtype != MEGB200_BF16) {
+      set_last_error("clip_logits: the tensor-core engine needs bf16 operands");
+      return MEGB200_ERR_UNSUPPORTED;
+    }
+    return tc::tc_clip_logits(Yp, Zp, raw, By, Bz, D, st);
+  }
+  MEGB_CHECK_ARG(backend == MEGB200_SIMT, "clip_logits: unknown backend %d", backend);
+  if (dtype == MEGB200_F32) return simt_clip_logits<float>(Yp, Zp, raw, By, Bz, D, st);
+  if (dtype == MEGB200_BF16) return simt_clip_logits<__nv_bfloat16>(Yp, Zp, raw, By, Bz, D, st);
+  MEGB_CHECK_ARG(false, "clip_logits: unknown dtype %d", dtype);
+}
+
+int megb200_clip_dz(const void* coef, int ldc, const void* Yp, const void* Z, const float* cvec, const float* gscale,
+                    void* dZ, int By, int Bz, long long D, int dtype, int backend, void* stream) {
+  MEGB_CHECK_ARG(coef && Yp && Z && cvec && gscale && dZ && By > 0 && Bz > 0 && D > 0 && ldc >= By,
+                 "clip_dz: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (backend == MEGB200_TC) {
+    if (dtype != MEGB200_BF16) {
+      set_last_error("clip_dz: the tensor-core engine needs bf16 operands");
+      return MEGB200_ERR_UNSUPPORTED;
+    }
+    return tc::tc_clip_dz(coef, ldc, Yp, Z, cvec, gscale, dZ, By, Bz, D, st);
+  }
+  MEGB_CHECK_ARG(backend == MEGB200_SIMT, "clip_dz: unknown backend %d", backend);
+  if (dtype == MEGB200_F32) return simt_clip_dz<float>(coef, ldc, Yp, Z, cvec, gscale, dZ, By, Bz, D, st);
+  if (dtype == MEGB200_BF16) return simt_clip_dz<__nv_bfloat16>(coef, ldc, Yp, Z, cvec, gscale, dZ, By, Bz, D, st);
+  MEGB_CHECK_ARG(false, "clip_dz: unknown dtype %d", dtype);
+}
+
+}  // extern "C"

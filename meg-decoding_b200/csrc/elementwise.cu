@@ -1,0 +1,663 @@
+// HBM-bound passes of the hot path: layout packing, BatchNorm statistics/apply, GELU, GLU, and their backward
+// forms.  All work on the PC layout [rows][Cs] with 8-channel (16 B bf16 / 32 B f32) vector accesses so that a
+// warp touches whole 128 B lines; per-channel reductions go registers -> shared atomics -> one global atomic per
+// channel per CTA.  Bound: HBM bandwidth; algorithmic bytes are stated per op in DESIGN.md.
+#include "common.cuh"
+
+namespace megb200 {
+
+static inline int ew_grid(long long work_items, int threads) {
+  long long blocks = (work_items + threads - 1) / threads;
+  long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// ------------------------------------------------------------------------------------------ transpose-pack
+// in f32 [B][C][T] -> out [B][T][Cs] (+ optional per-sample sum of squares of the unrounded input)
+template <typename T>
+__global__ void transpose_pack_kernel(const float* __restrict__ in, T* __restrict__ out, float* __restrict__ sq,
+                                      int B, int C, int Tn, int Cs) {
+  __shared__ float tile[32][33];
+  __shared__ float red[8];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + 8 * i, t = t0 + tx;
+    float v = 0.f;
+    if (c < C && t < Tn) v = in[((long long)b * C + c) * Tn + t];
+    tile[ty + 8 * i][tx] = v;
+    ss += v * v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int t = t0 + ty + 8 * i, c = c0 + tx;
+    if (t < Tn && c < Cs) out[((long long)b * Tn + t) * Cs + c] = from_f<T>(tile[tx][ty + 8 * i]);
+  }
+  if (sq != nullptr) {
+    ss = warp_sum(ss);
+    if (tx == 0) red[ty] = ss;
+    __syncthreads();
+    if (ty == 0 && tx == 0) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += red[i];
+      atomicAdd(&sq[b], s);
+    }
+  }
+}
+
+template <typename T>
+static int launch_transpose_pack(const float* in, void* out, float* sq, int B, int C, int Tn, int Cs,
+                                 cudaStream_t st) {
+  dim3 grid((Tn + 31) / 32, (Cs + 31) / 32, B), block(32, 8);
+  transpose_pack_kernel<T><<<grid, block, 0, st>>>(in, (T*)out, sq, B, C, Tn, Cs);
+  MEGB_LAUNCH_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ weight packing
+template <typename T>
+__global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int G, int O, int I, int Kt,
+                                   int Np, int Kp, int mode, long long total) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int kk = (int)(idx % ((long long)Kt * Kp));
+    const long long r = idx / ((long long)Kt * Kp);
+    const int n = (int)(r % Np);
+    const int g = (int)(r / Np);
+    const int j = kk / Kp, k = kk % Kp;
+    float v = 0.f;
+    if (mode == 0) {
+      if (n < O && k < I) v = w[(((long long)g * O + n) * I + k) * Kt + j];
+    } else {
+      if (n < I && k < O) v = w[(((long long)g * O + k) * I + n) * Kt + (Kt - 1 - j)];
+    }
+    out[idx] = from_f<T>(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ column reductions
+// One CTA owns a slab of rows; thread = (channel group of 8, row lane).  Op::row() consumes one 8-vector and adds
+// into two per-channel accumulators (and may write an output vector).
+template <class Op>
+__global__ void __launch_bounds__(256) colreduce_kernel(Op op, long long rows, long long rows_per_block, int C,
+                                                        int Cs, const int32_t* __restrict__ group, int Tn,
+                                                        float* __restrict__ out0, float* __restrict__ out1) {
+  extern __shared__ float sm[];  // [2][Cs]
+  float* sm0 = sm;
+  float* sm1 = sm + Cs;
+  for (int i = threadIdx.x; i < 2 * Cs; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const int cg = Cs >> 3;
+  const int W = cg < 256 ? cg : 256;
+  const int R = 256 / W;
+  const int lane_g = threadIdx.x % W, lane_r = threadIdx.x / W;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > rows) r1 = rows;
+  if (lane_r < R) {
+    for (int g = lane_g; g < cg; g += W) {
+      float a0[8], a1[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a0[i] = a1[i] = 0.f;
+      for (long long r = r0 + lane_r; r < r1; r += R) op.row(r, g * 8, a0, a1);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        atomicAdd(&sm0[g * 8 + i], a0[i]);
+        if (Op::kTwo) atomicAdd(&sm1[g * 8 + i], a1[i]);
+      }
+    }
+  }
+  __syncthreads();
+  long long obase = 0;
+  if (group != nullptr) obase = (long long)group[r0 / Tn] * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    atomicAdd(&out0[obase + c], sm0[c]);
+    if (Op::kTwo) atomicAdd(&out1[obase + c], sm1[c]);
+  }
+}
+
+template <typename T>
+struct StatsOp {
+  static constexpr bool kTwo = true;
+  const T* u;
+  int Cs;
+  __device__ __forceinline__ void row(long long r, int c0, float (&a0)[8], float (&a1)[8]) const {
+    float x[8];
+    load8(u + r * Cs + c0, x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      a0[i] += x[i];
+      a1[i] += x[i] * x[i];
+    }
+  }
+};
+
+template <typename T>
+struct ColsumOp {
+  static constexpr bool kTwo = false;
+  const T* u;
+  int Cs;
+  __device__ __forceinline__ void row(long long r, int c0, float (&a0)[8], float (&a1)[8]) const {
+    float x[8];
+    load8(u + r * Cs + c0, x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a0[i] += x[i];
+  }
+};
+
+// dY = dH * gelu'(y), y = scale*u + shift; accumulates sum dY and sum dY*xhat
+template <typename T>
+struct BnGeluBwdOp {
+  static constexpr bool kTwo = true;
+  const T* dh;
+  const T* u;
+  T* dy;
+  const float *scale, *shift, *mean, *rstd;
+  int Cs, C;
+  __device__ __forceinline__ void row(long long r, int c0, float (&a0)[8], float (&a1)[8]) const {
+    float g[8], x[8], o[8];
+    load8(dh + r * Cs + c0, g);
+    load8(u + r * Cs + c0, x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = c0 + i;
+      float d = 0.f;
+      if (c < C) {
+        const float y = fmaf(x[i], __ldg(scale + c), __ldg(shift + c));
+        d = round_to<T>(g[i] * gelu_grad_f(y));
+        const float xh = (x[i] - __ldg(mean + c)) * __ldg(rstd + c);
+        a0[i] += d;
+        a1[i] += d * xh;
+      }
+      o[i] = d;
+    }
+    store8(dy + r * Cs + c0, o);
+  }
+};
+
+template <class Op>
+static int launch_colreduce(Op op, long long rows, int C, int Cs, const int32_t* group, int Tn, float* out0,
+                            float* out1, cudaStream_t st) {
+  MEGB_CHECK_ARG(Cs % 8 == 0 && Cs >= C && Cs <= 4096, "colreduce: bad channel stride %d (C=%d)", Cs, C);
+  long long rpb;
+  if (group != nullptr) {
+    rpb = Tn;
+  } else {
+    long long target_blocks = (long long)num_sms() * 4;
+    rpb = (rows + target_blocks - 1) / target_blocks;
+    if (rpb < 32) rpb = 32;
+  }
+  long long blocks = (rows + rpb - 1) / rpb;
+  if (blocks < 1) return 0;
+  colreduce_kernel<Op><<<(int)blocks, 256, 2 * Cs * sizeof(float), st>>>(op, rows, rpb, C, Cs, group, Tn, out0, out1);
+  MEGB_LAUNCH_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ maps
+template <typename T>
+__global__ void bn_gelu_kernel(const T* __restrict__ u, const float* __restrict__ scale,
+                               const float* __restrict__ shift, T* __restrict__ h, long long nvec, int C, int cg) {
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvec;
+       v += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(v % cg) * 8;
+    float x[8], o[8];
+    load8(u + v * 8, x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = c0 + i;
+      o[i] = (c < C) ? gelu_f(fmaf(x[i], __ldg(scale + c), __ldg(shift + c))) : 0.f;
+    }
+    store8(h + v * 8, o);
+  }
+}
+
+template <typename T>
+__global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ u,
+                                    const float* __restrict__ gamma, const float* __restrict__ mean,
+                                    const float* __restrict__ rstd, const float* __restrict__ sums2, float inv_n,
+                                    T* __restrict__ du, long long nvec, int C, int cg) {
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvec;
+       v += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(v % cg) * 8;
+    float g[8], x[8], o[8];
+    load8(dy + v * 8, g);
+    load8(u + v * 8, x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = c0 + i;
+      float r = 0.f;
+      if (c < C) {
+        const float rs = __ldg(rstd + c);
+        const float xh = (x[i] - __ldg(mean + c)) * rs;
+        r = __ldg(gamma + c) * rs * (g[i] - __ldg(sums2 + c) * inv_n - xh * __ldg(sums2 + C + c) * inv_n);
+      }
+      o[i] = r;
+    }
+    store8(du + v * 8, o);
+  }
+}
+
+template <typename T>
+__global__ void glu_kernel(const T* __restrict__ V, T* __restrict__ out, long long rows, int C, int Vs, int Os) {
+  const int og = Os >> 3;
+  const long long nvec = rows * og;
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvec;
+       v += (long long)gridDim.x * blockDim.x) {
+    const long long r = v / og;
+    const int c0 = (int)(v % og) * 8;
+    float o[8];
+    if (c0 + 8 <= C && (C % 8) == 0) {
+      float a[8], g[8];
+      load8(V + r * Vs + c0, a);
+      load8(V + r * Vs + C + c0, g);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = a[i] * sigmoid_f(g[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = c0 + i;
+        o[i] = (c < C) ? to_f(V[r * Vs + c]) * sigmoid_f(to_f(V[r * Vs + C + c])) : 0.f;
+      }
+    }
+    store8(out + r * Os + c0, o);
+  }
+}
+
+template <typename T>
+__global__ void glu_bwd_kernel(const T* __restrict__ dOut, const T* __restrict__ V, T* __restrict__ dV,
+                               long long rows, int C, int Vs, int Os) {
+  // one thread per 8 output channels; writes both halves of dV (and zeroes the pad of dV once)
+  const int og = Os >> 3;
+  const long long nvec = rows * og;
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvec;
+       v += (long long)gridDim.x * blockDim.x) {
+    const long long r = v / og;
+    const int c0 = (int)(v % og) * 8;
+    if (c0 + 8 <= C && (C % 8) == 0) {
+      float d[8], a[8], g[8], da[8], dg[8];
+      load8(dOut + r * Os + c0, d);
+      load8(V + r * Vs + c0, a);
+      load8(V + r * Vs + C + c0, g);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float s = sigmoid_f(g[i]);
+        da[i] = d[i] * s;
+        dg[i] = d[i] * a[i] * s * (1.f - s);
+      }
+      store8(dV + r * Vs + c0, da);
+      store8(dV + r * Vs + C + c0, dg);
+    } else {
+      for (int i = 0; i < 8; ++i) {
+        const int c = c0 + i;
+        if (c < C) {
+          const float d = to_f(dOut[r * Os + c]);
+          const float a = to_f(V[r * Vs + c]);
+          const float s = sigmoid_f(to_f(V[r * Vs + C + c]));
+          dV[r * Vs + c] = from_f<T>(d * s);
+          dV[r * Vs + C + c] = from_f<T>(d * a * s * (1.f - s));
+        }
+      }
+    }
+    if (c0 == 0) {
+      for (int c = 2 * C; c < Vs; ++c) dV[r * Vs + c] = from_f<T>(0.f);
+    }
+  }
+}
+
+template <typename T, bool kBwd>
+__global__ void gelu_kernel(const T* __restrict__ dq, const T* __restrict__ p, T* __restrict__ o, long long nvec) {
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvec;
+       v += (long long)gridDim.x * blockDim.x) {
+    float x[8], r[8];
+    load8(p + v * 8, x);
+    if (kBwd) {
+      float g[8];
+      load8(dq + v * 8, g);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r[i] = g[i] * gelu_grad_f(x[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r[i] = gelu_f(x[i]);
+    }
+    store8(o + v * 8, r);
+  }
+}
+
+template <typename T>
+__global__ void time_mean_kernel(const T* __restrict__ Z, T* __restrict__ Zm, int B, int Tn, int Fs) {
+  const int fg = Fs >> 3;
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < (long long)B * fg;
+       v += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(v / fg), f0 = (int)(v % fg) * 8;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int t = 0; t < Tn; ++t) {
+      float x[8];
+      load8(Z + ((long long)b * Tn + t) * Fs + f0, x);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += x[i];
+    }
+    const float inv = 1.f / (float)Tn;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] *= inv;
+    store8(Zm + (long long)b * Fs + f0, acc);
+  }
+}
+
+template <typename T>
+__global__ void time_mean_bwd_kernel(const T* __restrict__ dZm, T* __restrict__ dZ, int B, int Tn, int Fs) {
+  const int fg = Fs >> 3;
+  const long long nvec = (long long)B * Tn * fg;
+  const float inv = 1.f / (float)Tn;
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvec;
+       v += (long long)gridDim.x * blockDim.x) {
+    const int f0 = (int)(v % fg) * 8;
+    const int b = (int)(v / ((long long)fg * Tn));
+    float x[8];
+    load8(dZm + (long long)b * Fs + f0, x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] *= inv;
+    store8(dZ + v * 8, x);
+  }
+}
+
+template <typename T>
+__global__ void rowsumsq_kernel(const T* __restrict__ Z, float* __restrict__ sq, long long D, int chunks) {
+  // grid = (chunks, B); D % 8 == 0
+  __shared__ float red[8];
+  const int b = blockIdx.y;
+  const long long nvec = D >> 3;
+  const long long per = (nvec + chunks - 1) / chunks;
+  const long long v0 = blockIdx.x * per;
+  long long v1 = v0 + per;
+  if (v1 > nvec) v1 = nvec;
+  float s = 0.f;
+  for (long long v = v0 + threadIdx.x; v < v1; v += blockDim.x) {
+    float x[8];
+    load8(Z + b * D + v * 8, x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += x[i] * x[i];
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    atomicAdd(&sq[b], t);
+  }
+}
+
+template <typename S, typename D>
+__global__ void cast_kernel(const S* __restrict__ s, D* __restrict__ d, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    d[i] = from_f<D>(to_f(s[i]));
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ rm, float* __restrict__ rv,
+                                   float count, float eps, float momentum, int training, float* __restrict__ scale,
+                                   float* __restrict__ shift, float* __restrict__ mean, float* __restrict__ rstd,
+                                   int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float m, var;
+  if (training) {
+    m = sums[c] / count;
+    var = fmaxf(sums[C + c] / count - m * m, 0.f);
+    const float unbiased = count > 1.f ? var * count / (count - 1.f) : var;
+    rm[c] = (1.f - momentum) * rm[c] + momentum * m;
+    rv[c] = (1.f - momentum) * rv[c] + momentum * unbiased;
+  } else {
+    m = rm[c];
+    var = rv[c];
+  }
+  const float rs = rsqrtf(var + eps);
+  const float sc = gamma[c] * rs;
+  scale[c] = sc;
+  shift[c] = beta[c] - m * sc;
+  mean[c] = m;
+  rstd[c] = rs;
+}
+
+// softmax over sensors + dropout mask folded into the weights (rows = D1 outputs)
+__global__ void sa_softmax_kernel(const float* __restrict__ a, const float* __restrict__ mask,
+                                  float* __restrict__ W, float* __restrict__ Wm, int C) {
+  __shared__ float red[32];
+  const int o = blockIdx.x;
+  const float* row = a + (long long)o * C;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) mx = fmaxf(mx, row[i]);
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int i = 1; i < (int)(blockDim.x >> 5); ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float s = 0.f;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) s += expf(row[i] - mx);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  s = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+  const float inv = 1.f / s;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    const float w = expf(row[i] - mx) * inv;
+    W[(long long)o * C + i] = w;
+    Wm[(long long)o * C + i] = mask ? w * mask[i] : w;
+  }
+}
+
+__global__ void sa_softmax_bwd_kernel(const float* __restrict__ W, const float* __restrict__ dWm,
+                                      const float* __restrict__ mask, float* __restrict__ da, int C) {
+  __shared__ float red[32];
+  const int o = blockIdx.x;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    const float g = dWm[(long long)o * C + i] * (mask ? mask[i] : 1.f);
+    s += W[(long long)o * C + i] * g;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  s = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    const float g = dWm[(long long)o * C + i] * (mask ? mask[i] : 1.f);
+    da[(long long)o * C + i] = W[(long long)o * C + i] * (g - s);
+  }
+}
+
+}  // namespace megb200
+
+using namespace megb200;
+
+#define DISPATCH_DTYPE(dtype, ...)                                   \
+  if ((dtype) == MEGB200_F32) {                                      \
+    using DT = float;                                                 \
+    __VA_ARGS__                                                      \
+  } else if ((dtype) == MEGB200_BF16) {                              \
+    using DT = __nv_bfloat16;                                         \
+    __VA_ARGS__                                                      \
+  } else {                                                           \
+    set_last_error("unknown dtype %d", (int)(dtype));                \
+    return MEGB200_ERR_ARG;                                          \
+  }
+
+extern "C" {
+
+int megb200_pack_x(const float* X, void* Xp, int B, int C, int T, int Cs, int dtype, void* stream) {
+  MEGB_CHECK_ARG(X && Xp && B > 0 && C > 0 && T > 0 && Cs >= C && Cs % 8 == 0, "pack_x: bad arguments");
+  MEGB_CHECK_ARG(B <= 65535, "pack_x: B too large");
+  DISPATCH_DTYPE(dtype, return launch_transpose_pack<DT>(X, Xp, nullptr, B, C, T, Cs, (cudaStream_t)stream);)
+}
+
+int megb200_clip_prep_y(const float* Y, void* Yp, float* ysq, int B, int F, int T, int dtype, void* stream) {
+  MEGB_CHECK_ARG(Y && Yp && ysq && B > 0 && F > 0 && T > 0 && F % 8 == 0, "clip_prep_y: bad arguments (F %% 8)");
+  MEGB_CHECK_ARG(B <= 65535, "clip_prep_y: B too large");
+  DISPATCH_DTYPE(dtype, return launch_transpose_pack<DT>(Y, Yp, ysq, B, F, T, F, (cudaStream_t)stream);)
+}
+
+int megb200_pack_weight(const float* w, void* out, int G, int O, int I, int Kt, int Np, int Kp, int mode, int dtype,
+                        void* stream) {
+  MEGB_CHECK_ARG(w && out && G > 0 && O > 0 && I > 0 && Kt > 0, "pack_weight: bad arguments");
+  MEGB_CHECK_ARG(mode == 0 ? (Np >= O && Kp >= I) : (Np >= I && Kp >= O), "pack_weight: padded dims too small");
+  const long long total = (long long)G * Np * Kt * Kp;
+  DISPATCH_DTYPE(dtype, pack_weight_kernel<DT><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                            w, (DT*)out, G, O, I, Kt, Np, Kp, mode, total);
+                 MEGB_LAUNCH_OK(); return 0;)
+}
+
+int megb200_colsum(const void* U, int B, int T, int C, int Cs, const int32_t* group, int G, float* out, int dtype,
+                   void* stream) {
+  MEGB_CHECK_ARG(U && out && B > 0 && T > 0 && G >= 1, "colsum: bad arguments");
+  DISPATCH_DTYPE(dtype, ColsumOp<DT> op{(const DT*)U, Cs};
+                 return launch_colreduce(op, (long long)B * T, C, Cs, group, T, out, nullptr, (cudaStream_t)stream);)
+}
+
+int megb200_bn_stats(const void* U, long long rows, int C, int Cs, float* sums, int dtype, void* stream) {
+  MEGB_CHECK_ARG(U && sums && rows > 0, "bn_stats: bad arguments");
+  DISPATCH_DTYPE(dtype, StatsOp<DT> op{(const DT*)U, Cs};
+                 return launch_colreduce(op, rows, C, Cs, nullptr, 1, sums, sums + C, (cudaStream_t)stream);)
+}
+
+int megb200_bn_finalize(const float* sums, const float* gamma, const float* beta, float* running_mean,
+                        float* running_var, long long count, float eps, float momentum, int training, float* scale,
+                        float* shift, float* mean, float* rstd, int C, void* stream) {
+  MEGB_CHECK_ARG(gamma && beta && running_mean && running_var && scale && shift && mean && rstd && C > 0,
+                 "bn_finalize: null argument");
+  MEGB_CHECK_ARG(!training || (sums && count > 0), "bn_finalize: training needs sums and count");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      sums, gamma, beta, running_mean, running_var, (float)count, eps, momentum, training, scale, shift, mean, rstd, C);
+  MEGB_LAUNCH_OK();
+  return 0;
+}
+
+int megb200_bn_gelu(const void* U, const float* scale, const float* shift, void* H, long long rows, int C, int Cs,
+                    int dtype, void* stream) {
+  MEGB_CHECK_ARG(U && H && scale && shift && rows > 0 && Cs % 8 == 0 && Cs >= C, "bn_gelu: bad arguments");
+  const long long nvec = rows * (Cs / 8);
+  DISPATCH_DTYPE(dtype, bn_gelu_kernel<DT><<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)stream>>>(
+                            (const DT*)U, scale, shift, (DT*)H, nvec, C, Cs / 8);
+                 MEGB_LAUNCH_OK(); return 0;)
+}
+
+int megb200_bn_gelu_bwd_reduce(const void* dH, const void* U, const float* scale, const float* shift,
+                               const float* mean, const float* rstd, void* dY, float* sums2, long long rows, int C,
+                               int Cs, int dtype, void* stream) {
+  MEGB_CHECK_ARG(dH && U && dY && sums2 && rows > 0, "bn_gelu_bwd_reduce: bad arguments");
+  DISPATCH_DTYPE(dtype, BnGeluBwdOp<DT> op{(const DT*)dH, (const DT*)U, (DT*)dY, scale, shift, mean, rstd, Cs, C};
+                 return launch_colreduce(op, rows, C, Cs, nullptr, 1, sums2, sums2 + C, (cudaStream_t)stream);)
+}
+
+int megb200_bn_bwd_apply(const void* dY, const void* U, const float* gamma, const float* mean, const float* rstd,
+                         const float* sums2, long long count, void* dU, long long rows, int C, int Cs, int dtype,
+                         void* stream) {
+  MEGB_CHECK_ARG(dY && U && dU && sums2 && rows > 0 && count > 0 && Cs % 8 == 0, "bn_bwd_apply: bad arguments");
+  const long long nvec = rows * (Cs / 8);
+  DISPATCH_DTYPE(dtype, bn_bwd_apply_kernel<DT><<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)stream>>>(
+                            (const DT*)dY, (const DT*)U, gamma, mean, rstd, sums2, 1.f / (float)count, (DT*)dU, nvec, C,
+                            Cs / 8);
+                 MEGB_LAUNCH_OK(); return 0;)
+}
+
+int megb200_glu(const void* V, void* Out, long long rows, int C, int Vs, int Os, int dtype, void* stream) {
+  MEGB_CHECK_ARG(V && Out && rows > 0 && Vs >= 2 * C && Os >= C && Vs % 8 == 0 && Os % 8 == 0, "glu: bad arguments");
+  const long long nvec = rows * (Os / 8);
+  DISPATCH_DTYPE(dtype, glu_kernel<DT><<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)stream>>>((const DT*)V, (DT*)Out,
+                                                                                             rows, C, Vs, Os);
+                 MEGB_LAUNCH_OK(); return 0;)
+}
+
+int megb200_glu_bwd(const void* dOut, const void* V, void* dV, long long rows, int C, int Vs, int Os, int dtype,
+                    void* stream) {
+  MEGB_CHECK_ARG(dOut && V && dV && rows > 0 && Vs >= 2 * C && Os >= C && Vs % 8 == 0 && Os % 8 == 0,
+                 "glu_bwd: bad arguments");
+  const long long nvec = rows * (Os / 8);
+  DISPATCH_DTYPE(dtype, glu_bwd_kernel<DT><<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)stream>>>(
+                            (const DT*)dOut, (const DT*)V, (DT*)dV, rows, C, Vs, Os);
+                 MEGB_LAUNCH_OK(); return 0;)
+}
+
+int megb200_gelu(const void* P, void* Q, long long n, int dtype, void* stream) {
+  MEGB_CHECK_ARG(P && Q && n > 0 && n % 8 == 0, "gelu: n must be a positive multiple of 8");
+  DISPATCH_DTYPE(dtype, gelu_kernel<DT, false><<<ew_grid(n / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+                            nullptr, (const DT*)P, (DT*)Q, n / 8);
+                 MEGB_LAUNCH_OK(); return 0;)
+}
+
+int megb200_gelu_bwd(const void* dQ, const void* P, void* dP, long long n, int dtype, void* stream) {
+  MEGB_CHECK_ARG(dQ && P && dP && n > 0 && n % 8 == 0, "gelu_bwd: n must be a positive multiple of 8");
+  DISPATCH_DTYPE(dtype, gelu_kernel<DT, true><<<ew_grid(n / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+                            (const DT*)dQ, (const DT*)P, (DT*)dP, n / 8);
+                 MEGB_LAUNCH_OK(); return 0;)
+}
+
+int megb200_time_mean(const void* Z, void* Zm, int B, int T, int F, int Fs, int dtype, void* stream) {
+  MEGB_CHECK_ARG(Z && Zm && B > 0 && T > 0 && Fs % 8 == 0 && Fs >= F, "time_mean: bad arguments");
+  DISPATCH_DTYPE(dtype, time_mean_kernel<DT><<<ew_grid((long long)B * Fs / 8, 128), 128, 0, (cudaStream_t)stream>>>(
+                            (const DT*)Z, (DT*)Zm, B, T, Fs);
+                 MEGB_LAUNCH_OK(); return 0;)
+}
+
+int megb200_time_mean_bwd(const void* dZm, void* dZ, int B, int T, int F, int Fs, int dtype, void* stream) {
+  MEGB_CHECK_ARG(dZm && dZ && B > 0 && T > 0 && Fs % 8 == 0 && Fs >= F, "time_mean_bwd: bad arguments");
+  DISPATCH_DTYPE(dtype,
+                 time_mean_bwd_kernel<DT><<<ew_grid((long long)B * T * Fs / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+                     (const DT*)dZm, (DT*)dZ, B, T, Fs);
+                 MEGB_LAUNCH_OK(); return 0;)
+}
+
+int megb200_rowsumsq(const void* Z, float* sq, int B, long long D, int dtype, void* stream) {
+  MEGB_CHECK_ARG(Z && sq && B > 0 && D > 0 && D % 8 == 0 && B <= 65535, "rowsumsq: bad arguments (D %% 8)");
+  int chunks = (int)((D / 8 + 1023) / 1024);
+  const int cap = (num_sms() * 8 + B - 1) / B;
+  if (chunks > cap) chunks = cap;
+  if (chunks < 1) chunks = 1;
+  dim3 grid(chunks, B);
+  DISPATCH_DTYPE(dtype, rowsumsq_kernel<DT><<<grid, 256, 0, (cudaStream_t)stream>>>((const DT*)Z, sq, D, chunks);
+                 MEGB_LAUNCH_OK(); return 0;)
+}
+
+int megb200_cast(const void* src, void* dst, long long n, int src_dtype, int dst_dtype, void* stream) {
+  MEGB_CHECK_ARG(src && dst && n > 0, "cast: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int g = ew_grid(n, 256);
+  if (src_dtype == MEGB200_F32 && dst_dtype == MEGB200_BF16)
+    cast_kernel<float, __nv_bfloat16><<<g, 256, 0, st>>>((const float*)src, (__nv_bfloat16*)dst, n);
+  else if (src_dtype == MEGB200_BF16 && dst_dtype == MEGB200_F32)
+    cast_kernel<__nv_bfloat16, float><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, (float*)dst, n);
+  else if (src_dtype == MEGB200_F32 && dst_dtype == MEGB200_F32)
+    cast_kernel<float, float><<<g, 256, 0, st>>>((const float*)src, (float*)dst, n);
+  else if (src_dtype == MEGB200_BF16 && dst_dtype == MEGB200_BF16)
+    cast_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, n);
+  else
+    MEGB_CHECK_ARG(false, "cast: unknown dtype pair");
+  MEGB_LAUNCH_OK();
+  return 0;
+}
+
+int megb200_sa_softmax(const float* a, const float* mask, float* W, float* Wm, int D1, int C, void* stream) {
+  MEGB_CHECK_ARG(a && W && Wm && D1 > 0 && C > 0, "sa_softmax: bad arguments");
+  sa_softmax_kernel<<<D1, 128, 0, (cudaStream_t)stream>>>(a, mask, W, Wm, C);
+  MEGB_LAUNCH_OK();
+  return 0;
+}
+
+int megb200_sa_softmax_bwd(const float* W, const float* dWm, const float* mask, float* da, int D1, int C,
+                           void* stream) {
+  MEGB_CHECK_ARG(W && dWm && da && D1 > 0 && C > 0, "sa_softmax_bwd: bad arguments");
+  sa_softmax_bwd_kernel<<<D1, 128, 0, (cudaStream_t)stream>>>(W, dWm, mask, da, C);
+  MEGB_LAUNCH_OK();
+  return 0;
+}
+
+}  // extern "C"

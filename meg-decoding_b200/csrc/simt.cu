@@ -1,0 +1,346 @@
+// fp32 CUDA-core contraction engine ("check mode", MEGB200_SIMT): the same contractions as the tcgen05 engine in
+// tc_gemm.cu, accumulated in fp32 FMA on any storage dtype.  It is (a) the fp32 check mode the parity contract asks
+// for (1e-3 vs the fp32 reference) and (b) the on-device cross-check for every tensor-core kernel.  One 64x64x16
+// register-tiled core parameterised by operand loaders and an epilogue.
+#include "common.cuh"
+
+namespace megb200 {
+
+constexpr int kBM = 64, kBN = 64, kBK = 16;
+
+// kAK / kBK_: true when the operand's k index is the contiguous one in memory (keeps loads coalesced)
+template <bool kAKMajor, bool kBKMajor, class LoadA, class LoadB>
+__device__ __forceinline__ void simt_tile(const LoadA& la, const LoadB& lb, int k0, int k1, float (&acc)[4][4]) {
+  __shared__ float As[kBK][kBM + 1];
+  __shared__ float Bs[kBK][kBN + 1];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k = k0; k < k1; k += kBK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + i * 256;
+      {
+        const int r = kAKMajor ? (e >> 4) : (e & 63);
+        const int kk = kAKMajor ? (e & 15) : (e >> 6);
+        As[kk][r] = (k + kk < k1) ? la(r, k + kk) : 0.f;
+      }
+      {
+        const int r = kBKMajor ? (e >> 4) : (e & 63);
+        const int kk = kBKMajor ? (e & 15) : (e >> 6);
+        Bs[kk][r] = (k + kk < k1) ? lb(r, k + kk) : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kBK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------ tap GEMM
+template <typename T>
+__global__ void __launch_bounds__(256)
+simt_tapgemm_kernel(const T* __restrict__ A, int Tn, int Ca, int Cas, const T* __restrict__ W, int N, int Np, int Kp,
+                    int taps, int dil, const float* __restrict__ bias, const T* __restrict__ Res, int Crs,
+                    const int32_t* __restrict__ group, T* __restrict__ Out, int Cos, int tiles_per_sample) {
+  const int b = blockIdx.x / tiles_per_sample;
+  const int t0 = (blockIdx.x % tiles_per_sample) * kBM;
+  const int n0 = blockIdx.y * kBN;
+  const int g = group ? group[b] : 0;
+  const T* Ab = A + (long long)b * Tn * Cas;
+  const T* Wg = W + (long long)g * Np * taps * Kp;
+  const int half = taps / 2;
+  auto la = [&](int r, int k) -> float {
+    const int j = k / Kp, c = k - j * Kp;
+    const int t = t0 + r + (j - half) * dil;
+    if (c >= Ca || t < 0 || t >= Tn || t0 + r >= Tn) return 0.f;
+    return to_f(Ab[(long long)t * Cas + c]);
+  };
+  auto lb = [&](int r, int k) -> float {
+    const int n = n0 + r;
+    if (n >= N) return 0.f;
+    return to_f(Wg[(long long)n * taps * Kp + k]);
+  };
+  float acc[4][4];
+  simt_tile<true, true>(la, lb, 0, taps * Kp, acc);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int t = t0 + ty * 4 + i;
+    if (t >= Tn) continue;
+    const long long row = (long long)b * Tn + t;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= Cos) continue;
+      float v = 0.f;
+      if (n < N) {
+        v = acc[i][j];
+        if (bias) v += bias[(long long)g * N + n];
+        if (Res) v += to_f(Res[row * Crs + n]);
+      }
+      Out[row * Cos + n] = from_f<T>(v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ weight gradient
+// block = (m tile, c tile) x tap x sample-range; fp32 register accumulation over the samples of one group run
+template <typename T>
+__global__ void __launch_bounds__(256)
+simt_wgrad_kernel(const T* __restrict__ dU, int M, int Ms, const T* __restrict__ Xin, int C, int Cs, int B, int Tn,
+                  int taps, int dil, const int32_t* __restrict__ group, float* __restrict__ dW, int ctiles,
+                  int samples_per_block) {
+  const int m0 = (blockIdx.x / ctiles) * kBM;
+  const int c0 = (blockIdx.x % ctiles) * kBN;
+  const int j = blockIdx.y;
+  const int b0 = blockIdx.z * samples_per_block;
+  int b1 = b0 + samples_per_block;
+  if (b1 > B) b1 = B;
+  const int off = (j - taps / 2) * dil;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float tot[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) tot[i][q] = 0.f;
+  auto flush = [&](int g) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + ty * 4 + i;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int c = c0 + tx * 4 + q;
+        if (m < M && c < C && tot[i][q] != 0.f)
+          atomicAdd(&dW[(((long long)g * M + m) * C + c) * taps + j], tot[i][q]);
+        tot[i][q] = 0.f;
+      }
+    }
+  };
+  int cur = group ? group[b0] : 0;
+  for (int b = b0; b < b1; ++b) {
+    const int g = group ? group[b] : 0;
+    if (g != cur) {
+      flush(cur);
+      cur = g;
+    }
+    const T* Ub = dU + (long long)b * Tn * Ms;
+    const T* Xb = Xin + (long long)b * Tn * Cs;
+    auto la = [&](int r, int k) -> float {  // A[m][k=t]
+      const int m = m0 + r;
+      return (m < M) ? to_f(Ub[(long long)k * Ms + m]) : 0.f;
+    };
+    auto lb = [&](int r, int k) -> float {  // B[c][k=t] = Xin[t+off][c]
+      const int c = c0 + r, t = k + off;
+      return (c < C && t >= 0 && t < Tn) ? to_f(Xb[(long long)t * Cs + c]) : 0.f;
+    };
+    float acc[4][4];
+    simt_tile<false, false>(la, lb, 0, Tn, acc);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) tot[i][q] += acc[i][q];
+  }
+  flush(cur);
+}
+
+// ------------------------------------------------------------------------------------------ small f32 GEMM
+__global__ void __launch_bounds__(256)
+simt_sgemm_kernel(int transA, int transB, int M, int N, int K, float alpha, const float* __restrict__ A, int lda,
+                  long long sA, const float* __restrict__ Bm, int ldb, long long sB, float beta,
+                  float* __restrict__ Cm, int ldc, long long sC) {
+  const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * kBN;
+  const float* Ab = A + blockIdx.z * sA;
+  const float* Bb = Bm + blockIdx.z * sB;
+  float* Cb = Cm + blockIdx.z * sC;
+  auto la = [&](int r, int k) -> float {
+    const int m = m0 + r;
+    if (m >= M) return 0.f;
+    return transA ? Ab[(long long)k * lda + m] : Ab[(long long)m * lda + k];
+  };
+  auto lb = [&](int r, int k) -> float {
+    const int n = n0 + r;
+    if (n >= N) return 0.f;
+    return transB ? Bb[(long long)n * ldb + k] : Bb[(long long)k * ldb + n];
+  };
+  float acc[4][4];
+  // loader index mapping only affects coalescing; pick by the common case per flag
+  if (!transA && transB) simt_tile<true, true>(la, lb, 0, K, acc);
+  else if (!transA && !transB) simt_tile<true, false>(la, lb, 0, K, acc);
+  else if (transA && !transB) simt_tile<false, false>(la, lb, 0, K, acc);
+  else simt_tile<false, true>(la, lb, 0, K, acc);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = alpha * acc[i][j];
+      if (beta != 0.f) v += beta * Cb[(long long)m * ldc + n];
+      Cb[(long long)m * ldc + n] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ CLIP contractions
+template <typename T>
+__global__ void __launch_bounds__(256)
+simt_clip_logits_kernel(const T* __restrict__ Yp, const T* __restrict__ Zp, float* __restrict__ raw, int By, int Bz,
+                        long long D, long long kchunk) {
+  const int i0 = blockIdx.x * kBM, j0 = blockIdx.y * kBN;
+  const long long k0 = blockIdx.z * kchunk;
+  long long k1 = k0 + kchunk;
+  if (k1 > D) k1 = D;
+  const T* Ya = Yp + k0;
+  const T* Za = Zp + k0;
+  auto la = [&](int r, int k) -> float { return (i0 + r < By) ? to_f(Ya[(long long)(i0 + r) * D + k]) : 0.f; };
+  auto lb = [&](int r, int k) -> float { return (j0 + r < Bz) ? to_f(Za[(long long)(j0 + r) * D + k]) : 0.f; };
+  float acc[4][4];
+  simt_tile<true, true>(la, lb, 0, (int)(k1 - k0), acc);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = i0 + ty * 4 + i, c = j0 + tx * 4 + j;
+      if (r < By && c < Bz) atomicAdd(&raw[(long long)r * Bz + c], acc[i][j]);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+simt_clip_dz_kernel(const T* __restrict__ coef, int ldc, const T* __restrict__ Yp, const T* __restrict__ Z,
+                    const float* __restrict__ cvec, const float* __restrict__ gscale, T* __restrict__ dZ, int By,
+                    int Bz, long long D) {
+  const int j0 = blockIdx.y * kBM;
+  const long long d0 = (long long)blockIdx.x * kBN;
+  auto la = [&](int r, int k) -> float { return (j0 + r < Bz) ? to_f(coef[(long long)(j0 + r) * ldc + k]) : 0.f; };
+  auto lb = [&](int r, int k) -> float { return (d0 + r < D) ? to_f(Yp[(long long)k * D + d0 + r]) : 0.f; };
+  float acc[4][4];
+  simt_tile<true, false>(la, lb, 0, By, acc);
+  const float gs = gscale[0];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int j = j0 + ty * 4 + i;
+    if (j >= Bz) continue;
+    const float cj = cvec[j];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const long long d = d0 + tx * 4 + q;
+      if (d >= D) continue;
+      const float z = to_f(Z[(long long)j * D + d]);
+      dZ[(long long)j * D + d] = from_f<T>(gs * (acc[i][q] - z * cj));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ launchers
+template <typename T>
+int simt_tapgemm(const void* A, int B, int Tn, int Ca, int Cas, const void* W, int N, int Np, int Kp, int taps,
+                 int dil, const float* bias, const void* Res, int Crs, const int32_t* group, void* Out, int Cos,
+                 cudaStream_t st) {
+  const int tps = (Tn + kBM - 1) / kBM;
+  dim3 grid(B * tps, (Cos + kBN - 1) / kBN);
+  simt_tapgemm_kernel<T><<<grid, 256, 0, st>>>((const T*)A, Tn, Ca, Cas, (const T*)W, N, Np, Kp, taps, dil, bias,
+                                                (const T*)Res, Crs, group, (T*)Out, Cos, tps);
+  MEGB_LAUNCH_OK();
+  return 0;
+}
+template int simt_tapgemm<float>(const void*, int, int, int, int, const void*, int, int, int, int, int, const float*,
+                                 const void*, int, const int32_t*, void*, int, cudaStream_t);
+template int simt_tapgemm<__nv_bfloat16>(const void*, int, int, int, int, const void*, int, int, int, int, int,
+                                         const float*, const void*, int, const int32_t*, void*, int, cudaStream_t);
+
+template <typename T>
+int simt_wgrad(const void* dU, int M, int Ms, const void* Xin, int C, int Cs, int B, int Tn, int taps, int dil,
+               const int32_t* group, float* dW, cudaStream_t st) {
+  const int mt = (M + kBM - 1) / kBM, ct = (C + kBN - 1) / kBN;
+  int spb = 1;
+  if (group == nullptr) {
+    // enough CTAs to fill the machine, long enough runs to amortise the atomics
+    const long long base = (long long)mt * ct * taps;
+    long long want = ((long long)num_sms() * 4 + base - 1) / base;
+    if (want < 1) want = 1;
+    spb = (int)((B + want - 1) / want);
+    if (spb < 1) spb = 1;
+  } else {
+    spb = 4;
+  }
+  dim3 grid(mt * ct, taps, (B + spb - 1) / spb);
+  MEGB_CHECK_ARG(grid.z <= 65535, "wgrad: too many sample blocks");
+  simt_wgrad_kernel<T><<<grid, 256, 0, st>>>((const T*)dU, M, Ms, (const T*)Xin, C, Cs, B, Tn, taps, dil, group, dW,
+                                              ct, spb);
+  MEGB_LAUNCH_OK();
+  return 0;
+}
+template int simt_wgrad<float>(const void*, int, int, const void*, int, int, int, int, int, int, const int32_t*,
+                               float*, cudaStream_t);
+template int simt_wgrad<__nv_bfloat16>(const void*, int, int, const void*, int, int, int, int, int, int,
+                                       const int32_t*, float*, cudaStream_t);
+
+template <typename T>
+int simt_clip_logits(const void* Yp, const void* Zp, float* raw, int By, int Bz, long long D, cudaStream_t st) {
+  const int it = (By + kBM - 1) / kBM, jt = (Bz + kBN - 1) / kBN;
+  long long splits = ((long long)num_sms() * 4 + (long long)it * jt - 1) / ((long long)it * jt);
+  long long kchunk = (D + splits - 1) / splits;
+  kchunk = ((kchunk + 255) / 256) * 256;
+  if (kchunk > (1ll << 30)) kchunk = 1ll << 30;
+  splits = (D + kchunk - 1) / kchunk;
+  MEGB_CHECK_ARG(splits <= 65535, "clip_logits: too many k splits");
+  dim3 grid(it, jt, (int)splits);
+  simt_clip_logits_kernel<T><<<grid, 256, 0, st>>>((const T*)Yp, (const T*)Zp, raw, By, Bz, D, kchunk);
+  MEGB_LAUNCH_OK();
+  return 0;
+}
+template int simt_clip_logits<float>(const void*, const void*, float*, int, int, long long, cudaStream_t);
+template int simt_clip_logits<__nv_bfloat16>(const void*, const void*, float*, int, int, long long, cudaStream_t);
+
+template <typename T>
+int simt_clip_dz(const void* coef, int ldc, const void* Yp, const void* Z, const float* cvec, const float* gscale,
+                 void* dZ, int By, int Bz, long long D, cudaStream_t st) {
+  const long long dt = (D + kBN - 1) / kBN;
+  MEGB_CHECK_ARG(dt <= 2147483647ll && (Bz + kBM - 1) / kBM <= 65535, "clip_dz: grid too large");
+  dim3 grid((unsigned)dt, (Bz + kBM - 1) / kBM);
+  simt_clip_dz_kernel<T><<<grid, 256, 0, st>>>((const T*)coef, ldc, (const T*)Yp, (const T*)Z, cvec, gscale, (T*)dZ, By,
+                                                Bz, D);
+  MEGB_LAUNCH_OK();
+  return 0;
+}
+template int simt_clip_dz<float>(const void*, int, const void*, const void*, const float*, const float*, void*, int,
+                                 int, long long, cudaStream_t);
+template int simt_clip_dz<__nv_bfloat16>(const void*, int, const void*, const void*, const float*, const float*,
+                                         void*, int, int, long long, cudaStream_t);
+
+}  // namespace megb200
+
+using namespace megb200;
+
+extern "C" int megb200_sgemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
+                             long long strideA, const float* Bm, int ldb, long long strideB, float beta, float* C,
+                             int ldc, long long strideC, int batch, void* stream) {
+  MEGB_CHECK_ARG(A && Bm && C && M > 0 && N > 0 && K > 0 && batch > 0 && batch <= 65535, "sgemm: bad arguments");
+  dim3 grid((M + kBM - 1) / kBM, (N + kBN - 1) / kBN, batch);
+  MEGB_CHECK_ARG(grid.y <= 65535, "sgemm: N too large");
+  simt_sgemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(transA, transB, M, N, K, alpha, A, lda, strideA, Bm, ldb,
+                                                           strideB, beta, C, ldc, strideC);
+  MEGB_LAUNCH_OK();
+  return 0;
+}

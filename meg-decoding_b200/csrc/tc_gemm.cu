@@ -1,0 +1,761 @@
+// Tensor-core contraction engine (MEGB200_TC): tcgen05.mma kind::f16 (bf16 x bf16 -> f32 in TMEM), operands staged
+// in shared memory by TMA through an mbarrier ring, warp-specialised CTAs (warp 0 = TMA producer, warp 1 = TMEM
+// allocator + single-thread MMA issuer, warps 2-5 = epilogue, one TMEM lane quarter each).
+//
+//   tc_tapgemm      out[pos][n] = sum_{tap,c} A[pos + off(tap)][c] * W[g][n][tap*Kp + c]   (conv fwd / dgrad / 1x1 /
+//                   grouped subject GEMM).  A: 3-D tensor map (c, t, b); the tap shift is a coordinate offset and TMA's
+//                   out-of-bounds zero fill is the "same" padding.  Both operands K-major, SWIZZLE_128B.
+//   tc_wgrad        dW[m][c][tap] += sum_pos dU[pos][m] * X[pos + off(tap)][c]; positions are the reduction, so both
+//                   operands are MN-major straight from the PC layout; split over sample ranges.
+//   tc_clip_logits  raw[i][j] += sum_d Y[i][d] Z[j][d]; split-K over D, f32 atomics.
+//   tc_clip_dz      dZ[j][d] = gs * (sum_i coef[j][i] Y[i][d] - Z[j][d] cvec[j]); A K-major, B MN-major.
+#include "tc_common.cuh"
+
+namespace megb200 {
+namespace tc {
+
+constexpr int kThreads = 192;
+constexpr int kHeaderBytes = 1024;  // barriers + tmem slot + small per-CTA tables live in front of the stage ring
+
+struct Header {
+  uint64_t full[8];
+  uint64_t empty[8];
+  uint64_t tmem_full;
+  uint64_t tmem_empty;
+  uint32_t tmem_slot;
+  uint32_t pad;
+};
+
+__device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
+  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023);
+}
+
+// ================================================================================================ tap GEMM
+struct TapGemmParams {
+  int T, N, Cos, Crs, taps, dil, Kp, kchunks, tiles_per_sample, ntiles, NT, stages;
+  uint32_t tmem_cols, idesc;
+  const float* bias;
+  const __nv_bfloat16* Res;
+  const int32_t* group;
+  __nv_bfloat16* Out;
+};
+
+__global__ void __launch_bounds__(kThreads)
+tc_tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                  const TapGemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  Header* hdr = reinterpret_cast<Header*>(smem);
+  float* sbias = reinterpret_cast<float*>(smem + 512);  // NT <= 128 floats fit in the header; larger go below
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t a_bytes = kTileM * 128, b_bytes = (uint32_t)p.NT * 128;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  uint8_t* ring = smem + kHeaderBytes;
+  float* sbias_big = reinterpret_cast<float*>(ring + (size_t)p.stages * stage_bytes);
+  if (p.NT > 128) sbias = sbias_big;
+
+  const int n_tile = blockIdx.x % p.ntiles;
+  const int m_tile = blockIdx.x / p.ntiles;
+  const int b = m_tile / p.tiles_per_sample;
+  const int t0 = (m_tile % p.tiles_per_sample) * kTileM;
+  const int n0 = n_tile * p.NT;
+  const int g = p.group ? p.group[b] : 0;
+  const int num_k = p.taps * p.kchunks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&hdr->full[s]), 1);
+      mbar_init(smem_u32(&hdr->empty[s]), 1);
+    }
+    mbar_init(smem_u32(&hdr->tmem_full), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&hdr->tmem_slot), p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = hdr->tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < num_k; ++it) {
+        const int s = it % p.stages;
+        mbar_wait(smem_u32(&hdr->empty[s]), ((it / p.stages) & 1) ^ 1);
+        const uint32_t full = smem_u32(&hdr->full[s]);
+        mbar_arrive_expect_tx(full, stage_bytes);
+        const int tap = it / p.kchunks, kc = it % p.kchunks;
+        const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
+        tma_load_3d(sa, &tmA, kc * kBlockK, t0 + (tap - p.taps / 2) * p.dil, b, full);
+        tma_load_3d(sa + a_bytes, &tmW, tap * p.Kp + kc * kBlockK, n0, g, full);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int it = 0; it < num_k; ++it) {
+        const int s = it % p.stages;
+        mbar_wait(smem_u32(&hdr->full[s]), (it / p.stages) & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
+        const uint64_t da = make_smem_desc(sa, 16, 1024);
+        const uint64_t db = make_smem_desc(sa + a_bytes, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < kBlockK / kUmmaK; ++k)
+          umma_bf16(tmem_base, desc_advance(da, k * 32), desc_advance(db, k * 32), p.idesc, (it | k) != 0);
+        umma_commit(smem_u32(&hdr->empty[s]));
+      }
+      umma_commit(smem_u32(&hdr->tmem_full));
+    }
+  } else {
+    // ---------------- epilogue: TMEM -> registers -> (+bias, +residual) -> bf16 -> global (thread = one position)
+    const int et = threadIdx.x - 64;
+    for (int i = et; i < p.NT; i += 128) {
+      const int n = n0 + i;
+      sbias[i] = (p.bias != nullptr && n < p.N) ? p.bias[(long long)g * p.N + n] : 0.f;
+    }
+    named_bar_sync(1, 128);
+    mbar_wait(smem_u32(&hdr->tmem_full), 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int t = t0 + q * 32 + lane;
+    const bool valid = t < p.T;
+    const long long row = (long long)b * p.T + t;
+    __nv_bfloat16* orow = p.Out + row * p.Cos;
+    const __nv_bfloat16* rrow = p.Res ? p.Res + row * p.Crs : nullptr;
+    for (int ch = 0; ch < p.NT / 16; ++ch) {
+      float v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 16), v);
+      if (!valid) continue;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c0 = n0 + ch * 16 + h * 8;
+        if (c0 >= p.Cos) continue;
+        float o[8];
+        float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (rrow != nullptr && c0 < p.Crs) load8(rrow + c0, r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int n = c0 + i;
+          o[i] = (n < p.N) ? v[h * 8 + i] + sbias[ch * 16 + h * 8 + i] + r[i] : 0.f;
+        }
+        store8(orow + c0, o);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ================================================================================================ weight gradient
+struct WgradParams {
+  int T, M, C, taps, dil, B, kchunks /*per sample*/, ctile /*channels per CTA, multiple of 64*/, c_tiles, m_tiles;
+  int samples_per_cta, stages, mode /*0 = partial slot store, 1 = atomic (grouped)*/;
+  uint32_t tmem_cols, idesc0, idesc1;
+  int n0_cols, n1_cols;  // the c tile is issued as one or two MMAs of n0 (+ n1) columns (multiples of 64)
+  const int32_t* group;
+  const int32_t* order;
+  float* out;  // mode 0: partial[slot][tap][M][C]; mode 1: dW[g][M][C][taps]
+};
+
+__global__ void __launch_bounds__(kThreads)
+tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmX,
+                const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  Header* hdr = reinterpret_cast<Header*>(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t atom_bytes = kBlockK * 128;                // 64 k-rows x 128 B
+  const uint32_t a_bytes = 2 * atom_bytes;                  // 128 m channels = 2 atoms
+  const uint32_t b_bytes = (uint32_t)(p.ctile / 64) * atom_bytes;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  uint8_t* ring = smem + kHeaderBytes;
+
+  // blockIdx.x = (m tile, c tile), blockIdx.y = tap, blockIdx.z = sample range
+  const int m0 = (blockIdx.x / p.c_tiles) * kTileM;
+  const int c0 = (blockIdx.x % p.c_tiles) * p.ctile;
+  const int tap = blockIdx.y;
+  const int s0 = blockIdx.z * p.samples_per_cta;
+  const int s1 = min(s0 + p.samples_per_cta, p.B);
+  const int off = (tap - p.taps / 2) * p.dil;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmU);
+    tma_prefetch_desc(&tmX);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&hdr->full[s]), 1);
+      mbar_init(smem_u32(&hdr->empty[s]), 1);
+    }
+    mbar_init(smem_u32(&hdr->tmem_full), 1);
+    mbar_init(smem_u32(&hdr->tmem_empty), 128);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&hdr->tmem_slot), p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = hdr->tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int si = s0; si < s1; ++si) {
+        const int b = p.order ? p.order[si] : si;
+        for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
+          const int s = it % p.stages;
+          mbar_wait(smem_u32(&hdr->empty[s]), ((it / p.stages) & 1) ^ 1);
+          const uint32_t full = smem_u32(&hdr->full[s]);
+          mbar_arrive_expect_tx(full, stage_bytes);
+          const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
+          tma_load_3d(sa, &tmU, m0, kc * kBlockK, b, full);
+          tma_load_3d(sa + atom_bytes, &tmU, m0 + 64, kc * kBlockK, b, full);
+          for (int a = 0; a < p.ctile / 64; ++a)
+            tma_load_3d(sa + a_bytes + a * atom_bytes, &tmX, c0 + a * 64, kc * kBlockK + off, b, full);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int it = 0, flushes = 0;
+      int cur = (p.group && s0 < s1) ? p.group[p.order ? p.order[s0] : s0] : 0;
+      bool fresh = true;
+      for (int si = s0; si < s1; ++si) {
+        const int b = p.order ? p.order[si] : si;
+        const int g = p.group ? p.group[b] : 0;
+        if (g != cur) {
+          // hand the finished group to the epilogue and wait until it has drained the accumulator
+          umma_commit(smem_u32(&hdr->tmem_full));
+          mbar_wait(smem_u32(&hdr->tmem_empty), flushes & 1);
+          tc_fence_after();
+          ++flushes;
+          cur = g;
+          fresh = true;
+        }
+        for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
+          const int s = it % p.stages;
+          mbar_wait(smem_u32(&hdr->full[s]), (it / p.stages) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
+          // MN-major: LBO = distance between 64-channel atoms, SBO = distance between 8-position groups
+          const uint64_t da = make_smem_desc(sa, atom_bytes, 1024);
+          const uint64_t db0 = make_smem_desc(sa + a_bytes, atom_bytes, 1024);
+          const uint64_t db1 = make_smem_desc(sa + a_bytes + (uint32_t)(p.n0_cols / 64) * atom_bytes, atom_bytes, 1024);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            const uint32_t acc = (!fresh || k != 0) ? 1u : 0u;
+            umma_bf16(tmem_base, desc_advance(da, k * kUmmaK * 128), desc_advance(db0, k * kUmmaK * 128), p.idesc0,
+                      acc);
+            if (p.n1_cols > 0)
+              umma_bf16(tmem_base + (uint32_t)p.n0_cols, desc_advance(da, k * kUmmaK * 128),
+                        desc_advance(db1, k * kUmmaK * 128), p.idesc1, acc);
+          }
+          fresh = false;
+          umma_commit(smem_u32(&hdr->empty[s]));
+        }
+      }
+      umma_commit(smem_u32(&hdr->tmem_full));
+    }
+  } else {
+    // ---------------- epilogue: thread = one output channel m (TMEM lane); columns = input channels c
+    const int q = warp & 3;
+    const int m = m0 + q * 32 + lane;
+    int flushes = 0;
+    int si = s0;
+    while (si < s1) {
+      // the run of samples [si, se) shares one group
+      const int g = p.group ? p.group[p.order ? p.order[si] : si] : 0;
+      int se = si + 1;
+      if (p.group) {
+        while (se < s1 && p.group[p.order ? p.order[se] : se] == g) ++se;
+      } else {
+        se = s1;
+      }
+      mbar_wait(smem_u32(&hdr->tmem_full), flushes & 1);
+      tc_fence_after();
+      const int ncols = p.n0_cols + p.n1_cols;
+      for (int ch = 0; ch < ncols / 16; ++ch) {
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 16), v);
+        if (m >= p.M) continue;
+        const int cb = c0 + ch * 16;
+        if (p.mode == 0) {
+          float* dst = p.out + (((long long)blockIdx.z * p.taps + tap) * p.M + m) * p.C;
+          if (cb + 16 <= p.C && (p.C & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              *reinterpret_cast<float4*>(dst + cb + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (cb + i < p.C) dst[cb + i] = v[i];
+          }
+        } else {
+          float* dst = p.out + (((long long)g * p.M + m) * p.C) * p.taps + tap;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (cb + i < p.C) atomicAdd(dst + (long long)(cb + i) * p.taps, v[i]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(&hdr->tmem_empty));
+      ++flushes;
+      si = se;
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// partial[slot][tap][M][C] -> dW[m][c][tap] += sum_slot
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dW, int slots, int taps, int M,
+                                    int C) {
+  const long long n = (long long)taps * M * C;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n;
+       idx += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < slots; ++k) s += part[(long long)k * n + idx];
+    const int c = (int)(idx % C);
+    const long long r = idx / C;
+    const int m = (int)(r % M);
+    const int tap = (int)(r / M);
+    dW[((long long)m * C + c) * taps + tap] += s;
+  }
+}
+
+// ================================================================================================ CLIP logits
+struct LogitsParams {
+  int By, Bz, NT, stages, kchunks_total, kchunks_per_cta, i_tiles;
+  uint32_t tmem_cols, idesc;
+  float* raw;
+};
+
+__global__ void __launch_bounds__(kThreads)
+tc_clip_logits_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmZ,
+                      const LogitsParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  Header* hdr = reinterpret_cast<Header*>(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t a_bytes = kTileM * 128, b_bytes = (uint32_t)p.NT * 128;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  uint8_t* ring = smem + kHeaderBytes;
+  const int i0 = (blockIdx.x % p.i_tiles) * kTileM;
+  const int j0 = (blockIdx.x / p.i_tiles) * p.NT;
+  const int kc0 = blockIdx.y * p.kchunks_per_cta;
+  const int kc1 = min(kc0 + p.kchunks_per_cta, p.kchunks_total);
+  const int num_k = kc1 - kc0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmY);
+    tma_prefetch_desc(&tmZ);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&hdr->full[s]), 1);
+      mbar_init(smem_u32(&hdr->empty[s]), 1);
+    }
+    mbar_init(smem_u32(&hdr->tmem_full), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&hdr->tmem_slot), p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = hdr->tmem_slot;
+
+  if (num_k > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        for (int it = 0; it < num_k; ++it) {
+          const int s = it % p.stages;
+          mbar_wait(smem_u32(&hdr->empty[s]), ((it / p.stages) & 1) ^ 1);
+          const uint32_t full = smem_u32(&hdr->full[s]);
+          mbar_arrive_expect_tx(full, stage_bytes);
+          const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
+          tma_load_2d(sa, &tmY, (kc0 + it) * kBlockK, i0, full);
+          tma_load_2d(sa + a_bytes, &tmZ, (kc0 + it) * kBlockK, j0, full);
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        for (int it = 0; it < num_k; ++it) {
+          const int s = it % p.stages;
+          mbar_wait(smem_u32(&hdr->full[s]), (it / p.stages) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
+          const uint64_t da = make_smem_desc(sa, 16, 1024);
+          const uint64_t db = make_smem_desc(sa + a_bytes, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)
+            umma_bf16(tmem_base, desc_advance(da, k * 32), desc_advance(db, k * 32), p.idesc, (it | k) != 0);
+          umma_commit(smem_u32(&hdr->empty[s]));
+        }
+        umma_commit(smem_u32(&hdr->tmem_full));
+      }
+    } else {
+      mbar_wait(smem_u32(&hdr->tmem_full), 0);
+      tc_fence_after();
+      const int q = warp & 3;
+      const int i = i0 + q * 32 + lane;
+      for (int ch = 0; ch < p.NT / 16; ++ch) {
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 16), v);
+        if (i >= p.By) continue;
+        float* dst = p.raw + (long long)i * p.Bz + j0 + ch * 16;
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+          if (j0 + ch * 16 + e < p.Bz) atomicAdd(dst + e, v[e]);
+      }
+      tc_fence_before();
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ================================================================================================ CLIP dZ
+struct DzParams {
+  int By, Bz, NT /*d columns per CTA, multiple of 64*/, stages, kchunks;
+  long long D;
+  uint32_t tmem_cols, idesc;
+  const __nv_bfloat16* Z;
+  const float* cvec;
+  const float* gscale;
+  __nv_bfloat16* dZ;
+};
+
+__global__ void __launch_bounds__(kThreads)
+tc_clip_dz_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmY,
+                  const DzParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  Header* hdr = reinterpret_cast<Header*>(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t atom_bytes = kBlockK * 128;
+  const uint32_t a_bytes = kTileM * 128;
+  const uint32_t b_bytes = (uint32_t)(p.NT / 64) * atom_bytes;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  uint8_t* ring = smem + kHeaderBytes;
+  const long long d0 = (long long)blockIdx.x * p.NT;
+  const int j0 = blockIdx.y * kTileM;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmC);
+    tma_prefetch_desc(&tmY);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&hdr->full[s]), 1);
+      mbar_init(smem_u32(&hdr->empty[s]), 1);
+    }
+    mbar_init(smem_u32(&hdr->tmem_full), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&hdr->tmem_slot), p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = hdr->tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < p.kchunks; ++it) {
+        const int s = it % p.stages;
+        mbar_wait(smem_u32(&hdr->empty[s]), ((it / p.stages) & 1) ^ 1);
+        const uint32_t full = smem_u32(&hdr->full[s]);
+        mbar_arrive_expect_tx(full, stage_bytes);
+        const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
+        tma_load_2d(sa, &tmC, it * kBlockK, j0, full);                                    // coef[j][i]: K-major
+        for (int a = 0; a < p.NT / 64; ++a)                                               // Y[i][d]: MN-major
+          tma_load_2d(sa + a_bytes + a * atom_bytes, &tmY, (int)(d0 + a * 64), it * kBlockK, full);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int it = 0; it < p.kchunks; ++it) {
+        const int s = it % p.stages;
+        mbar_wait(smem_u32(&hdr->full[s]), (it / p.stages) & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
+        const uint64_t da = make_smem_desc(sa, 16, 1024);
+        const uint64_t db = make_smem_desc(sa + a_bytes, atom_bytes, 1024);
+#pragma unroll
+        for (int k = 0; k < kBlockK / kUmmaK; ++k)
+          umma_bf16(tmem_base, desc_advance(da, k * 32), desc_advance(db, k * kUmmaK * 128), p.idesc, (it | k) != 0);
+        umma_commit(smem_u32(&hdr->empty[s]));
+      }
+      umma_commit(smem_u32(&hdr->tmem_full));
+    }
+  } else {
+    mbar_wait(smem_u32(&hdr->tmem_full), 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int j = j0 + q * 32 + lane;
+    const bool valid = j < p.Bz;
+    const float cj = valid ? p.cvec[j] : 0.f;
+    const float gs = p.gscale[0];
+    for (int ch = 0; ch < p.NT / 16; ++ch) {
+      float v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 16), v);
+      if (!valid) continue;
+      const long long d = d0 + ch * 16;
+      if (d >= p.D) continue;   // D is a multiple of 16 on this path
+      float z[16];
+      load8(p.Z + (long long)j * p.D + d, reinterpret_cast<float(&)[8]>(z[0]));
+      load8(p.Z + (long long)j * p.D + d + 8, reinterpret_cast<float(&)[8]>(z[8]));
+#pragma unroll
+      for (int e = 0; e < 16; ++e) z[e] = gs * (v[e] - z[e] * cj);
+      store8(p.dZ + (long long)j * p.D + d, reinterpret_cast<float(&)[8]>(z[0]));
+      store8(p.dZ + (long long)j * p.D + d + 8, reinterpret_cast<float(&)[8]>(z[8]));
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ================================================================================================ host launchers
+static int pick_stages(uint32_t stage_bytes, uint32_t budget, int max_stages) {
+  int s = (int)(budget / stage_bytes);
+  if (s > max_stages) s = max_stages;
+  return s;
+}
+
+static int pick_ntile(int Np) {
+  if (Np <= 256) return Np;
+  for (int nt = 256; nt >= 128; nt -= 16)
+    if (Np % nt == 0) return nt;
+  const int tiles = (Np + 255) / 256;
+  return (((Np + tiles - 1) / tiles) + 15) / 16 * 16;
+}
+
+template <class K>
+static int set_smem(K kernel, size_t bytes) {
+  MEGB_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+
+int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int N, int Np, int Kp, int taps, int dil,
+               const float* bias, const void* Res, int Crs, const int32_t* group, int G, void* Out, int Cos,
+               cudaStream_t st) {
+  MEGB_CHECK_ARG(Cas % 8 == 0 && Cos % 8 == 0 && (Res == nullptr || Crs % 8 == 0), "tc_tapgemm: strides must be multiples of 8");
+  MEGB_CHECK_ARG(Kp % 64 == 0 && Np % 16 == 0 && Np >= N, "tc_tapgemm: Kp %% 64 and Np %% 16 required (Kp=%d Np=%d)", Kp, Np);
+  TapGemmParams p;
+  p.T = T; p.N = N; p.Cos = Cos; p.Crs = Crs; p.taps = taps; p.dil = dil; p.Kp = Kp;
+  p.kchunks = (Ca + kBlockK - 1) / kBlockK;
+  p.tiles_per_sample = (T + kTileM - 1) / kTileM;
+  p.NT = pick_ntile(Np);
+  // output channels up to Cos must be covered so that pad channels are written as zero
+  const int ncover = Cos > Np ? Cos : Np;
+  p.ntiles = (ncover + p.NT - 1) / p.NT;
+  const uint32_t stage_bytes = kTileM * 128 + p.NT * 128;
+  p.stages = pick_stages(stage_bytes, 112000 - (p.NT > 128 ? p.NT * 4 : 0), 6);
+  MEGB_CHECK_ARG(p.stages >= 2, "tc_tapgemm: tile too large for the stage ring");
+  p.tmem_cols = tmem_cols_for(p.NT);
+  p.idesc = make_idesc(p.NT, 0, 0);
+  p.bias = bias; p.Res = (const __nv_bfloat16*)Res; p.group = group; p.Out = (__nv_bfloat16*)Out;
+
+  CUtensorMap tmA, tmW;
+  {
+    const uint64_t dims[3] = {(uint64_t)Ca, (uint64_t)T, (uint64_t)B};
+    const uint64_t strides[2] = {(uint64_t)Cas * 2, (uint64_t)T * Cas * 2};
+    const uint32_t box[3] = {kBlockK, kTileM, 1};
+    int rc = encode_tmap_bf16(&tmA, A, 3, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)taps * Kp, (uint64_t)Np, (uint64_t)G};
+    const uint64_t strides[2] = {(uint64_t)taps * Kp * 2, (uint64_t)Np * taps * Kp * 2};
+    const uint32_t box[3] = {kBlockK, (uint32_t)p.NT, 1};
+    int rc = encode_tmap_bf16(&tmW, W, 3, dims, strides, box);
+    if (rc) return rc;
+  }
+  const size_t smem = 1024 + kHeaderBytes + (size_t)p.stages * stage_bytes + (p.NT > 128 ? p.NT * 4 : 0);
+  int rc = set_smem(tc_tapgemm_kernel, smem);
+  if (rc) return rc;
+  const long long blocks = (long long)B * p.tiles_per_sample * p.ntiles;
+  MEGB_CHECK_ARG(blocks > 0 && blocks < 2147483647ll, "tc_tapgemm: grid too large");
+  tc_tapgemm_kernel<<<(unsigned)blocks, kThreads, smem, st>>>(tmA, tmW, p);
+  MEGB_LAUNCH_OK();
+  return 0;
+}
+
+int tc_wgrad(const void* dU, int M, int Ms, const void* Xin, int C, int Cs, int B, int T, int taps, int dil,
+             const int32_t* group, const int32_t* order, int G, float* dW, float* workspace, size_t ws_bytes,
+             cudaStream_t st) {
+  MEGB_CHECK_ARG(Ms % 8 == 0 && Cs % 8 == 0, "tc_wgrad: strides must be multiples of 8");
+  WgradParams p;
+  p.T = T; p.M = M; p.C = C; p.taps = taps; p.dil = dil; p.B = B;
+  p.kchunks = (T + kBlockK - 1) / kBlockK;
+  const int c64 = (C + 63) / 64 * 64;
+  // c tile <= 320 columns: issued as (192 + 128) / 256 / 192 / 128 / 64
+  p.c_tiles = (c64 + 319) / 320;
+  p.ctile = ((c64 / 64 + p.c_tiles - 1) / p.c_tiles) * 64;
+  if (p.ctile > 256) { p.n0_cols = 192; p.n1_cols = p.ctile - 192; }
+  else { p.n0_cols = p.ctile; p.n1_cols = 0; }
+  p.idesc0 = make_idesc(p.n0_cols, 1, 1);
+  p.idesc1 = p.n1_cols ? make_idesc(p.n1_cols, 1, 1) : 0;
+  p.m_tiles = (M + kTileM - 1) / kTileM;
+  p.tmem_cols = tmem_cols_for(p.ctile);
+  const uint32_t stage_bytes = 2 * kBlockK * 128 + (p.ctile / 64) * kBlockK * 128;
+  p.stages = pick_stages(stage_bytes, 200 * 1024, 6);
+  MEGB_CHECK_ARG(p.stages >= 2, "tc_wgrad: tile too large");
+  p.group = group; p.order = order;
+  const long long base = (long long)p.m_tiles * p.c_tiles * taps;
+  const long long slot_elems = (long long)taps * M * C;
+  int splits;
+  if (group == nullptr) {
+    p.mode = 0;
+    splits = (int)((num_sms() + base - 1) / base);
+    if (splits > B) splits = B;
+    const long long max_slots = (long long)(ws_bytes / sizeof(float)) / slot_elems;
+    if (splits > max_slots) splits = (int)max_slots;
+    MEGB_CHECK_ARG(splits >= 1, "tc_wgrad: workspace too small (%zu bytes, need >= %lld)", ws_bytes, slot_elems * 4);
+    p.out = workspace;
+  } else {
+    MEGB_CHECK_ARG(order != nullptr, "tc_wgrad: grouped mode needs the group-sorted sample order");
+    p.mode = 1;
+    splits = (int)((num_sms() + base - 1) / base);
+    if (splits > B) splits = B;
+    if (splits < 1) splits = 1;
+    p.out = dW;
+  }
+  p.samples_per_cta = (B + splits - 1) / splits;
+  splits = (B + p.samples_per_cta - 1) / p.samples_per_cta;
+
+  CUtensorMap tmU, tmX;
+  {
+    const uint64_t dims[3] = {(uint64_t)M, (uint64_t)T, (uint64_t)B};
+    const uint64_t strides[2] = {(uint64_t)Ms * 2, (uint64_t)T * Ms * 2};
+    const uint32_t box[3] = {64, kBlockK, 1};
+    int rc = encode_tmap_bf16(&tmU, dU, 3, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)C, (uint64_t)T, (uint64_t)B};
+    const uint64_t strides[2] = {(uint64_t)Cs * 2, (uint64_t)T * Cs * 2};
+    const uint32_t box[3] = {64, kBlockK, 1};
+    int rc = encode_tmap_bf16(&tmX, Xin, 3, dims, strides, box);
+    if (rc) return rc;
+  }
+  const size_t smem = 1024 + kHeaderBytes + (size_t)p.stages * stage_bytes;
+  int rc = set_smem(tc_wgrad_kernel, smem);
+  if (rc) return rc;
+  dim3 grid(p.m_tiles * p.c_tiles, taps, splits);
+  tc_wgrad_kernel<<<grid, kThreads, smem, st>>>(tmU, tmX, p);
+  MEGB_LAUNCH_OK();
+  if (p.mode == 0) {
+    long long blocks = (slot_elems + 255) / 256;
+    if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+    wgrad_reduce_kernel<<<(int)blocks, 256, 0, st>>>(workspace, dW, splits, taps, M, C);
+    MEGB_LAUNCH_OK();
+  }
+  return 0;
+}
+
+int tc_clip_logits(const void* Yp, const void* Zp, float* raw, int By, int Bz, long long D, cudaStream_t st) {
+  MEGB_CHECK_ARG(D % 8 == 0, "tc_clip_logits: D must be a multiple of 8");
+  LogitsParams p;
+  p.By = By; p.Bz = Bz;
+  const int bz16 = (Bz + 15) / 16 * 16;
+  p.NT = bz16 > 256 ? 256 : bz16;
+  const int j_tiles = (Bz + p.NT - 1) / p.NT;
+  p.i_tiles = (By + kTileM - 1) / kTileM;
+  p.kchunks_total = (int)((D + kBlockK - 1) / kBlockK);
+  const long long tiles = (long long)p.i_tiles * j_tiles;
+  long long splits = ((long long)num_sms() + tiles - 1) / tiles;
+  if (splits > p.kchunks_total) splits = p.kchunks_total;
+  if (splits < 1) splits = 1;
+  p.kchunks_per_cta = (int)((p.kchunks_total + splits - 1) / splits);
+  splits = (p.kchunks_total + p.kchunks_per_cta - 1) / p.kchunks_per_cta;
+  MEGB_CHECK_ARG(splits <= 65535, "tc_clip_logits: too many splits");
+  const uint32_t stage_bytes = kTileM * 128 + p.NT * 128;
+  p.stages = pick_stages(stage_bytes, 200 * 1024, 6);
+  p.tmem_cols = tmem_cols_for(p.NT);
+  p.idesc = make_idesc(p.NT, 0, 0);
+  p.raw = raw;
+  CUtensorMap tmY, tmZ;
+  {
+    const uint64_t dims[2] = {(uint64_t)D, (uint64_t)By};
+    const uint64_t strides[1] = {(uint64_t)D * 2};
+    const uint32_t box[2] = {kBlockK, kTileM};
+    int rc = encode_tmap_bf16(&tmY, Yp, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)D, (uint64_t)Bz};
+    const uint64_t strides[1] = {(uint64_t)D * 2};
+    const uint32_t box[2] = {kBlockK, (uint32_t)p.NT};
+    int rc = encode_tmap_bf16(&tmZ, Zp, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  const size_t smem = 1024 + kHeaderBytes + (size_t)p.stages * stage_bytes;
+  int rc = set_smem(tc_clip_logits_kernel, smem);
+  if (rc) return rc;
+  dim3 grid((unsigned)tiles, (unsigned)splits);
+  tc_clip_logits_kernel<<<grid, kThreads, smem, st>>>(tmY, tmZ, p);
+  MEGB_LAUNCH_OK();
+  return 0;
+}
+
+int tc_clip_dz(const void* coef, int ldc, const void* Yp, const void* Z, const float* cvec, const float* gscale,
+               void* dZ, int By, int Bz, long long D, cudaStream_t st) {
+  MEGB_CHECK_ARG(D % 16 == 0 && ldc % 8 == 0, "tc_clip_dz: D %% 16 and ldc %% 8 required (D=%lld ldc=%d)", D, ldc);
+  DzParams p;
+  p.By = By; p.Bz = Bz; p.D = D;
+  p.NT = D >= 256 ? 256 : (int)((D + 63) / 64 * 64);
+  p.kchunks = (By + kBlockK - 1) / kBlockK;
+  const uint32_t stage_bytes = kTileM * 128 + (p.NT / 64) * kBlockK * 128;
+  p.stages = pick_stages(stage_bytes, 100 * 1024, 4);
+  p.tmem_cols = tmem_cols_for(p.NT);
+  p.idesc = make_idesc(p.NT, 0, 1);
+  p.Z = (const __nv_bfloat16*)Z; p.cvec = cvec; p.gscale = gscale; p.dZ = (__nv_bfloat16*)dZ;
+  CUtensorMap tmC, tmY;
+  {
+    const uint64_t dims[2] = {(uint64_t)By, (uint64_t)Bz};
+    const uint64_t strides[1] = {(uint64_t)ldc * 2};
+    const uint32_t box[2] = {kBlockK, kTileM};
+    int rc = encode_tmap_bf16(&tmC, coef, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)D, (uint64_t)By};
+    const uint64_t strides[1] = {(uint64_t)D * 2};
+    const uint32_t box[2] = {64, kBlockK};
+    int rc = encode_tmap_bf16(&tmY, Yp, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  const size_t smem = 1024 + kHeaderBytes + (size_t)p.stages * stage_bytes;
+  int rc = set_smem(tc_clip_dz_kernel, smem);
+  if (rc) return rc;
+  const long long dt = (D + p.NT - 1) / p.NT;
+  MEGB_CHECK_ARG(dt < 2147483647ll, "tc_clip_dz: grid too large");
+  dim3 grid((unsigned)dt, (Bz + kTileM - 1) / kTileM);
+  tc_clip_dz_kernel<<<grid, kThreads, smem, st>>>(tmC, tmY, p);
+  MEGB_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace tc
+}  // namespace megb200

@@ -1,0 +1,278 @@
+"""Step orchestration of the hot path on top of the op interface (ops.CudaOps): BrainEncoder forward/backward
+and CLIPLoss forward/backward as explicit kernel sequences (no autograd inside, no tracing compiler).
+
+Math follows SURVEY appendix A (verified against the reference): reference op sites are cited inline
+(paths relative to the reference tree).  Design points:
+
+* The linear chain spatial-attention mix -> shared 1x1 conv -> per-subject 1x1 conv (models.py:220,269-272) is
+  pre-multiplied in fp32 per step into one effective (D1 x C) matrix and bias per subject and executed as ONE grouped
+  GEMM keyed by the subject index; the spatial-dropout mask (models.py:235-239) is a column mask of that matrix.
+  X needs no gradient, so the backward of the whole block is one grouped weight-gradient GEMM plus small fp32 algebra.
+* Activations live in the position-major "PC" layout [B][T][Cs]; one rounding to the storage dtype per stored tensor;
+  BN statistics, residual adds and GELU/GLU are evaluated in fp32.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from .ops import pad8, pad16, pad64
+
+
+def _f32(dev, *shape):
+    return torch.empty(*shape, dtype=torch.float32, device=dev)
+
+
+def _zeros(dev, *shape):
+    return torch.zeros(*shape, dtype=torch.float32, device=dev)
+
+
+class EncoderEngine:
+    """BrainEncoder.forward / backward (models.py:367-383 and the modules it owns)."""
+
+    def __init__(self, ops, *, C: int, D1: int, D2: int, F: int, S: int, seq2seq: bool, dilations=None,
+                 eps: float = 1e-5, momentum: float = 0.1):
+        self.ops, self.C, self.D1, self.D2, self.F, self.S = ops, C, D1, D2, F, S
+        self.seq2seq = seq2seq
+        self.dil = dilations if dilations is not None else [(1, 1, 1)] * 5
+        self.eps, self.momentum = eps, momentum
+
+    # ------------------------------------------------------------------------------------------ forward
+    def forward(self, P: Dict, X: torch.Tensor, subj: torch.Tensor, mask: Optional[torch.Tensor], training: bool):
+        ops, dev = self.ops, X.device
+        B, C, T = X.shape
+        D1, D2, Fo, S = self.D1, self.D2, self.F, self.S
+        assert C == self.C, f"expected {self.C} sensors, got {C}"                       # models.py:233
+        ctx = {"B": B, "T": T, "subj": subj, "mask": mask}
+
+        # ---- spatial attention weights + subject chain, fp32 (models.py:204-213, 252, 269-272)
+        a = _f32(dev, D1, C)
+        ops.matmul(P["z_re"], P["cos"], a)
+        ops.matmul(P["z_im"], P["sin"], a, beta=1.0)
+        Wt, Wm = _f32(dev, D1, C), _f32(dev, D1, C)
+        ops.sa_softmax(a, mask, Wt, Wm)
+        M1 = _f32(dev, D1, C)
+        ops.matmul(P["Wc"], Wm, M1)
+        Weff = _f32(dev, S, D1, C)
+        ops.matmul(P["Ws"], M1, Weff)
+        beff = _f32(dev, S, D1, 1)
+        ops.matmul(P["Ws"], P["bc"].view(D1, 1), beff)
+        Wp = ops.empty(S, pad16(D1), pad64(C), device=dev)
+        ops.pack_weight(Weff.view(S, D1, C, 1), Wp, 0)
+        Xp = ops.empty(B, T, pad8(C), device=dev)
+        ops.pack_x(X, Xp)
+        H2 = ops.empty(B, T, pad8(D1), device=dev)
+        ops.tapgemm(Xp, C, Wp, D1, 1, 1, beff.view(S, D1), None, subj, H2)
+        ctx.update(Wt=Wt, Wm=Wm, M1=M1, Xp=Xp, H2=H2)
+
+        # ---- five residual conv blocks (models.py:308-322)
+        x, cin = H2, D1
+        blocks = []
+        for k in range(5):
+            pk, d = P["blocks"][k], self.dil[k]
+            bc = {"x": x, "cin": cin}
+            u0 = self._conv(x, cin, pk["w0"], pk["b0"], D2, d[0], x if k > 0 else None)
+            h0, bc["bn0"] = self._bn_gelu(u0, pk, "0", training)
+            u1 = self._conv(h0, D2, pk["w1"], pk["b1"], D2, d[1], h0)
+            h1, bc["bn1"] = self._bn_gelu(u1, pk, "1", training)
+            v = self._conv(h1, D2, pk["w2"], pk["b2"], 2 * D2, d[2], None)
+            out = ops.empty(B, T, pad8(D2), device=dev)
+            ops.glu(v, out, D2)
+            bc.update(u0=u0, h0=h0, u1=u1, h1=h1, v=v)
+            blocks.append(bc)
+            x, cin = out, D2
+        ctx["blocks"] = blocks
+        ctx["x5"] = x
+
+        # ---- 1x1 head (models.py:373-374): GELU after both convs
+        p1 = self._conv(x, D2, P["wf1"], P["bf1"], 2 * D2, 1, None, taps=1)
+        q1 = ops.empty(*p1.shape, device=dev)
+        ops.gelu(p1, q1)
+        p2 = self._conv(q1, 2 * D2, P["wf2"], P["bf2"], Fo, 1, None, taps=1)
+        Z = ops.empty(*p2.shape, device=dev)
+        ops.gelu(p2, Z)
+        ctx.update(p1=p1, q1=q1, p2=p2)
+        if not self.seq2seq:                                                            # models.py:382
+            Zm = ops.empty(B, 1, pad8(Fo), device=dev)
+            ops.time_mean(Z, Zm, Fo)
+            return Zm, ctx
+        return Z, ctx
+
+    def _conv(self, x, cin, w, b, N, dil, res, taps=3):
+        ops = self.ops
+        Wpk = ops.empty(1, pad16(N), taps * pad64(cin), device=x.device)
+        ops.pack_weight(w.view(1, N, cin, taps), Wpk, 0)
+        out = ops.empty(x.shape[0], x.shape[1], pad8(N), device=x.device)
+        ops.tapgemm(x, cin, Wpk, N, taps, dil, b, res, None, out)
+        return out
+
+    def _bn_gelu(self, u, pk, i, training):
+        ops, dev, D2 = self.ops, u.device, self.D2
+        n = u.shape[0] * u.shape[1]
+        sums = None
+        if training:
+            sums = _zeros(dev, 2, D2)
+            ops.bn_stats(u, D2, sums)
+        st = {k: _f32(dev, D2) for k in ("scale", "shift", "mean", "rstd")}
+        ops.bn_finalize(sums, pk["g" + i], pk["be" + i], pk["rm" + i], pk["rv" + i], n, self.eps, self.momentum,
+                        training, st["scale"], st["shift"], st["mean"], st["rstd"])
+        h = ops.empty(*u.shape, device=dev)
+        ops.bn_gelu(u, st["scale"], st["shift"], h, D2)
+        return h, st
+
+    # ------------------------------------------------------------------------------------------ backward
+    def backward(self, P: Dict, ctx: Dict, dZ: torch.Tensor):
+        """dZ: gradient w.r.t. the returned embedding, PC layout ([B,T,Fs] or [B,1,Fs]).  Returns a dict of f32
+        gradients keyed like P."""
+        ops, dev = self.ops, dZ.device
+        B, T = ctx["B"], ctx["T"]
+        D1, D2, Fo, S, C = self.D1, self.D2, self.F, self.S, self.C
+        n = B * T
+        G: Dict = {"blocks": [dict() for _ in range(5)]}
+
+        if not self.seq2seq:
+            full = ops.empty(B, T, pad8(Fo), device=dev)
+            ops.time_mean_bwd(dZ, full, Fo)
+            dZ = full
+        # ---- head
+        dp2 = ops.empty(*dZ.shape, device=dev)
+        ops.gelu_bwd(dZ, ctx["p2"], dp2)
+        G["wf2"], G["bf2"] = self._wgrad(dp2, Fo, ctx["q1"], 2 * D2, 1, 1)
+        dq1 = self._dgrad(dp2, Fo, P["wf2"], 2 * D2, 1, None, taps=1)
+        dp1 = ops.empty(*dq1.shape, device=dev)
+        ops.gelu_bwd(dq1, ctx["p1"], dp1)
+        G["wf1"], G["bf1"] = self._wgrad(dp1, 2 * D2, ctx["x5"], D2, 1, 1)
+        dx = self._dgrad(dp1, 2 * D2, P["wf1"], D2, 1, None, taps=1)
+
+        # ---- conv blocks, last to first
+        for k in range(4, -1, -1):
+            pk, bc, d, g = P["blocks"][k], ctx["blocks"][k], self.dil[k], G["blocks"][k]
+            dv = ops.empty(*bc["v"].shape, device=dev)
+            ops.glu_bwd(dx, bc["v"], dv, D2)
+            g["w2"], g["b2"] = self._wgrad(dv, 2 * D2, bc["h1"], D2, 3, d[2])
+            dh1 = self._dgrad(dv, 2 * D2, pk["w2"], D2, d[2], None)
+            du1, g["g1"], g["be1"] = self._bn_gelu_bwd(dh1, bc["u1"], bc["bn1"], pk["g1"], n)
+            g["w1"], g["b1"] = self._wgrad(du1, D2, bc["h0"], D2, 3, d[1])
+            dh0 = self._dgrad(du1, D2, pk["w1"], D2, d[1], du1)
+            du0, g["g0"], g["be0"] = self._bn_gelu_bwd(dh0, bc["u0"], bc["bn0"], pk["g0"], n)
+            g["w0"], g["b0"] = self._wgrad(du0, D2, bc["x"], bc["cin"], 3, d[0])
+            dx = self._dgrad(du0, D2, pk["w0"], bc["cin"], d[0], du0 if k > 0 else None)
+        dH2 = dx
+
+        # ---- subject block + spatial attention, fp32 small algebra
+        subj = ctx["subj"]
+        order = torch.empty_like(subj)
+        ops.group_order(subj, S, order)
+        dWeff = _zeros(dev, S, D1, C, 1)
+        ops.wgrad(dH2, D1, ctx["Xp"], C, 1, 1, subj, order, dWeff)
+        dWeff = dWeff.view(S, D1, C)
+        dbeff = _zeros(dev, S, D1)
+        ops.colsum(dH2, D1, subj, dbeff)
+        dWs = _f32(dev, S, D1, D1)
+        ops.matmul(dWeff, ctx["M1"], dWs, transB=True)
+        ops.matmul(dbeff.view(S, D1, 1), P["bc"].view(1, D1), dWs, beta=1.0)
+        Ws2d = P["Ws"].view(S * D1, D1)
+        dM1 = _f32(dev, D1, C)
+        ops.matmul(Ws2d, dWeff.view(S * D1, C), dM1, transA=True)
+        dbc = _f32(dev, D1, 1)
+        ops.matmul(Ws2d, dbeff.view(S * D1, 1), dbc, transA=True)
+        dWc = _f32(dev, D1, D1)
+        ops.matmul(dM1, ctx["Wm"], dWc, transB=True)
+        dWm = _f32(dev, D1, C)
+        ops.matmul(P["Wc"], dM1, dWm, transA=True)
+        da = _f32(dev, D1, C)
+        ops.sa_softmax_bwd(ctx["Wt"], dWm, ctx["mask"], da)
+        dzr, dzi = _f32(dev, *P["z_re"].shape), _f32(dev, *P["z_im"].shape)
+        ops.matmul(da, P["cos"], dzr, transB=True)
+        ops.matmul(da, P["sin"], dzi, transB=True)
+        G.update(Ws=dWs, Wc=dWc, bc=dbc.view(D1), z_re=dzr, z_im=dzi)
+        return G
+
+    def _wgrad(self, dU, M, Xin, C, taps, dil):
+        ops, dev = self.ops, dU.device
+        dW = _zeros(dev, 1, M, C, taps)
+        ops.wgrad(dU, M, Xin, C, taps, dil, None, None, dW)
+        db = _zeros(dev, M)
+        ops.colsum(dU, M, None, db)
+        return dW.view(M, C, taps), db
+
+    def _dgrad(self, dU, M, w, cin, dil, res, taps=3):
+        """dX = conv_transpose(dU): same tap-GEMM with the transposed, tap-flipped weight pack."""
+        ops = self.ops
+        Wd = ops.empty(1, pad16(cin), taps * pad64(M), device=dU.device)
+        ops.pack_weight(w.view(1, M, cin, taps), Wd, 1)
+        out = ops.empty(dU.shape[0], dU.shape[1], pad8(cin), device=dU.device)
+        ops.tapgemm(dU, M, Wd, cin, taps, dil, None, res, None, out)
+        return out
+
+    def _bn_gelu_bwd(self, dh, u, st, gamma, n):
+        ops, dev, D2 = self.ops, dh.device, self.D2
+        dy = ops.empty(*u.shape, device=dev)
+        sums2 = _zeros(dev, 2, D2)
+        ops.bn_gelu_bwd_reduce(dh, u, st["scale"], st["shift"], st["mean"], st["rstd"], dy, sums2, D2)
+        du = ops.empty(*u.shape, device=dev)
+        ops.bn_bwd_apply(dy, u, gamma, st["mean"], st["rstd"], sums2, n, du, D2)
+        return du, sums2[1], sums2[0]
+
+
+class ClipEngine:
+    """CLIPLoss.forward / backward (loss.py:66-112), one-sided data-parallel form of SURVEY appendix A6.
+
+    Rows of the logits are the speech targets (x = Y), columns the brain embeddings (y = Z), exactly as
+    ``train.py:203`` calls ``loss_func(Y, Z)``.  With ``world > 1`` every rank gathers the (constant) normalised
+    targets, contracts them against its own brain shard, and the per-row log-sum-exp over all brains is completed
+    by a MAX / SUM all-reduce of B_glob floats; no gradient crosses ranks except through the parameter all-reduce.
+    """
+
+    def __init__(self, ops):
+        self.ops = ops
+
+    def forward(self, Y, Zi, temp, reduction="mean", dist_ctx=None, want_logits=False):
+        """Y: f32 targets [B,F,T] | [B,F]; Zi: embeddings in PC layout, contiguous [B, T, F] | [B, 1, F]."""
+        ops, dev = self.ops, Zi.device
+        B = Zi.shape[0]
+        D = Zi.numel() // B
+        assert Y.numel() == B * D, f"targets {tuple(Y.shape)} and embeddings {tuple(Zi.shape)} differ in size"
+        Yp = ops.empty(B, D, device=dev)
+        ysq = _zeros(dev, B)
+        ops.clip_prep_y(Y, Yp, ysq)
+        zsq = _zeros(dev, B)
+        Zf = Zi.view(B, D)
+        ops.rowsumsq(Zf, zsq)
+        world, rank = (dist_ctx.world, dist_ctx.rank) if dist_ctx is not None else (1, 0)
+        if world > 1:
+            Yp, ysq = dist_ctx.all_gather_rows(Yp), dist_ctx.all_gather_rows(ysq)
+        Bg, off = B * world, rank * B
+        raw = _zeros(dev, Bg, B)
+        ops.clip_logits(Yp, Zf, raw)
+        Lg = _f32(dev, Bg, B)
+        row_max, row_se, col_lse = _f32(dev, Bg), _f32(dev, Bg), _f32(dev, B)
+        ops.clip_ce_partial(raw, ysq, zsq, temp, Lg, row_max, row_se, col_lse)
+        if world > 1:
+            m = dist_ctx.all_reduce_max(row_max.clone())
+            row_se = dist_ctx.all_reduce_sum(row_se * torch.exp(row_max - m))
+            row_max = m
+        row_lse = row_max + torch.log(row_se)
+        if reduction == "mean":
+            wscale = 0.5 / Bg
+        elif reduction == "sum":
+            wscale = 0.5
+        else:
+            raise ValueError(f"unsupported reduction {reduction!r}")
+        out2 = _zeros(dev, 2)
+        coef = ops.empty(B, pad8(Bg), device=dev)
+        cvec = _zeros(dev, B)
+        ops.clip_ce_finish(Lg, row_lse, col_lse, ysq, zsq, temp, off, wscale, out2, coef, cvec)
+        loss = out2[0:1].clone()
+        if world > 1:
+            loss = dist_ctx.all_reduce_sum(loss)
+        ctx = dict(coef=coef, Yp=Yp, Zf=Zf, cvec=cvec, dtemp=out2[1:2], shape=Zi.shape)
+        return loss.view(()), (Lg if want_logits else None), ctx
+
+    def backward(self, ctx, gscale):
+        """gscale: f32 [1] upstream gradient of the (scalar) loss.  Returns (dZ in PC layout, dtemp f32 [1])."""
+        ops = self.ops
+        dZ = ops.empty(*ctx["Zf"].shape, device=gscale.device)
+        ops.clip_dz(ctx["coef"], ctx["Yp"], ctx["Zf"], ctx["cvec"], gscale, dZ)
+        return dZ.view(ctx["shape"]), ctx["dtemp"] * gscale

@@ -1,0 +1,270 @@
+"""Tensor-level wrappers over the C-ABI: every method launches hand-written kernels on torch's current CUDA
+stream and writes into caller-provided tensors.  torch supplies device memory and streams only.
+
+``CudaOps(dtype, backend)`` fixes the activation storage type (torch.bfloat16 | torch.float32) and the contraction
+engine (TC = tcgen05, SIMT = fp32 CUDA cores).  The engine code (engine.py) is written against this interface; the
+test-suite's oracle implements the same interface in plain torch to check the orchestration on CPU.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import lib as L
+
+
+def pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+def pad16(n: int) -> int:
+    return (n + 15) // 16 * 16
+
+
+def pad64(n: int) -> int:
+    return (n + 63) // 64 * 64
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+class CudaOps:
+    def __init__(self, dtype: torch.dtype = torch.bfloat16, backend: str = "tc"):
+        if dtype not in (torch.bfloat16, torch.float32):
+            raise ValueError("activation dtype must be bfloat16 or float32")
+        if backend not in ("tc", "simt"):
+            raise ValueError("backend must be 'tc' or 'simt'")
+        if backend == "tc" and dtype != torch.bfloat16:
+            raise ValueError("the tensor-core engine computes in bf16; use backend='simt' for the fp32 check mode")
+        L.load()
+        self.act_dtype = dtype
+        self.dt = L.BF16 if dtype == torch.bfloat16 else L.F32
+        self.be = L.TC if backend == "tc" else L.SIMT
+        self.backend = backend
+        self._ws = {}
+
+    # ------------------------------------------------------------------ helpers
+    @staticmethod
+    def _stream():
+        return torch.cuda.current_stream().cuda_stream
+
+    def _chk_act(self, *ts):
+        for t in ts:
+            if t is not None:
+                assert t.is_cuda and t.dtype == self.act_dtype and t.is_contiguous(), (t.dtype, t.shape, t.is_contiguous())
+
+    @staticmethod
+    def _chk_f32(*ts):
+        for t in ts:
+            if t is not None:
+                assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), (t.dtype, t.shape)
+
+    def workspace(self, device, nbytes: int = 96 << 20):
+        key = (device.index, torch.cuda.current_stream().cuda_stream)
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() * 4 < nbytes:
+            ws = torch.empty(nbytes // 4, dtype=torch.float32, device=device)
+            self._ws[key] = ws
+        return ws
+
+    def empty(self, *shape, device):
+        return torch.empty(*shape, dtype=self.act_dtype, device=device)
+
+    # ------------------------------------------------------------------ packing
+    def pack_x(self, X, Xp):
+        self._chk_f32(X)
+        self._chk_act(Xp)
+        B, C, T = X.shape
+        assert Xp.shape[0] == B and Xp.shape[1] == T
+        L.call("megb200_pack_x", X.data_ptr(), Xp.data_ptr(), B, C, T, Xp.shape[2], self.dt, self._stream())
+
+    def pack_weight(self, w, out, mode: int):
+        """w f32 [G,O,I,Kt] -> out [G,Np,Kt*Kp]; mode 0 forward (N=O,K=I), 1 dgrad (N=I,K=O, flipped taps)."""
+        self._chk_f32(w)
+        self._chk_act(out)
+        G, O, I, Kt = w.shape
+        Np = out.shape[1]
+        Kp = out.shape[2] // Kt
+        assert out.shape[0] == G and out.shape[2] == Kt * Kp
+        L.call("megb200_pack_weight", w.data_ptr(), out.data_ptr(), G, O, I, Kt, Np, Kp, mode, self.dt, self._stream())
+
+    # ------------------------------------------------------------------ contractions
+    def tapgemm(self, A, Ca, W, N, taps, dil, bias, Res, group, Out):
+        self._chk_act(A, W, Res, Out)
+        self._chk_f32(bias)
+        B, T, Cas = A.shape
+        G, Np, Ktot = W.shape
+        Kp = Ktot // taps
+        assert Out.shape[0] == B and Out.shape[1] == T
+        if group is not None:
+            assert group.dtype == torch.int32 and group.is_cuda and group.numel() == B
+        else:
+            assert G == 1
+        if bias is not None:
+            assert bias.numel() == G * N
+        L.call("megb200_tapgemm", A.data_ptr(), B, T, Ca, Cas, W.data_ptr(), N, Np, Kp, taps, dil, _ptr(bias),
+               _ptr(Res), 0 if Res is None else Res.shape[2], _ptr(group), G, Out.data_ptr(), Out.shape[2], self.dt,
+               self.be, self._stream())
+
+    def group_order(self, group, G, order):
+        assert group.dtype == torch.int32 and order.dtype == torch.int32
+        L.call("megb200_group_order", group.data_ptr(), group.numel(), G, order.data_ptr(), self._stream())
+
+    def wgrad(self, dU, M, Xin, C, taps, dil, group, order, dW):
+        """dW f32 [G,M,C,taps] += ...  (caller zeroes)."""
+        self._chk_act(dU, Xin)
+        self._chk_f32(dW)
+        B, T, Ms = dU.shape
+        G = dW.shape[0] if dW.dim() == 4 else 1
+        assert dW.numel() == G * M * C * taps
+        ws = self.workspace(dU.device) if self.be == L.TC else None
+        L.call("megb200_wgrad", dU.data_ptr(), M, Ms, Xin.data_ptr(), C, Xin.shape[2], B, T, taps, dil, _ptr(group),
+               _ptr(order), G, dW.data_ptr(), _ptr(ws), 0 if ws is None else ws.numel() * 4, self.dt, self.be,
+               self._stream())
+
+    def colsum(self, U, C, group, out):
+        self._chk_act(U)
+        self._chk_f32(out)
+        B, T, Cs = U.shape
+        G = out.numel() // C
+        L.call("megb200_colsum", U.data_ptr(), B, T, C, Cs, _ptr(group), G, out.data_ptr(), self.dt, self._stream())
+
+    def matmul(self, A, Bm, out, transA=False, transB=False, alpha=1.0, beta=0.0):
+        """out = alpha * op(A) @ op(B) + beta * out for small f32 matrices; 2-D operands broadcast over the batch."""
+        self._chk_f32(A, Bm, out)
+        batch = out.shape[0] if out.dim() == 3 else 1
+        M, N = out.shape[-2], out.shape[-1]
+        K = A.shape[-2] if transA else A.shape[-1]
+        assert (A.shape[-1] if transA else A.shape[-2]) == M, (A.shape, out.shape, transA)
+        assert (Bm.shape[-2] if transB else Bm.shape[-1]) == N and (Bm.shape[-1] if transB else Bm.shape[-2]) == K
+        sA = A.shape[-2] * A.shape[-1] if A.dim() == 3 else 0
+        sB = Bm.shape[-2] * Bm.shape[-1] if Bm.dim() == 3 else 0
+        sC = M * N if out.dim() == 3 else 0
+        L.call("megb200_sgemm", int(transA), int(transB), M, N, K, float(alpha), A.data_ptr(), A.shape[-1], sA,
+               Bm.data_ptr(), Bm.shape[-1], sB, float(beta), out.data_ptr(), N, sC, batch, self._stream())
+
+    # ------------------------------------------------------------------ spatial attention
+    def sa_softmax(self, a, mask, W, Wm):
+        self._chk_f32(a, mask, W, Wm)
+        L.call("megb200_sa_softmax", a.data_ptr(), _ptr(mask), W.data_ptr(), Wm.data_ptr(), a.shape[0], a.shape[1],
+               self._stream())
+
+    def sa_softmax_bwd(self, W, dWm, mask, da):
+        self._chk_f32(W, dWm, mask, da)
+        L.call("megb200_sa_softmax_bwd", W.data_ptr(), dWm.data_ptr(), _ptr(mask), da.data_ptr(), W.shape[0],
+               W.shape[1], self._stream())
+
+    # ------------------------------------------------------------------ BN / GELU / GLU
+    def bn_stats(self, U, C, sums):
+        self._chk_act(U)
+        self._chk_f32(sums)
+        rows = U.shape[0] * U.shape[1]
+        L.call("megb200_bn_stats", U.data_ptr(), rows, C, U.shape[2], sums.data_ptr(), self.dt, self._stream())
+
+    def bn_finalize(self, sums, gamma, beta, rm, rv, count, eps, momentum, training, scale, shift, mean, rstd):
+        self._chk_f32(sums, gamma, beta, rm, rv, scale, shift, mean, rstd)
+        L.call("megb200_bn_finalize", _ptr(sums), gamma.data_ptr(), beta.data_ptr(), rm.data_ptr(), rv.data_ptr(),
+               int(count), float(eps), float(momentum), int(training), scale.data_ptr(), shift.data_ptr(),
+               mean.data_ptr(), rstd.data_ptr(), gamma.numel(), self._stream())
+
+    def bn_gelu(self, U, scale, shift, H, C):
+        self._chk_act(U, H)
+        rows = U.shape[0] * U.shape[1]
+        L.call("megb200_bn_gelu", U.data_ptr(), scale.data_ptr(), shift.data_ptr(), H.data_ptr(), rows, C, U.shape[2],
+               self.dt, self._stream())
+
+    def bn_gelu_bwd_reduce(self, dH, U, scale, shift, mean, rstd, dY, sums2, C):
+        self._chk_act(dH, U, dY)
+        self._chk_f32(sums2)
+        rows = U.shape[0] * U.shape[1]
+        L.call("megb200_bn_gelu_bwd_reduce", dH.data_ptr(), U.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+               mean.data_ptr(), rstd.data_ptr(), dY.data_ptr(), sums2.data_ptr(), rows, C, U.shape[2], self.dt,
+               self._stream())
+
+    def bn_bwd_apply(self, dY, U, gamma, mean, rstd, sums2, count, dU, C):
+        self._chk_act(dY, U, dU)
+        rows = U.shape[0] * U.shape[1]
+        L.call("megb200_bn_bwd_apply", dY.data_ptr(), U.data_ptr(), gamma.data_ptr(), mean.data_ptr(),
+               rstd.data_ptr(), sums2.data_ptr(), int(count), dU.data_ptr(), rows, C, U.shape[2], self.dt,
+               self._stream())
+
+    def glu(self, V, Out, C):
+        self._chk_act(V, Out)
+        rows = V.shape[0] * V.shape[1]
+        L.call("megb200_glu", V.data_ptr(), Out.data_ptr(), rows, C, V.shape[2], Out.shape[2], self.dt, self._stream())
+
+    def glu_bwd(self, dOut, V, dV, C):
+        self._chk_act(dOut, V, dV)
+        rows = V.shape[0] * V.shape[1]
+        L.call("megb200_glu_bwd", dOut.data_ptr(), V.data_ptr(), dV.data_ptr(), rows, C, V.shape[2], dOut.shape[2],
+               self.dt, self._stream())
+
+    def gelu(self, P, Q):
+        self._chk_act(P, Q)
+        L.call("megb200_gelu", P.data_ptr(), Q.data_ptr(), P.numel(), self.dt, self._stream())
+
+    def gelu_bwd(self, dQ, P, dP):
+        self._chk_act(dQ, P, dP)
+        L.call("megb200_gelu_bwd", dQ.data_ptr(), P.data_ptr(), dP.data_ptr(), P.numel(), self.dt, self._stream())
+
+    def time_mean(self, Z, Zm, F):
+        self._chk_act(Z, Zm)
+        B, T, Fs = Z.shape
+        L.call("megb200_time_mean", Z.data_ptr(), Zm.data_ptr(), B, T, F, Fs, self.dt, self._stream())
+
+    def time_mean_bwd(self, dZm, dZ, F):
+        self._chk_act(dZm, dZ)
+        B, T, Fs = dZ.shape
+        L.call("megb200_time_mean_bwd", dZm.data_ptr(), dZ.data_ptr(), B, T, F, Fs, self.dt, self._stream())
+
+    # ------------------------------------------------------------------ CLIP
+    def clip_prep_y(self, Y, Yp, ysq):
+        """Y f32 [B,F,T] or [B,F] -> Yp [B, T*F] (position-major) and ysq[b] += |Y_b|^2."""
+        self._chk_f32(Y, ysq)
+        self._chk_act(Yp)
+        B, F = Y.shape[0], Y.shape[1]
+        T = Y.shape[2] if Y.dim() == 3 else 1
+        assert Yp.numel() == B * F * T
+        L.call("megb200_clip_prep_y", Y.data_ptr(), Yp.data_ptr(), ysq.data_ptr(), B, F, T, self.dt, self._stream())
+
+    def rowsumsq(self, Z, sq):
+        self._chk_act(Z)
+        self._chk_f32(sq)
+        B = Z.shape[0]
+        L.call("megb200_rowsumsq", Z.data_ptr(), sq.data_ptr(), B, Z.numel() // B, self.dt, self._stream())
+
+    def clip_logits(self, Yp, Zp, raw):
+        self._chk_act(Yp, Zp)
+        self._chk_f32(raw)
+        By, Bz = raw.shape
+        L.call("megb200_clip_logits", Yp.data_ptr(), Zp.data_ptr(), raw.data_ptr(), By, Bz, Yp.numel() // By, self.dt,
+               self.be, self._stream())
+
+    def clip_ce_partial(self, raw, ysq, zsq, temp, Lg, row_max, row_sumexp, col_lse):
+        self._chk_f32(raw, ysq, zsq, temp, Lg, row_max, row_sumexp, col_lse)
+        By, Bz = raw.shape
+        L.call("megb200_clip_ce_partial", raw.data_ptr(), ysq.data_ptr(), zsq.data_ptr(), temp.data_ptr(),
+               Lg.data_ptr(), row_max.data_ptr(), row_sumexp.data_ptr(), col_lse.data_ptr(), By, Bz, self._stream())
+
+    def clip_ce_finish(self, Lg, row_lse, col_lse, ysq, zsq, temp, off, wscale, out2, coef, cvec):
+        self._chk_f32(Lg, row_lse, col_lse, ysq, zsq, temp, out2, cvec)
+        self._chk_act(coef)
+        By, Bz = Lg.shape
+        assert coef.shape[0] == Bz and coef.shape[1] >= By
+        L.call("megb200_clip_ce_finish", Lg.data_ptr(), row_lse.data_ptr(), col_lse.data_ptr(), ysq.data_ptr(),
+               zsq.data_ptr(), temp.data_ptr(), int(off), float(wscale), out2.data_ptr(), coef.data_ptr(),
+               coef.shape[1], cvec.data_ptr(), By, Bz, self.dt, self._stream())
+
+    def clip_dz(self, coef, Yp, Z, cvec, gscale, dZ):
+        """coef: [Bz, ldc] (ldc = By rounded up to 8); Yp: [By, D]; Z, dZ: [Bz, D]."""
+        self._chk_act(coef, Yp, Z, dZ)
+        self._chk_f32(cvec, gscale)
+        Bz, By = coef.shape[0], Yp.shape[0]
+        L.call("megb200_clip_dz", coef.data_ptr(), coef.shape[1], Yp.data_ptr(), Z.data_ptr(), cvec.data_ptr(), gscale.data_ptr(),
+               dZ.data_ptr(), By, Bz, Z.numel() // Bz, self.dt, self.be, self._stream())
+
+    def cast(self, src, dst):
+        code = {torch.float32: L.F32, torch.bfloat16: L.BF16}
+        assert src.is_contiguous() and dst.is_contiguous() and src.numel() == dst.numel()
+        L.call("megb200_cast", src.data_ptr(), dst.data_ptr(), src.numel(), code[src.dtype], code[dst.dtype],
+               self._stream())
