@@ -1,0 +1,271 @@
+"""Drop-in ``meg_decoding.models`` for the training hot path: same constructor / forward signatures and
+``state_dict`` layout as the reference (``meg_decoding/models.py:167-383``), computed by the megb200 kernels.
+
+    brain_encoder = BrainEncoder(args).to(device)        # train.py:147
+    Z = brain_encoder(X, subject_idxs)                   # train.py:201
+
+The sub-modules (``nn.Conv1d`` / ``nn.BatchNorm1d``) are parameter containers only: they give the reference's
+parameter names, shapes, init distribution, ``.to()`` / ``.train()`` / ``state_dict()`` behaviour; the arithmetic is
+one explicit kernel sequence (``megb200.engine.EncoderEngine``) inside a single autograd node.  Without the built
+CUDA library the forward raises — there is no PyTorch fallback.
+
+Intentional differences from the reference, all documented in DESIGN.md: ``z`` is a properly registered complex
+Parameter on every device (the reference loses it on CUDA, models.py:186-188); the spatial-dropout centre can be
+pinned through ``drop_center`` (the reference draws ``np.random.randint`` per call, models.py:236 — still the default).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+import megb200
+from megb200.engine import EncoderEngine
+from meg_decoding.utils.layout import ch_locations_2d
+
+
+def get_model(args):
+    """models.py:18-30; only the BrainEncoder branch is on the accelerated path."""
+    if args.model == "brain_encoder":
+        return BrainEncoder(args)
+    raise ValueError("no model named {} is prepared by megb200 (only 'brain_encoder' is on the hot path)".format(args.model))
+
+
+class SpatialDropout(nn.Module):
+    """models.py:223-241.  Holds the sensor layout; the mask is folded into the attention weights by the engine."""
+
+    def __init__(self, loc, d_drop):
+        super().__init__()
+        self.loc = loc
+        self.d_drop = d_drop
+        self.num_channels = loc.shape[0]
+
+    def all_masks(self):
+        """masks[c] = mask used when sensor c is the centre: 0 where ||loc - loc_c|| < d_drop (strict), else 1."""
+        d = (self.loc[None, :, :] - self.loc[:, None, :]).norm(dim=-1)
+        return torch.where(d < self.d_drop, 0.0, 1.0).to(torch.float32)
+
+
+class SpatialAttention(nn.Module):
+    """models.py:167-220."""
+
+    def __init__(self, args):
+        super().__init__()
+        K = args.K
+        loc = torch.as_tensor(ch_locations_2d(args), dtype=torch.float32)
+        kk = torch.arange(K).repeat_interleave(K).to(torch.float32)
+        ll = torch.arange(K).repeat(K).to(torch.float32)
+        self.z = nn.Parameter(torch.rand(size=(args.D1, K ** 2), dtype=torch.cfloat))
+        phi = 2 * torch.pi * (torch.einsum("k,x->kx", kk, loc[:, 0]) + torch.einsum("l,y->ly", ll, loc[:, 1]))
+        # like the reference these are plain (non-persistent) tensors: not part of state_dict
+        self.register_buffer("cos", torch.cos(phi).contiguous(), persistent=False)
+        self.register_buffer("sin", torch.sin(phi).contiguous(), persistent=False)
+        self.spatial_dropout = SpatialDropout(loc, args.d_drop)
+        self.register_buffer("drop_masks", self.spatial_dropout.all_masks().contiguous(), persistent=False)
+
+
+class SubjectBlock(nn.Module):
+    """models.py:244-273."""
+
+    def __init__(self, args):
+        super().__init__()
+        self.num_subjects = args.num_subjects
+        self.D1 = args.D1
+        self.K = args.K
+        self.spatial_attention = SpatialAttention(args)
+        self.conv = nn.Conv1d(self.D1, self.D1, kernel_size=1, stride=1)
+        self.subject_layer = nn.ModuleList(
+            [nn.Conv1d(self.D1, self.D1, kernel_size=1, bias=False, stride=1) for _ in range(self.num_subjects)])
+
+
+class ConvBlock(nn.Module):
+    """models.py:276-322 (dilation 1 everywhere, as the reference code runs: :289,297,305)."""
+
+    def __init__(self, k, D1, D2, ks=3):
+        super().__init__()
+        self.k = k
+        self.D2 = D2
+        self.in_channels = D1 if k == 0 else D2
+        self.conv0 = nn.Conv1d(self.in_channels, D2, kernel_size=ks, padding="same")
+        self.batchnorm0 = nn.BatchNorm1d(num_features=D2)
+        self.conv1 = nn.Conv1d(D2, D2, kernel_size=ks, padding="same")
+        self.batchnorm1 = nn.BatchNorm1d(num_features=D2)
+        self.conv2 = nn.Conv1d(D2, 2 * D2, kernel_size=ks, padding="same")
+
+
+class _EncoderFn(torch.autograd.Function):
+    """One autograd node for the whole encoder: forward and backward are explicit kernel sequences."""
+
+    @staticmethod
+    def forward(ctx, module, X, subj_dev, mask, present, *params):
+        P = module._param_dict(params)
+        eng = module._engine()
+        Z, saved = eng.forward(P, X, subj_dev, mask, module.training)
+        ctx.module, ctx.saved, ctx.P, ctx.present = module, saved, P, present
+        ctx.was_training = module.training
+        ctx.nparams = len(params)
+        return Z
+
+    @staticmethod
+    def backward(ctx, dZ):
+        module = ctx.module
+        if not ctx.was_training:
+            raise NotImplementedError("megb200: backward through an eval-mode BrainEncoder forward is not implemented "
+                                      "(the reference scripts evaluate under torch.no_grad())")
+        eng = module._engine()
+        ops = eng.ops
+        if dZ.dtype != ops.act_dtype or not dZ.is_contiguous():
+            dZ = dZ.to(ops.act_dtype).contiguous()
+        G = eng.backward(ctx.P, ctx.saved, dZ)
+        grads = module._grad_list(G, ctx.present)
+        ctx.saved = None
+        return (None, None, None, None, None) + tuple(grads)
+
+
+class BrainEncoder(nn.Module):
+    """models.py:341-383."""
+
+    def __init__(self, args):
+        super().__init__()
+        self.num_subjects = args.num_subjects
+        self.D1 = args.D1
+        self.D2 = args.D2
+        self.F = args.F if not args.preprocs["last4layers"] else 1024
+        self.K = args.K
+        self.dataset_name = args.dataset
+        self.seq2seq = bool(args.seq2seq)
+        if self.F % 8 != 0:
+            raise ValueError("megb200: the embedding width F must be a multiple of 8")
+
+        self.subject_block = SubjectBlock(args)
+        self.conv_blocks = nn.Sequential()
+        for k in range(5):
+            self.conv_blocks.add_module(f"conv{k}", ConvBlock(k, self.D1, self.D2))
+        self.conv_final1 = nn.Conv1d(self.D2, 2 * self.D2, kernel_size=1)
+        self.conv_final2 = nn.Conv1d(2 * self.D2, self.F, kernel_size=1)
+
+        try:
+            self.precision = args.get("precision") if hasattr(args, "get") else getattr(args, "precision", None)
+        except Exception:
+            self.precision = None
+        self.drop_center = None          # set to an int to pin the spatial-dropout centre (tests, data parallel)
+        self._eng = None
+
+    # ------------------------------------------------------------------ plumbing
+    def _engine(self) -> EncoderEngine:
+        ops = megb200.get_ops(self.precision)
+        if self._eng is None or self._eng.ops is not ops:
+            C = self.subject_block.spatial_attention.cos.shape[1]
+            self._eng = EncoderEngine(ops, C=C, D1=self.D1, D2=self.D2, F=self.F, S=self.num_subjects,
+                                      seq2seq=self.seq2seq)
+        return self._eng
+
+    def _param_list(self):
+        sb = self.subject_block
+        ps = [sb.spatial_attention.z, sb.conv.weight, sb.conv.bias]
+        ps += [m.weight for m in sb.subject_layer]
+        for k in range(5):
+            cb = getattr(self.conv_blocks, f"conv{k}")
+            ps += [cb.conv0.weight, cb.conv0.bias, cb.batchnorm0.weight, cb.batchnorm0.bias,
+                   cb.conv1.weight, cb.conv1.bias, cb.batchnorm1.weight, cb.batchnorm1.bias,
+                   cb.conv2.weight, cb.conv2.bias]
+        ps += [self.conv_final1.weight, self.conv_final1.bias, self.conv_final2.weight, self.conv_final2.bias]
+        return ps
+
+    def _param_dict(self, params):
+        """Flat autograd inputs -> the engine's parameter dict (f32, contiguous; BN buffers by reference)."""
+        S, D1 = self.num_subjects, self.D1
+        sa = self.subject_block.spatial_attention
+        it = iter(params)
+        z = next(it).detach()
+        zr = torch.view_as_real(z)
+        P = {"z_re": zr[..., 0].contiguous(), "z_im": zr[..., 1].contiguous(), "cos": sa.cos, "sin": sa.sin}
+        P["Wc"] = next(it).detach().reshape(D1, D1)
+        P["bc"] = next(it).detach()
+        P["Ws"] = torch.stack([next(it).detach().reshape(D1, D1) for _ in range(S)])
+        P["blocks"] = []
+        for k in range(5):
+            cb = getattr(self.conv_blocks, f"conv{k}")
+            d = {}
+            for i, bn in (("0", cb.batchnorm0), ("1", cb.batchnorm1)):
+                d["w" + i], d["b" + i] = next(it).detach(), next(it).detach()
+                d["g" + i], d["be" + i] = next(it).detach(), next(it).detach()
+                d["rm" + i], d["rv" + i] = bn.running_mean, bn.running_var
+            d["w2"], d["b2"] = next(it).detach(), next(it).detach()
+            P["blocks"].append(d)
+        P["wf1"], P["bf1"], P["wf2"], P["bf2"] = (next(it).detach() for _ in range(4))
+        return P
+
+    def _grad_list(self, G, present):
+        """Engine gradient dict -> gradients in ``_param_list`` order (reference shapes / dtypes)."""
+        S, D1 = self.num_subjects, self.D1
+        out = [torch.complex(G["z_re"], G["z_im"]), G["Wc"].view(D1, D1, 1), G["bc"]]
+        for s in range(S):
+            # the reference leaves grad=None for subjects absent from the batch
+            out.append(G["Ws"][s].view(D1, D1, 1) if (present is None or s in present) else None)
+        for k in range(5):
+            g = G["blocks"][k]
+            out += [g["w0"], g["b0"], g["g0"], g["be0"], g["w1"], g["b1"], g["g1"], g["be1"], g["w2"], g["b2"]]
+        out += [G["wf1"], G["bf1"], G["wf2"], G["bf2"]]
+        return out
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, X, subject_idxs):
+        return self._forward(X, subject_idxs)
+
+    def _forward(self, X, subject_idxs):
+        sa = self.subject_block.spatial_attention
+        dev = sa.cos.device
+        C = sa.cos.shape[1]
+        assert X.shape[1] == C                                                  # models.py:233
+        S = self.num_subjects
+        present = None
+        subject_idxs = torch.as_tensor(subject_idxs)
+        if not subject_idxs.is_cuda:
+            if subject_idxs.numel() and (int(subject_idxs.max()) >= S or int(subject_idxs.min()) < -S):
+                raise IndexError("index {} is out of range".format(int(subject_idxs.max())))  # ModuleList semantics
+            subject_idxs = torch.where(subject_idxs < 0, subject_idxs + S, subject_idxs)
+            present = set(int(s) for s in subject_idxs.tolist())
+        subj = subject_idxs.to(device=dev, dtype=torch.int32, non_blocking=True).contiguous()
+        X = X.to(device=dev, dtype=torch.float32).contiguous()
+        mask = None
+        if self.training:
+            # models.py:236 — one centre per forward call from the global NumPy RNG unless pinned
+            c = self.drop_center if self.drop_center is not None else int(np.random.randint(C))
+            mask = sa.drop_masks[c]
+            for k in range(5):
+                cb = getattr(self.conv_blocks, f"conv{k}")
+                cb.batchnorm0.num_batches_tracked += 1
+                cb.batchnorm1.num_batches_tracked += 1
+        params = self._param_list()
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            Zi = _EncoderFn.apply(self, X, subj, mask, present, *params)
+        else:
+            Zi, _ = self._engine().forward(self._param_dict(params), X, subj, mask, self.training)
+        # PC layout [B,T,F] -> the reference's (B, F, T) (a view) or (B, F)
+        if self.seq2seq:
+            return Zi.permute(0, 2, 1)
+        return Zi[:, 0, : self.F]
+
+
+class Classifier(nn.Module):
+    """models.py:386-460 — top-1 / top-10 retrieval accuracy of speech segments against brain embeddings.
+
+    Metric only (no grad).  "Next" row N1 of the scope table: restated here without the reference's O(B^2) Python loop.
+    """
+
+    def __init__(self, args):
+        super().__init__()
+        self.batch_size = getattr(args, "batch_size", None) if not isinstance(args, dict) else args.get("batch_size")
+
+    @torch.no_grad()
+    def forward(self, Z: torch.Tensor, Y: torch.Tensor, test=False):
+        B = Z.size(0)
+        z = Z.reshape(B, -1).float()
+        y = Y.reshape(B, -1).float()
+        sim = (y / y.norm(dim=-1, keepdim=True)) @ (z / z.norm(dim=-1, keepdim=True)).T
+        t = torch.arange(B, device=sim.device)
+        top1 = (sim.argmax(dim=1) == t).float().mean().item()
+        k = min(10, B)
+        top10 = (sim.topk(k, dim=1).indices == t[:, None]).any(dim=1).float().mean().item()
+        return top1, top10

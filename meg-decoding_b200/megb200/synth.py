@@ -66,9 +66,14 @@ def out_features(cfg) -> int:
     return 1024 if cfg.preprocs["last4layers"] else cfg.F
 
 
+def sensor_locations_raw(C: int, seed: int = 0) -> np.ndarray:
+    """Raw synthetic 2-D sensor coordinates (what mne's layout would return), uniform in the unit square."""
+    return np.random.Generator(np.random.PCG64(seed)).random((C, 2))
+
+
 def sensor_locations(C: int, seed: int = 0) -> np.ndarray:
     """Synthetic 2-D layout: uniform in the unit square, min-max normalised then *0.8+0.1 (layout.py:42-45)."""
-    loc = np.random.Generator(np.random.PCG64(seed)).random((C, 2))
+    loc = sensor_locations_raw(C, seed)
     loc = (loc - loc.min(axis=0)) / (loc.max(axis=0) - loc.min(axis=0))
     return (loc * 0.8 + 0.1).astype(np.float32)
 

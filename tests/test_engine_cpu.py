@@ -1,0 +1,106 @@
+"""CPU tier: the step orchestration (megb200.engine, the hand-derived backward chain, the drop-in nn.Module
+surface) run on top of the oracle's plain-torch restatement of the ops, checked against the reference's golden
+outputs.  No kernels run here; this pins the math and the module protocol the CUDA path is built on."""
+import numpy as np
+import pytest
+import torch
+
+import megb200
+from megb200 import synth
+from oracle.ops_restatement import TorchOps
+from tests import helpers as H
+
+
+@pytest.fixture()
+def torch_ops():
+    megb200._set_ops_override(TorchOps(torch.float32))
+    yield
+    megb200._set_ops_override(None)
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny_static", "narrow_static"])
+def test_orchestration_matches_reference_golden(torch_ops, name):
+    cfg = synth.get_config(name)
+    enc, lossf = H.make_modules(cfg)
+    X, Y, subj = H.make_inputs(cfg)
+    Z, loss, grads = H.train_step(enc, lossf, X, Y, subj, synth.drop_center(cfg))
+    bn = {k: v for k, v in enc.state_dict().items() if "running_" in k or "num_batches" in k}
+    errs = H.compare_with_golden(name, Z, loss, grads, tol_z=2e-5, tol_loss=2e-5, tol_grad=1e-3, bn=bn, tol_bn=2e-5)
+    print(name, errs)
+
+
+def test_eval_mode_matches_reference_golden(torch_ops):
+    cfg = synth.get_config("tiny")
+    enc, lossf = H.make_modules(cfg)
+    X, Y, subj = H.make_inputs(cfg)
+    # one train step first so that the running statistics are the ones the golden eval pass used
+    H.train_step(enc, lossf, X, Y, subj, synth.drop_center(cfg))
+    enc.eval()
+    with torch.no_grad():
+        Z = enc(X, subj)
+        logits, loss = lossf(Y, Z, return_logits=True)
+    g = H.load_golden("tiny")
+    assert H.rel_fro(H.subsample(Z), g["Z_eval_sample"]) < 2e-5
+    assert abs(float(loss) - float(g["loss_eval"])) / abs(float(g["loss_eval"])) < 2e-5
+    assert H.rel_fro(H.subsample(logits), g["logits_eval_sample"]) < 2e-5
+
+
+def test_state_dict_layout_matches_reference(torch_ops):
+    cfg = synth.get_config("tiny")
+    enc, lossf = H.make_modules(cfg)
+    keys = set(enc.state_dict().keys())
+    assert keys == set(synth.make_state(cfg).keys())
+    assert len(keys) == 87 + cfg.num_subjects                           # SURVEY §5 checkpoint row
+    assert enc.state_dict()["subject_block.spatial_attention.z"].dtype == torch.complex64
+    assert list(lossf.state_dict().keys()) == ["temp"]
+
+
+def test_reference_error_conventions(torch_ops):
+    cfg = synth.get_config("tiny")
+    enc, lossf = H.make_modules(cfg)
+    X, Y, subj = H.make_inputs(cfg)
+    with pytest.raises(AssertionError):                                  # models.py:233
+        enc(X[:, :-1], subj)
+    with pytest.raises(IndexError):                                      # ModuleList index out of range
+        enc(X, torch.full_like(subj, cfg.num_subjects))
+    with pytest.raises(AssertionError):                                  # loss.py:68
+        lossf(Y[:1], torch.zeros(1, Y.shape[1], Y.shape[2]))
+
+
+def test_subject_routing_is_permutation_equivariant(torch_ops):
+    cfg = synth.get_config("tiny")
+    enc, _ = H.make_modules(cfg)
+    X, _, subj = H.make_inputs(cfg)
+    enc.eval()
+    with torch.no_grad():
+        Z = enc(X, subj)
+        perm = torch.randperm(X.shape[0], generator=torch.Generator().manual_seed(3))
+        Zp = enc(X[perm], subj[perm])
+    assert torch.equal(Zp, Z[perm])
+    # int64 indices (Brennan's default collate) behave like int32
+    with torch.no_grad():
+        assert torch.equal(enc(X, subj.long()), Z)
+
+
+def test_absent_subjects_get_no_gradient(torch_ops):
+    cfg = synth.get_config("tiny")
+    enc, lossf = H.make_modules(cfg)
+    X, Y, subj = H.make_inputs(cfg)
+    subj = torch.zeros_like(subj)
+    subj[1] = 2
+    _, _, grads = H.train_step(enc, lossf, X, Y, subj, 0)
+    assert grads["subject_block.subject_layer.0.weight"] is not None
+    assert grads["subject_block.subject_layer.1.weight"] is None
+    assert grads["subject_block.subject_layer.3.weight"] is None
+
+
+def test_one_sided_dp_loss_equals_global(torch_ops):
+    """SURVEY appendix A6 with emulated ranks: per-rank contributions sum to the single-process loss."""
+    from oracle import restatement as R
+    torch.manual_seed(0)
+    Bg, D, world = 12, 40, 3
+    Y, Z = torch.randn(Bg, D), torch.randn(Bg, D)
+    temp = torch.tensor([1.3])
+    full = R.clip_loss(Y, Z, temp)
+    parts = R.clip_loss_one_sided(Y, list(Z.chunk(world)), temp)
+    assert abs(float(sum(parts)) - float(full)) < 1e-6
