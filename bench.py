@@ -1,0 +1,325 @@
+"""Benchmark of the hot path: BrainEncoder forward + CLIPLoss + backward on synthetic Gwilliams2022-shaped batches.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config gwilliams] [--impl megb200|reference]
+
+One JSON line on stdout (rank 0).  `value` = train samples/s with the batch resident in HBM; `e2e` = the same step
+through the public modules with HOST (pinned) buffers, H2D copies and the loss read-back inside the timed region;
+`roofline` = the dominant kernel (tcgen05 tap-GEMM: conv forward + data gradients + 1x1 convs) timed per launch with
+CUDA events inside the timed region against the measured bf16 peak; `cpu_baseline` = the oracle port of the reference
+on the host cores (bounded sample).  `--impl reference` times that CPU port alone (the reference is CPU-runnable pure
+PyTorch; /root/reference does not exist on the GPU box, so its pinned restatement is what runs).
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "meg-decoding_b200"), ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "train samples/sec (fwd+bwd+CLIP)"
+UNIT = "samples/s"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"bf16_sustained": d.get("bf16_tflops_sustained"), "bf16_burst": d.get("bf16_tflops"),
+                "hbm": d.get("hbm_gbs"), "source": "measured"}
+    return {"bf16_sustained": 1400.0, "bf16_burst": 1590.0, "hbm": 6650.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz, self.err = index, [], set(), False, None, None
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            while not self.stop_flag:
+                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                try:
+                    r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.02)
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+
+    def result(self):
+        self.stop_flag = True
+        self.join(timeout=2)
+        out = {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+               "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        if self.err:
+            out["error"] = self.err
+        return out
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference_step_time(cfg, B_sample, steps, warmup, threads=None):
+    """fwd + CLIPLoss + bwd of the oracle port (fp32, all host threads) on a B_sample-sized slice of the workload."""
+    from megb200 import synth
+    from oracle import restatement as R
+    if threads:
+        torch.set_num_threads(threads)
+    P = R.state_to_torch(synth.make_state(cfg), requires_grad=True)
+    temp = torch.tensor([float(cfg.init_temperature)], requires_grad=True)
+    X, Y, subj = synth.make_batch(cfg, 0, B=B_sample)
+    X, Y, subj = torch.from_numpy(X), torch.from_numpy(Y), torch.from_numpy(subj)
+    loc = synth.sensor_locations(cfg.C)
+    center = synth.drop_center(cfg)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        R.train_step(P, temp, X, Y, subj, loc, K=cfg.K, d_drop=cfg.d_drop, seq2seq=cfg.seq2seq, drop_center=center)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from megb200 import synth
+    cfg = synth.get_config(args.config)
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    B_sample = min(cfg.B, args.cpu_sample)
+    # keep the whole run within a few minutes: probe one step, shrink the sample if needed
+    probe = cpu_reference_step_time(cfg, B_sample, 1, 0)[0]
+    budget = 150.0
+    while B_sample > 8 and probe * (args.steps + args.warmup) > budget:
+        B_sample //= 2
+        probe = cpu_reference_step_time(cfg, B_sample, 1, 0)[0]
+    times = cpu_reference_step_time(cfg, B_sample, args.steps, args.warmup)
+    ms = 1e3 * sum(times) / len(times)
+    value = B_sample / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": workload_config(cfg, 1, cfg.B),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{B_sample} of {cfg.B} samples per step (same shapes), fwd+CLIP+bwd, fp32, "
+                                   f"oracle/restatement.py pinned to the reference by tests/golden"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(cfg, world, b_loc):
+    from megb200 import synth
+    return {"workload": f"{cfg.name}: BrainEncoder+CLIPLoss fwd+bwd, C={cfg.C} sensors, S={cfg.num_subjects} subjects, "
+                        f"T={cfg.T}, D1={cfg.D1}, D2={cfg.D2}, F={synth.out_features(cfg)}, seq2seq={cfg.seq2seq}",
+            "batch_per_gpu": b_loc, "global_batch": b_loc * world,
+            "parallelism": f"dp{world}" if world > 1 else "single",
+            "l2": "inputs larger than L2: X+Y per step = "
+                  f"{(b_loc * cfg.C * cfg.T + b_loc * synth.out_features(cfg) * (cfg.T if cfg.seq2seq else 1)) * 4 / 1e6:.0f} MB f32, "
+                  "activations ~3 GB per step"}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_megb200(args):
+    import torch.distributed as dist
+    import megb200
+    from megb200 import lib, parallel, synth
+    from tests import helpers as H
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the hot path has no CPU fallback (use --impl reference for "
+                           "the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        parallel.init()
+    megb200.set_precision(args.precision)
+    cfg = synth.get_config(args.config)
+    if args.batch:
+        cfg["B"] = args.batch
+    B = cfg.B
+    enc, lossf = H.make_modules(cfg, dev)
+    enc.train()
+    enc.drop_center = synth.drop_center(cfg)
+    params = list(enc.parameters()) + list(lossf.parameters())
+    opt = torch.optim.Adam(params, lr=3e-4)                               # train.py:160-162
+
+    # synthetic batch: each rank its own shard (seed = rank), pinned host copies for the end-to-end leg
+    Xh, Yh, subj_h = synth.make_batch(cfg, seed=rank)
+    Xh, Yh, subj_h = torch.from_numpy(Xh).pin_memory(), torch.from_numpy(Yh).pin_memory(), torch.from_numpy(subj_h)
+    Xd, Yd = Xh.to(dev), Yh.to(dev)
+
+    def step(X, Y, subj):
+        for p in params:
+            p.grad = None
+        Z = enc(X, subj)
+        loss = lossf(Y, Z)
+        loss.backward()
+        if world > 1:
+            parallel.allreduce_grads(params)
+        return loss
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(max(args.warmup, 3)):
+        loss = step(Xd, Yd, subj_h)
+    barrier()
+
+    # ---- timed region: K steps, batch resident in HBM, per-launch CUDA events on the contraction kernels
+    ops = megb200.get_ops()
+    ops.prof = []
+    n0 = lib.launch_count()
+    nvml_index = local_rank
+    try:
+        nvml_index = int(os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")[local_rank])
+    except (ValueError, IndexError):
+        pass
+    sampler = ClockSampler(nvml_index)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        loss = step(Xd, Yd, subj_h)
+    ev1.record()
+    barrier()
+    clocks = sampler.result()
+    launches = (lib.launch_count() - n0) // args.steps
+    ms = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
+    prof, ops.prof = ops.prof, None
+    loss_value = float(loss)
+
+    kern = {}
+    for name, flops, a, b in prof:
+        k = kern.setdefault(name, [0.0, 0.0, 0])
+        k[0] += flops
+        k[1] += a.elapsed_time(b)
+        k[2] += 1
+    peaks = measured_peaks()
+    roofline = None
+    if "tapgemm" in kern and kern["tapgemm"][1] > 0:
+        fl, tms, n = kern["tapgemm"]
+        ach = fl / (tms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "tc_tapgemm_kernel (conv fwd + dgrad + 1x1 + subject GEMM)",
+                    "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                    "frac": ach / peaks["bf16_sustained"], "traffic": None, "peak_source": peaks["source"] + " sustained",
+                    "launches_per_step": n // args.steps, "avg_launch_ms": tms / n,
+                    "share_of_step": tms / args.steps / ms}
+        if "wgrad" in kern:
+            fl2, t2, n2 = kern["wgrad"]
+            roofline["wgrad"] = {"achieved": fl2 / (t2 * 1e-3) / 1e12, "launches_per_step": n2 // args.steps,
+                                 "avg_launch_ms": t2 / n2, "share_of_step": t2 / args.steps / ms}
+
+    # ---- optimizer step, reported separately
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        opt.step()
+    e1.record()
+    barrier()
+    adam_ms = e0.elapsed_time(e1) / 3
+
+    # ---- end to end: host buffers in, loss out, every step
+    def e2e_step():
+        X = Xh.to(dev, non_blocking=True)
+        Y = Yh.to(dev, non_blocking=True)
+        return float(step(X, Y, subj_h))          # .item(): device -> host read of the loss, as train.py:208
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    g1.record()
+    barrier()
+    e2e_ms = max_over_ranks(max(g0.elapsed_time(g1), (time.perf_counter() - t0) * 1e3) / args.steps)
+    h2d = Xh.numel() * 4 + Yh.numel() * 4 + subj_h.numel() * 4
+    e2e = {"value": B * world / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+           "ms_per_step": e2e_ms}
+
+    flops_step = B * synth.encoder_flops_per_sample(cfg) + synth.clip_flops(cfg, B, B * world)
+    line = {
+        "metric": METRIC, "value": B * world / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16" if args.precision.startswith("bf16") else "f32", "data": "synthetic",
+        "config": workload_config(cfg, world, B), "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": roofline,
+        "step_tflops": flops_step / (ms * 1e-3) / 1e12,
+        "step_frac_of_peak": flops_step / (ms * 1e-3) / 1e12 / peaks["bf16_sustained"],
+        "adam_ms": adam_ms, "loss": loss_value, "precision": args.precision,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        Bs = min(B, args.cpu_sample)
+        times = cpu_reference_step_time(cfg, Bs, 2, 1, threads=os.cpu_count())
+        v = Bs / (sum(times) / len(times))
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": f"{Bs} of {B} samples per step, 1 warm-up + 2 timed steps, fwd+CLIP+bwd fp32"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="megb200", choices=["megb200", "reference"])
+    ap.add_argument("--config", default="gwilliams")
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (default: the config's)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "bf16_simt"])
+    ap.add_argument("--cpu-sample", type=int, default=32, help="samples per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_megb200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

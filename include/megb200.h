@@ -37,6 +37,8 @@ extern "C" {
 
 int megb200_version(void);
 const char* megb200_last_error(void);
+/* number of kernels this library has launched in this process (for the bench's gpu_launches claim) */
+long long megb200_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------- packing */
 /* X f32 [B][C][T] (NCW, as the collator delivers it: gwilliams2022.py:654-662) -> PC [B][T][Cs]; pad

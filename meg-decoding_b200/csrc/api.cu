@@ -15,6 +15,9 @@ void set_last_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
+
 int num_sms() {
   static int cached[64] = {0};
   int dev = 0;
@@ -136,6 +139,7 @@ extern "C" {
 
 int megb200_version(void) { return MEGB200_VERSION; }
 const char* megb200_last_error(void) { return g_err; }
+long long megb200_launch_count(void) { return (long long)__atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 int megb200_group_order(const int32_t* group, int B, int G, int32_t* order, void* stream) {
   MEGB_CHECK_ARG(group && order && B > 0 && G > 0 && G < 8192, "group_order: bad arguments");

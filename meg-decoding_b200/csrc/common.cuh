@@ -38,9 +38,11 @@ void set_last_error(const char* fmt, ...);
       ::megb200::set_last_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
       return (int)_e;                                                                        \
     }                                                                                        \
+    ::megb200::count_launch();                                                               \
   } while (0)
 
 int num_sms();
+void count_launch();
 
 // ------------------------------------------------------------------------------------------ dtype helpers
 template <typename T> struct Vec8;              // 8 consecutive channels

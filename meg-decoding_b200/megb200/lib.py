@@ -64,6 +64,8 @@ def load():
     lib.megb200_version.argtypes = []
     lib.megb200_last_error.restype = C.c_char_p
     lib.megb200_last_error.argtypes = []
+    lib.megb200_launch_count.restype = C.c_longlong
+    lib.megb200_launch_count.argtypes = []
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
@@ -77,6 +79,10 @@ def check(rc: int, what: str):
         msg = load().megb200_last_error().decode("utf-8", "replace")
         kind = "argument error" if rc < 0 else f"cudaError {rc}"
         raise RuntimeError(f"{what}: {kind}: {msg}")
+
+
+def launch_count() -> int:
+    return int(load().megb200_launch_count())
 
 
 def call(name: str, *args):

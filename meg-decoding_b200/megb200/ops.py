@@ -42,8 +42,23 @@ class CudaOps:
         self.be = L.TC if backend == "tc" else L.SIMT
         self.backend = backend
         self._ws = {}
+        self.prof = None      # set to a list to time individual contraction launches with CUDA events (bench.py)
 
     # ------------------------------------------------------------------ helpers
+    def _prof_begin(self):
+        if self.prof is None:
+            return None
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        return ev
+
+    def _prof_end(self, ev, name, flops):
+        if ev is None:
+            return
+        end = torch.cuda.Event(enable_timing=True)
+        end.record()
+        self.prof.append((name, flops, ev, end))
+
     @staticmethod
     def _stream():
         return torch.cuda.current_stream().cuda_stream
@@ -102,9 +117,11 @@ class CudaOps:
             assert G == 1
         if bias is not None:
             assert bias.numel() == G * N
+        ev = self._prof_begin()
         L.call("megb200_tapgemm", A.data_ptr(), B, T, Ca, Cas, W.data_ptr(), N, Np, Kp, taps, dil, _ptr(bias),
                _ptr(Res), 0 if Res is None else Res.shape[2], _ptr(group), G, Out.data_ptr(), Out.shape[2], self.dt,
                self.be, self._stream())
+        self._prof_end(ev, "tapgemm", 2.0 * B * T * N * taps * Ca)
 
     def group_order(self, group, G, order):
         assert group.dtype == torch.int32 and order.dtype == torch.int32
@@ -118,9 +135,11 @@ class CudaOps:
         G = dW.shape[0] if dW.dim() == 4 else 1
         assert dW.numel() == G * M * C * taps
         ws = self.workspace(dU.device) if self.be == L.TC else None
+        ev = self._prof_begin()
         L.call("megb200_wgrad", dU.data_ptr(), M, Ms, Xin.data_ptr(), C, Xin.shape[2], B, T, taps, dil, _ptr(group),
                _ptr(order), G, dW.data_ptr(), _ptr(ws), 0 if ws is None else ws.numel() * 4, self.dt, self.be,
                self._stream())
+        self._prof_end(ev, "wgrad", 2.0 * B * T * M * C * taps)
 
     def colsum(self, U, C, group, out):
         self._chk_act(U)

@@ -1,0 +1,337 @@
+"""GPU tier, op level: every C-ABI kernel against the oracle's plain-torch restatement of the same op on identical
+seeded inputs.  fp32 storage is compared tightly; bf16 storage within one output rounding.  The contraction ops are
+run on both engines (SIMT fp32 CUDA cores and tcgen05 tensor cores)."""
+import pytest
+import torch
+
+from megb200.ops import pad8, pad16, pad64
+from oracle.ops_restatement import TorchOps
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _ops(dtype, backend):
+    from megb200.ops import CudaOps
+    return CudaOps(dtype, backend)
+
+
+def _rand(gen, *shape, scale=1.0):
+    return (torch.randn(*shape, generator=gen) * scale).float()
+
+
+def _act(gen, dtype, B, T, C, Cs=None):
+    """Activation tensor [B,T,Cs] with zero pad channels; returns (cpu tensor in `dtype`, cuda copy)."""
+    Cs = Cs or pad8(C)
+    t = torch.zeros(B, T, Cs)
+    t[:, :, :C] = _rand(gen, B, T, C)
+    t = t.to(dtype)
+    return t, t.to(DEV)
+
+
+def _close(got, ref, dtype, what, atol_scale=1.0):
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    assert torch.isfinite(got).all(), f"{what}: non-finite values"
+    scale = float(ref.abs().max()) + 1e-30
+    tol = (2e-5 if dtype == torch.float32 else 1.2e-2) * atol_scale
+    err = float((got - ref).abs().max()) / scale
+    assert err <= tol, f"{what}: max abs err / max|ref| = {err:.3e} > {tol:.1e}"
+
+
+CONTRACTION_MODES = [(torch.float32, "simt"), (torch.bfloat16, "simt"), (torch.bfloat16, "tc")]
+EW_DTYPES = [torch.float32, torch.bfloat16]
+
+
+# ------------------------------------------------------------------------------------------------ packing
+@pytest.mark.parametrize("dtype", EW_DTYPES)
+def test_pack_x_and_weight(dtype):
+    gen = torch.Generator().manual_seed(0)
+    ops, ref = _ops(dtype, "simt"), TorchOps(dtype)
+    X = _rand(gen, 3, 20, 45)
+    Xp = ops.empty(3, 45, 24, device=DEV)
+    ops.pack_x(X.to(DEV), Xp)
+    Xr = ref.empty(3, 45, 24, device="cpu")
+    ref.pack_x(X, Xr)
+    _close(Xp, Xr, dtype, "pack_x")
+    for mode, (O, I, Kt) in ((0, (30, 20, 3)), (1, (30, 20, 3)), (0, (270, 208, 1))):
+        w = _rand(gen, 2, O, I, Kt)
+        N, K = (O, I) if mode == 0 else (I, O)
+        out = ops.empty(2, pad16(N), Kt * pad64(K), device=DEV)
+        ops.pack_weight(w.to(DEV), out, mode)
+        outr = ref.empty(2, pad16(N), Kt * pad64(K), device="cpu")
+        ref.pack_weight(w, outr, mode)
+        _close(out, outr, dtype, f"pack_weight mode {mode}")
+
+
+# ------------------------------------------------------------------------------------------------ contractions
+TAPGEMM_CASES = [
+    # B, T, Ca, N, taps, dil, G, bias, res
+    (3, 40, 20, 30, 1, 1, 4, True, False),        # grouped 1x1 (subject GEMM), ragged dims
+    (2, 40, 30, 32, 3, 1, 1, True, False),        # block-0 conv0
+    (2, 40, 32, 32, 3, 1, 1, True, True),         # residual conv
+    (2, 200, 32, 64, 3, 2, 1, True, False),       # two M tiles per sample, dilation 2, GLU conv width
+    (2, 360, 270, 320, 3, 1, 1, True, False),     # real widths: K chunk with OOB channels, N = 2 x 160
+    (2, 360, 320, 640, 3, 1, 1, True, False),
+    (1, 360, 640, 1024, 1, 1, 1, True, False),    # head conv, N tile 256
+    (3, 130, 208, 270, 1, 1, 5, True, False),     # subject GEMM at real widths (N = 272 -> 2 x 144)
+    (2, 129, 320, 320, 3, 1, 1, False, True),     # dgrad-like: no bias, residual, T = 128 + 1
+]
+
+
+@pytest.mark.parametrize("dtype,backend", CONTRACTION_MODES)
+@pytest.mark.parametrize("case", TAPGEMM_CASES)
+def test_tapgemm(dtype, backend, case):
+    B, T, Ca, N, taps, dil, G, has_bias, has_res = case
+    gen = torch.Generator().manual_seed(1)
+    ops, ref = _ops(dtype, backend), TorchOps(dtype)
+    A, Ad = _act(gen, dtype, B, T, Ca)
+    W = torch.zeros(G, pad16(N), taps, pad64(Ca))
+    W[:, :N, :, :Ca] = _rand(gen, G, N, taps, Ca, scale=(Ca * taps) ** -0.5)
+    W = W.view(G, pad16(N), taps * pad64(Ca)).to(dtype)
+    bias = _rand(gen, G, N) if has_bias else None
+    Res, Resd = _act(gen, dtype, B, T, N) if has_res else (None, None)
+    group = torch.randint(0, G, (B,), generator=gen, dtype=torch.int32) if G > 1 else None
+    Out = ops.empty(B, T, pad8(N), device=DEV)
+    ops.tapgemm(Ad, Ca, W.to(DEV), N, taps, dil, None if bias is None else bias.to(DEV), Resd,
+                None if group is None else group.to(DEV), Out)
+    Outr = ref.empty(B, T, pad8(N), device="cpu")
+    ref.tapgemm(A, Ca, W, N, taps, dil, bias, Res, group, Outr)
+    torch.cuda.synchronize()
+    _close(Out, Outr, dtype, f"tapgemm {case} {backend}")
+
+
+WGRAD_CASES = [
+    # B, T, M, C, taps, dil, G
+    (3, 40, 32, 30, 3, 1, 1),
+    (4, 40, 30, 20, 1, 1, 4),        # grouped (subject) wgrad
+    (3, 200, 64, 32, 3, 2, 1),
+    (4, 360, 320, 320, 3, 1, 1),     # real widths: 3 m tiles, c tile 320 = 192 + 128
+    (3, 360, 640, 320, 3, 1, 1),
+    (2, 360, 1024, 640, 1, 1, 1),    # head: two c tiles
+    (5, 130, 270, 208, 1, 1, 3),     # grouped at real widths
+    (20, 72, 320, 270, 3, 1, 1),     # more samples than one CTA range; c = 270 (OOB channels)
+]
+
+
+@pytest.mark.parametrize("dtype,backend", CONTRACTION_MODES)
+@pytest.mark.parametrize("case", WGRAD_CASES)
+def test_wgrad(dtype, backend, case):
+    B, T, M, C, taps, dil, G = case
+    gen = torch.Generator().manual_seed(2)
+    ops, ref = _ops(dtype, backend), TorchOps(dtype)
+    dU, dUd = _act(gen, dtype, B, T, M)
+    X, Xd = _act(gen, dtype, B, T, C)
+    group = torch.randint(0, G, (B,), generator=gen, dtype=torch.int32) if G > 1 else None
+    order = None
+    if group is not None:
+        order = torch.empty(B, dtype=torch.int32, device=DEV)
+        ops.group_order(group.to(DEV), G, order)
+        assert torch.equal(order.cpu().long(), torch.sort(group.long(), stable=True).indices)   # bit-exact
+    dW = torch.zeros(G, M, C, taps, device=DEV)
+    ops.wgrad(dUd, M, Xd, C, taps, dil, None if group is None else group.to(DEV), order, dW)
+    dWr = torch.zeros(G, M, C, taps)
+    ref.wgrad(dU, M, X, C, taps, dil, group, None, dWr)
+    torch.cuda.synchronize()
+    # fp32 accumulation of the same stored operands: only the summation order differs
+    got, want = dW.cpu(), dWr
+    err = float((got - want).abs().max()) / (float(want.abs().max()) + 1e-30)
+    assert torch.isfinite(got).all() and err < 2e-4, f"wgrad {case} {backend}: {err:.3e}"
+
+
+@pytest.mark.parametrize("dtype", EW_DTYPES)
+def test_colsum_and_sgemm(dtype):
+    gen = torch.Generator().manual_seed(3)
+    ops, ref = _ops(dtype, "simt"), TorchOps(dtype)
+    U, Ud = _act(gen, dtype, 5, 33, 30)
+    for group in (None, torch.tensor([2, 0, 2, 1, 0], dtype=torch.int32)):
+        G = 1 if group is None else 3
+        out = torch.zeros(G, 30, device=DEV)
+        ops.colsum(Ud, 30, None if group is None else group.to(DEV), out)
+        outr = torch.zeros(G, 30)
+        ref.colsum(U, 30, group, outr)
+        _close(out, outr, torch.float32, "colsum", atol_scale=5)
+    if dtype == torch.float32:
+        for tA, tB, beta in ((False, False, 0.0), (True, False, 0.0), (False, True, 1.0), (True, True, 0.5)):
+            M, N, K, batch = 70, 45, 130, 3
+            A = _rand(gen, batch, *((K, M) if tA else (M, K)))
+            Bm = _rand(gen, *((N, K) if tB else (K, N)))           # 2-D: broadcast over the batch
+            C0 = _rand(gen, batch, M, N)
+            Cd = C0.to(DEV)
+            ops.matmul(A.to(DEV), Bm.to(DEV), Cd, transA=tA, transB=tB, alpha=0.7, beta=beta)
+            Cr = C0.clone()
+            ref.matmul(A, Bm, Cr, transA=tA, transB=tB, alpha=0.7, beta=beta)
+            _close(Cd, Cr, torch.float32, f"sgemm tA={tA} tB={tB}", atol_scale=5)
+
+
+def test_sa_softmax_fwd_bwd():
+    gen = torch.Generator().manual_seed(4)
+    ops, ref = _ops(torch.float32, "simt"), TorchOps()
+    a = _rand(gen, 30, 20, scale=9.0)
+    mask = (torch.rand(20, generator=gen) > 0.2).float()
+    for m in (mask, None):
+        W, Wm = torch.empty(30, 20, device=DEV), torch.empty(30, 20, device=DEV)
+        ops.sa_softmax(a.to(DEV), None if m is None else m.to(DEV), W, Wm)
+        Wr, Wmr = torch.empty(30, 20), torch.empty(30, 20)
+        ref.sa_softmax(a, m, Wr, Wmr)
+        _close(W, Wr, torch.float32, "sa_softmax W")
+        _close(Wm, Wmr, torch.float32, "sa_softmax Wm")
+        g = _rand(gen, 30, 20)
+        da, dar = torch.empty(30, 20, device=DEV), torch.empty(30, 20)
+        ops.sa_softmax_bwd(W, g.to(DEV), None if m is None else m.to(DEV), da)
+        ref.sa_softmax_bwd(Wr, g, m, dar)
+        _close(da, dar, torch.float32, "sa_softmax_bwd")
+
+
+# ------------------------------------------------------------------------------------------------ elementwise
+@pytest.mark.parametrize("dtype", EW_DTYPES)
+@pytest.mark.parametrize("shape", [(3, 40, 30), (2, 360, 320), (70, 37, 320)])
+def test_batchnorm_gelu_chain(dtype, shape):
+    B, T, C = shape
+    gen = torch.Generator().manual_seed(5)
+    ops, ref = _ops(dtype, "simt"), TorchOps(dtype)
+    U, Ud = _act(gen, dtype, B, T, C)
+    n = B * T
+    gamma, beta = torch.rand(C, generator=gen) + 0.5, _rand(gen, C, scale=0.2)
+    for training in (1, 0):
+        rm, rv = _rand(gen, C, scale=0.1), torch.rand(C, generator=gen) + 0.5
+        rmd, rvd = rm.to(DEV), rv.to(DEV)
+        sums, sumsr = torch.zeros(2, C, device=DEV), torch.zeros(2, C)
+        ops.bn_stats(Ud, C, sums)
+        ref.bn_stats(U, C, sumsr)
+        _close(sums, sumsr, torch.float32, "bn_stats", atol_scale=5)
+        st = {k: torch.empty(C, device=DEV) for k in ("scale", "shift", "mean", "rstd")}
+        str_ = {k: torch.empty(C) for k in st}
+        ops.bn_finalize(sums, gamma.to(DEV), beta.to(DEV), rmd, rvd, n, 1e-5, 0.1, training, st["scale"], st["shift"],
+                        st["mean"], st["rstd"])
+        ref.bn_finalize(sumsr, gamma, beta, rm, rv, n, 1e-5, 0.1, training, str_["scale"], str_["shift"], str_["mean"],
+                        str_["rstd"])
+        for k in st:
+            _close(st[k], str_[k], torch.float32, f"bn_finalize {k}", atol_scale=20)
+        _close(rmd, rm, torch.float32, "running_mean", atol_scale=20)
+        _close(rvd, rv, torch.float32, "running_var", atol_scale=20)
+        H = ops.empty(B, T, pad8(C), device=DEV)
+        Hr = ref.empty(B, T, pad8(C), device="cpu")
+        # feed both sides the same statistics so that only the kernel under test differs
+        stc = {k: v.cpu() for k, v in st.items()}
+        ops.bn_gelu(Ud, st["scale"], st["shift"], H, C)
+        ref.bn_gelu(U, stc["scale"], stc["shift"], Hr, C)
+        _close(H, Hr, dtype, "bn_gelu")
+        if training:
+            dH, dHd = _act(gen, dtype, B, T, C)
+            dY, dYr = ops.empty(B, T, pad8(C), device=DEV), ref.empty(B, T, pad8(C), device="cpu")
+            s2, s2r = torch.zeros(2, C, device=DEV), torch.zeros(2, C)
+            ops.bn_gelu_bwd_reduce(dHd, Ud, st["scale"], st["shift"], st["mean"], st["rstd"], dY, s2, C)
+            ref.bn_gelu_bwd_reduce(dH, U, stc["scale"], stc["shift"], stc["mean"], stc["rstd"], dYr, s2r, C)
+            _close(dY, dYr, dtype, "bn_gelu_bwd_reduce dY")
+            _close(s2, s2r, torch.float32, "bn_gelu_bwd_reduce sums", atol_scale=500 if dtype == torch.bfloat16 else 20)
+            dU, dUr = ops.empty(B, T, pad8(C), device=DEV), ref.empty(B, T, pad8(C), device="cpu")
+            ops.bn_bwd_apply(dY, Ud, gamma.to(DEV), st["mean"], st["rstd"], s2, n, dU, C)
+            ref.bn_bwd_apply(dY.cpu(), U, gamma, stc["mean"], stc["rstd"], s2.cpu(), n, dUr, C)
+            _close(dU, dUr, dtype, "bn_bwd_apply")
+
+
+@pytest.mark.parametrize("dtype", EW_DTYPES)
+@pytest.mark.parametrize("C", [30, 320])
+def test_glu_gelu_timemean(dtype, C):
+    gen = torch.Generator().manual_seed(6)
+    ops, ref = _ops(dtype, "simt"), TorchOps(dtype)
+    B, T = 3, 50
+    V, Vd = _act(gen, dtype, B, T, 2 * C)
+    out, outr = ops.empty(B, T, pad8(C), device=DEV), ref.empty(B, T, pad8(C), device="cpu")
+    ops.glu(Vd, out, C)
+    ref.glu(V, outr, C)
+    _close(out, outr, dtype, "glu")
+    d, dd = _act(gen, dtype, B, T, C)
+    dV, dVr = ops.empty(*V.shape, device=DEV), ref.empty(*V.shape, device="cpu")
+    ops.glu_bwd(dd, Vd, dV, C)
+    ref.glu_bwd(d, V, dVr, C)
+    _close(dV, dVr, dtype, "glu_bwd")
+    P, Pd = _act(gen, dtype, B, T, pad8(C))
+    Q, Qr = ops.empty(*P.shape, device=DEV), ref.empty(*P.shape, device="cpu")
+    ops.gelu(Pd, Q)
+    ref.gelu(P, Qr)
+    _close(Q, Qr, dtype, "gelu")
+    g, gd = _act(gen, dtype, B, T, pad8(C))
+    dP, dPr = ops.empty(*P.shape, device=DEV), ref.empty(*P.shape, device="cpu")
+    ops.gelu_bwd(gd, Pd, dP)
+    ref.gelu_bwd(g, P, dPr)
+    _close(dP, dPr, dtype, "gelu_bwd")
+    Fs = pad8(C)
+    Zm, Zmr = ops.empty(B, 1, Fs, device=DEV), ref.empty(B, 1, Fs, device="cpu")
+    ops.time_mean(Pd, Zm, C)
+    ref.time_mean(P, Zmr, C)
+    _close(Zm, Zmr, dtype, "time_mean")
+    dZ, dZr = ops.empty(B, T, Fs, device=DEV), ref.empty(B, T, Fs, device="cpu")
+    ops.time_mean_bwd(Zm, dZ, C)
+    ref.time_mean_bwd(Zm.cpu(), dZr, C)
+    _close(dZ, dZr, dtype, "time_mean_bwd")
+
+
+# ------------------------------------------------------------------------------------------------ CLIP
+CLIP_CASES = [
+    # By (speech rows, all ranks), Bz (local brains), off, F, T
+    (6, 6, 0, 64, 40),
+    (5, 5, 0, 48, 1),          # static targets, ragged batch
+    (24, 8, 8, 64, 24),        # one-sided data-parallel shard: rank 1 of 3
+    (16, 16, 0, 1024, 360),    # the real contraction length D = 368 640
+    (300, 150, 150, 512, 1),   # GOD-like: several tiles in both directions
+]
+
+
+@pytest.mark.parametrize("dtype,backend", CONTRACTION_MODES)
+@pytest.mark.parametrize("case", CLIP_CASES)
+def test_clip_pipeline(dtype, backend, case):
+    By, Bz, off, Fo, T = case
+    gen = torch.Generator().manual_seed(7)
+    ops, ref = _ops(dtype, backend), TorchOps(dtype)
+    D = Fo * T
+    Y = _rand(gen, By, Fo, T) if T > 1 else _rand(gen, By, Fo)
+    Z = (_rand(gen, Bz, D) * 0.3).to(dtype)
+    temp = torch.tensor([5.1])
+    # -- prep + norms
+    Yp, Ypr = ops.empty(By, D, device=DEV), ref.empty(By, D, device="cpu")
+    ysq, ysqr = torch.zeros(By, device=DEV), torch.zeros(By)
+    ops.clip_prep_y(Y.to(DEV), Yp, ysq)
+    ref.clip_prep_y(Y, Ypr, ysqr)
+    _close(Yp, Ypr, dtype, "clip_prep_y")
+    _close(ysq, ysqr, torch.float32, "ysq", atol_scale=5)
+    zsq, zsqr = torch.zeros(Bz, device=DEV), torch.zeros(Bz)
+    Zd = Z.to(DEV)
+    ops.rowsumsq(Zd, zsq)
+    ref.rowsumsq(Z, zsqr)
+    _close(zsq, zsqr, torch.float32, "zsq", atol_scale=5)
+    # -- logits contraction (same stored operands on both sides: fp32 accumulation order only)
+    raw, rawr = torch.zeros(By, Bz, device=DEV), torch.zeros(By, Bz)
+    ops.clip_logits(Yp, Zd, raw)
+    ref.clip_logits(Yp.cpu(), Z, rawr)
+    _close(raw, rawr, torch.float32, f"clip_logits {backend}", atol_scale=20)
+    # -- softmax / CE stage on identical inputs
+    rawc, ysqc, zsqc = raw.cpu(), ysq.cpu(), zsq.cpu()
+    Lg, Lgr = torch.empty(By, Bz, device=DEV), torch.empty(By, Bz)
+    st = {k: torch.empty(n, device=DEV) for k, n in (("rm", By), ("rs", By), ("cl", Bz))}
+    str_ = {k: torch.empty(v.numel()) for k, v in st.items()}
+    ops.clip_ce_partial(raw, ysq, zsq, temp.to(DEV), Lg, st["rm"], st["rs"], st["cl"])
+    ref.clip_ce_partial(rawc, ysqc, zsqc, temp, Lgr, str_["rm"], str_["rs"], str_["cl"])
+    _close(Lg, Lgr, torch.float32, "logits", atol_scale=5)
+    _close(st["rm"] + torch.log(st["rs"]), str_["rm"] + torch.log(str_["rs"]), torch.float32, "row lse", atol_scale=5)
+    _close(st["cl"], str_["cl"], torch.float32, "col lse", atol_scale=5)
+    # complete the row LSE as a single rank would see it (other ranks' brains contribute nothing here)
+    row_lse = (st["rm"] + torch.log(st["rs"])).contiguous()
+    wscale = 0.5 / By
+    out2, out2r = torch.zeros(2, device=DEV), torch.zeros(2)
+    coef, coefr = ops.empty(Bz, pad8(By), device=DEV), ref.empty(Bz, pad8(By), device="cpu")
+    cvec, cvecr = torch.zeros(Bz, device=DEV), torch.zeros(Bz)
+    ops.clip_ce_finish(Lg, row_lse, st["cl"], ysq, zsq, temp.to(DEV), off, wscale, out2, coef, cvec)
+    ref.clip_ce_finish(Lg.cpu(), row_lse.cpu(), st["cl"].cpu(), ysqc, zsqc, temp, off, wscale, out2r, coefr, cvecr)
+    _close(out2, out2r, torch.float32, "loss/dtemp", atol_scale=50)
+    _close(coef[:, :By], coefr[:, :By], dtype, "coef")
+    _close(cvec, cvecr, torch.float32, "cvec", atol_scale=50)
+    # -- dZ contraction
+    gs = torch.tensor([0.7])
+    dZ, dZr = ops.empty(Bz, D, device=DEV), ref.empty(Bz, D, device="cpu")
+    ops.clip_dz(coef, Yp, Zd, cvec, gs.to(DEV), dZ)
+    ref.clip_dz(coef.cpu(), Yp.cpu(), Z, cvec.cpu(), gs, dZr)
+    torch.cuda.synchronize()
+    _close(dZ, dZr, dtype, f"clip_dz {backend}")

@@ -1,0 +1,152 @@
+"""GPU tier, path level: the drop-in modules (public API -> C-ABI -> sm_100a kernels) against
+
+  * the committed golden fixtures = outputs of the UNMODIFIED reference on the same seeded inputs and weights
+    (tests/golden/*.npz, made by oracle/make_golden.py);
+  * the oracle restatement run on the host CPU at mid size;
+  * size-independent properties at the full BASELINE.json shape (batch-permutation equivariance, bit-exact subject
+    routing, agreement of the tensor-core path with the fp32 check mode).
+
+Tolerances are north_star's: loss and embeddings within 1e-3 relative in the fp32 check mode, 2e-2 in bf16; subject
+and segment indexing bit-exact.  Metrics: ||Z - Z_ref||_F / ||Z_ref||_F and |l - l_ref| / |l_ref|.
+"""
+import numpy as np
+import pytest
+import torch
+
+import megb200
+from megb200 import synth
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+# precision mode -> (Z tol, loss tol, grad tol)
+MODES = {
+    "fp32": (1e-3, 1e-3, 5e-3),
+    "bf16": (2e-2, 2e-2, 0.35),          # tcgen05 engine (the product path)
+    "bf16_simt": (2e-2, 2e-2, 0.35),     # same storage on the fp32 CUDA-core engine (cross-check)
+}
+
+
+@pytest.fixture(params=list(MODES))
+def mode(request):
+    old = megb200.get_precision()
+    megb200.set_precision(request.param)
+    yield request.param
+    megb200.set_precision(old)
+
+
+def test_native_library_is_loaded():
+    from megb200 import lib
+    assert lib.load().megb200_version() == 100
+    maps = open("/proc/self/maps").read()
+    assert "libmegb200.so" in maps
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny_static", "narrow", "narrow_static"])
+def test_train_step_matches_reference_golden(mode, name):
+    tz, tl, tg = MODES[mode]
+    cfg = synth.get_config(name)
+    enc, lossf = H.make_modules(cfg, DEV)
+    X, Y, subj = H.make_inputs(cfg, DEV)
+    Z, loss, grads = H.train_step(enc, lossf, X, Y, subj, synth.drop_center(cfg))
+    torch.cuda.synchronize()
+    assert Z.is_cuda and loss.is_cuda
+    bn = {k: v for k, v in enc.state_dict().items() if "running_" in k or "num_batches" in k}
+    errs = H.compare_with_golden(name, Z, loss, grads, tz, tl, tg, bn=bn, tol_bn=5e-3 if mode == "fp32" else 3e-2)
+    print(f"[parity] {name} {mode}: " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()))
+
+
+def test_eval_mode_matches_reference_golden(mode):
+    tz, tl, _ = MODES[mode]
+    cfg = synth.get_config("narrow")
+    enc, lossf = H.make_modules(cfg, DEV)
+    X, Y, subj = H.make_inputs(cfg, DEV)
+    H.train_step(enc, lossf, X, Y, subj, synth.drop_center(cfg))
+    enc.eval()
+    with torch.no_grad():
+        Z = enc(X, subj)
+        logits, loss = lossf(Y, Z, return_logits=True)
+    g = H.load_golden("narrow")
+    assert H.rel_fro(H.subsample(Z), g["Z_eval_sample"]) <= tz
+    assert abs(float(loss) - float(g["loss_eval"])) / abs(float(g["loss_eval"])) <= tl
+    assert H.rel_fro(H.subsample(logits), g["logits_eval_sample"]) <= 5 * tz
+
+
+def test_mid_size_against_cpu_oracle(mode):
+    """Brennan2018 shape (60 channels, 33 subjects, T=360) at B=16: oracle on the host CPU, same inputs."""
+    from oracle import restatement as R
+    tz, tl, _ = MODES[mode]
+    cfg = synth.get_config("brennan", B=16)
+    enc, lossf = H.make_modules(cfg, DEV)
+    X, Y, subj = H.make_inputs(cfg, DEV)
+    center = synth.drop_center(cfg)
+    Z, loss, grads = H.train_step(enc, lossf, X, Y, subj, center)
+    P = R.state_to_torch(synth.make_state(cfg), requires_grad=True)
+    temp = torch.tensor([float(cfg.init_temperature)], requires_grad=True)
+    Zr, lr, gr = R.train_step(P, temp, X.cpu(), Y.cpu(), subj, synth.sensor_locations(cfg.C), K=cfg.K,
+                              d_drop=cfg.d_drop, seq2seq=True, drop_center=center)
+    ez, el = H.rel_fro(Z.float().cpu(), Zr), abs(float(loss) - float(lr)) / abs(float(lr))
+    gt = abs(float(grads["temp"]) - float(gr["temp"])) / abs(float(gr["temp"]))
+    gw = H.rel_fro(grads["conv_final2.weight"].cpu(), gr["conv_final2.weight"])
+    print(f"[parity] brennan B=16 {mode}: Z={ez:.2e} loss={el:.2e} dtemp={gt:.2e} dWf2={gw:.2e}")
+    assert ez <= tz and el <= tl
+    assert gt <= (5e-3 if mode == "fp32" else 5e-2)
+    assert gw <= (5e-3 if mode == "fp32" else 5e-2)
+
+
+def test_subject_routing_bit_exact_and_permutation_equivariant(mode):
+    cfg = synth.get_config("narrow")
+    enc, _ = H.make_modules(cfg, DEV)
+    X, _, _ = H.make_inputs(cfg, DEV, B=12)
+    subj = torch.tensor([0, 1, 2, 3, 4, 4, 3, 2, 1, 0, 2, 2], dtype=torch.int32)
+    enc.eval()
+    with torch.no_grad():
+        Z = enc(X, subj)
+        perm = torch.randperm(12, generator=torch.Generator().manual_seed(5))
+        Zp = enc(X[perm.to(DEV)], subj[perm])
+        Z64 = enc(X, subj.long())
+        Zdev = enc(X, subj.to(DEV))
+    assert torch.equal(Zp, Z[perm.to(DEV)]), "batch permutation must permute the outputs bit-exactly"
+    assert torch.equal(Z64, Z) and torch.equal(Zdev, Z), "int64 / device-resident indices must route identically"
+    # one-hot routing: give two samples identical inputs but different subjects -> different outputs; same subject -> equal
+    X2 = X.clone()
+    X2[1] = X2[0]
+    with torch.no_grad():
+        Za = enc(X2, torch.tensor([3, 3] + [0] * 10, dtype=torch.int32))
+        Zb = enc(X2, torch.tensor([3, 4] + [0] * 10, dtype=torch.int32))
+    assert torch.equal(Za[0], Za[1])
+    assert not torch.equal(Zb[0], Zb[1])
+
+
+def test_full_size_tensor_core_path_agrees_with_check_mode():
+    """BASELINE.json configs[1] shape at B=32: bf16/tcgen05 path vs the fp32 check mode on the same device,
+    plus a checksum-style invariant: every logits row/column softmax sums to one (sum of dL over a row is 0)."""
+    cfg = synth.get_config("gwilliams", B=32)
+    res = {}
+    for mode in ("fp32", "bf16"):
+        megb200.set_precision(mode)
+        enc, lossf = H.make_modules(cfg, DEV)
+        X, Y, subj = H.make_inputs(cfg, DEV)
+        Z, loss, grads = H.train_step(enc, lossf, X, Y, subj, synth.drop_center(cfg))
+        res[mode] = (Z.float(), float(loss), grads)
+    megb200.set_precision("bf16")
+    ez = H.rel_fro(res["bf16"][0], res["fp32"][0])
+    el = abs(res["bf16"][1] - res["fp32"][1]) / abs(res["fp32"][1])
+    print(f"[parity] gwilliams B=32 bf16 vs fp32 check mode: Z={ez:.2e} loss={el:.2e}")
+    assert ez <= 2e-2 and el <= 2e-2
+    for k in ("conv_final2.weight", "conv_blocks.conv2.conv1.weight", "subject_block.conv.weight", "temp"):
+        e = H.rel_fro(res["bf16"][2][k].float(), res["fp32"][2][k].float())
+        print(f"[parity]   grad {k}: {e:.2e}")
+        assert e <= 0.2, k
+
+
+def test_bf16_is_the_default_precision_and_output_is_bf16():
+    assert megb200.get_precision() == "bf16"
+    cfg = synth.get_config("tiny")
+    enc, _ = H.make_modules(cfg, DEV)
+    X, _, subj = H.make_inputs(cfg, DEV)
+    enc.eval()
+    with torch.no_grad():
+        Z = enc(X, subj)
+    assert Z.dtype == torch.bfloat16 and Z.shape == (cfg.B, cfg.F, cfg.T)
