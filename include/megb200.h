@@ -31,6 +31,13 @@ extern "C" {
 #define MEGB200_SIMT 0
 #define MEGB200_TC 1
 
+/* tap-GEMM epilogues (all evaluated on the fp32 accumulator: exactly one rounding per stored tensor) */
+#define MEGB200_EPI_STORE 0     /* Out = acc + bias + Res                       (storage dtype)                  */
+#define MEGB200_EPI_STORE_F32 1 /* same, Out stored as f32: the pre-BatchNorm tensors u0/u1 (models.py:312,316)  */
+#define MEGB200_EPI_GELU 2      /* Out2 = P = acc + bias, Out = gelu(P)         (models.py:373-374)              */
+#define MEGB200_EPI_GLU 3       /* N = 2*Ch: Out2 = V = acc + bias [..,2Ch], Out[..,c] = V[c]*sigmoid(V[Ch+c])   */
+                                /*                                              (models.py:319-320)              */
+
 #define MEGB200_ERR_ARG (-1)
 #define MEGB200_ERR_UNSUPPORTED (-2)
 #define MEGB200_ERR_DRIVER (-3)
@@ -59,10 +66,11 @@ int megb200_pack_weight(const float* w, void* out, int G, int O, int I, int Kt, 
  * zero outside [0,T) ("same" padding).  One kernel serves: the spatial-attention mix + shared 1x1 + per-subject
  * 1x1 chain pre-multiplied into one grouped GEMM keyed by subject index (models.py:220,269-272), Conv1d k=3
  * forward (models.py:310-319), its data gradient (flipped/transposed pack), and the 1x1 head convs
- * (models.py:373-374).  N = logical output channels; channels N..Cos-1 of Out are written as zero. */
+ * (models.py:373-374).  N = logical output channels; channels N..Cos-1 of Out are written as zero.  `epilogue`
+ * is one of MEGB200_EPI_*; Out2/Co2s are used by the GELU and GLU epilogues only. */
 int megb200_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int N, int Np, int Kp, int taps,
-                    int dil, const float* bias, const void* Res, int Crs, const int32_t* group, int G, void* Out,
-                    int Cos, int dtype, int backend, void* stream);
+                    int dil, const float* bias, const void* Res, int Crs, const int32_t* group, int G,
+                    int epilogue, void* Out, int Cos, void* Out2, int Co2s, int dtype, int backend, void* stream);
 
 /* Weight gradient: dW[g][m][c][j] += sum_{b: group[b]==g} sum_t dU[b][t][m] * Xin[b][t + (j - taps/2)*dil][c]
  * (f32, nn.Conv1d layout [G][M][C][taps]; accumulated — caller zeroes).  Replaces autograd's
@@ -96,8 +104,10 @@ int megb200_sa_softmax_bwd(const float* W, const float* dWm, const float* mask, 
                            void* stream);
 
 /* ---------------------------------------------------------------------------------------------- BatchNorm/GELU/GLU */
-/* sums[0][c] += sum u, sums[1][c] += sum u^2 over all (b,t)   (models.py:291,299 train-mode statistics) */
-int megb200_bn_stats(const void* U, long long rows, int C, int Cs, float* sums, int dtype, void* stream);
+/* The pre-BatchNorm tensor U may be stored in f32 while the activations around it are bf16 (`u_dtype`): the
+ * normalisation then sees the unrounded convolution output, as in the reference.
+ * sums[0][c] += sum u, sums[1][c] += sum u^2 over all (b,t)   (models.py:291,299 train-mode statistics) */
+int megb200_bn_stats(const void* U, long long rows, int C, int Cs, float* sums, int u_dtype, void* stream);
 /* training != 0: mean/var from sums (biased var), running stats updated in place (momentum, unbiased var);
  * training == 0: running stats used.  Writes scale = gamma*rstd, shift = beta - mean*scale, mean, rstd. */
 int megb200_bn_finalize(const float* sums, const float* gamma, const float* beta, float* running_mean,
@@ -105,15 +115,15 @@ int megb200_bn_finalize(const float* sums, const float* gamma, const float* beta
                         float* shift, float* mean, float* rstd, int C, void* stream);
 /* H = gelu(scale*U + shift)   (models.py:314,317) */
 int megb200_bn_gelu(const void* U, const float* scale, const float* shift, void* H, long long rows, int C, int Cs,
-                    int dtype, void* stream);
+                    int u_dtype, int dtype, void* stream);
 /* dY = dH * gelu'(scale*U+shift); sums2[0][c] += sum dY, sums2[1][c] += sum dY*xhat, xhat = (U-mean)*rstd */
 int megb200_bn_gelu_bwd_reduce(const void* dH, const void* U, const float* scale, const float* shift,
                                const float* mean, const float* rstd, void* dY, float* sums2, long long rows, int C,
-                               int Cs, int dtype, void* stream);
+                               int Cs, int u_dtype, int dtype, void* stream);
 /* dU = gamma*rstd * (dY - sums2[0]/n - xhat * sums2[1]/n)    */
 int megb200_bn_bwd_apply(const void* dY, const void* U, const float* gamma, const float* mean, const float* rstd,
-                         const float* sums2, long long count, void* dU, long long rows, int C, int Cs, int dtype,
-                         void* stream);
+                         const float* sums2, long long count, void* dU, long long rows, int C, int Cs, int u_dtype,
+                         int dtype, void* stream);
 /* eval-mode backward is never needed (no grad in eval). */
 
 /* Out[.., c] = V[.., c] * sigmoid(V[.., C + c]),  V: [rows][Vs] with 2C logical channels (models.py:320) */

@@ -52,6 +52,9 @@ static EncodeTiledFn get_encode() {
 
 int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box) {
+  // Driver entry points need the primary context current on THIS thread; autograd's backward threads may not have
+  // issued a runtime call yet (cuTensorMapEncodeTiled then fails with CUDA_ERROR_INVALID_CONTEXT).
+  cudaFree(nullptr);
   EncodeTiledFn fn = get_encode();
   if (fn == nullptr) {
     set_last_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -89,8 +92,8 @@ int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_
 }
 
 int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int N, int Np, int Kp, int taps, int dil,
-               const float* bias, const void* Res, int Crs, const int32_t* group, int G, void* Out, int Cos,
-               cudaStream_t st);
+               const float* bias, const void* Res, int Crs, const int32_t* group, int G, int epi, void* Out, int Cos,
+               void* Out2, int Co2s, cudaStream_t st);
 int tc_wgrad(const void* dU, int M, int Ms, const void* Xin, int C, int Cs, int B, int T, int taps, int dil,
              const int32_t* group, const int32_t* order, int G, float* dW, float* workspace, size_t ws_bytes,
              cudaStream_t st);
@@ -101,8 +104,8 @@ int tc_clip_dz(const void* coef, int ldc, const void* Yp, const void* Z, const f
 
 template <typename T>
 int simt_tapgemm(const void* A, int B, int Tn, int Ca, int Cas, const void* W, int N, int Np, int Kp, int taps,
-                 int dil, const float* bias, const void* Res, int Crs, const int32_t* group, void* Out, int Cos,
-                 cudaStream_t st);
+                 int dil, const float* bias, const void* Res, int Crs, const int32_t* group, int epi, void* Out,
+                 int Cos, void* Out2, int Co2s, cudaStream_t st);
 template <typename T>
 int simt_wgrad(const void* dU, int M, int Ms, const void* Xin, int C, int Cs, int B, int Tn, int taps, int dil,
                const int32_t* group, float* dW, cudaStream_t st);
@@ -149,25 +152,34 @@ int megb200_group_order(const int32_t* group, int B, int G, int32_t* order, void
 }
 
 int megb200_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int N, int Np, int Kp, int taps,
-                    int dil, const float* bias, const void* Res, int Crs, const int32_t* group, int G, void* Out,
-                    int Cos, int dtype, int backend, void* stream) {
+                    int dil, const float* bias, const void* Res, int Crs, const int32_t* group, int G, int epilogue,
+                    void* Out, int Cos, void* Out2, int Co2s, int dtype, int backend, void* stream) {
   MEGB_CHECK_ARG(A && W && Out && B > 0 && T > 0 && Ca > 0 && N > 0 && taps >= 1 && (taps & 1) && dil >= 1 && G >= 1,
                  "tapgemm: bad arguments");
-  MEGB_CHECK_ARG(Cas >= Ca && Cos >= N && Np >= N && Kp >= Ca, "tapgemm: strides/padding smaller than extents");
+  MEGB_CHECK_ARG(epilogue >= MEGB200_EPI_STORE && epilogue <= MEGB200_EPI_GLU, "tapgemm: unknown epilogue %d", epilogue);
+  const int n_out = epilogue == MEGB200_EPI_GLU ? N / 2 : N;
+  MEGB_CHECK_ARG(Cas >= Ca && Cos >= n_out && Np >= N && Kp >= Ca, "tapgemm: strides/padding smaller than extents");
   MEGB_CHECK_ARG(Res == nullptr || Crs >= N, "tapgemm: residual stride smaller than N");
+  if (epilogue == MEGB200_EPI_GLU || epilogue == MEGB200_EPI_GELU) {
+    MEGB_CHECK_ARG(Out2 != nullptr && Co2s >= N, "tapgemm: this epilogue needs the second output (stride >= N)");
+    MEGB_CHECK_ARG(epilogue != MEGB200_EPI_GLU || (N % 2 == 0 && Res == nullptr), "tapgemm: GLU needs even N, no residual");
+  }
   cudaStream_t st = (cudaStream_t)stream;
   if (backend == MEGB200_TC) {
     if (dtype != MEGB200_BF16) {
       set_last_error("tapgemm: the tensor-core engine needs bf16 activations");
       return MEGB200_ERR_UNSUPPORTED;
     }
-    return tc::tc_tapgemm(A, B, T, Ca, Cas, W, N, Np, Kp, taps, dil, bias, Res, Crs, group, G, Out, Cos, st);
+    return tc::tc_tapgemm(A, B, T, Ca, Cas, W, N, Np, Kp, taps, dil, bias, Res, Crs, group, G, epilogue, Out, Cos, Out2,
+                          Co2s, st);
   }
   MEGB_CHECK_ARG(backend == MEGB200_SIMT, "tapgemm: unknown backend %d", backend);
   if (dtype == MEGB200_F32)
-    return simt_tapgemm<float>(A, B, T, Ca, Cas, W, N, Np, Kp, taps, dil, bias, Res, Crs, group, Out, Cos, st);
+    return simt_tapgemm<float>(A, B, T, Ca, Cas, W, N, Np, Kp, taps, dil, bias, Res, Crs, group, epilogue, Out, Cos,
+                               Out2, Co2s, st);
   if (dtype == MEGB200_BF16)
-    return simt_tapgemm<__nv_bfloat16>(A, B, T, Ca, Cas, W, N, Np, Kp, taps, dil, bias, Res, Crs, group, Out, Cos, st);
+    return simt_tapgemm<__nv_bfloat16>(A, B, T, Ca, Cas, W, N, Np, Kp, taps, dil, bias, Res, Crs, group, epilogue, Out,
+                                       Cos, Out2, Co2s, st);
   MEGB_CHECK_ARG(false, "tapgemm: unknown dtype %d", dtype);
 }
 

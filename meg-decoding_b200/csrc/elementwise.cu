@@ -153,11 +153,11 @@ struct ColsumOp {
 };
 
 // dY = dH * gelu'(y), y = scale*u + shift; accumulates sum dY and sum dY*xhat
-template <typename T>
+template <typename TU, typename T>
 struct BnGeluBwdOp {
   static constexpr bool kTwo = true;
   const T* dh;
-  const T* u;
+  const TU* u;
   T* dy;
   const float *scale, *shift, *mean, *rstd;
   int Cs, C;
@@ -202,8 +202,8 @@ static int launch_colreduce(Op op, long long rows, int C, int Cs, const int32_t*
 }
 
 // ------------------------------------------------------------------------------------------ maps
-template <typename T>
-__global__ void bn_gelu_kernel(const T* __restrict__ u, const float* __restrict__ scale,
+template <typename TU, typename T>
+__global__ void bn_gelu_kernel(const TU* __restrict__ u, const float* __restrict__ scale,
                                const float* __restrict__ shift, T* __restrict__ h, long long nvec, int C, int cg) {
   for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvec;
        v += (long long)gridDim.x * blockDim.x) {
@@ -219,8 +219,8 @@ __global__ void bn_gelu_kernel(const T* __restrict__ u, const float* __restrict_
   }
 }
 
-template <typename T>
-__global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ u,
+template <typename TU, typename T>
+__global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, const TU* __restrict__ u,
                                     const float* __restrict__ gamma, const float* __restrict__ mean,
                                     const float* __restrict__ rstd, const float* __restrict__ sums2, float inv_n,
                                     T* __restrict__ du, long long nvec, int C, int cg) {
@@ -492,6 +492,18 @@ using namespace megb200;
     return MEGB200_ERR_ARG;                                          \
   }
 
+#define DISPATCH_U(u_dtype, ...)                                     \
+  if ((u_dtype) == MEGB200_F32) {                                    \
+    using TU = float;                                                \
+    __VA_ARGS__                                                      \
+  } else if ((u_dtype) == MEGB200_BF16) {                            \
+    using TU = __nv_bfloat16;                                        \
+    __VA_ARGS__                                                      \
+  } else {                                                           \
+    set_last_error("unknown u_dtype %d", (int)(u_dtype));            \
+    return MEGB200_ERR_ARG;                                          \
+  }
+
 extern "C" {
 
 int megb200_pack_x(const float* X, void* Xp, int B, int C, int T, int Cs, int dtype, void* stream) {
@@ -523,9 +535,9 @@ int megb200_colsum(const void* U, int B, int T, int C, int Cs, const int32_t* gr
                  return launch_colreduce(op, (long long)B * T, C, Cs, group, T, out, nullptr, (cudaStream_t)stream);)
 }
 
-int megb200_bn_stats(const void* U, long long rows, int C, int Cs, float* sums, int dtype, void* stream) {
+int megb200_bn_stats(const void* U, long long rows, int C, int Cs, float* sums, int u_dtype, void* stream) {
   MEGB_CHECK_ARG(U && sums && rows > 0, "bn_stats: bad arguments");
-  DISPATCH_DTYPE(dtype, StatsOp<DT> op{(const DT*)U, Cs};
+  DISPATCH_DTYPE(u_dtype, StatsOp<DT> op{(const DT*)U, Cs};
                  return launch_colreduce(op, rows, C, Cs, nullptr, 1, sums, sums + C, (cudaStream_t)stream);)
 }
 
@@ -542,31 +554,33 @@ int megb200_bn_finalize(const float* sums, const float* gamma, const float* beta
 }
 
 int megb200_bn_gelu(const void* U, const float* scale, const float* shift, void* H, long long rows, int C, int Cs,
-                    int dtype, void* stream) {
+                    int u_dtype, int dtype, void* stream) {
   MEGB_CHECK_ARG(U && H && scale && shift && rows > 0 && Cs % 8 == 0 && Cs >= C, "bn_gelu: bad arguments");
   const long long nvec = rows * (Cs / 8);
-  DISPATCH_DTYPE(dtype, bn_gelu_kernel<DT><<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)stream>>>(
-                            (const DT*)U, scale, shift, (DT*)H, nvec, C, Cs / 8);
-                 MEGB_LAUNCH_OK(); return 0;)
+  DISPATCH_U(u_dtype, DISPATCH_DTYPE(dtype, bn_gelu_kernel<TU, DT><<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)stream>>>(
+                                                (const TU*)U, scale, shift, (DT*)H, nvec, C, Cs / 8);
+                                     MEGB_LAUNCH_OK(); return 0;))
 }
 
 int megb200_bn_gelu_bwd_reduce(const void* dH, const void* U, const float* scale, const float* shift,
                                const float* mean, const float* rstd, void* dY, float* sums2, long long rows, int C,
-                               int Cs, int dtype, void* stream) {
+                               int Cs, int u_dtype, int dtype, void* stream) {
   MEGB_CHECK_ARG(dH && U && dY && sums2 && rows > 0, "bn_gelu_bwd_reduce: bad arguments");
-  DISPATCH_DTYPE(dtype, BnGeluBwdOp<DT> op{(const DT*)dH, (const DT*)U, (DT*)dY, scale, shift, mean, rstd, Cs, C};
-                 return launch_colreduce(op, rows, C, Cs, nullptr, 1, sums2, sums2 + C, (cudaStream_t)stream);)
+  DISPATCH_U(u_dtype,
+             DISPATCH_DTYPE(dtype, BnGeluBwdOp<TU, DT> op{(const DT*)dH, (const TU*)U, (DT*)dY, scale, shift, mean, rstd, Cs, C};
+                            return launch_colreduce(op, rows, C, Cs, nullptr, 1, sums2, sums2 + C, (cudaStream_t)stream);))
 }
 
 int megb200_bn_bwd_apply(const void* dY, const void* U, const float* gamma, const float* mean, const float* rstd,
-                         const float* sums2, long long count, void* dU, long long rows, int C, int Cs, int dtype,
-                         void* stream) {
+                         const float* sums2, long long count, void* dU, long long rows, int C, int Cs, int u_dtype,
+                         int dtype, void* stream) {
   MEGB_CHECK_ARG(dY && U && dU && sums2 && rows > 0 && count > 0 && Cs % 8 == 0, "bn_bwd_apply: bad arguments");
   const long long nvec = rows * (Cs / 8);
-  DISPATCH_DTYPE(dtype, bn_bwd_apply_kernel<DT><<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)stream>>>(
-                            (const DT*)dY, (const DT*)U, gamma, mean, rstd, sums2, 1.f / (float)count, (DT*)dU, nvec, C,
-                            Cs / 8);
-                 MEGB_LAUNCH_OK(); return 0;)
+  DISPATCH_U(u_dtype,
+             DISPATCH_DTYPE(dtype, bn_bwd_apply_kernel<TU, DT><<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)stream>>>(
+                                       (const DT*)dY, (const TU*)U, gamma, mean, rstd, sums2, 1.f / (float)count,
+                                       (DT*)dU, nvec, C, Cs / 8);
+                            MEGB_LAUNCH_OK(); return 0;))
 }
 
 int megb200_glu(const void* V, void* Out, long long rows, int C, int Vs, int Os, int dtype, void* stream) {

@@ -9,7 +9,9 @@ namespace megb200 {
 constexpr int kBM = 64, kBN = 64, kBK = 16;
 
 // kAK / kBK_: true when the operand's k index is the contiguous one in memory (keeps loads coalesced)
-template <bool kAKMajor, bool kBKMajor, class LoadA, class LoadB>
+// kGluCols: the 64-column tile is [32 "a" channels | their 32 gate channels]; a thread then owns 2 a-columns
+// (j = 0,1 -> 2*tx + j) and the 2 matching gate columns (j = 2,3 -> 32 + 2*tx + j - 2) so that GLU is thread-local.
+template <bool kAKMajor, bool kBKMajor, bool kGluCols = false, class LoadA, class LoadB>
 __device__ __forceinline__ void simt_tile(const LoadA& la, const LoadB& lb, int k0, int k1, float (&acc)[4][4]) {
   __shared__ float As[kBK][kBM + 1];
   __shared__ float Bs[kBK][kBN + 1];
@@ -41,7 +43,7 @@ __device__ __forceinline__ void simt_tile(const LoadA& la, const LoadB& lb, int 
 #pragma unroll
       for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][kGluCols ? ((j < 2) ? (tx * 2 + j) : (32 + tx * 2 + j - 2)) : (tx * 4 + j)];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -52,14 +54,17 @@ __device__ __forceinline__ void simt_tile(const LoadA& la, const LoadB& lb, int 
 }
 
 // ------------------------------------------------------------------------------------------ tap GEMM
-template <typename T>
+template <typename T, int kEpi>
 __global__ void __launch_bounds__(256)
 simt_tapgemm_kernel(const T* __restrict__ A, int Tn, int Ca, int Cas, const T* __restrict__ W, int N, int Np, int Kp,
                     int taps, int dil, const float* __restrict__ bias, const T* __restrict__ Res, int Crs,
-                    const int32_t* __restrict__ group, T* __restrict__ Out, int Cos, int tiles_per_sample) {
+                    const int32_t* __restrict__ group, void* __restrict__ OutV, int Cos, T* __restrict__ Out2, int Co2s,
+                    int tiles_per_sample) {
+  constexpr bool kGlu = (kEpi == MEGB200_EPI_GLU);
   const int b = blockIdx.x / tiles_per_sample;
   const int t0 = (blockIdx.x % tiles_per_sample) * kBM;
-  const int n0 = blockIdx.y * kBN;
+  const int Ch = N / 2;                                   // GLU only
+  const int n0 = blockIdx.y * (kGlu ? kBN / 2 : kBN);     // first output channel of this tile
   const int g = group ? group[b] : 0;
   const T* Ab = A + (long long)b * Tn * Cas;
   const T* Wg = W + (long long)g * Np * taps * Kp;
@@ -71,18 +76,45 @@ simt_tapgemm_kernel(const T* __restrict__ A, int Tn, int Ca, int Cas, const T* _
     return to_f(Ab[(long long)t * Cas + c]);
   };
   auto lb = [&](int r, int k) -> float {
-    const int n = n0 + r;
-    if (n >= N) return 0.f;
+    int n;
+    if (kGlu) {
+      const int c = n0 + (r & 31);
+      if (c >= Ch) return 0.f;
+      n = (r < 32) ? c : Ch + c;
+    } else {
+      n = n0 + r;
+      if (n >= N) return 0.f;
+    }
     return to_f(Wg[(long long)n * taps * Kp + k]);
   };
   float acc[4][4];
-  simt_tile<true, true>(la, lb, 0, taps * Kp, acc);
+  simt_tile<true, true, kGlu>(la, lb, 0, taps * Kp, acc);
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  T* Out = reinterpret_cast<T*>(OutV);
+  float* OutF = reinterpret_cast<float*>(OutV);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int t = t0 + ty * 4 + i;
     if (t >= Tn) continue;
     const long long row = (long long)b * Tn + t;
+    if (kGlu) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int c = n0 + tx * 2 + j;
+        if (c < Ch) {
+          const float a = acc[i][j] + (bias ? bias[(long long)g * N + c] : 0.f);
+          const float gt = acc[i][j + 2] + (bias ? bias[(long long)g * N + Ch + c] : 0.f);
+          Out2[row * Co2s + c] = from_f<T>(a);
+          Out2[row * Co2s + Ch + c] = from_f<T>(gt);
+          Out[row * Cos + c] = from_f<T>(a * sigmoid_f(gt));
+        } else if (c < Cos) {
+          Out[row * Cos + c] = from_f<T>(0.f);
+        }
+      }
+      if (blockIdx.y == 0 && tx == 0)
+        for (int c = N; c < Co2s; ++c) Out2[row * Co2s + c] = from_f<T>(0.f);
+      continue;
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx * 4 + j;
@@ -93,7 +125,14 @@ simt_tapgemm_kernel(const T* __restrict__ A, int Tn, int Ca, int Cas, const T* _
         if (bias) v += bias[(long long)g * N + n];
         if (Res) v += to_f(Res[row * Crs + n]);
       }
-      Out[row * Cos + n] = from_f<T>(v);
+      if (kEpi == MEGB200_EPI_STORE_F32) {
+        OutF[row * Cos + n] = v;
+      } else if (kEpi == MEGB200_EPI_GELU) {
+        if (n < Co2s) Out2[row * Co2s + n] = from_f<T>(v);
+        Out[row * Cos + n] = from_f<T>(n < N ? gelu_f(v) : 0.f);
+      } else {
+        Out[row * Cos + n] = from_f<T>(v);
+      }
     }
   }
 }
@@ -255,19 +294,30 @@ simt_clip_dz_kernel(const T* __restrict__ coef, int ldc, const T* __restrict__ Y
 // ------------------------------------------------------------------------------------------ launchers
 template <typename T>
 int simt_tapgemm(const void* A, int B, int Tn, int Ca, int Cas, const void* W, int N, int Np, int Kp, int taps,
-                 int dil, const float* bias, const void* Res, int Crs, const int32_t* group, void* Out, int Cos,
-                 cudaStream_t st) {
+                 int dil, const float* bias, const void* Res, int Crs, const int32_t* group, int epi, void* Out,
+                 int Cos, void* Out2, int Co2s, cudaStream_t st) {
   const int tps = (Tn + kBM - 1) / kBM;
-  dim3 grid(B * tps, (Cos + kBN - 1) / kBN);
-  simt_tapgemm_kernel<T><<<grid, 256, 0, st>>>((const T*)A, Tn, Ca, Cas, (const T*)W, N, Np, Kp, taps, dil, bias,
-                                                (const T*)Res, Crs, group, (T*)Out, Cos, tps);
+  const int cover = (epi == MEGB200_EPI_GLU) ? (Cos + kBN / 2 - 1) / (kBN / 2) : (Cos + kBN - 1) / kBN;
+  dim3 grid(B * tps, cover);
+#define MEGB_SIMT_TAP(E)                                                                                          \
+  simt_tapgemm_kernel<T, E><<<grid, 256, 0, st>>>((const T*)A, Tn, Ca, Cas, (const T*)W, N, Np, Kp, taps, dil, bias, \
+                                                   (const T*)Res, Crs, group, Out, Cos, (T*)Out2, Co2s, tps)
+  switch (epi) {
+    case MEGB200_EPI_STORE: MEGB_SIMT_TAP(MEGB200_EPI_STORE); break;
+    case MEGB200_EPI_STORE_F32: MEGB_SIMT_TAP(MEGB200_EPI_STORE_F32); break;
+    case MEGB200_EPI_GELU: MEGB_SIMT_TAP(MEGB200_EPI_GELU); break;
+    case MEGB200_EPI_GLU: MEGB_SIMT_TAP(MEGB200_EPI_GLU); break;
+    default: MEGB_CHECK_ARG(false, "tapgemm: unknown epilogue %d", epi);
+  }
+#undef MEGB_SIMT_TAP
   MEGB_LAUNCH_OK();
   return 0;
 }
 template int simt_tapgemm<float>(const void*, int, int, int, int, const void*, int, int, int, int, int, const float*,
-                                 const void*, int, const int32_t*, void*, int, cudaStream_t);
+                                 const void*, int, const int32_t*, int, void*, int, void*, int, cudaStream_t);
 template int simt_tapgemm<__nv_bfloat16>(const void*, int, int, int, int, const void*, int, int, int, int, int,
-                                         const float*, const void*, int, const int32_t*, void*, int, cudaStream_t);
+                                         const float*, const void*, int, const int32_t*, int, void*, int, void*, int,
+                                         cudaStream_t);
 
 template <typename T>
 int simt_wgrad(const void* dU, int M, int Ms, const void* Xin, int C, int Cs, int B, int Tn, int taps, int dil,

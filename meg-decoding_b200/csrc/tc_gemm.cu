@@ -32,12 +32,13 @@ __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
 
 // ================================================================================================ tap GEMM
 struct TapGemmParams {
-  int T, N, Cos, Crs, taps, dil, Kp, kchunks, tiles_per_sample, ntiles, NT, stages;
+  int T, N, Cos, Crs, Co2s, taps, dil, Kp, kchunks, tiles_per_sample, ntiles, NT, stages, epi;
   uint32_t tmem_cols, idesc;
   const float* bias;
   const __nv_bfloat16* Res;
   const int32_t* group;
-  __nv_bfloat16* Out;
+  void* Out;
+  __nv_bfloat16* Out2;
 };
 
 __global__ void __launch_bounds__(kThreads)
@@ -54,11 +55,14 @@ tc_tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   float* sbias_big = reinterpret_cast<float*>(ring + (size_t)p.stages * stage_bytes);
   if (p.NT > 128) sbias = sbias_big;
 
+  const bool glu = p.epi == MEGB200_EPI_GLU;
+  const int half = p.NT / 2;          // GLU: the tile is [half "a" channels | the matching half gate channels]
+  const int Ch = p.N / 2;
   const int n_tile = blockIdx.x % p.ntiles;
   const int m_tile = blockIdx.x / p.ntiles;
   const int b = m_tile / p.tiles_per_sample;
   const int t0 = (m_tile % p.tiles_per_sample) * kTileM;
-  const int n0 = n_tile * p.NT;
+  const int n0 = n_tile * (glu ? half : p.NT);   // first output channel of this tile
   const int g = p.group ? p.group[b] : 0;
   const int num_k = p.taps * p.kchunks;
 
@@ -91,7 +95,14 @@ tc_tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int tap = it / p.kchunks, kc = it % p.kchunks;
         const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
         tma_load_3d(sa, &tmA, kc * kBlockK, t0 + (tap - p.taps / 2) * p.dil, b, full);
-        tma_load_3d(sa + a_bytes, &tmW, tap * p.Kp + kc * kBlockK, n0, g, full);
+        const int kw = tap * p.Kp + kc * kBlockK;
+        if (glu) {
+          // two half-height boxes of the naturally packed weights: rows [n0, n0+half) and [Ch+n0, Ch+n0+half)
+          tma_load_3d(sa + a_bytes, &tmW, kw, n0, g, full);
+          tma_load_3d(sa + a_bytes + (uint32_t)half * 128, &tmW, kw, Ch + n0, g, full);
+        } else {
+          tma_load_3d(sa + a_bytes, &tmW, kw, n0, g, full);
+        }
       }
     }
   } else if (warp == 1) {
@@ -111,11 +122,20 @@ tc_tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       umma_commit(smem_u32(&hdr->tmem_full));
     }
   } else {
-    // ---------------- epilogue: TMEM -> registers -> (+bias, +residual) -> bf16 -> global (thread = one position)
+    // ---------------- epilogue: TMEM -> registers -> fused element-wise tail -> global (thread = one position)
     const int et = threadIdx.x - 64;
     for (int i = et; i < p.NT; i += 128) {
-      const int n = n0 + i;
-      sbias[i] = (p.bias != nullptr && n < p.N) ? p.bias[(long long)g * p.N + n] : 0.f;
+      int n;
+      bool ok;
+      if (glu) {
+        const int c = n0 + (i < half ? i : i - half);
+        ok = c < Ch;
+        n = (i < half) ? c : Ch + c;
+      } else {
+        n = n0 + i;
+        ok = n < p.N;
+      }
+      sbias[i] = (p.bias != nullptr && ok) ? p.bias[(long long)g * p.N + n] : 0.f;
     }
     named_bar_sync(1, 128);
     mbar_wait(smem_u32(&hdr->tmem_full), 0);
@@ -124,25 +144,66 @@ tc_tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int t = t0 + q * 32 + lane;
     const bool valid = t < p.T;
     const long long row = (long long)b * p.T + t;
-    __nv_bfloat16* orow = p.Out + row * p.Cos;
-    const __nv_bfloat16* rrow = p.Res ? p.Res + row * p.Crs : nullptr;
-    for (int ch = 0; ch < p.NT / 16; ++ch) {
-      float v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 16), v);
-      if (!valid) continue;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    if (glu) {
+      __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.Out) + row * p.Cos;
+      __nv_bfloat16* vrow = p.Out2 + row * p.Co2s;
+      for (int ch = 0; ch < half / 16; ++ch) {
+        float va[16], vg[16];
+        tmem_ld16(trow + (uint32_t)(ch * 16), va);
+        tmem_ld16(trow + (uint32_t)(half + ch * 16), vg);
+        if (!valid) continue;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int c0 = n0 + ch * 16 + h * 8;
-        if (c0 >= p.Cos) continue;
-        float o[8];
-        float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (rrow != nullptr && c0 < p.Crs) load8(rrow + c0, r);
+        for (int h = 0; h < 2; ++h) {
+          const int c0 = n0 + ch * 16 + h * 8;
+          if (c0 >= p.Cos) continue;
+          float o[8], a8[8], g8[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int n = c0 + i;
-          o[i] = (n < p.N) ? v[h * 8 + i] + sbias[ch * 16 + h * 8 + i] + r[i] : 0.f;
+          for (int i = 0; i < 8; ++i) {
+            const bool in = (c0 + i) < Ch;
+            a8[i] = in ? va[h * 8 + i] + sbias[ch * 16 + h * 8 + i] : 0.f;
+            g8[i] = in ? vg[h * 8 + i] + sbias[half + ch * 16 + h * 8 + i] : 0.f;
+            o[i] = in ? a8[i] * sigmoid_f(g8[i]) : 0.f;
+          }
+          store8(orow + c0, o);
+          if (c0 + 8 <= Ch) {                  // Ch % 8 == 0 is required by the launcher for this epilogue
+            store8(vrow + c0, a8);
+            store8(vrow + Ch + c0, g8);
+          }
         }
-        store8(orow + c0, o);
+      }
+    } else {
+      __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.Out) + row * p.Cos;
+      float* frow = reinterpret_cast<float*>(p.Out) + row * p.Cos;
+      __nv_bfloat16* prow = p.Out2 ? p.Out2 + row * p.Co2s : nullptr;
+      const __nv_bfloat16* rrow = p.Res ? p.Res + row * p.Crs : nullptr;
+      for (int ch = 0; ch < p.NT / 16; ++ch) {
+        float v[16];
+        tmem_ld16(trow + (uint32_t)(ch * 16), v);
+        if (!valid) continue;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c0 = n0 + ch * 16 + h * 8;
+          if (c0 >= p.Cos) continue;
+          float o[8];
+          float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if (rrow != nullptr && c0 < p.Crs) load8(rrow + c0, r);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int n = c0 + i;
+            o[i] = (n < p.N) ? v[h * 8 + i] + sbias[ch * 16 + h * 8 + i] + r[i] : 0.f;
+          }
+          if (p.epi == MEGB200_EPI_STORE_F32) {
+            store8(frow + c0, o);
+          } else if (p.epi == MEGB200_EPI_GELU) {
+            if (c0 < p.Co2s) store8(prow + c0, o);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = (c0 + i < p.N) ? gelu_f(o[i]) : 0.f;
+            store8(orow + c0, o);
+          } else {
+            store8(orow + c0, o);
+          }
+        }
       }
     }
     tc_fence_before();
@@ -557,24 +618,41 @@ static int set_smem(K kernel, size_t bytes) {
 }
 
 int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int N, int Np, int Kp, int taps, int dil,
-               const float* bias, const void* Res, int Crs, const int32_t* group, int G, void* Out, int Cos,
-               cudaStream_t st) {
+               const float* bias, const void* Res, int Crs, const int32_t* group, int G, int epi, void* Out, int Cos,
+               void* Out2, int Co2s, cudaStream_t st) {
   MEGB_CHECK_ARG(Cas % 8 == 0 && Cos % 8 == 0 && (Res == nullptr || Crs % 8 == 0), "tc_tapgemm: strides must be multiples of 8");
   MEGB_CHECK_ARG(Kp % 64 == 0 && Np % 16 == 0 && Np >= N, "tc_tapgemm: Kp %% 64 and Np %% 16 required (Kp=%d Np=%d)", Kp, Np);
+  const bool glu = epi == MEGB200_EPI_GLU;
   TapGemmParams p;
-  p.T = T; p.N = N; p.Cos = Cos; p.Crs = Crs; p.taps = taps; p.dil = dil; p.Kp = Kp;
+  p.T = T; p.N = N; p.Cos = Cos; p.Crs = Crs; p.Co2s = Co2s; p.taps = taps; p.dil = dil; p.Kp = Kp; p.epi = epi;
   p.kchunks = (Ca + kBlockK - 1) / kBlockK;
   p.tiles_per_sample = (T + kTileM - 1) / kTileM;
-  p.NT = pick_ntile(Np);
-  // output channels up to Cos must be covered so that pad channels are written as zero
-  const int ncover = Cos > Np ? Cos : Np;
-  p.ntiles = (ncover + p.NT - 1) / p.NT;
+  if (glu) {
+    const int Ch = N / 2;
+    MEGB_CHECK_ARG(N % 16 == 0 && Res == nullptr && Out2 != nullptr && Co2s % 8 == 0 && Co2s >= N,
+                   "tc_tapgemm: the GLU epilogue needs N %% 16 == 0, no residual and a V output (N=%d)", N);
+    // tile = [half a-channels | half gate channels], half a multiple of 16 dividing Ch if possible
+    int half = 0;
+    for (int h = 128; h >= 16; h -= 16)
+      if (Ch % h == 0 && 2 * h <= 160) { half = h; break; }
+    if (half == 0) half = Ch >= 80 ? 80 : (Ch + 15) / 16 * 16;
+    p.NT = 2 * half;
+    const int cover = Cos > Ch ? Cos : Ch;
+    p.ntiles = (cover + half - 1) / half;
+  } else {
+    MEGB_CHECK_ARG(epi != MEGB200_EPI_GELU || (Out2 != nullptr && Co2s % 8 == 0 && Co2s >= N),
+                   "tc_tapgemm: the GELU epilogue needs a pre-activation output");
+    p.NT = pick_ntile(Np);
+    // output channels up to Cos must be covered so that pad channels are written as zero
+    const int ncover = Cos > Np ? Cos : Np;
+    p.ntiles = (ncover + p.NT - 1) / p.NT;
+  }
   const uint32_t stage_bytes = kTileM * 128 + p.NT * 128;
   p.stages = pick_stages(stage_bytes, 112000 - (p.NT > 128 ? p.NT * 4 : 0), 6);
   MEGB_CHECK_ARG(p.stages >= 2, "tc_tapgemm: tile too large for the stage ring");
   p.tmem_cols = tmem_cols_for(p.NT);
   p.idesc = make_idesc(p.NT, 0, 0);
-  p.bias = bias; p.Res = (const __nv_bfloat16*)Res; p.group = group; p.Out = (__nv_bfloat16*)Out;
+  p.bias = bias; p.Res = (const __nv_bfloat16*)Res; p.group = group; p.Out = Out; p.Out2 = (__nv_bfloat16*)Out2;
 
   CUtensorMap tmA, tmW;
   {
@@ -587,7 +665,7 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
   {
     const uint64_t dims[3] = {(uint64_t)taps * Kp, (uint64_t)Np, (uint64_t)G};
     const uint64_t strides[2] = {(uint64_t)taps * Kp * 2, (uint64_t)Np * taps * Kp * 2};
-    const uint32_t box[3] = {kBlockK, (uint32_t)p.NT, 1};
+    const uint32_t box[3] = {kBlockK, (uint32_t)(glu ? p.NT / 2 : p.NT), 1};
     int rc = encode_tmap_bf16(&tmW, W, 3, dims, strides, box);
     if (rc) return rc;
   }

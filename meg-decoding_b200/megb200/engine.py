@@ -72,13 +72,12 @@ class EncoderEngine:
         for k in range(5):
             pk, d = P["blocks"][k], self.dil[k]
             bc = {"x": x, "cin": cin}
-            u0 = self._conv(x, cin, pk["w0"], pk["b0"], D2, d[0], x if k > 0 else None)
+            # pre-BatchNorm tensors stay in f32: the normalisation sees the unrounded convolution (+ residual)
+            u0 = self._conv(x, cin, pk["w0"], pk["b0"], D2, d[0], x if k > 0 else None, epi="store_f32")
             h0, bc["bn0"] = self._bn_gelu(u0, pk, "0", training)
-            u1 = self._conv(h0, D2, pk["w1"], pk["b1"], D2, d[1], h0)
+            u1 = self._conv(h0, D2, pk["w1"], pk["b1"], D2, d[1], h0, epi="store_f32")
             h1, bc["bn1"] = self._bn_gelu(u1, pk, "1", training)
-            v = self._conv(h1, D2, pk["w2"], pk["b2"], 2 * D2, d[2], None)
-            out = ops.empty(B, T, pad8(D2), device=dev)
-            ops.glu(v, out, D2)
+            out, v = self._conv(h1, D2, pk["w2"], pk["b2"], 2 * D2, d[2], None, epi="glu")
             bc.update(u0=u0, h0=h0, u1=u1, h1=h1, v=v)
             blocks.append(bc)
             x, cin = out, D2
@@ -86,12 +85,8 @@ class EncoderEngine:
         ctx["x5"] = x
 
         # ---- 1x1 head (models.py:373-374): GELU after both convs
-        p1 = self._conv(x, D2, P["wf1"], P["bf1"], 2 * D2, 1, None, taps=1)
-        q1 = ops.empty(*p1.shape, device=dev)
-        ops.gelu(p1, q1)
-        p2 = self._conv(q1, 2 * D2, P["wf2"], P["bf2"], Fo, 1, None, taps=1)
-        Z = ops.empty(*p2.shape, device=dev)
-        ops.gelu(p2, Z)
+        q1, p1 = self._conv(x, D2, P["wf1"], P["bf1"], 2 * D2, 1, None, taps=1, epi="gelu")
+        Z, p2 = self._conv(q1, 2 * D2, P["wf2"], P["bf2"], Fo, 1, None, taps=1, epi="gelu")
         ctx.update(p1=p1, q1=q1, p2=p2)
         if not self.seq2seq:                                                            # models.py:382
             Zm = ops.empty(B, 1, pad8(Fo), device=dev)
@@ -99,11 +94,26 @@ class EncoderEngine:
             return Zm, ctx
         return Z, ctx
 
-    def _conv(self, x, cin, w, b, N, dil, res, taps=3):
-        ops = self.ops
-        Wpk = ops.empty(1, pad16(N), taps * pad64(cin), device=x.device)
+    def _conv(self, x, cin, w, b, N, dil, res, taps=3, epi="store"):
+        """Conv1d (k = taps, "same") as a tap-GEMM with a fused tail.  Returns Out, or (Out, Out2) for the GELU / GLU
+        epilogues (Out2 = the pre-activation kept for backward)."""
+        ops, dev = self.ops, x.device
+        B, T = x.shape[0], x.shape[1]
+        Wpk = ops.empty(1, pad16(N), taps * pad64(cin), device=dev)
         ops.pack_weight(w.view(1, N, cin, taps), Wpk, 0)
-        out = ops.empty(x.shape[0], x.shape[1], pad8(N), device=x.device)
+        if epi == "store_f32":
+            out = _f32(dev, B, T, pad8(N))
+            ops.tapgemm(x, cin, Wpk, N, taps, dil, b, res, None, out, epi=epi)
+            return out
+        if epi == "glu":
+            out, v = ops.empty(B, T, pad8(N // 2), device=dev), ops.empty(B, T, pad8(N), device=dev)
+            ops.tapgemm(x, cin, Wpk, N, taps, dil, b, None, None, out, epi=epi, Out2=v)
+            return out, v
+        out = ops.empty(B, T, pad8(N), device=dev)
+        if epi == "gelu":
+            pre = ops.empty(B, T, pad8(N), device=dev)
+            ops.tapgemm(x, cin, Wpk, N, taps, dil, b, res, None, out, epi=epi, Out2=pre)
+            return out, pre
         ops.tapgemm(x, cin, Wpk, N, taps, dil, b, res, None, out)
         return out
 

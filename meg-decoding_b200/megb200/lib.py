@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmegb200.so")
 
 F32, BF16 = 0, 1
+EPI_STORE, EPI_STORE_F32, EPI_GELU, EPI_GLU = 0, 1, 2, 3
 SIMT, TC = 0, 1
 
 _p, _i, _ll, _f, _sz = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_size_t
@@ -20,7 +21,7 @@ _p, _i, _ll, _f, _sz = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_size_t
 SIGNATURES = {
     "megb200_pack_x": [_p, _p, _i, _i, _i, _i, _i, _p],
     "megb200_pack_weight": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
-    "megb200_tapgemm": [_p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p, _p, _i, _p, _i, _p, _i, _i, _i, _p],
+    "megb200_tapgemm": [_p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p, _p, _i, _p, _i, _i, _p, _i, _p, _i, _i, _i, _p],
     "megb200_wgrad": [_p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _p, _sz, _i, _i, _p],
     "megb200_group_order": [_p, _i, _i, _p, _p],
     "megb200_colsum": [_p, _i, _i, _i, _i, _p, _i, _p, _i, _p],
@@ -29,9 +30,9 @@ SIGNATURES = {
     "megb200_sa_softmax_bwd": [_p, _p, _p, _p, _i, _i, _p],
     "megb200_bn_stats": [_p, _ll, _i, _i, _p, _i, _p],
     "megb200_bn_finalize": [_p, _p, _p, _p, _p, _ll, _f, _f, _i, _p, _p, _p, _p, _i, _p],
-    "megb200_bn_gelu": [_p, _p, _p, _p, _ll, _i, _i, _i, _p],
-    "megb200_bn_gelu_bwd_reduce": [_p, _p, _p, _p, _p, _p, _p, _p, _ll, _i, _i, _i, _p],
-    "megb200_bn_bwd_apply": [_p, _p, _p, _p, _p, _p, _ll, _p, _ll, _i, _i, _i, _p],
+    "megb200_bn_gelu": [_p, _p, _p, _p, _ll, _i, _i, _i, _i, _p],
+    "megb200_bn_gelu_bwd_reduce": [_p, _p, _p, _p, _p, _p, _p, _p, _ll, _i, _i, _i, _i, _p],
+    "megb200_bn_bwd_apply": [_p, _p, _p, _p, _p, _p, _ll, _p, _ll, _i, _i, _i, _i, _p],
     "megb200_glu": [_p, _p, _ll, _i, _i, _i, _i, _p],
     "megb200_glu_bwd": [_p, _p, _p, _ll, _i, _i, _i, _i, _p],
     "megb200_gelu": [_p, _p, _ll, _i, _p],

@@ -104,13 +104,21 @@ class CudaOps:
         L.call("megb200_pack_weight", w.data_ptr(), out.data_ptr(), G, O, I, Kt, Np, Kp, mode, self.dt, self._stream())
 
     # ------------------------------------------------------------------ contractions
-    def tapgemm(self, A, Ca, W, N, taps, dil, bias, Res, group, Out):
-        self._chk_act(A, W, Res, Out)
+    def tapgemm(self, A, Ca, W, N, taps, dil, bias, Res, group, Out, epi="store", Out2=None):
+        """epi: "store" | "store_f32" (Out is f32: pre-BatchNorm tensors) | "gelu" (Out2 = pre-activation, Out =
+        gelu) | "glu" (N = 2*Ch; Out2 = V [.., 2Ch], Out = GLU(V) [.., Ch])."""
+        code = {"store": L.EPI_STORE, "store_f32": L.EPI_STORE_F32, "gelu": L.EPI_GELU, "glu": L.EPI_GLU}[epi]
+        self._chk_act(A, W, Res, Out2)
+        if epi == "store_f32":
+            self._chk_f32(Out)
+        else:
+            self._chk_act(Out)
         self._chk_f32(bias)
         B, T, Cas = A.shape
         G, Np, Ktot = W.shape
         Kp = Ktot // taps
         assert Out.shape[0] == B and Out.shape[1] == T
+        assert (Out2 is not None) == (epi in ("gelu", "glu"))
         if group is not None:
             assert group.dtype == torch.int32 and group.is_cuda and group.numel() == B
         else:
@@ -119,8 +127,8 @@ class CudaOps:
             assert bias.numel() == G * N
         ev = self._prof_begin()
         L.call("megb200_tapgemm", A.data_ptr(), B, T, Ca, Cas, W.data_ptr(), N, Np, Kp, taps, dil, _ptr(bias),
-               _ptr(Res), 0 if Res is None else Res.shape[2], _ptr(group), G, Out.data_ptr(), Out.shape[2], self.dt,
-               self.be, self._stream())
+               _ptr(Res), 0 if Res is None else Res.shape[2], _ptr(group), G, code, Out.data_ptr(), Out.shape[2],
+               _ptr(Out2), 0 if Out2 is None else Out2.shape[2], self.dt, self.be, self._stream())
         self._prof_end(ev, "tapgemm", 2.0 * B * T * N * taps * Ca)
 
     def group_order(self, group, G, order):
@@ -174,11 +182,16 @@ class CudaOps:
                W.shape[1], self._stream())
 
     # ------------------------------------------------------------------ BN / GELU / GLU
+    @staticmethod
+    def _udt(U):
+        """Storage code of a pre-BatchNorm tensor (f32 in bf16 mode: models.py:312,316 normalise the unrounded conv)."""
+        assert U.is_cuda and U.is_contiguous() and U.dtype in (torch.float32, torch.bfloat16)
+        return L.F32 if U.dtype == torch.float32 else L.BF16
+
     def bn_stats(self, U, C, sums):
-        self._chk_act(U)
         self._chk_f32(sums)
         rows = U.shape[0] * U.shape[1]
-        L.call("megb200_bn_stats", U.data_ptr(), rows, C, U.shape[2], sums.data_ptr(), self.dt, self._stream())
+        L.call("megb200_bn_stats", U.data_ptr(), rows, C, U.shape[2], sums.data_ptr(), self._udt(U), self._stream())
 
     def bn_finalize(self, sums, gamma, beta, rm, rv, count, eps, momentum, training, scale, shift, mean, rstd):
         self._chk_f32(sums, gamma, beta, rm, rv, scale, shift, mean, rstd)
@@ -187,25 +200,28 @@ class CudaOps:
                mean.data_ptr(), rstd.data_ptr(), gamma.numel(), self._stream())
 
     def bn_gelu(self, U, scale, shift, H, C):
-        self._chk_act(U, H)
+        self._chk_act(H)
+        assert H.shape == U.shape
         rows = U.shape[0] * U.shape[1]
         L.call("megb200_bn_gelu", U.data_ptr(), scale.data_ptr(), shift.data_ptr(), H.data_ptr(), rows, C, U.shape[2],
-               self.dt, self._stream())
+               self._udt(U), self.dt, self._stream())
 
     def bn_gelu_bwd_reduce(self, dH, U, scale, shift, mean, rstd, dY, sums2, C):
-        self._chk_act(dH, U, dY)
+        self._chk_act(dH, dY)
         self._chk_f32(sums2)
+        assert dH.shape == U.shape == dY.shape
         rows = U.shape[0] * U.shape[1]
         L.call("megb200_bn_gelu_bwd_reduce", dH.data_ptr(), U.data_ptr(), scale.data_ptr(), shift.data_ptr(),
-               mean.data_ptr(), rstd.data_ptr(), dY.data_ptr(), sums2.data_ptr(), rows, C, U.shape[2], self.dt,
-               self._stream())
+               mean.data_ptr(), rstd.data_ptr(), dY.data_ptr(), sums2.data_ptr(), rows, C, U.shape[2], self._udt(U),
+               self.dt, self._stream())
 
     def bn_bwd_apply(self, dY, U, gamma, mean, rstd, sums2, count, dU, C):
-        self._chk_act(dY, U, dU)
+        self._chk_act(dY, dU)
+        assert dY.shape == U.shape == dU.shape
         rows = U.shape[0] * U.shape[1]
         L.call("megb200_bn_bwd_apply", dY.data_ptr(), U.data_ptr(), gamma.data_ptr(), mean.data_ptr(),
-               rstd.data_ptr(), sums2.data_ptr(), int(count), dU.data_ptr(), rows, C, U.shape[2], self.dt,
-               self._stream())
+               rstd.data_ptr(), sums2.data_ptr(), int(count), dU.data_ptr(), rows, C, U.shape[2], self._udt(U),
+               self.dt, self._stream())
 
     def glu(self, V, Out, C):
         self._chk_act(V, Out)

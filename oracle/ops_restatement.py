@@ -49,7 +49,7 @@ class TorchOps:
             o4[:, :I, :, :O] = self._r(w.flip(3).permute(0, 2, 3, 1))
 
     # ------------------------------------------------------------------ contractions
-    def tapgemm(self, A, Ca, W, N, taps, dil, bias, Res, group, Out):
+    def tapgemm(self, A, Ca, W, N, taps, dil, bias, Res, group, Out, epi="store", Out2=None):
         B, T, _ = A.shape
         G, Np, Ktot = W.shape
         Kp = Ktot // taps
@@ -72,7 +72,21 @@ class TorchOps:
         if Res is not None:
             acc += Res[:, :, :N].float()
         Out.zero_()
-        Out[:, :, :N] = self._r(acc)
+        if epi == "store":
+            Out[:, :, :N] = self._r(acc)
+        elif epi == "store_f32":
+            Out[:, :, :N] = acc
+        elif epi == "gelu":
+            Out2.zero_()
+            Out2[:, :, :N] = self._r(acc)
+            Out[:, :, :N] = self._r(F.gelu(acc))
+        elif epi == "glu":
+            Ch = N // 2
+            Out2.zero_()
+            Out2[:, :, :N] = self._r(acc)
+            Out[:, :, :Ch] = self._r(acc[:, :, :Ch] * torch.sigmoid(acc[:, :, Ch:]))
+        else:
+            raise ValueError(epi)
 
     def group_order(self, group, G, order):
         order.copy_(torch.sort(group.long(), stable=True).indices.to(torch.int32))

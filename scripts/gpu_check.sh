@@ -19,6 +19,7 @@ for s in ${stages}; do
   case "${s}" in
     ops_simt)         run ops_simt 900 ${PT} tests/test_ops_gpu.py -k "not tc" ;;
     tc_tapgemm)       run tc_tapgemm 300 ${PT} tests/test_ops_gpu.py -k "tapgemm and tc" ;;
+    tc_all)           run tc_all 600 ${PT} tests/test_ops_gpu.py -k "tc" ;;
     tc_wgrad)         run tc_wgrad 300 ${PT} tests/test_ops_gpu.py -k "wgrad and tc" ;;
     tc_clip)          run tc_clip 300 ${PT} tests/test_ops_gpu.py -k "clip and tc" ;;
     parity_fp32)      run parity_fp32 900 ${PT} -s tests/test_parity_gpu.py -k "fp32 and not full_size" ;;
@@ -28,6 +29,13 @@ for s in ${stages}; do
     bench)            run bench 900 python bench.py --steps 5 --warmup 3 ;;
     bench_b32)        run bench_b32 600 python bench.py --steps 3 --warmup 3 --batch 32 --no-cpu-baseline ;;
     smoke)            run smoke 300 python __graft_entry__.py smoke ;;
+    ncu_launches)     run ncu_plain 300 python bench.py --ncu-step --warmup 3 &&
+                      run ncu_launches 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off \
+                          --csv --log-file gpurun_out/launches.csv python bench.py --ncu-step --warmup 3 ;;
+    ncu_full)         run ncu_plain2 300 python bench.py --ncu-step --warmup 3 &&
+                      run ncu_full 1200 ncu --set full --clock-control none --import-source on --profile-from-start off \
+                          -k regex:"${NCU_KERNEL:-tc_tapgemm}" -s "${NCU_SKIP:-8}" -c "${NCU_COUNT:-2}" -f -o gpurun_out/prof_${NCU_TAG:-tapgemm} \
+                          python bench.py --ncu-step --warmup 3 ;;
     all_gpu_tests)    run all_gpu_tests 1800 ${PT} tests ;;
     *) echo "unknown stage ${s}" ;;
   esac

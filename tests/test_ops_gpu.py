@@ -102,6 +102,49 @@ def test_tapgemm(dtype, backend, case):
     _close(Out, Outr, dtype, f"tapgemm {case} {backend}")
 
 
+EPI_CASES = [
+    # B, T, Ca, N, taps, epi
+    (2, 40, 32, 32, 3, "store_f32"),
+    (2, 360, 320, 320, 3, "store_f32"),
+    (2, 40, 32, 64, 3, "glu"),              # D2 = 32
+    (2, 360, 320, 640, 3, "glu"),           # D2 = 320: tile = 80 a-channels + 80 gates
+    (3, 130, 32, 64, 1, "gelu"),
+    (2, 360, 320, 640, 1, "gelu"),
+    (1, 360, 640, 1024, 1, "gelu"),
+]
+
+
+@pytest.mark.parametrize("dtype,backend", CONTRACTION_MODES)
+@pytest.mark.parametrize("case", EPI_CASES)
+def test_tapgemm_fused_epilogues(dtype, backend, case):
+    B, T, Ca, N, taps, epi = case
+    gen = torch.Generator().manual_seed(11)
+    ops, ref = _ops(dtype, backend), TorchOps(dtype)
+    A, Ad = _act(gen, dtype, B, T, Ca)
+    W = torch.zeros(1, pad16(N), taps, pad64(Ca))
+    W[:, :N, :, :Ca] = _rand(gen, 1, N, taps, Ca, scale=(Ca * taps) ** -0.5)
+    W = W.view(1, pad16(N), taps * pad64(Ca)).to(dtype)
+    bias = _rand(gen, 1, N)
+    Res, Resd = (None, None)
+    if epi == "store_f32":
+        Res, Resd = _act(gen, dtype, B, T, N)
+        Out, Outr = torch.empty(B, T, pad8(N), device=DEV), torch.empty(B, T, pad8(N))
+        Out2 = Out2r = None
+    elif epi == "glu":
+        Out, Outr = ops.empty(B, T, pad8(N // 2), device=DEV), ref.empty(B, T, pad8(N // 2), device="cpu")
+        Out2, Out2r = ops.empty(B, T, pad8(N), device=DEV), ref.empty(B, T, pad8(N), device="cpu")
+    else:
+        Out, Outr = ops.empty(B, T, pad8(N), device=DEV), ref.empty(B, T, pad8(N), device="cpu")
+        Out2, Out2r = ops.empty(B, T, pad8(N), device=DEV), ref.empty(B, T, pad8(N), device="cpu")
+    ops.tapgemm(Ad, Ca, W.to(DEV), N, taps, 1, bias.to(DEV), Resd, None, Out, epi=epi, Out2=Out2)
+    ref.tapgemm(A, Ca, W, N, taps, 1, bias, Res, None, Outr, epi=epi, Out2=Out2r)
+    torch.cuda.synchronize()
+    _close(Out, Outr, torch.float32 if epi == "store_f32" else dtype, f"tapgemm {epi} Out {backend}",
+           atol_scale=5 if epi == "store_f32" else 1)
+    if Out2 is not None:
+        _close(Out2, Out2r, dtype, f"tapgemm {epi} Out2 {backend}")
+
+
 WGRAD_CASES = [
     # B, T, M, C, taps, dil, G
     (3, 40, 32, 30, 3, 1, 1),
@@ -186,12 +229,13 @@ def test_sa_softmax_fwd_bwd():
 
 # ------------------------------------------------------------------------------------------------ elementwise
 @pytest.mark.parametrize("dtype", EW_DTYPES)
+@pytest.mark.parametrize("u_f32", [True, False])
 @pytest.mark.parametrize("shape", [(3, 40, 30), (2, 360, 320), (70, 37, 320)])
-def test_batchnorm_gelu_chain(dtype, shape):
+def test_batchnorm_gelu_chain(dtype, u_f32, shape):
     B, T, C = shape
     gen = torch.Generator().manual_seed(5)
     ops, ref = _ops(dtype, "simt"), TorchOps(dtype)
-    U, Ud = _act(gen, dtype, B, T, C)
+    U, Ud = _act(gen, torch.float32 if u_f32 else dtype, B, T, C)      # the pre-BN tensor may stay in f32
     n = B * T
     gamma, beta = torch.rand(C, generator=gen) + 0.5, _rand(gen, C, scale=0.2)
     for training in (1, 0):
