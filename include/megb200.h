@@ -120,19 +120,23 @@ int megb200_bn_gelu(const void* U, const float* scale, const float* shift, void*
 int megb200_bn_gelu_bwd_reduce(const void* dH, const void* U, const float* scale, const float* shift,
                                const float* mean, const float* rstd, void* dY, float* sums2, long long rows, int C,
                                int Cs, int u_dtype, int dtype, void* stream);
-/* dU = gamma*rstd * (dY - sums2[0]/n - xhat * sums2[1]/n)    */
+/* dU = gamma*rstd * (dY - sums2[0]/n - xhat * sums2[1]/n)   (SURVEY appendix A3);
+ * dbias[c] += sum dU (the gradient of the conv bias in front of the BatchNorm; may be NULL) */
 int megb200_bn_bwd_apply(const void* dY, const void* U, const float* gamma, const float* mean, const float* rstd,
-                         const float* sums2, long long count, void* dU, long long rows, int C, int Cs, int u_dtype,
-                         int dtype, void* stream);
+                         const float* sums2, long long count, void* dU, float* dbias, long long rows, int C, int Cs,
+                         int u_dtype, int dtype, void* stream);
 /* eval-mode backward is never needed (no grad in eval). */
 
 /* Out[.., c] = V[.., c] * sigmoid(V[.., C + c]),  V: [rows][Vs] with 2C logical channels (models.py:320) */
 int megb200_glu(const void* V, void* Out, long long rows, int C, int Vs, int Os, int dtype, void* stream);
-int megb200_glu_bwd(const void* dOut, const void* V, void* dV, long long rows, int C, int Vs, int Os, int dtype,
-                    void* stream);
+/* dV from dOut; dbias[0..2C) += column sums of dV (gradient of the conv2 bias; may be NULL) */
+int megb200_glu_bwd(const void* dOut, const void* V, void* dV, float* dbias, long long rows, int C, int Vs, int Os,
+                    int dtype, void* stream);
 /* Q = gelu(P) ; dP = dQ * gelu'(P)   (models.py:373-374) */
 int megb200_gelu(const void* P, void* Q, long long n, int dtype, void* stream);
-int megb200_gelu_bwd(const void* dQ, const void* P, void* dP, long long n, int dtype, void* stream);
+/* dP = dQ * gelu'(P) on [rows][Cs]; dbias[c] += sum dP (gradient of the 1x1 head bias; may be NULL) */
+int megb200_gelu_bwd(const void* dQ, const void* P, void* dP, float* dbias, long long rows, int C, int Cs, int dtype,
+                     void* stream);
 /* seq2static head (models.py:382): Zm[b][f] = mean_t Z[b][t][f] ; backward broadcasts dZm/T */
 int megb200_time_mean(const void* Z, void* Zm, int B, int T, int F, int Fs, int dtype, void* stream);
 int megb200_time_mean_bwd(const void* dZm, void* dZ, int B, int T, int F, int Fs, int dtype, void* stream);

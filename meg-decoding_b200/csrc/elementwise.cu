@@ -82,18 +82,22 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
   }
 }
 
-// ------------------------------------------------------------------------------------------ column reductions
-// One CTA owns a slab of rows; thread = (channel group of 8, row lane).  Op::row() consumes one 8-vector and adds
-// into two per-channel accumulators (and may write an output vector).
+// ------------------------------------------------------------------------------------------ row-loop passes
+// One CTA owns a slab of rows; thread = (channel group of 8, row lane) and keeps its channel group for the whole
+// slab, so per-channel parameters are loaded ONCE into registers (Op::init) and the loop body is pure streaming:
+// 16/32-byte vector loads and stores, no parameter traffic.  Op::row() consumes one 8-vector, may write outputs, and
+// may add into up to two per-channel accumulators that end in one global atomic per channel per CTA.
 template <class Op>
-__global__ void __launch_bounds__(256) colreduce_kernel(Op op, long long rows, long long rows_per_block, int C,
-                                                        int Cs, const int32_t* __restrict__ group, int Tn,
-                                                        float* __restrict__ out0, float* __restrict__ out1) {
-  extern __shared__ float sm[];  // [2][Cs]
+__global__ void __launch_bounds__(256) rowloop_kernel(Op op, long long rows, long long rows_per_block, int C, int Cs,
+                                                      const int32_t* __restrict__ group, int Tn,
+                                                      float* __restrict__ out0, float* __restrict__ out1) {
+  extern __shared__ float sm[];  // [2][Cs] when the op reduces
   float* sm0 = sm;
   float* sm1 = sm + Cs;
-  for (int i = threadIdx.x; i < 2 * Cs; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
+  if (Op::kAcc > 0) {
+    for (int i = threadIdx.x; i < 2 * Cs; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+  }
   const int cg = Cs >> 3;
   const int W = cg < 256 ? cg : 256;
   const int R = 256 / W;
@@ -106,28 +110,35 @@ __global__ void __launch_bounds__(256) colreduce_kernel(Op op, long long rows, l
       float a0[8], a1[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) a0[i] = a1[i] = 0.f;
+      op.init(g * 8);
+#pragma unroll 2
       for (long long r = r0 + lane_r; r < r1; r += R) op.row(r, g * 8, a0, a1);
+      if (Op::kAcc > 0) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        atomicAdd(&sm0[g * 8 + i], a0[i]);
-        if (Op::kTwo) atomicAdd(&sm1[g * 8 + i], a1[i]);
+        for (int i = 0; i < 8; ++i) {
+          atomicAdd(&sm0[g * 8 + i], a0[i]);
+          if (Op::kAcc > 1) atomicAdd(&sm1[g * 8 + i], a1[i]);
+        }
       }
     }
   }
-  __syncthreads();
-  long long obase = 0;
-  if (group != nullptr) obase = (long long)group[r0 / Tn] * C;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    atomicAdd(&out0[obase + c], sm0[c]);
-    if (Op::kTwo) atomicAdd(&out1[obase + c], sm1[c]);
+  if (Op::kAcc > 0) {
+    __syncthreads();
+    long long obase = 0;
+    if (group != nullptr) obase = (long long)group[r0 / Tn] * C;
+    if (out0 != nullptr)
+      for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(&out0[obase + c], sm0[c]);
+    if (Op::kAcc > 1 && out1 != nullptr)
+      for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(&out1[obase + c], sm1[c]);
   }
 }
 
 template <typename T>
 struct StatsOp {
-  static constexpr bool kTwo = true;
+  static constexpr int kAcc = 2;
   const T* u;
   int Cs;
+  __device__ __forceinline__ void init(int) {}
   __device__ __forceinline__ void row(long long r, int c0, float (&a0)[8], float (&a1)[8]) const {
     float x[8];
     load8(u + r * Cs + c0, x);
@@ -141,9 +152,10 @@ struct StatsOp {
 
 template <typename T>
 struct ColsumOp {
-  static constexpr bool kTwo = false;
+  static constexpr int kAcc = 1;
   const T* u;
   int Cs;
+  __device__ __forceinline__ void init(int) {}
   __device__ __forceinline__ void row(long long r, int c0, float (&a0)[8], float (&a1)[8]) const {
     float x[8];
     load8(u + r * Cs + c0, x);
@@ -152,29 +164,63 @@ struct ColsumOp {
   }
 };
 
+// H = gelu(scale*U + shift)
+template <typename TU, typename T>
+struct BnGeluOp {
+  static constexpr int kAcc = 0;
+  const TU* u;
+  T* h;
+  const float *scale, *shift;
+  int Cs, C;
+  float sc[8], sh[8];
+  __device__ __forceinline__ void init(int c0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const bool in = c0 + i < C;
+      sc[i] = in ? scale[c0 + i] : 0.f;
+      sh[i] = in ? shift[c0 + i] : 0.f;
+    }
+  }
+  __device__ __forceinline__ void row(long long r, int c0, float (&a0)[8], float (&a1)[8]) const {
+    float x[8], o[8];
+    load8(u + r * Cs + c0, x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = (c0 + i < C) ? gelu_f(fmaf(x[i], sc[i], sh[i])) : 0.f;
+    store8(h + r * Cs + c0, o);
+  }
+};
+
 // dY = dH * gelu'(y), y = scale*u + shift; accumulates sum dY and sum dY*xhat
 template <typename TU, typename T>
 struct BnGeluBwdOp {
-  static constexpr bool kTwo = true;
+  static constexpr int kAcc = 2;
   const T* dh;
   const TU* u;
   T* dy;
   const float *scale, *shift, *mean, *rstd;
   int Cs, C;
+  float sc[8], sh[8], mu[8], rs[8];
+  __device__ __forceinline__ void init(int c0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const bool in = c0 + i < C;
+      sc[i] = in ? scale[c0 + i] : 0.f;
+      sh[i] = in ? shift[c0 + i] : 0.f;
+      mu[i] = in ? mean[c0 + i] : 0.f;
+      rs[i] = in ? rstd[c0 + i] : 0.f;
+    }
+  }
   __device__ __forceinline__ void row(long long r, int c0, float (&a0)[8], float (&a1)[8]) const {
     float g[8], x[8], o[8];
     load8(dh + r * Cs + c0, g);
     load8(u + r * Cs + c0, x);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int c = c0 + i;
       float d = 0.f;
-      if (c < C) {
-        const float y = fmaf(x[i], __ldg(scale + c), __ldg(shift + c));
-        d = round_to<T>(g[i] * gelu_grad_f(y));
-        const float xh = (x[i] - __ldg(mean + c)) * __ldg(rstd + c);
+      if (c0 + i < C) {
+        d = round_to<T>(g[i] * gelu_grad_f(fmaf(x[i], sc[i], sh[i])));
         a0[i] += d;
-        a1[i] += d * xh;
+        a1[i] += d * (x[i] - mu[i]) * rs[i];
       }
       o[i] = d;
     }
@@ -182,69 +228,116 @@ struct BnGeluBwdOp {
   }
 };
 
+// dU = gamma*rstd*(dY - s0/n - xhat*s1/n) = A*dY + Bc*U + Cc per channel; accumulates sum dU (the conv bias gradient)
+template <typename TU, typename T>
+struct BnBwdApplyOp {
+  static constexpr int kAcc = 1;
+  const T* dy;
+  const TU* u;
+  T* du;
+  const float *gamma, *mean, *rstd, *sums2;
+  float inv_n;
+  int Cs, C;
+  float ca[8], cb[8], cc[8];
+  __device__ __forceinline__ void init(int c0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = c0 + i;
+      if (c < C) {
+        const float rsd = rstd[c], A = gamma[c] * rsd;
+        ca[i] = A;
+        cb[i] = -A * rsd * sums2[C + c] * inv_n;
+        cc[i] = -A * sums2[c] * inv_n - cb[i] * mean[c];
+      } else {
+        ca[i] = cb[i] = cc[i] = 0.f;
+      }
+    }
+  }
+  __device__ __forceinline__ void row(long long r, int c0, float (&a0)[8], float (&a1)[8]) const {
+    float g[8], x[8], o[8];
+    load8(dy + r * Cs + c0, g);
+    load8(u + r * Cs + c0, x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      o[i] = round_to<T>(fmaf(ca[i], g[i], fmaf(cb[i], x[i], cc[i])));
+      a0[i] += o[i];
+    }
+    store8(du + r * Cs + c0, o);
+  }
+};
+
+// dP = dQ * gelu'(P); accumulates sum dP (bias gradient of the 1x1 head convs)
+template <typename T>
+struct GeluBwdOp {
+  static constexpr int kAcc = 1;
+  const T* dq;
+  const T* p;
+  T* dp;
+  int Cs, C;
+  __device__ __forceinline__ void init(int) {}
+  __device__ __forceinline__ void row(long long r, int c0, float (&a0)[8], float (&a1)[8]) const {
+    float g[8], x[8], o[8];
+    load8(dq + r * Cs + c0, g);
+    load8(p + r * Cs + c0, x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      o[i] = (c0 + i < C) ? round_to<T>(g[i] * gelu_grad_f(x[i])) : 0.f;
+      a0[i] += o[i];
+    }
+    store8(dp + r * Cs + c0, o);
+  }
+};
+
+// GLU backward over 8 output channels: dV[c] = d*s, dV[C+c] = d*a*s*(1-s); accumulates both halves' column sums.
+// Requires C % 8 == 0 (the launcher falls back to the scalar kernel otherwise).
+template <typename T>
+struct GluBwdOp {
+  static constexpr int kAcc = 2;
+  const T* dout;
+  const T* V;
+  T* dV;
+  int Vs, Os, C;
+  __device__ __forceinline__ void init(int) {}
+  __device__ __forceinline__ void row(long long r, int c0, float (&a0)[8], float (&a1)[8]) const {
+    if (c0 >= C) return;
+    float d[8], a[8], g[8], da[8], dg[8];
+    load8(dout + r * Os + c0, d);
+    load8(V + r * Vs + c0, a);
+    load8(V + r * Vs + C + c0, g);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float s = sigmoid_f(g[i]);
+      da[i] = round_to<T>(d[i] * s);
+      dg[i] = round_to<T>(d[i] * a[i] * s * (1.f - s));
+      a0[i] += da[i];
+      a1[i] += dg[i];
+    }
+    store8(dV + r * Vs + c0, da);
+    store8(dV + r * Vs + C + c0, dg);
+  }
+};
+
 template <class Op>
-static int launch_colreduce(Op op, long long rows, int C, int Cs, const int32_t* group, int Tn, float* out0,
-                            float* out1, cudaStream_t st) {
-  MEGB_CHECK_ARG(Cs % 8 == 0 && Cs >= C && Cs <= 4096, "colreduce: bad channel stride %d (C=%d)", Cs, C);
+static int launch_rowloop(Op op, long long rows, int C, int Cs, const int32_t* group, int Tn, float* out0,
+                          float* out1, cudaStream_t st) {
+  MEGB_CHECK_ARG(Cs % 8 == 0 && Cs >= C && Cs <= 4096, "rowloop: bad channel stride %d (C=%d)", Cs, C);
   long long rpb;
   if (group != nullptr) {
     rpb = Tn;
   } else {
-    long long target_blocks = (long long)num_sms() * 4;
+    long long target_blocks = (long long)num_sms() * 8;
     rpb = (rows + target_blocks - 1) / target_blocks;
-    if (rpb < 32) rpb = 32;
+    if (rpb < 16) rpb = 16;
   }
   long long blocks = (rows + rpb - 1) / rpb;
   if (blocks < 1) return 0;
-  colreduce_kernel<Op><<<(int)blocks, 256, 2 * Cs * sizeof(float), st>>>(op, rows, rpb, C, Cs, group, Tn, out0, out1);
+  const size_t smem = Op::kAcc > 0 ? 2 * Cs * sizeof(float) : 0;
+  rowloop_kernel<Op><<<(int)blocks, 256, smem, st>>>(op, rows, rpb, C, Cs, group, Tn, out0, out1);
   MEGB_LAUNCH_OK();
   return 0;
 }
 
 // ------------------------------------------------------------------------------------------ maps
-template <typename TU, typename T>
-__global__ void bn_gelu_kernel(const TU* __restrict__ u, const float* __restrict__ scale,
-                               const float* __restrict__ shift, T* __restrict__ h, long long nvec, int C, int cg) {
-  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvec;
-       v += (long long)gridDim.x * blockDim.x) {
-    const int c0 = (int)(v % cg) * 8;
-    float x[8], o[8];
-    load8(u + v * 8, x);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = c0 + i;
-      o[i] = (c < C) ? gelu_f(fmaf(x[i], __ldg(scale + c), __ldg(shift + c))) : 0.f;
-    }
-    store8(h + v * 8, o);
-  }
-}
-
-template <typename TU, typename T>
-__global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, const TU* __restrict__ u,
-                                    const float* __restrict__ gamma, const float* __restrict__ mean,
-                                    const float* __restrict__ rstd, const float* __restrict__ sums2, float inv_n,
-                                    T* __restrict__ du, long long nvec, int C, int cg) {
-  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvec;
-       v += (long long)gridDim.x * blockDim.x) {
-    const int c0 = (int)(v % cg) * 8;
-    float g[8], x[8], o[8];
-    load8(dy + v * 8, g);
-    load8(u + v * 8, x);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = c0 + i;
-      float r = 0.f;
-      if (c < C) {
-        const float rs = __ldg(rstd + c);
-        const float xh = (x[i] - __ldg(mean + c)) * rs;
-        r = __ldg(gamma + c) * rs * (g[i] - __ldg(sums2 + c) * inv_n - xh * __ldg(sums2 + C + c) * inv_n);
-      }
-      o[i] = r;
-    }
-    store8(du + v * 8, o);
-  }
-}
-
 template <typename T>
 __global__ void glu_kernel(const T* __restrict__ V, T* __restrict__ out, long long rows, int C, int Vs, int Os) {
   const int og = Os >> 3;
@@ -532,13 +625,13 @@ int megb200_colsum(const void* U, int B, int T, int C, int Cs, const int32_t* gr
                    void* stream) {
   MEGB_CHECK_ARG(U && out && B > 0 && T > 0 && G >= 1, "colsum: bad arguments");
   DISPATCH_DTYPE(dtype, ColsumOp<DT> op{(const DT*)U, Cs};
-                 return launch_colreduce(op, (long long)B * T, C, Cs, group, T, out, nullptr, (cudaStream_t)stream);)
+                 return launch_rowloop(op, (long long)B * T, C, Cs, group, T, out, nullptr, (cudaStream_t)stream);)
 }
 
 int megb200_bn_stats(const void* U, long long rows, int C, int Cs, float* sums, int u_dtype, void* stream) {
   MEGB_CHECK_ARG(U && sums && rows > 0, "bn_stats: bad arguments");
   DISPATCH_DTYPE(u_dtype, StatsOp<DT> op{(const DT*)U, Cs};
-                 return launch_colreduce(op, rows, C, Cs, nullptr, 1, sums, sums + C, (cudaStream_t)stream);)
+                 return launch_rowloop(op, rows, C, Cs, nullptr, 1, sums, sums + C, (cudaStream_t)stream);)
 }
 
 int megb200_bn_finalize(const float* sums, const float* gamma, const float* beta, float* running_mean,
@@ -556,10 +649,9 @@ int megb200_bn_finalize(const float* sums, const float* gamma, const float* beta
 int megb200_bn_gelu(const void* U, const float* scale, const float* shift, void* H, long long rows, int C, int Cs,
                     int u_dtype, int dtype, void* stream) {
   MEGB_CHECK_ARG(U && H && scale && shift && rows > 0 && Cs % 8 == 0 && Cs >= C, "bn_gelu: bad arguments");
-  const long long nvec = rows * (Cs / 8);
-  DISPATCH_U(u_dtype, DISPATCH_DTYPE(dtype, bn_gelu_kernel<TU, DT><<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)stream>>>(
-                                                (const TU*)U, scale, shift, (DT*)H, nvec, C, Cs / 8);
-                                     MEGB_LAUNCH_OK(); return 0;))
+  DISPATCH_U(u_dtype, DISPATCH_DTYPE(dtype, BnGeluOp<TU, DT> op{(const TU*)U, (DT*)H, scale, shift, Cs, C};
+                                     return launch_rowloop(op, rows, C, Cs, nullptr, 1, nullptr, nullptr,
+                                                           (cudaStream_t)stream);))
 }
 
 int megb200_bn_gelu_bwd_reduce(const void* dH, const void* U, const float* scale, const float* shift,
@@ -568,19 +660,17 @@ int megb200_bn_gelu_bwd_reduce(const void* dH, const void* U, const float* scale
   MEGB_CHECK_ARG(dH && U && dY && sums2 && rows > 0, "bn_gelu_bwd_reduce: bad arguments");
   DISPATCH_U(u_dtype,
              DISPATCH_DTYPE(dtype, BnGeluBwdOp<TU, DT> op{(const DT*)dH, (const TU*)U, (DT*)dY, scale, shift, mean, rstd, Cs, C};
-                            return launch_colreduce(op, rows, C, Cs, nullptr, 1, sums2, sums2 + C, (cudaStream_t)stream);))
+                            return launch_rowloop(op, rows, C, Cs, nullptr, 1, sums2, sums2 + C, (cudaStream_t)stream);))
 }
 
 int megb200_bn_bwd_apply(const void* dY, const void* U, const float* gamma, const float* mean, const float* rstd,
-                         const float* sums2, long long count, void* dU, long long rows, int C, int Cs, int u_dtype,
-                         int dtype, void* stream) {
+                         const float* sums2, long long count, void* dU, float* dbias, long long rows, int C, int Cs,
+                         int u_dtype, int dtype, void* stream) {
   MEGB_CHECK_ARG(dY && U && dU && sums2 && rows > 0 && count > 0 && Cs % 8 == 0, "bn_bwd_apply: bad arguments");
-  const long long nvec = rows * (Cs / 8);
   DISPATCH_U(u_dtype,
-             DISPATCH_DTYPE(dtype, bn_bwd_apply_kernel<TU, DT><<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)stream>>>(
-                                       (const DT*)dY, (const TU*)U, gamma, mean, rstd, sums2, 1.f / (float)count,
-                                       (DT*)dU, nvec, C, Cs / 8);
-                            MEGB_LAUNCH_OK(); return 0;))
+             DISPATCH_DTYPE(dtype, BnBwdApplyOp<TU, DT> op{(const DT*)dY, (const TU*)U, (DT*)dU, gamma, mean, rstd, sums2,
+                                                          1.f / (float)count, Cs, C};
+                            return launch_rowloop(op, rows, C, Cs, nullptr, 1, dbias, nullptr, (cudaStream_t)stream);))
 }
 
 int megb200_glu(const void* V, void* Out, long long rows, int C, int Vs, int Os, int dtype, void* stream) {
@@ -591,10 +681,17 @@ int megb200_glu(const void* V, void* Out, long long rows, int C, int Vs, int Os,
                  MEGB_LAUNCH_OK(); return 0;)
 }
 
-int megb200_glu_bwd(const void* dOut, const void* V, void* dV, long long rows, int C, int Vs, int Os, int dtype,
-                    void* stream) {
+int megb200_glu_bwd(const void* dOut, const void* V, void* dV, float* dbias, long long rows, int C, int Vs, int Os,
+                    int dtype, void* stream) {
   MEGB_CHECK_ARG(dOut && V && dV && rows > 0 && Vs >= 2 * C && Os >= C && Vs % 8 == 0 && Os % 8 == 0,
                  "glu_bwd: bad arguments");
+  if (C % 8 == 0 && Vs == 2 * C) {
+    // streaming row-loop form with the bias gradient (column sums of both halves) fused in
+    DISPATCH_DTYPE(dtype, GluBwdOp<DT> op{(const DT*)dOut, (const DT*)V, (DT*)dV, Vs, Os, C};
+                   return launch_rowloop(op, rows, C, Os, nullptr, 1, dbias, dbias ? dbias + C : nullptr,
+                                         (cudaStream_t)stream);)
+  }
+  MEGB_CHECK_ARG(dbias == nullptr, "glu_bwd: the fused bias gradient needs C %% 8 == 0 and an unpadded V");
   const long long nvec = rows * (Os / 8);
   DISPATCH_DTYPE(dtype, glu_bwd_kernel<DT><<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)stream>>>(
                             (const DT*)dOut, (const DT*)V, (DT*)dV, rows, C, Vs, Os);
@@ -608,11 +705,11 @@ int megb200_gelu(const void* P, void* Q, long long n, int dtype, void* stream) {
                  MEGB_LAUNCH_OK(); return 0;)
 }
 
-int megb200_gelu_bwd(const void* dQ, const void* P, void* dP, long long n, int dtype, void* stream) {
-  MEGB_CHECK_ARG(dQ && P && dP && n > 0 && n % 8 == 0, "gelu_bwd: n must be a positive multiple of 8");
-  DISPATCH_DTYPE(dtype, gelu_kernel<DT, true><<<ew_grid(n / 8, 256), 256, 0, (cudaStream_t)stream>>>(
-                            (const DT*)dQ, (const DT*)P, (DT*)dP, n / 8);
-                 MEGB_LAUNCH_OK(); return 0;)
+int megb200_gelu_bwd(const void* dQ, const void* P, void* dP, float* dbias, long long rows, int C, int Cs, int dtype,
+                     void* stream) {
+  MEGB_CHECK_ARG(dQ && P && dP && rows > 0 && Cs % 8 == 0 && Cs >= C, "gelu_bwd: bad arguments");
+  DISPATCH_DTYPE(dtype, GeluBwdOp<DT> op{(const DT*)dQ, (const DT*)P, (DT*)dP, Cs, C};
+                 return launch_rowloop(op, rows, C, Cs, nullptr, 1, dbias, nullptr, (cudaStream_t)stream);)
 }
 
 int megb200_time_mean(const void* Z, void* Zm, int B, int T, int F, int Fs, int dtype, void* stream) {

@@ -146,27 +146,34 @@ class EncoderEngine:
             ops.time_mean_bwd(dZ, full, Fo)
             dZ = full
         # ---- head
-        dp2 = ops.empty(*dZ.shape, device=dev)
-        ops.gelu_bwd(dZ, ctx["p2"], dp2)
-        G["wf2"], G["bf2"] = self._wgrad(dp2, Fo, ctx["q1"], 2 * D2, 1, 1)
+        # bias gradients are column sums of the tensors the element-wise backward passes write: fused there
+        dp2, G["bf2"] = ops.empty(*dZ.shape, device=dev), _zeros(dev, Fo)
+        ops.gelu_bwd(dZ, ctx["p2"], dp2, Fo, G["bf2"])
+        G["wf2"] = self._wgrad(dp2, Fo, ctx["q1"], 2 * D2, 1, 1)
         dq1 = self._dgrad(dp2, Fo, P["wf2"], 2 * D2, 1, None, taps=1)
-        dp1 = ops.empty(*dq1.shape, device=dev)
-        ops.gelu_bwd(dq1, ctx["p1"], dp1)
-        G["wf1"], G["bf1"] = self._wgrad(dp1, 2 * D2, ctx["x5"], D2, 1, 1)
+        dp1, G["bf1"] = ops.empty(*dq1.shape, device=dev), _zeros(dev, 2 * D2)
+        ops.gelu_bwd(dq1, ctx["p1"], dp1, 2 * D2, G["bf1"])
+        G["wf1"] = self._wgrad(dp1, 2 * D2, ctx["x5"], D2, 1, 1)
         dx = self._dgrad(dp1, 2 * D2, P["wf1"], D2, 1, None, taps=1)
 
         # ---- conv blocks, last to first
         for k in range(4, -1, -1):
             pk, bc, d, g = P["blocks"][k], ctx["blocks"][k], self.dil[k], G["blocks"][k]
             dv = ops.empty(*bc["v"].shape, device=dev)
-            ops.glu_bwd(dx, bc["v"], dv, D2)
-            g["w2"], g["b2"] = self._wgrad(dv, 2 * D2, bc["h1"], D2, 3, d[2])
+            if D2 % 8 == 0 and bc["v"].shape[2] == 2 * D2:
+                g["b2"] = _zeros(dev, 2 * D2)
+                ops.glu_bwd(dx, bc["v"], dv, D2, g["b2"])
+            else:
+                ops.glu_bwd(dx, bc["v"], dv, D2)
+                g["b2"] = _zeros(dev, 2 * D2)
+                ops.colsum(dv, 2 * D2, None, g["b2"])
+            g["w2"] = self._wgrad(dv, 2 * D2, bc["h1"], D2, 3, d[2])
             dh1 = self._dgrad(dv, 2 * D2, pk["w2"], D2, d[2], None)
-            du1, g["g1"], g["be1"] = self._bn_gelu_bwd(dh1, bc["u1"], bc["bn1"], pk["g1"], n)
-            g["w1"], g["b1"] = self._wgrad(du1, D2, bc["h0"], D2, 3, d[1])
+            du1, g["g1"], g["be1"], g["b1"] = self._bn_gelu_bwd(dh1, bc["u1"], bc["bn1"], pk["g1"], n)
+            g["w1"] = self._wgrad(du1, D2, bc["h0"], D2, 3, d[1])
             dh0 = self._dgrad(du1, D2, pk["w1"], D2, d[1], du1)
-            du0, g["g0"], g["be0"] = self._bn_gelu_bwd(dh0, bc["u0"], bc["bn0"], pk["g0"], n)
-            g["w0"], g["b0"] = self._wgrad(du0, D2, bc["x"], bc["cin"], 3, d[0])
+            du0, g["g0"], g["be0"], g["b0"] = self._bn_gelu_bwd(dh0, bc["u0"], bc["bn0"], pk["g0"], n)
+            g["w0"] = self._wgrad(du0, D2, bc["x"], bc["cin"], 3, d[0])
             dx = self._dgrad(du0, D2, pk["w0"], bc["cin"], d[0], du0 if k > 0 else None)
         dH2 = dx
 
@@ -203,9 +210,7 @@ class EncoderEngine:
         ops, dev = self.ops, dU.device
         dW = _zeros(dev, 1, M, C, taps)
         ops.wgrad(dU, M, Xin, C, taps, dil, None, None, dW)
-        db = _zeros(dev, M)
-        ops.colsum(dU, M, None, db)
-        return dW.view(M, C, taps), db
+        return dW.view(M, C, taps)
 
     def _dgrad(self, dU, M, w, cin, dil, res, taps=3):
         """dX = conv_transpose(dU): same tap-GEMM with the transposed, tap-flipped weight pack."""
@@ -222,8 +227,9 @@ class EncoderEngine:
         sums2 = _zeros(dev, 2, D2)
         ops.bn_gelu_bwd_reduce(dh, u, st["scale"], st["shift"], st["mean"], st["rstd"], dy, sums2, D2)
         du = ops.empty(*u.shape, device=dev)
-        ops.bn_bwd_apply(dy, u, gamma, st["mean"], st["rstd"], sums2, n, du, D2)
-        return du, sums2[1], sums2[0]
+        db = _zeros(dev, D2)
+        ops.bn_bwd_apply(dy, u, gamma, st["mean"], st["rstd"], sums2, n, du, D2, db)
+        return du, sums2[1], sums2[0], db
 
 
 class ClipEngine:

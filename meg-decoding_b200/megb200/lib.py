@@ -32,11 +32,11 @@ SIGNATURES = {
     "megb200_bn_finalize": [_p, _p, _p, _p, _p, _ll, _f, _f, _i, _p, _p, _p, _p, _i, _p],
     "megb200_bn_gelu": [_p, _p, _p, _p, _ll, _i, _i, _i, _i, _p],
     "megb200_bn_gelu_bwd_reduce": [_p, _p, _p, _p, _p, _p, _p, _p, _ll, _i, _i, _i, _i, _p],
-    "megb200_bn_bwd_apply": [_p, _p, _p, _p, _p, _p, _ll, _p, _ll, _i, _i, _i, _i, _p],
+    "megb200_bn_bwd_apply": [_p, _p, _p, _p, _p, _p, _ll, _p, _p, _ll, _i, _i, _i, _i, _p],
     "megb200_glu": [_p, _p, _ll, _i, _i, _i, _i, _p],
-    "megb200_glu_bwd": [_p, _p, _p, _ll, _i, _i, _i, _i, _p],
+    "megb200_glu_bwd": [_p, _p, _p, _p, _ll, _i, _i, _i, _i, _p],
     "megb200_gelu": [_p, _p, _ll, _i, _p],
-    "megb200_gelu_bwd": [_p, _p, _p, _ll, _i, _p],
+    "megb200_gelu_bwd": [_p, _p, _p, _p, _ll, _i, _i, _i, _p],
     "megb200_time_mean": [_p, _p, _i, _i, _i, _i, _i, _p],
     "megb200_time_mean_bwd": [_p, _p, _i, _i, _i, _i, _i, _p],
     "megb200_clip_prep_y": [_p, _p, _p, _i, _i, _i, _i, _p],

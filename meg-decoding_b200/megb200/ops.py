@@ -215,32 +215,41 @@ class CudaOps:
                mean.data_ptr(), rstd.data_ptr(), dY.data_ptr(), sums2.data_ptr(), rows, C, U.shape[2], self._udt(U),
                self.dt, self._stream())
 
-    def bn_bwd_apply(self, dY, U, gamma, mean, rstd, sums2, count, dU, C):
+    def bn_bwd_apply(self, dY, U, gamma, mean, rstd, sums2, count, dU, C, dbias=None):
+        """dbias (f32 [C], accumulated): column sums of dU = gradient of the conv bias in front of the BatchNorm."""
         self._chk_act(dY, dU)
+        self._chk_f32(dbias)
         assert dY.shape == U.shape == dU.shape
         rows = U.shape[0] * U.shape[1]
         L.call("megb200_bn_bwd_apply", dY.data_ptr(), U.data_ptr(), gamma.data_ptr(), mean.data_ptr(),
-               rstd.data_ptr(), sums2.data_ptr(), int(count), dU.data_ptr(), rows, C, U.shape[2], self._udt(U),
-               self.dt, self._stream())
+               rstd.data_ptr(), sums2.data_ptr(), int(count), dU.data_ptr(), _ptr(dbias), rows, C, U.shape[2],
+               self._udt(U), self.dt, self._stream())
 
     def glu(self, V, Out, C):
         self._chk_act(V, Out)
         rows = V.shape[0] * V.shape[1]
         L.call("megb200_glu", V.data_ptr(), Out.data_ptr(), rows, C, V.shape[2], Out.shape[2], self.dt, self._stream())
 
-    def glu_bwd(self, dOut, V, dV, C):
+    def glu_bwd(self, dOut, V, dV, C, dbias=None):
+        """dbias (f32 [2C], accumulated): column sums of dV (needs C % 8 == 0)."""
         self._chk_act(dOut, V, dV)
+        self._chk_f32(dbias)
         rows = V.shape[0] * V.shape[1]
-        L.call("megb200_glu_bwd", dOut.data_ptr(), V.data_ptr(), dV.data_ptr(), rows, C, V.shape[2], dOut.shape[2],
-               self.dt, self._stream())
+        L.call("megb200_glu_bwd", dOut.data_ptr(), V.data_ptr(), dV.data_ptr(), _ptr(dbias), rows, C, V.shape[2],
+               dOut.shape[2], self.dt, self._stream())
 
     def gelu(self, P, Q):
         self._chk_act(P, Q)
         L.call("megb200_gelu", P.data_ptr(), Q.data_ptr(), P.numel(), self.dt, self._stream())
 
-    def gelu_bwd(self, dQ, P, dP):
+    def gelu_bwd(self, dQ, P, dP, C, dbias=None):
+        """dP = dQ * gelu'(P) on [B,T,Cs]; dbias (f32 [C], accumulated): column sums of dP."""
         self._chk_act(dQ, P, dP)
-        L.call("megb200_gelu_bwd", dQ.data_ptr(), P.data_ptr(), dP.data_ptr(), P.numel(), self.dt, self._stream())
+        self._chk_f32(dbias)
+        assert dQ.shape == P.shape == dP.shape
+        rows = P.shape[0] * P.shape[1]
+        L.call("megb200_gelu_bwd", dQ.data_ptr(), P.data_ptr(), dP.data_ptr(), _ptr(dbias), rows, C, P.shape[2],
+               self.dt, self._stream())
 
     def time_mean(self, Z, Zm, F):
         self._chk_act(Z, Zm)

@@ -167,27 +167,34 @@ class TorchOps:
         sums2[0] += dy.sum((0, 1))
         sums2[1] += (dy * xh).sum((0, 1))
 
-    def bn_bwd_apply(self, dY, U, gamma, mean, rstd, sums2, count, dU, C):
+    def bn_bwd_apply(self, dY, U, gamma, mean, rstd, sums2, count, dU, C, dbias=None):
         xh = (U[:, :, :C].float() - mean) * rstd
         du = gamma * rstd * (dY[:, :, :C].float() - sums2[0] / count - xh * sums2[1] / count)
         dU.zero_()
         dU[:, :, :C] = self._r(du)
+        if dbias is not None:
+            dbias += dU[:, :, :C].float().sum((0, 1))
 
     def glu(self, V, Out, C):
         Out.zero_()
         Out[:, :, :C] = self._r(V[:, :, :C].float() * torch.sigmoid(V[:, :, C:2 * C].float()))
 
-    def glu_bwd(self, dOut, V, dV, C):
+    def glu_bwd(self, dOut, V, dV, C, dbias=None):
         d, a, s = dOut[:, :, :C].float(), V[:, :, :C].float(), torch.sigmoid(V[:, :, C:2 * C].float())
         dV.zero_()
         dV[:, :, :C] = self._r(d * s)
         dV[:, :, C:2 * C] = self._r(d * a * s * (1 - s))
+        if dbias is not None:
+            dbias += dV[:, :, :2 * C].float().sum((0, 1))
 
     def gelu(self, P, Q):
         Q.copy_(self._r(F.gelu(P.float())))
 
-    def gelu_bwd(self, dQ, P, dP):
-        dP.copy_(self._r(dQ.float() * _gelu_grad(P.float())))
+    def gelu_bwd(self, dQ, P, dP, C, dbias=None):
+        dP.zero_()
+        dP[:, :, :C] = self._r(dQ[:, :, :C].float() * _gelu_grad(P[:, :, :C].float()))
+        if dbias is not None:
+            dbias += dP[:, :, :C].float().sum((0, 1))
 
     def time_mean(self, Z, Zm, Fo):
         Zm.copy_(self._r(Z.float().mean(1, keepdim=True)))

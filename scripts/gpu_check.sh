@@ -10,6 +10,7 @@ run() {  # name, timeout, command...
   local rc=$?
   echo "rc=${rc} $(tail -n 1 gpurun_out/${name}.log | cut -c1-300)" | tee -a gpurun_out/summary.txt
   grep -E "^(FAILED|ERROR)|\[parity\]|megb200: mbarrier" "gpurun_out/${name}.log" | cut -c1-400 | head -40 | tee -a gpurun_out/summary.txt
+  return ${rc}
 }
 stages="${*:-ops_simt tc_tapgemm tc_wgrad tc_clip parity_fp32 parity_bf16_simt parity_bf16 parity_misc bench}"
 : > gpurun_out/summary.txt

@@ -271,9 +271,13 @@ def test_batchnorm_gelu_chain(dtype, u_f32, shape):
             _close(dY, dYr, dtype, "bn_gelu_bwd_reduce dY")
             _close(s2, s2r, torch.float32, "bn_gelu_bwd_reduce sums", atol_scale=500 if dtype == torch.bfloat16 else 20)
             dU, dUr = ops.empty(B, T, pad8(C), device=DEV), ref.empty(B, T, pad8(C), device="cpu")
-            ops.bn_bwd_apply(dY, Ud, gamma.to(DEV), st["mean"], st["rstd"], s2, n, dU, C)
+            db = torch.zeros(C, device=DEV)
+            ops.bn_bwd_apply(dY, Ud, gamma.to(DEV), st["mean"], st["rstd"], s2, n, dU, C, db)
             ref.bn_bwd_apply(dY.cpu(), U, gamma, stc["mean"], stc["rstd"], s2.cpu(), n, dUr, C)
             _close(dU, dUr, dtype, "bn_bwd_apply")
+            # fused conv-bias gradient = column sums of the dU just written (analytically ~0: compare absolutely)
+            want = dU.float().cpu()[:, :, :C].sum((0, 1))
+            assert float((db.cpu() - want).abs().max()) <= 1e-3 * float(dU.float().abs().max()) * (n ** 0.5)
 
 
 @pytest.mark.parametrize("dtype", EW_DTYPES)
@@ -289,9 +293,13 @@ def test_glu_gelu_timemean(dtype, C):
     _close(out, outr, dtype, "glu")
     d, dd = _act(gen, dtype, B, T, C)
     dV, dVr = ops.empty(*V.shape, device=DEV), ref.empty(*V.shape, device="cpu")
-    ops.glu_bwd(dd, Vd, dV, C)
-    ref.glu_bwd(d, V, dVr, C)
+    fused = C % 8 == 0
+    db, dbr = (torch.zeros(2 * C, device=DEV), torch.zeros(2 * C)) if fused else (None, None)
+    ops.glu_bwd(dd, Vd, dV, C, db)
+    ref.glu_bwd(d, V, dVr, C, dbr)
     _close(dV, dVr, dtype, "glu_bwd")
+    if fused:
+        _close(db, dV.float().cpu()[:, :, :2 * C].sum((0, 1)), torch.float32, "glu_bwd dbias", atol_scale=20)
     P, Pd = _act(gen, dtype, B, T, pad8(C))
     Q, Qr = ops.empty(*P.shape, device=DEV), ref.empty(*P.shape, device="cpu")
     ops.gelu(Pd, Q)
@@ -299,9 +307,11 @@ def test_glu_gelu_timemean(dtype, C):
     _close(Q, Qr, dtype, "gelu")
     g, gd = _act(gen, dtype, B, T, pad8(C))
     dP, dPr = ops.empty(*P.shape, device=DEV), ref.empty(*P.shape, device="cpu")
-    ops.gelu_bwd(gd, Pd, dP)
-    ref.gelu_bwd(g, P, dPr)
+    db, dbr = torch.zeros(C, device=DEV), torch.zeros(C)
+    ops.gelu_bwd(gd, Pd, dP, C, db)
+    ref.gelu_bwd(g, P, dPr, C, dbr)
     _close(dP, dPr, dtype, "gelu_bwd")
+    _close(db, dP.float().cpu()[:, :, :C].sum((0, 1)), torch.float32, "gelu_bwd dbias", atol_scale=20)
     Fs = pad8(C)
     Zm, Zmr = ops.empty(B, 1, Fs, device=DEV), ref.empty(B, 1, Fs, device="cpu")
     ops.time_mean(Pd, Zm, C)
