@@ -198,42 +198,84 @@ simt_wgrad_kernel(const T* __restrict__ dU, int M, int Ms, const T* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------ small f32 GEMM
+// 128x128x8 tile, 256 threads, 8x8 outputs per thread from two float4 shared loads per operand and k (FMA-bound, not
+// LDS-bound); optional split-K with f32 atomics when the output has too few tiles to fill the machine (e.g. the
+// (270 x C) reductions over all subjects, K = S*270).
+constexpr int kSgM = 128, kSgN = 128, kSgK = 8, kSgPad = 4;
+
 __global__ void __launch_bounds__(256)
 simt_sgemm_kernel(int transA, int transB, int M, int N, int K, float alpha, const float* __restrict__ A, int lda,
                   long long sA, const float* __restrict__ Bm, int ldb, long long sB, float beta,
-                  float* __restrict__ Cm, int ldc, long long sC) {
-  const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * kBN;
-  const float* Ab = A + blockIdx.z * sA;
-  const float* Bb = Bm + blockIdx.z * sB;
-  float* Cb = Cm + blockIdx.z * sC;
-  auto la = [&](int r, int k) -> float {
-    const int m = m0 + r;
-    if (m >= M) return 0.f;
-    return transA ? Ab[(long long)k * lda + m] : Ab[(long long)m * lda + k];
-  };
-  auto lb = [&](int r, int k) -> float {
-    const int n = n0 + r;
-    if (n >= N) return 0.f;
-    return transB ? Bb[(long long)n * ldb + k] : Bb[(long long)k * ldb + n];
-  };
-  float acc[4][4];
-  // loader index mapping only affects coalescing; pick by the common case per flag
-  if (!transA && transB) simt_tile<true, true>(la, lb, 0, K, acc);
-  else if (!transA && !transB) simt_tile<true, false>(la, lb, 0, K, acc);
-  else if (transA && !transB) simt_tile<false, false>(la, lb, 0, K, acc);
-  else simt_tile<false, true>(la, lb, 0, K, acc);
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+                  float* __restrict__ Cm, int ldc, long long sC, int splits, int kchunk) {
+  __shared__ __align__(16) float As[kSgK][kSgM + kSgPad];
+  __shared__ __align__(16) float Bs[kSgK][kSgN + kSgPad];
+  const int batch = blockIdx.z / splits, split = blockIdx.z % splits;
+  const int m0 = blockIdx.x * kSgM, n0 = blockIdx.y * kSgN;
+  const float* Ab = A + batch * sA;
+  const float* Bb = Bm + batch * sB;
+  float* Cb = Cm + batch * sC;
+  const int k_begin = split * kchunk;
+  const int k_end = min(K, k_begin + kchunk);
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  float acc[8][8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  for (int k0 = k_begin; k0 < k_end; k0 += kSgK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + i * 256;
+      {
+        // transposed A is m-contiguous in memory, plain A is k-contiguous: keep the fast index on the lanes
+        const int m = transA ? (e & 127) : (e >> 3);
+        const int kk = transA ? (e >> 7) : (e & 7);
+        const int gm = m0 + m, gk = k0 + kk;
+        float v = 0.f;
+        if (gm < M && gk < k_end) v = transA ? Ab[(long long)gk * lda + gm] : Ab[(long long)gm * lda + gk];
+        As[kk][m] = v;
+      }
+      {
+        const int n = transB ? (e >> 3) : (e & 127);
+        const int kk = transB ? (e & 7) : (e >> 7);
+        const int gn = n0 + n, gk = k0 + kk;
+        float v = 0.f;
+        if (gn < N && gk < k_end) v = transB ? Bb[(long long)gn * ldb + gk] : Bb[(long long)gk * ldb + gn];
+        Bs[kk][n] = v;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kSgK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 8]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 8 + 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + ty * 8 + i;
     if (m >= M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
+    for (int j = 0; j < 8; ++j) {
+      const int n = n0 + tx * 8 + j;
       if (n >= N) continue;
-      float v = alpha * acc[i][j];
-      if (beta != 0.f) v += beta * Cb[(long long)m * ldc + n];
-      Cb[(long long)m * ldc + n] = v;
+      float* dst = Cb + (long long)m * ldc + n;
+      if (splits > 1) {
+        atomicAdd(dst, alpha * acc[i][j]);          // C was pre-scaled by beta (0 or 1) by the launcher
+      } else {
+        float v = alpha * acc[i][j];
+        if (beta != 0.f) v += beta * *dst;
+        *dst = v;
+      }
     }
   }
 }
@@ -386,11 +428,27 @@ using namespace megb200;
 extern "C" int megb200_sgemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
                              long long strideA, const float* Bm, int ldb, long long strideB, float beta, float* C,
                              int ldc, long long strideC, int batch, void* stream) {
-  MEGB_CHECK_ARG(A && Bm && C && M > 0 && N > 0 && K > 0 && batch > 0 && batch <= 65535, "sgemm: bad arguments");
-  dim3 grid((M + kBM - 1) / kBM, (N + kBN - 1) / kBN, batch);
-  MEGB_CHECK_ARG(grid.y <= 65535, "sgemm: N too large");
-  simt_sgemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(transA, transB, M, N, K, alpha, A, lda, strideA, Bm, ldb,
-                                                           strideB, beta, C, ldc, strideC);
+  MEGB_CHECK_ARG(A && Bm && C && M > 0 && N > 0 && K > 0 && batch > 0, "sgemm: bad arguments");
+  const int mt = (M + kSgM - 1) / kSgM, nt = (N + kSgN - 1) / kSgN;
+  MEGB_CHECK_ARG(nt <= 65535, "sgemm: N too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  // split-K only when the output is small, K is long and C can be cleared / kept as a whole (beta 0 or 1, dense rows)
+  int splits = 1;
+  const long long tiles = (long long)mt * nt * batch;
+  if (tiles < num_sms() && K >= 512 && (beta == 0.f || beta == 1.f) && ldc == N &&
+      (batch == 1 || strideC == (long long)M * N)) {
+    splits = (int)((num_sms() + tiles - 1) / tiles);
+    if (splits > K / 128) splits = K / 128;
+    if (splits < 1) splits = 1;
+  }
+  int kchunk = (K + splits - 1) / splits;
+  kchunk = (kchunk + kSgK - 1) / kSgK * kSgK;
+  splits = (K + kchunk - 1) / kchunk;
+  if (splits > 1 && beta == 0.f) MEGB_CUDA_OK(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)batch * M * N, st));
+  MEGB_CHECK_ARG((long long)batch * splits <= 65535, "sgemm: batch too large");
+  dim3 grid(mt, nt, batch * splits);
+  simt_sgemm_kernel<<<grid, 256, 0, st>>>(transA, transB, M, N, K, alpha, A, lda, strideA, Bm, ldb, strideB, beta, C,
+                                          ldc, strideC, splits, kchunk);
   MEGB_LAUNCH_OK();
   return 0;
 }

@@ -196,8 +196,9 @@ def test_colsum_and_sgemm(dtype):
         ref.colsum(U, 30, group, outr)
         _close(out, outr, torch.float32, "colsum", atol_scale=5)
     if dtype == torch.float32:
-        for tA, tB, beta in ((False, False, 0.0), (True, False, 0.0), (False, True, 1.0), (True, True, 0.5)):
-            M, N, K, batch = 70, 45, 130, 3
+        for tA, tB, beta, K, batch in ((False, False, 0.0, 130, 3), (True, False, 0.0, 130, 3), (False, True, 1.0, 130, 3),
+                                       (True, True, 0.5, 130, 3), (True, False, 0.0, 3000, 1), (False, True, 1.0, 2048, 2)):
+            M, N = 270, 45          # the long-K cases take the split-K path
             A = _rand(gen, batch, *((K, M) if tA else (M, K)))
             Bm = _rand(gen, *((N, K) if tB else (K, N)))           # 2-D: broadcast over the batch
             C0 = _rand(gen, batch, M, N)
