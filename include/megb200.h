@@ -90,10 +90,11 @@ int megb200_colsum(const void* U, int B, int T, int C, int Cs, const int32_t* gr
 
 /* Row-major f32 batched GEMM for the small per-step matrices of the subject block / spatial attention
  * (models.py:204-208 and the chain rule of SURVEY appendix A1-A2):
- *   C[b] = alpha * op(A[b]) * op(B[b]) + beta * C[b],   op = transpose when the flag is set. */
+ *   C[b] = alpha * op(A[b]) * op(B[b]) + beta * C[b],   op = transpose when the flag is set.
+ * `workspace` (optional, f32) enables a deterministic split-K for long reductions with few output tiles. */
 int megb200_sgemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
                   long long strideA, const float* Bm, int ldb, long long strideB, float beta, float* C, int ldc,
-                  long long strideC, int batch, void* stream);
+                  long long strideC, int batch, float* workspace, size_t ws_bytes, void* stream);
 
 /* -------------------------------------------------------------------------------------- spatial attention */
 /* W[o][:] = softmax(a[o][:]) ; Wm = W * mask[None,:]  (models.py:213 and :235-239 folded into the weights).

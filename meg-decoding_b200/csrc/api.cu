@@ -54,7 +54,12 @@ int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_
                      const uint64_t* strides_bytes, const uint32_t* box) {
   // Driver entry points need the primary context current on THIS thread; autograd's backward threads may not have
   // issued a runtime call yet (cuTensorMapEncodeTiled then fails with CUDA_ERROR_INVALID_CONTEXT).
-  cudaFree(nullptr);
+  // Once per thread: cudaFree synchronises the device, so doing it per call would serialise host and GPU.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaFree(nullptr);
+    ctx_bound = true;
+  }
   EncodeTiledFn fn = get_encode();
   if (fn == nullptr) {
     set_last_error("cuTensorMapEncodeTiled is not available from the driver");

@@ -185,7 +185,7 @@ struct BnGeluOp {
     float x[8], o[8];
     load8(u + r * Cs + c0, x);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = (c0 + i < C) ? gelu_f(fmaf(x[i], sc[i], sh[i])) : 0.f;
+    for (int i = 0; i < 8; ++i) o[i] = (c0 + i < C) ? gelu_t<T>(fmaf(x[i], sc[i], sh[i])) : 0.f;
     store8(h + r * Cs + c0, o);
   }
 };
@@ -218,7 +218,7 @@ struct BnGeluBwdOp {
     for (int i = 0; i < 8; ++i) {
       float d = 0.f;
       if (c0 + i < C) {
-        d = round_to<T>(g[i] * gelu_grad_f(fmaf(x[i], sc[i], sh[i])));
+        d = round_to<T>(g[i] * gelu_grad_t<T>(fmaf(x[i], sc[i], sh[i])));
         a0[i] += d;
         a1[i] += d * (x[i] - mu[i]) * rs[i];
       }
@@ -281,7 +281,7 @@ struct GeluBwdOp {
     load8(p + r * Cs + c0, x);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      o[i] = (c0 + i < C) ? round_to<T>(g[i] * gelu_grad_f(x[i])) : 0.f;
+      o[i] = (c0 + i < C) ? round_to<T>(g[i] * gelu_grad_t<T>(x[i])) : 0.f;
       a0[i] += o[i];
     }
     store8(dp + r * Cs + c0, o);
@@ -415,10 +415,10 @@ __global__ void gelu_kernel(const T* __restrict__ dq, const T* __restrict__ p, T
       float g[8];
       load8(dq + v * 8, g);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) r[i] = g[i] * gelu_grad_f(x[i]);
+      for (int i = 0; i < 8; ++i) r[i] = g[i] * gelu_grad_t<T>(x[i]);
     } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) r[i] = gelu_f(x[i]);
+      for (int i = 0; i < 8; ++i) r[i] = gelu_t<T>(x[i]);
     }
     store8(o + v * 8, r);
   }

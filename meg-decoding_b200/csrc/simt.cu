@@ -129,7 +129,7 @@ simt_tapgemm_kernel(const T* __restrict__ A, int Tn, int Ca, int Cas, const T* _
         OutF[row * Cos + n] = v;
       } else if (kEpi == MEGB200_EPI_GELU) {
         if (n < Co2s) Out2[row * Co2s + n] = from_f<T>(v);
-        Out[row * Cos + n] = from_f<T>(n < N ? gelu_f(v) : 0.f);
+        Out[row * Cos + n] = from_f<T>(n < N ? gelu_t<T>(v) : 0.f);
       } else {
         Out[row * Cos + n] = from_f<T>(v);
       }
@@ -206,7 +206,7 @@ constexpr int kSgM = 128, kSgN = 128, kSgK = 8, kSgPad = 4;
 __global__ void __launch_bounds__(256)
 simt_sgemm_kernel(int transA, int transB, int M, int N, int K, float alpha, const float* __restrict__ A, int lda,
                   long long sA, const float* __restrict__ Bm, int ldb, long long sB, float beta,
-                  float* __restrict__ Cm, int ldc, long long sC, int splits, int kchunk) {
+                  float* __restrict__ Cm, int ldc, long long sC, int splits, int kchunk, float* __restrict__ part) {
   __shared__ __align__(16) float As[kSgK][kSgM + kSgPad];
   __shared__ __align__(16) float Bs[kSgK][kSgN + kSgPad];
   const int batch = blockIdx.z / splits, split = blockIdx.z % splits;
@@ -270,7 +270,8 @@ simt_sgemm_kernel(int transA, int transB, int M, int N, int K, float alpha, cons
       if (n >= N) continue;
       float* dst = Cb + (long long)m * ldc + n;
       if (splits > 1) {
-        atomicAdd(dst, alpha * acc[i][j]);          // C was pre-scaled by beta (0 or 1) by the launcher
+        // deterministic split-K: plain stores of the partial sums, combined in a fixed order by sgemm_reduce_kernel
+        part[(((long long)split * (gridDim.z / splits) + batch) * M + m) * N + n] = acc[i][j];
       } else {
         float v = alpha * acc[i][j];
         if (beta != 0.f) v += beta * *dst;
@@ -425,30 +426,54 @@ template int simt_clip_dz<__nv_bfloat16>(const void*, int, const void*, const vo
 
 using namespace megb200;
 
+__global__ void sgemm_reduce_kernel(const float* __restrict__ part, int splits, long long per_split, int M, int N,
+                                    float alpha, float beta, float* __restrict__ Cm, int ldc, long long sC) {
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < per_split;
+       idx += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += part[k * per_split + idx];
+    const int n = (int)(idx % N);
+    const long long r = idx / N;
+    const int m = (int)(r % M);
+    const long long b = r / M;
+    float* dst = Cm + b * sC + (long long)m * ldc + n;
+    float v = alpha * s;
+    if (beta != 0.f) v += beta * *dst;
+    *dst = v;
+  }
+}
+
 extern "C" int megb200_sgemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
                              long long strideA, const float* Bm, int ldb, long long strideB, float beta, float* C,
-                             int ldc, long long strideC, int batch, void* stream) {
+                             int ldc, long long strideC, int batch, float* workspace, size_t ws_bytes, void* stream) {
   MEGB_CHECK_ARG(A && Bm && C && M > 0 && N > 0 && K > 0 && batch > 0, "sgemm: bad arguments");
   const int mt = (M + kSgM - 1) / kSgM, nt = (N + kSgN - 1) / kSgN;
   MEGB_CHECK_ARG(nt <= 65535, "sgemm: N too large");
   cudaStream_t st = (cudaStream_t)stream;
-  // split-K only when the output is small, K is long and C can be cleared / kept as a whole (beta 0 or 1, dense rows)
+  // split-K (through the workspace, deterministic) when the output has too few tiles to fill the machine and K is long
   int splits = 1;
   const long long tiles = (long long)mt * nt * batch;
-  if (tiles < num_sms() && K >= 512 && (beta == 0.f || beta == 1.f) && ldc == N &&
-      (batch == 1 || strideC == (long long)M * N)) {
+  const long long per_split = (long long)batch * M * N;
+  if (workspace != nullptr && tiles < num_sms() && K >= 512) {
     splits = (int)((num_sms() + tiles - 1) / tiles);
     if (splits > K / 128) splits = K / 128;
+    const long long fit = (long long)(ws_bytes / sizeof(float)) / per_split;
+    if (splits > fit) splits = (int)fit;
     if (splits < 1) splits = 1;
   }
   int kchunk = (K + splits - 1) / splits;
   kchunk = (kchunk + kSgK - 1) / kSgK * kSgK;
   splits = (K + kchunk - 1) / kchunk;
-  if (splits > 1 && beta == 0.f) MEGB_CUDA_OK(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)batch * M * N, st));
   MEGB_CHECK_ARG((long long)batch * splits <= 65535, "sgemm: batch too large");
   dim3 grid(mt, nt, batch * splits);
   simt_sgemm_kernel<<<grid, 256, 0, st>>>(transA, transB, M, N, K, alpha, A, lda, strideA, Bm, ldb, strideB, beta, C,
-                                          ldc, strideC, splits, kchunk);
+                                          ldc, strideC, splits, kchunk, workspace);
   MEGB_LAUNCH_OK();
+  if (splits > 1) {
+    long long blocks = (per_split + 255) / 256;
+    if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+    sgemm_reduce_kernel<<<(int)blocks, 256, 0, st>>>(workspace, splits, per_split, M, N, alpha, beta, C, ldc, strideC);
+    MEGB_LAUNCH_OK();
+  }
   return 0;
 }

@@ -198,7 +198,7 @@ tc_tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           } else if (p.epi == MEGB200_EPI_GELU) {
             if (c0 < p.Co2s) store8(prow + c0, o);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = (c0 + i < p.N) ? gelu_f(o[i]) : 0.f;
+            for (int i = 0; i < 8; ++i) o[i] = (c0 + i < p.N) ? gelu_t<__nv_bfloat16>(o[i]) : 0.f;
             store8(orow + c0, o);
           } else {
             store8(orow + c0, o);

@@ -25,7 +25,7 @@ SIGNATURES = {
     "megb200_wgrad": [_p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _p, _sz, _i, _i, _p],
     "megb200_group_order": [_p, _i, _i, _p, _p],
     "megb200_colsum": [_p, _i, _i, _i, _i, _p, _i, _p, _i, _p],
-    "megb200_sgemm": [_i, _i, _i, _i, _i, _f, _p, _i, _ll, _p, _i, _ll, _f, _p, _i, _ll, _i, _p],
+    "megb200_sgemm": [_i, _i, _i, _i, _i, _f, _p, _i, _ll, _p, _i, _ll, _f, _p, _i, _ll, _i, _p, _sz, _p],
     "megb200_sa_softmax": [_p, _p, _p, _p, _i, _i, _p],
     "megb200_sa_softmax_bwd": [_p, _p, _p, _p, _i, _i, _p],
     "megb200_bn_stats": [_p, _ll, _i, _i, _p, _i, _p],

@@ -167,8 +167,10 @@ class CudaOps:
         sA = A.shape[-2] * A.shape[-1] if A.dim() == 3 else 0
         sB = Bm.shape[-2] * Bm.shape[-1] if Bm.dim() == 3 else 0
         sC = M * N if out.dim() == 3 else 0
+        ws = self.workspace(out.device)
         L.call("megb200_sgemm", int(transA), int(transB), M, N, K, float(alpha), A.data_ptr(), A.shape[-1], sA,
-               Bm.data_ptr(), Bm.shape[-1], sB, float(beta), out.data_ptr(), N, sC, batch, self._stream())
+               Bm.data_ptr(), Bm.shape[-1], sB, float(beta), out.data_ptr(), N, sC, batch, ws.data_ptr(),
+               ws.numel() * 4, self._stream())
 
     # ------------------------------------------------------------------ spatial attention
     def sa_softmax(self, a, mask, W, Wm):
