@@ -9,6 +9,8 @@
 //                   operands are MN-major straight from the PC layout; split over sample ranges.
 //   tc_clip_logits  raw[i][j] += sum_d Y[i][d] Z[j][d]; split-K over D, f32 atomics.
 //   tc_clip_dz      dZ[j][d] = gs * (sum_i coef[j][i] Y[i][d] - Z[j][d] cvec[j]); A K-major, B MN-major.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace megb200 {
@@ -40,6 +42,76 @@ struct TapGemmParams {
   void* Out;
   __nv_bfloat16* Out2;
 };
+
+// Epilogue tail shared by the single-CTA and the CTA-pair kernels: one thread = one output position (TMEM lane);
+// `trow` addresses this thread's lane at the first accumulator column of the tile, `n0` is the tile's first channel.
+__device__ __forceinline__ void tap_epilogue(const TapGemmParams& p, uint32_t trow, const float* sbias, int n0,
+                                             long long row, bool valid) {
+  const bool glu = p.epi == MEGB200_EPI_GLU;
+  const int half = p.NT / 2;
+  const int Ch = p.N / 2;
+  if (glu) {
+    __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.Out) + row * p.Cos;
+    __nv_bfloat16* vrow = p.Out2 + row * p.Co2s;
+    for (int ch = 0; ch < half / 16; ++ch) {
+      float va[16], vg[16];
+      tmem_ld16(trow + (uint32_t)(ch * 16), va);
+      tmem_ld16(trow + (uint32_t)(half + ch * 16), vg);
+      if (!valid) continue;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c0 = n0 + ch * 16 + h * 8;
+        if (c0 >= p.Cos) continue;
+        float o[8], a8[8], g8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const bool in = (c0 + i) < Ch;
+          a8[i] = in ? va[h * 8 + i] + sbias[ch * 16 + h * 8 + i] : 0.f;
+          g8[i] = in ? vg[h * 8 + i] + sbias[half + ch * 16 + h * 8 + i] : 0.f;
+          o[i] = in ? a8[i] * sigmoid_f(g8[i]) : 0.f;
+        }
+        store8(orow + c0, o);
+        if (c0 + 8 <= Ch) {                  // Ch % 8 == 0 is required by the launcher for this epilogue
+          store8(vrow + c0, a8);
+          store8(vrow + Ch + c0, g8);
+        }
+      }
+    }
+  } else {
+    __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.Out) + row * p.Cos;
+    float* frow = reinterpret_cast<float*>(p.Out) + row * p.Cos;
+    __nv_bfloat16* prow = p.Out2 ? p.Out2 + row * p.Co2s : nullptr;
+    const __nv_bfloat16* rrow = p.Res ? p.Res + row * p.Crs : nullptr;
+    for (int ch = 0; ch < p.NT / 16; ++ch) {
+      float v[16];
+      tmem_ld16(trow + (uint32_t)(ch * 16), v);
+      if (!valid) continue;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c0 = n0 + ch * 16 + h * 8;
+        if (c0 >= p.Cos) continue;
+        float o[8];
+        float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (rrow != nullptr && c0 < p.Crs) load8(rrow + c0, r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int n = c0 + i;
+          o[i] = (n < p.N) ? v[h * 8 + i] + sbias[ch * 16 + h * 8 + i] + r[i] : 0.f;
+        }
+        if (p.epi == MEGB200_EPI_STORE_F32) {
+          store8(frow + c0, o);
+        } else if (p.epi == MEGB200_EPI_GELU) {
+          if (c0 < p.Co2s) store8(prow + c0, o);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = (c0 + i < p.N) ? gelu_t<__nv_bfloat16>(o[i]) : 0.f;
+          store8(orow + c0, o);
+        } else {
+          store8(orow + c0, o);
+        }
+      }
+    }
+  }
+}
 
 __global__ void __launch_bounds__(kThreads)
 tc_tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
@@ -142,76 +214,162 @@ tc_tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tc_fence_after();
     const int q = warp & 3;
     const int t = t0 + q * 32 + lane;
-    const bool valid = t < p.T;
     const long long row = (long long)b * p.T + t;
-    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    if (glu) {
-      __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.Out) + row * p.Cos;
-      __nv_bfloat16* vrow = p.Out2 + row * p.Co2s;
-      for (int ch = 0; ch < half / 16; ++ch) {
-        float va[16], vg[16];
-        tmem_ld16(trow + (uint32_t)(ch * 16), va);
-        tmem_ld16(trow + (uint32_t)(half + ch * 16), vg);
-        if (!valid) continue;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int c0 = n0 + ch * 16 + h * 8;
-          if (c0 >= p.Cos) continue;
-          float o[8], a8[8], g8[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const bool in = (c0 + i) < Ch;
-            a8[i] = in ? va[h * 8 + i] + sbias[ch * 16 + h * 8 + i] : 0.f;
-            g8[i] = in ? vg[h * 8 + i] + sbias[half + ch * 16 + h * 8 + i] : 0.f;
-            o[i] = in ? a8[i] * sigmoid_f(g8[i]) : 0.f;
-          }
-          store8(orow + c0, o);
-          if (c0 + 8 <= Ch) {                  // Ch % 8 == 0 is required by the launcher for this epilogue
-            store8(vrow + c0, a8);
-            store8(vrow + Ch + c0, g8);
-          }
-        }
-      }
-    } else {
-      __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.Out) + row * p.Cos;
-      float* frow = reinterpret_cast<float*>(p.Out) + row * p.Cos;
-      __nv_bfloat16* prow = p.Out2 ? p.Out2 + row * p.Co2s : nullptr;
-      const __nv_bfloat16* rrow = p.Res ? p.Res + row * p.Crs : nullptr;
-      for (int ch = 0; ch < p.NT / 16; ++ch) {
-        float v[16];
-        tmem_ld16(trow + (uint32_t)(ch * 16), v);
-        if (!valid) continue;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int c0 = n0 + ch * 16 + h * 8;
-          if (c0 >= p.Cos) continue;
-          float o[8];
-          float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          if (rrow != nullptr && c0 < p.Crs) load8(rrow + c0, r);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int n = c0 + i;
-            o[i] = (n < p.N) ? v[h * 8 + i] + sbias[ch * 16 + h * 8 + i] + r[i] : 0.f;
-          }
-          if (p.epi == MEGB200_EPI_STORE_F32) {
-            store8(frow + c0, o);
-          } else if (p.epi == MEGB200_EPI_GELU) {
-            if (c0 < p.Co2s) store8(prow + c0, o);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = (c0 + i < p.N) ? gelu_t<__nv_bfloat16>(o[i]) : 0.f;
-            store8(orow + c0, o);
-          } else {
-            store8(orow + c0, o);
-          }
-        }
-      }
-    }
+    tap_epilogue(p, tmem_base + ((uint32_t)(q * 32) << 16), sbias, n0, row, t < p.T);
     tc_fence_before();
   }
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ================================================================================================ tap GEMM, CTA pair
+// Persistent cta_group::2 form of the tap GEMM: a cluster of two CTAs (one TPC) computes a 256-position x NT-channel
+// tile with ONE tcgen05.mma.cta_group::2 stream issued by the leader; each CTA stages its own 128 activation rows and
+// HALF of the weight tile, which halves the per-SM shared-memory operand traffic (the single-CTA kernel is bound by
+// it).  Accumulators are double-buffered in TMEM so that the epilogue of tile i overlaps the main loop of tile i+1.
+struct Header2 {
+  uint64_t full[8];
+  uint64_t empty[8];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_slot;
+  uint32_t pad;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+tc_tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                   const TapGemmParams p, const int total_m_tiles, const int num_items) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  Header2* hdr = reinterpret_cast<Header2*>(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int half = p.NT / 2;                                  // weight rows staged by each CTA
+  const uint32_t a_bytes = kTileM * 128, b_bytes = (uint32_t)half * 128;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  uint8_t* ring = smem + kHeaderBytes;
+  float* sbias = reinterpret_cast<float*>(ring + (size_t)p.stages * stage_bytes);   // [2][NT]: one table per acc stage
+  const bool glu = p.epi == MEGB200_EPI_GLU;
+  const int Ch = p.N / 2;
+  const int num_k = p.taps * p.kchunks;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&hdr->full[s]), 1);      // the leader's producer arrives once and expects both CTAs' bytes
+      mbar_init(smem_u32(&hdr->empty[s]), 1);     // one multicast tcgen05.commit per use
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&hdr->tmem_full[a]), 1);
+      mbar_init(smem_u32(&hdr->tmem_empty[a]), 8);  // 4 epilogue warps x 2 CTAs (used on the leader only)
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2sm(smem_u32(&hdr->tmem_slot), p.tmem_cols);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  cluster_sync_all();                              // barriers of both CTAs initialised before any remote traffic
+  tc_fence_after();
+  const uint32_t tmem_base = hdr->tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int item = cluster_id; item < num_items; item += num_clusters) {
+        const int n_tile = item % p.ntiles;
+        const int m_tile = (item / p.ntiles) * 2 + (int)rank;
+        // a missing second tile of the last pair reads sample index B: fully out of bounds, zero filled
+        const int b = m_tile < total_m_tiles ? m_tile / p.tiles_per_sample : 0x3fffffff;
+        const int t0 = (m_tile % p.tiles_per_sample) * kTileM;
+        // weight rows of this CTA: plain tiles split [n0, n0+half) | [n0+half, n0+NT); GLU tiles are
+        // [half a-channels | their half gate channels], i.e. the leader stages the a rows and the peer the gates
+        const int wrow = glu ? (n_tile * half + (rank ? Ch : 0)) : (n_tile * p.NT + (int)rank * half);
+        for (int kit = 0; kit < num_k; ++kit, ++it) {
+          const int s = it % p.stages;
+          mbar_wait(smem_u32(&hdr->empty[s]), ((it / p.stages) & 1) ^ 1);
+          const uint32_t full = smem_u32(&hdr->full[s]);
+          if (leader) mbar_arrive_expect_tx(full, 2 * stage_bytes);
+          const int tap = kit / p.kchunks, kc = kit % p.kchunks;
+          const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
+          tma_load_3d_2sm(sa, &tmA, kc * kBlockK, t0 + (tap - p.taps / 2) * p.dil, b, full);
+          tma_load_3d_2sm(sa + a_bytes, &tmW, tap * p.Kp + kc * kBlockK, wrow, 0, full);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      int it = 0, tile = 0;
+      for (int item = cluster_id; item < num_items; item += num_clusters, ++tile) {
+        const int acc = tile & 1;
+        mbar_wait(smem_u32(&hdr->tmem_empty[acc]), ((tile >> 1) & 1) ^ 1);   // epilogues of both CTAs drained it
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.NT);
+        for (int kit = 0; kit < num_k; ++kit, ++it) {
+          const int s = it % p.stages;
+          mbar_wait(smem_u32(&hdr->full[s]), (it / p.stages) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
+          const uint64_t da = make_smem_desc(sa, 16, 1024);
+          const uint64_t db = make_smem_desc(sa + a_bytes, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)
+            umma_bf16_2sm(d_tmem, desc_advance(da, k * 32), desc_advance(db, k * 32), p.idesc, (kit | k) != 0);
+          umma_commit_2sm(smem_u32(&hdr->empty[s]), 3);                      // frees the slot in BOTH CTAs
+        }
+        umma_commit_2sm(smem_u32(&hdr->tmem_full[acc]), 3);                  // accumulator ready in BOTH CTAs
+      }
+    }
+  } else {
+    // ---------------- epilogue (both CTAs): each CTA drains its own 128 rows of the 256-row accumulator
+    const int et = threadIdx.x - 64;
+    const int q = warp & 3;
+    int tile = 0;
+    for (int item = cluster_id; item < num_items; item += num_clusters, ++tile) {
+      const int acc = tile & 1;
+      const int n_tile = item % p.ntiles;
+      const int m_tile = (item / p.ntiles) * 2 + (int)rank;
+      const int b = m_tile / p.tiles_per_sample;
+      const int t0 = (m_tile % p.tiles_per_sample) * kTileM;
+      const int n0 = n_tile * (glu ? half : p.NT);
+      float* sb = sbias + acc * p.NT;
+      for (int i = et; i < p.NT; i += 128) {
+        int n;
+        bool ok;
+        if (glu) {
+          const int c = n0 + (i < half ? i : i - half);
+          ok = c < Ch;
+          n = (i < half) ? c : Ch + c;
+        } else {
+          n = n0 + i;
+          ok = n < p.N;
+        }
+        sb[i] = (p.bias != nullptr && ok) ? p.bias[n] : 0.f;
+      }
+      named_bar_sync(1, 128);
+      mbar_wait(smem_u32(&hdr->tmem_full[acc]), (tile >> 1) & 1);
+      tc_fence_after();
+      const int t = t0 + q * 32 + lane;
+      const long long row = (long long)b * p.T + t;
+      tap_epilogue(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.NT), sb, n0, row,
+                   m_tile < total_m_tiles && t < p.T);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(smem_u32(&hdr->tmem_empty[acc]), 0);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();                              // nobody leaves while the peer may still touch its smem / TMEM
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, p.tmem_cols);
   }
 }
 
@@ -647,6 +805,60 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
     const int ncover = Cos > Np ? Cos : Np;
     p.ntiles = (ncover + p.NT - 1) / p.NT;
   }
+  p.bias = bias; p.Res = (const __nv_bfloat16*)Res; p.group = group; p.Out = Out; p.Out2 = (__nv_bfloat16*)Out2;
+
+  // MEGB200_TAPGEMM_1CTA forces the single-CTA kernel; MEGB200_TAPGEMM_2CTA_MIN_ITEMS lowers the work threshold of the
+  // CTA-pair kernel (tests use it to exercise the pair kernel on small shapes)
+  static const bool force_1cta = getenv("MEGB200_TAPGEMM_1CTA") != nullptr;
+  static const char* min_items_env = getenv("MEGB200_TAPGEMM_2CTA_MIN_ITEMS");
+  const long long min_items = min_items_env ? atoll(min_items_env) : 2ll * num_sms();
+  const long long m_tiles_total = (long long)B * p.tiles_per_sample;
+  if (group == nullptr && G == 1 && !force_1cta && p.NT % 32 == 0 && m_tiles_total * p.ntiles >= min_items) {
+    // ---- CTA-pair persistent kernel
+    const int half = p.NT / 2;
+    const uint32_t stage2 = kTileM * 128 + half * 128;
+    p.stages = pick_stages(stage2, 200 * 1024 - 2 * p.NT * 4, 8);
+    p.tmem_cols = tmem_cols_for(2 * p.NT);
+    p.idesc = make_idesc_m(256, p.NT, 0, 0);
+    CUtensorMap tmA2, tmW2;
+    {
+      const uint64_t dims[3] = {(uint64_t)Ca, (uint64_t)T, (uint64_t)B};
+      const uint64_t strides[2] = {(uint64_t)Cas * 2, (uint64_t)T * Cas * 2};
+      const uint32_t box[3] = {kBlockK, kTileM, 1};
+      int rc = encode_tmap_bf16(&tmA2, A, 3, dims, strides, box);
+      if (rc) return rc;
+    }
+    {
+      const uint64_t dims[3] = {(uint64_t)taps * Kp, (uint64_t)Np, 1};
+      const uint64_t strides[2] = {(uint64_t)taps * Kp * 2, (uint64_t)Np * taps * Kp * 2};
+      const uint32_t box[3] = {kBlockK, (uint32_t)half, 1};
+      int rc = encode_tmap_bf16(&tmW2, W, 3, dims, strides, box);
+      if (rc) return rc;
+    }
+    const size_t smem2 = 1024 + kHeaderBytes + (size_t)p.stages * stage2 + 2 * p.NT * 4;
+    int rc = set_smem(tc_tapgemm2_kernel, smem2);
+    if (rc) return rc;
+    const int m_pairs = (int)((m_tiles_total + 1) / 2);
+    const int num_items = m_pairs * p.ntiles;
+    int clusters = num_sms() / 2;
+    if (clusters > num_items) clusters = num_items;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem2;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MEGB_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_tapgemm2_kernel, tmA2, tmW2, p, (int)m_tiles_total, num_items));
+    MEGB_LAUNCH_OK();
+    return 0;
+  }
+
   const uint32_t stage_bytes = kTileM * 128 + p.NT * 128;
   p.stages = pick_stages(stage_bytes, 112000 - (p.NT > 128 ? p.NT * 4 : 0), 6);
   MEGB_CHECK_ARG(p.stages >= 2, "tc_tapgemm: tile too large for the stage ring");
