@@ -52,6 +52,11 @@ static EncodeTiledFn get_encode() {
 
 int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box) {
+  return encode_tmap(map, base, 2, 128, rank, dims, strides_bytes, box);
+}
+
+int encode_tmap(CUtensorMap* map, const void* base, int elem_bytes, int swizzle_bytes, int rank, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box) {
   // Driver entry points need the primary context current on THIS thread; autograd's backward threads may not have
   // issued a runtime call yet (cuTensorMapEncodeTiled then fails with CUDA_ERROR_INVALID_CONTEXT).
   // Once per thread: cudaFree synchronises the device, so doing it per call would serialise host and GPU.
@@ -84,8 +89,12 @@ int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_
       }
     }
   }
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  const CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(map, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu box %u,%u)", (int)r, rank,

@@ -34,7 +34,8 @@ __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
 
 // ================================================================================================ tap GEMM
 struct TapGemmParams {
-  int T, N, Cos, Crs, Co2s, taps, dil, Kp, kchunks, tiles_per_sample, ntiles, NT, stages, epi;
+  int T, N, Cos, Crs, Co2s, taps, dil, Kp, kchunks, tiles_per_sample, ntiles, NT, stages, epi, debug_skip_io, tma_epi;
+  uint32_t stg_bytes;   // CTA-pair kernel: dedicated staging area of the TMA-store epilogue
   uint32_t tmem_cols, idesc;
   const float* bias;
   const __nv_bfloat16* Res;
@@ -50,6 +51,7 @@ __device__ __forceinline__ void tap_epilogue(const TapGemmParams& p, uint32_t tr
   const bool glu = p.epi == MEGB200_EPI_GLU;
   const int half = p.NT / 2;
   const int Ch = p.N / 2;
+  if (p.debug_skip_io) valid = false;     // profiling experiment: TMEM drain only, no global traffic
   if (glu) {
     __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.Out) + row * p.Cos;
     __nv_bfloat16* vrow = p.Out2 + row * p.Co2s;
@@ -113,9 +115,139 @@ __device__ __forceinline__ void tap_epilogue(const TapGemmParams& p, uint32_t tr
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// TMA-store epilogue.  The direct-store epilogue above makes every thread write its own row: 32 different 128-byte
+// lines per warp instruction and a dependent residual load per chunk; measured, it halves the kernel's throughput.
+// Here a thread still owns one accumulator row (TMEM lane), but the tile leaves through shared memory: 32-channel
+// slices are written in the TMA swizzle pattern (conflict-free 16-byte stores), one elected thread issues
+// cp.async.bulk.tensor stores (coalesced, asynchronous, rows >= T and pad channels clipped by the TMA unit), and the
+// residual row is prefetched one slice ahead.  `stg` is a 1024-aligned staging area of `stg_bytes`.
+struct TapStoreMaps {
+  CUtensorMap out;    // Out:  (Cos, T, B), box (32, 128, 1); bf16 -> SWIZZLE_64B, f32 -> SWIZZLE_128B
+  CUtensorMap out2;   // Out2: (Co2s, T, B) bf16, box (32, 128, 1), SWIZZLE_64B
+};
+
+__device__ __forceinline__ void stage_bf16_slice(uint32_t base, int rloc, const float (&o)[32]) {
+  const uint32_t rowaddr = base + (uint32_t)rloc * 64u;
+  const uint32_t sw = (uint32_t)(rloc >> 1) & 3u;
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    st_shared_v4(rowaddr + (((uint32_t)c ^ sw) << 4), pack_bf16x2(o[8 * c], o[8 * c + 1]),
+                 pack_bf16x2(o[8 * c + 2], o[8 * c + 3]), pack_bf16x2(o[8 * c + 4], o[8 * c + 5]),
+                 pack_bf16x2(o[8 * c + 6], o[8 * c + 7]));
+}
+__device__ __forceinline__ void stage_f32_slice(uint32_t base, int rloc, const float (&o)[32]) {
+  const uint32_t rowaddr = base + (uint32_t)rloc * 128u;
+  const uint32_t sw = (uint32_t)rloc & 7u;
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    st_shared_v4(rowaddr + (((uint32_t)c ^ sw) << 4), __float_as_uint(o[4 * c]), __float_as_uint(o[4 * c + 1]),
+                 __float_as_uint(o[4 * c + 2]), __float_as_uint(o[4 * c + 3]));
+}
+
+template <bool kPersistent>
+__device__ __forceinline__ void tap_epilogue_tma(const TapGemmParams& p, const TapStoreMaps& maps, uint32_t trow,
+                                                 const float* sbias, int n0, int b, int t0, int rloc, bool row_valid,
+                                                 bool tile_valid, uint32_t stg, uint32_t stg_bytes, int etid) {
+  const bool glu = p.epi == MEGB200_EPI_GLU;
+  const bool gelu = p.epi == MEGB200_EPI_GELU;
+  const bool f32 = p.epi == MEGB200_EPI_STORE_F32;
+  const int half = p.NT / 2;
+  const int Ch = p.N / 2;
+  const uint32_t slice_bytes = f32 ? 16384u : 8192u;
+  const int cap = (int)(stg_bytes / slice_bytes);
+  const int per_group = glu ? 3 : (gelu ? 2 : 1);
+  const int groups = (glu ? half : p.NT) / 32;
+  const long long row = (long long)b * p.T + t0 + rloc;
+  const __nv_bfloat16* rrow = (p.Res != nullptr && row_valid && tile_valid) ? p.Res + row * p.Crs + n0 : nullptr;
+  uint4 rnext[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) rnext[c] = make_uint4(0u, 0u, 0u, 0u);
+  if (rrow != nullptr) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (n0 + 8 * c < p.Crs) rnext[c] = *reinterpret_cast<const uint4*>(rrow + 8 * c);
+  }
+  if (kPersistent) {
+    // the staging area is reused every tile: the previous tile's stores must have finished reading it
+    if (etid == 0) tma_store_wait_read();
+    named_bar_sync(2, 128);
+  }
+  int slot = 0;
+  for (int j = 0; j < groups; ++j) {
+    if (slot + per_group > cap) {
+      if (etid == 0) tma_store_wait_read();
+      named_bar_sync(2, 128);
+      slot = 0;
+    }
+    float o[32];
+    tmem_ld32(trow + (uint32_t)(32 * j), o);
+    const int c_first = n0 + 32 * j;                       // first logical output channel of this group
+    if (glu) {
+      float g[32];
+      tmem_ld32(trow + (uint32_t)(half + 32 * j), g);
+      float r[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const bool in = (c_first + i) < Ch;
+        o[i] = in ? o[i] + sbias[32 * j + i] : 0.f;
+        g[i] = in ? g[i] + sbias[half + 32 * j + i] : 0.f;
+        r[i] = in ? o[i] * sigmoid_f(g[i]) : 0.f;
+      }
+      stage_bf16_slice(stg + (uint32_t)slot * slice_bytes, rloc, o);
+      stage_bf16_slice(stg + (uint32_t)(slot + 1) * slice_bytes, rloc, g);
+      stage_bf16_slice(stg + (uint32_t)(slot + 2) * slice_bytes, rloc, r);
+    } else {
+      uint4 rc[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) rc[c] = rnext[c];
+      if (rrow != nullptr && j + 1 < groups) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          rnext[c] = (n0 + 32 * (j + 1) + 8 * c < p.Crs) ? *reinterpret_cast<const uint4*>(rrow + 32 * (j + 1) + 8 * c)
+                                                          : make_uint4(0u, 0u, 0u, 0u);
+      }
+      const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(rc);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float2 rf = __bfloat1622float2(rh[i]);
+        o[2 * i] = (c_first + 2 * i < p.N) ? o[2 * i] + sbias[32 * j + 2 * i] + rf.x : 0.f;
+        o[2 * i + 1] = (c_first + 2 * i + 1 < p.N) ? o[2 * i + 1] + sbias[32 * j + 2 * i + 1] + rf.y : 0.f;
+      }
+      if (f32) {
+        stage_f32_slice(stg + (uint32_t)slot * slice_bytes, rloc, o);
+      } else if (gelu) {
+        stage_bf16_slice(stg + (uint32_t)slot * slice_bytes, rloc, o);           // pre-activation P
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = (c_first + i < p.N) ? gelu_t<__nv_bfloat16>(o[i]) : 0.f;
+        stage_bf16_slice(stg + (uint32_t)(slot + 1) * slice_bytes, rloc, o);     // Q = gelu(P)
+      } else {
+        stage_bf16_slice(stg + (uint32_t)slot * slice_bytes, rloc, o);
+      }
+    }
+    fence_proxy_async();
+    named_bar_sync(2, 128);
+    if (etid == 0 && tile_valid) {
+      if (glu) {
+        tma_store_3d(&maps.out2, stg + (uint32_t)slot * slice_bytes, c_first, t0, b);
+        tma_store_3d(&maps.out2, stg + (uint32_t)(slot + 1) * slice_bytes, Ch + c_first, t0, b);
+        tma_store_3d(&maps.out, stg + (uint32_t)(slot + 2) * slice_bytes, c_first, t0, b);
+      } else if (gelu) {
+        tma_store_3d(&maps.out2, stg + (uint32_t)slot * slice_bytes, c_first, t0, b);
+        tma_store_3d(&maps.out, stg + (uint32_t)(slot + 1) * slice_bytes, c_first, t0, b);
+      } else {
+        tma_store_3d(&maps.out, stg + (uint32_t)slot * slice_bytes, c_first, t0, b);
+      }
+      tma_store_commit();
+    }
+    slot += per_group;
+  }
+  if (!kPersistent && etid == 0) tma_store_wait_read();   // shared memory must stay alive until the stores have read it
+}
+
 __global__ void __launch_bounds__(kThreads)
 tc_tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                  const TapGemmParams p) {
+                  const __grid_constant__ TapStoreMaps maps, const TapGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   Header* hdr = reinterpret_cast<Header*>(smem);
@@ -215,7 +347,13 @@ tc_tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int q = warp & 3;
     const int t = t0 + q * 32 + lane;
     const long long row = (long long)b * p.T + t;
-    tap_epilogue(p, tmem_base + ((uint32_t)(q * 32) << 16), sbias, n0, row, t < p.T);
+    if (p.tma_epi) {
+      // every MMA has completed, so the whole stage ring is free: it becomes the staging area of the stores
+      tap_epilogue_tma<false>(p, maps, tmem_base + ((uint32_t)(q * 32) << 16), sbias, n0, b, t0, q * 32 + lane,
+                              t < p.T, true, smem_u32(ring), (uint32_t)p.stages * stage_bytes, et);
+    } else {
+      tap_epilogue(p, tmem_base + ((uint32_t)(q * 32) << 16), sbias, n0, row, t < p.T);
+    }
     tc_fence_before();
   }
   __syncthreads();
@@ -241,7 +379,8 @@ struct Header2 {
 
 __global__ void __launch_bounds__(kThreads, 1)
 tc_tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                   const TapGemmParams p, const int total_m_tiles, const int num_items) {
+                   const __grid_constant__ TapStoreMaps maps, const TapGemmParams p, const int total_m_tiles,
+                   const int num_items) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   Header2* hdr = reinterpret_cast<Header2*>(smem);
@@ -252,7 +391,8 @@ tc_tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const uint32_t a_bytes = kTileM * 128, b_bytes = (uint32_t)half * 128;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   uint8_t* ring = smem + kHeaderBytes;
-  float* sbias = reinterpret_cast<float*>(ring + (size_t)p.stages * stage_bytes);   // [2][NT]: one table per acc stage
+  uint8_t* stg = ring + (size_t)p.stages * stage_bytes;                              // TMA-store staging (1024-aligned)
+  float* sbias = reinterpret_cast<float*>(stg + p.stg_bytes);                        // [2][NT]: one table per acc stage
   const bool glu = p.epi == MEGB200_EPI_GLU;
   const int Ch = p.N / 2;
   const int num_k = p.taps * p.kchunks;
@@ -358,13 +498,19 @@ tc_tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       tc_fence_after();
       const int t = t0 + q * 32 + lane;
       const long long row = (long long)b * p.T + t;
-      tap_epilogue(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.NT), sb, n0, row,
-                   m_tile < total_m_tiles && t < p.T);
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.NT);
+      if (p.tma_epi) {
+        tap_epilogue_tma<true>(p, maps, trow, sb, n0, b, t0, q * 32 + lane, t < p.T, m_tile < total_m_tiles,
+                               smem_u32(stg), p.stg_bytes, et);
+      } else {
+        tap_epilogue(p, trow, sb, n0, row, m_tile < total_m_tiles && t < p.T);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(smem_u32(&hdr->tmem_empty[acc]), 0);
     }
   }
+  if (p.tma_epi && threadIdx.x == 64) tma_store_wait_read();
   tc_fence_before();
   cluster_sync_all();                              // nobody leaves while the peer may still touch its smem / TMEM
   if (warp == 1) {
@@ -782,17 +928,28 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
   MEGB_CHECK_ARG(Kp % 64 == 0 && Np % 16 == 0 && Np >= N, "tc_tapgemm: Kp %% 64 and Np %% 16 required (Kp=%d Np=%d)", Kp, Np);
   const bool glu = epi == MEGB200_EPI_GLU;
   TapGemmParams p;
+  static const bool skip_io = getenv("MEGB200_DEBUG_EPI_SKIP_IO") != nullptr;
+  p.debug_skip_io = skip_io ? 1 : 0;
   p.T = T; p.N = N; p.Cos = Cos; p.Crs = Crs; p.Co2s = Co2s; p.taps = taps; p.dil = dil; p.Kp = Kp; p.epi = epi;
   p.kchunks = (Ca + kBlockK - 1) / kBlockK;
   p.tiles_per_sample = (T + kTileM - 1) / kTileM;
+  static const bool direct_epi = getenv("MEGB200_TAPGEMM_DIRECT_EPI") != nullptr;
+  p.tma_epi = direct_epi ? 0 : 1;
+  p.stg_bytes = 0;
   if (glu) {
     const int Ch = N / 2;
     MEGB_CHECK_ARG(N % 16 == 0 && Res == nullptr && Out2 != nullptr && Co2s % 8 == 0 && Co2s >= N,
                    "tc_tapgemm: the GLU epilogue needs N %% 16 == 0, no residual and a V output (N=%d)", N);
     // tile = [half a-channels | half gate channels], half a multiple of 16 dividing Ch if possible
     int half = 0;
-    for (int h = 128; h >= 16; h -= 16)
-      if (Ch % h == 0 && 2 * h <= 160) { half = h; break; }
+    if (p.tma_epi) {                       // TMA-store epilogue works on 32-channel slices
+      for (int h = 64; h >= 32; h -= 32)
+        if (Ch % h == 0) { half = h; break; }
+      if (half == 0) p.tma_epi = 0;
+    }
+    if (half == 0)
+      for (int h = 128; h >= 16; h -= 16)
+        if (Ch % h == 0 && 2 * h <= 160) { half = h; break; }
     if (half == 0) half = Ch >= 80 ? 80 : (Ch + 15) / 16 * 16;
     p.NT = 2 * half;
     const int cover = Cos > Ch ? Cos : Ch;
@@ -804,6 +961,26 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
     // output channels up to Cos must be covered so that pad channels are written as zero
     const int ncover = Cos > Np ? Cos : Np;
     p.ntiles = (ncover + p.NT - 1) / p.NT;
+    if (p.NT % 32 != 0) p.tma_epi = 0;
+  }
+  TapStoreMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  if (p.tma_epi) {
+    const int eb = epi == MEGB200_EPI_STORE_F32 ? 4 : 2;
+    {
+      const uint64_t dims[3] = {(uint64_t)Cos, (uint64_t)T, (uint64_t)B};
+      const uint64_t strides[2] = {(uint64_t)Cos * eb, (uint64_t)T * Cos * eb};
+      const uint32_t box[3] = {32, kTileM, 1};
+      int rc = encode_tmap(&maps.out, Out, eb, eb == 4 ? 128 : 64, 3, dims, strides, box);
+      if (rc) return rc;
+    }
+    if (Out2 != nullptr) {
+      const uint64_t dims[3] = {(uint64_t)Co2s, (uint64_t)T, (uint64_t)B};
+      const uint64_t strides[2] = {(uint64_t)Co2s * 2, (uint64_t)T * Co2s * 2};
+      const uint32_t box[3] = {32, kTileM, 1};
+      int rc = encode_tmap(&maps.out2, Out2, 2, 64, 3, dims, strides, box);
+      if (rc) return rc;
+    }
   }
   p.bias = bias; p.Res = (const __nv_bfloat16*)Res; p.group = group; p.Out = Out; p.Out2 = (__nv_bfloat16*)Out2;
 
@@ -817,7 +994,13 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
     // ---- CTA-pair persistent kernel
     const int half = p.NT / 2;
     const uint32_t stage2 = kTileM * 128 + half * 128;
-    p.stages = pick_stages(stage2, 200 * 1024 - 2 * p.NT * 4, 8);
+    if (p.tma_epi) {
+      const uint32_t slice = epi == MEGB200_EPI_STORE_F32 ? 16384u : 8192u;
+      const int per_group = glu ? 3 : (epi == MEGB200_EPI_GELU ? 2 : 1);
+      const uint32_t want = (uint32_t)((glu ? half : p.NT) / 32) * per_group * slice;
+      p.stg_bytes = want > 80u * 1024 ? 80u * 1024 : want;
+    }
+    p.stages = pick_stages(stage2, 200 * 1024 - 2 * p.NT * 4 - p.stg_bytes, 8);
     p.tmem_cols = tmem_cols_for(2 * p.NT);
     p.idesc = make_idesc_m(256, p.NT, 0, 0);
     CUtensorMap tmA2, tmW2;
@@ -835,7 +1018,7 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
       int rc = encode_tmap_bf16(&tmW2, W, 3, dims, strides, box);
       if (rc) return rc;
     }
-    const size_t smem2 = 1024 + kHeaderBytes + (size_t)p.stages * stage2 + 2 * p.NT * 4;
+    const size_t smem2 = 1024 + kHeaderBytes + (size_t)p.stages * stage2 + p.stg_bytes + 2 * p.NT * 4;
     int rc = set_smem(tc_tapgemm2_kernel, smem2);
     if (rc) return rc;
     const int m_pairs = (int)((m_tiles_total + 1) / 2);
@@ -854,7 +1037,7 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    MEGB_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_tapgemm2_kernel, tmA2, tmW2, p, (int)m_tiles_total, num_items));
+    MEGB_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_tapgemm2_kernel, tmA2, tmW2, maps, p, (int)m_tiles_total, num_items));
     MEGB_LAUNCH_OK();
     return 0;
   }
@@ -886,7 +1069,7 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
   if (rc) return rc;
   const long long blocks = (long long)B * p.tiles_per_sample * p.ntiles;
   MEGB_CHECK_ARG(blocks > 0 && blocks < 2147483647ll, "tc_tapgemm: grid too large");
-  tc_tapgemm_kernel<<<(unsigned)blocks, kThreads, smem, st>>>(tmA, tmW, p);
+  tc_tapgemm_kernel<<<(unsigned)blocks, kThreads, smem, st>>>(tmA, tmW, maps, p);
   MEGB_LAUNCH_OK();
   return 0;
 }
