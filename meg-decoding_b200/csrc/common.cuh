@@ -95,7 +95,14 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
   return cdf + x * pdf;
 }
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// MUFU.RCP (1 ulp-ish): the IEEE reciprocal / division expands to ~10 instructions plus a slow path, which makes the
+// streaming passes ALU-bound instead of HBM-bound
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return fast_rcp(1.0f + __expf(-x)); }
 
 // Fast erf-GELU for the bf16 path (Abramowitz-Stegun 7.1.26, |erf error| <= 1.5e-7: two orders below bf16 rounding):
 // one MUFU.RCP + one MUFU.EX2 + 7 FMA instead of erff + expf; exp(-x^2/2) is shared between erf and the pdf.
@@ -104,7 +111,7 @@ struct GeluParts {
 };
 __device__ __forceinline__ GeluParts gelu_parts_fast(float x) {
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float t = fast_rcp(fmaf(0.3275911f, z, 1.0f));
   const float e = __expf(-z * z);
   float p = fmaf(t, 1.061405429f, -1.453152027f);
   p = fmaf(t, p, 1.421413741f);

@@ -984,10 +984,11 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
   }
   p.bias = bias; p.Res = (const __nv_bfloat16*)Res; p.group = group; p.Out = Out; p.Out2 = (__nv_bfloat16*)Out2;
 
-  // MEGB200_TAPGEMM_1CTA forces the single-CTA kernel; MEGB200_TAPGEMM_2CTA_MIN_ITEMS lowers the work threshold of the
-  // CTA-pair kernel (tests use it to exercise the pair kernel on small shapes)
-  static const bool force_1cta = getenv("MEGB200_TAPGEMM_1CTA") != nullptr;
+  // Kernel choice.  Measured at config 2 (profiles/): the single-CTA kernel with two co-resident CTAs per SM is currently
+  // the faster one (548 vs 498 TFLOP/s), so the CTA-pair kernel is opt-in: MEGB200_TAPGEMM_PAIR=1 enables it for large
+  // problems, MEGB200_TAPGEMM_2CTA_MIN_ITEMS=<n> additionally lowers its work threshold (the tests exercise it so).
   static const char* min_items_env = getenv("MEGB200_TAPGEMM_2CTA_MIN_ITEMS");
+  static const bool force_1cta = getenv("MEGB200_TAPGEMM_PAIR") == nullptr && min_items_env == nullptr;
   const long long min_items = min_items_env ? atoll(min_items_env) : 2ll * num_sms();
   const long long m_tiles_total = (long long)B * p.tiles_per_sample;
   if (group == nullptr && G == 1 && !force_1cta && p.NT % 32 == 0 && m_tiles_total * p.ntiles >= min_items) {

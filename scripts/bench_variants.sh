@@ -8,7 +8,7 @@ d = json.loads(sys.stdin.read().strip().splitlines()[-1])
 r = d['roofline']
 print('VARIANT $tag ms/step=%.3f tapgemm=%.1f TF/s (%.3f ms/launch) wgrad=%.1f TF/s' % (d['ms_per_step'], r['achieved'], r['avg_launch_ms'], r['wgrad']['achieved']))"
 }
-run pair_tma      A=1
-run pair_direct   MEGB200_TAPGEMM_DIRECT_EPI=1
-run 1cta_tma      MEGB200_TAPGEMM_1CTA=1
-run 1cta_direct   MEGB200_TAPGEMM_1CTA=1 MEGB200_TAPGEMM_DIRECT_EPI=1
+run 1cta_tma      A=1
+run 1cta_direct   MEGB200_TAPGEMM_DIRECT_EPI=1
+run pair_tma      MEGB200_TAPGEMM_PAIR=1
+run pair_direct   MEGB200_TAPGEMM_PAIR=1 MEGB200_TAPGEMM_DIRECT_EPI=1
