@@ -145,102 +145,120 @@ __device__ __forceinline__ void stage_f32_slice(uint32_t base, int rloc, const f
                  __float_as_uint(o[4 * c + 2]), __float_as_uint(o[4 * c + 3]));
 }
 
-template <bool kPersistent>
+// kHalves = number of epilogue warps per TMEM lane quarter (1: 4 warps / 128 threads, 2: 8 warps / 256 threads).
+// With two halves the 32-channel groups of a tile are dealt alternately to the two warps that share a lane quarter
+// (`h` = 0 / 1), which halves the per-tile epilogue time: measured, four warps per SM cannot keep up with the MMA
+// stream (their element-wise math, not memory, is the limit).
+template <bool kPersistent, int kHalves>
 __device__ __forceinline__ void tap_epilogue_tma(const TapGemmParams& p, const TapStoreMaps& maps, uint32_t trow,
                                                  const float* sbias, int n0, int b, int t0, int rloc, bool row_valid,
-                                                 bool tile_valid, uint32_t stg, uint32_t stg_bytes, int etid) {
+                                                 bool tile_valid, uint32_t stg, uint32_t stg_bytes, int etid, int h) {
+  constexpr int kEpiThreads = 128 * kHalves;
   const bool glu = p.epi == MEGB200_EPI_GLU;
   const bool gelu = p.epi == MEGB200_EPI_GELU;
   const bool f32 = p.epi == MEGB200_EPI_STORE_F32;
   const int half = p.NT / 2;
   const int Ch = p.N / 2;
   const uint32_t slice_bytes = f32 ? 16384u : 8192u;
-  const int cap = (int)(stg_bytes / slice_bytes);
   const int per_group = glu ? 3 : (gelu ? 2 : 1);
   const int groups = (glu ? half : p.NT) / 32;
+  const int iters = (groups + kHalves - 1) / kHalves;
+  int cap_iters = (int)(stg_bytes / slice_bytes) / (per_group * kHalves);   // iterations whose slices fit at once
+  if (cap_iters < 1) cap_iters = 1;
   const long long row = (long long)b * p.T + t0 + rloc;
   const __nv_bfloat16* rrow = (p.Res != nullptr && row_valid && tile_valid) ? p.Res + row * p.Crs + n0 : nullptr;
   uint4 rnext[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) rnext[c] = make_uint4(0u, 0u, 0u, 0u);
-  if (rrow != nullptr) {
+  if (rrow != nullptr && h < groups) {
 #pragma unroll
     for (int c = 0; c < 4; ++c)
-      if (n0 + 8 * c < p.Crs) rnext[c] = *reinterpret_cast<const uint4*>(rrow + 8 * c);
+      if (n0 + 32 * h + 8 * c < p.Crs) rnext[c] = *reinterpret_cast<const uint4*>(rrow + 32 * h + 8 * c);
   }
   if (kPersistent) {
     // the staging area is reused every tile: the previous tile's stores must have finished reading it
     if (etid == 0) tma_store_wait_read();
-    named_bar_sync(2, 128);
+    named_bar_sync(2, kEpiThreads);
   }
-  int slot = 0;
-  for (int j = 0; j < groups; ++j) {
-    if (slot + per_group > cap) {
+  for (int jj = 0; jj < iters; ++jj) {
+    if (jj > 0 && jj % cap_iters == 0) {
       if (etid == 0) tma_store_wait_read();
-      named_bar_sync(2, 128);
-      slot = 0;
+      named_bar_sync(2, kEpiThreads);
     }
-    float o[32];
-    tmem_ld32(trow + (uint32_t)(32 * j), o);
-    const int c_first = n0 + 32 * j;                       // first logical output channel of this group
-    if (glu) {
-      float g[32];
-      tmem_ld32(trow + (uint32_t)(half + 32 * j), g);
-      float r[32];
+    const int j = jj * kHalves + h;
+    const uint32_t sbase = stg + (uint32_t)(((jj % cap_iters) * kHalves + h) * per_group) * slice_bytes;
+    if (j < groups) {
+      float o[32];
+      tmem_ld32(trow + (uint32_t)(32 * j), o);
+      const int c_first = n0 + 32 * j;                       // first logical output channel of this group
+      if (glu) {
+        float g[32];
+        tmem_ld32(trow + (uint32_t)(half + 32 * j), g);
+        const bool full = c_first + 32 <= Ch;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const bool in = (c_first + i) < Ch;
-        o[i] = in ? o[i] + sbias[32 * j + i] : 0.f;
-        g[i] = in ? g[i] + sbias[half + 32 * j + i] : 0.f;
-        r[i] = in ? o[i] * sigmoid_f(g[i]) : 0.f;
-      }
-      stage_bf16_slice(stg + (uint32_t)slot * slice_bytes, rloc, o);
-      stage_bf16_slice(stg + (uint32_t)(slot + 1) * slice_bytes, rloc, g);
-      stage_bf16_slice(stg + (uint32_t)(slot + 2) * slice_bytes, rloc, r);
-    } else {
-      uint4 rc[4];
+        for (int i = 0; i < 32; ++i) {
+          const bool in = full || (c_first + i) < Ch;
+          o[i] = in ? o[i] + sbias[32 * j + i] : 0.f;
+          g[i] = in ? g[i] + sbias[half + 32 * j + i] : 0.f;
+        }
+        stage_bf16_slice(sbase, rloc, o);
+        stage_bf16_slice(sbase + slice_bytes, rloc, g);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) rc[c] = rnext[c];
-      if (rrow != nullptr && j + 1 < groups) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          rnext[c] = (n0 + 32 * (j + 1) + 8 * c < p.Crs) ? *reinterpret_cast<const uint4*>(rrow + 32 * (j + 1) + 8 * c)
-                                                          : make_uint4(0u, 0u, 0u, 0u);
-      }
-      const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(rc);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float2 rf = __bfloat1622float2(rh[i]);
-        o[2 * i] = (c_first + 2 * i < p.N) ? o[2 * i] + sbias[32 * j + 2 * i] + rf.x : 0.f;
-        o[2 * i + 1] = (c_first + 2 * i + 1 < p.N) ? o[2 * i + 1] + sbias[32 * j + 2 * i + 1] + rf.y : 0.f;
-      }
-      if (f32) {
-        stage_f32_slice(stg + (uint32_t)slot * slice_bytes, rloc, o);
-      } else if (gelu) {
-        stage_bf16_slice(stg + (uint32_t)slot * slice_bytes, rloc, o);           // pre-activation P
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = (c_first + i < p.N) ? gelu_t<__nv_bfloat16>(o[i]) : 0.f;
-        stage_bf16_slice(stg + (uint32_t)(slot + 1) * slice_bytes, rloc, o);     // Q = gelu(P)
+        for (int i = 0; i < 32; ++i) o[i] = o[i] * sigmoid_f(g[i]);      // out-of-range channels: 0 * 0.5 = 0
+        stage_bf16_slice(sbase + 2 * slice_bytes, rloc, o);
       } else {
-        stage_bf16_slice(stg + (uint32_t)slot * slice_bytes, rloc, o);
+        uint4 rc[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) rc[c] = rnext[c];
+        if (rrow != nullptr && j + kHalves < groups) {
+          const int jn = j + kHalves;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            rnext[c] = (n0 + 32 * jn + 8 * c < p.Crs) ? *reinterpret_cast<const uint4*>(rrow + 32 * jn + 8 * c)
+                                                       : make_uint4(0u, 0u, 0u, 0u);
+        }
+        const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(rc);
+        const bool full = c_first + 32 <= p.N;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float2 rf = __bfloat1622float2(rh[i]);
+          o[2 * i] = (full || c_first + 2 * i < p.N) ? o[2 * i] + sbias[32 * j + 2 * i] + rf.x : 0.f;
+          o[2 * i + 1] = (full || c_first + 2 * i + 1 < p.N) ? o[2 * i + 1] + sbias[32 * j + 2 * i + 1] + rf.y : 0.f;
+        }
+        if (f32) {
+          stage_f32_slice(sbase, rloc, o);
+        } else if (gelu) {
+          stage_bf16_slice(sbase, rloc, o);                                   // pre-activation P
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = (full || c_first + i < p.N) ? gelu_t<__nv_bfloat16>(o[i]) : 0.f;
+          stage_bf16_slice(sbase + slice_bytes, rloc, o);                     // Q = gelu(P)
+        } else {
+          stage_bf16_slice(sbase, rloc, o);
+        }
       }
     }
     fence_proxy_async();
-    named_bar_sync(2, 128);
+    named_bar_sync(2, kEpiThreads);
     if (etid == 0 && tile_valid) {
-      if (glu) {
-        tma_store_3d(&maps.out2, stg + (uint32_t)slot * slice_bytes, c_first, t0, b);
-        tma_store_3d(&maps.out2, stg + (uint32_t)(slot + 1) * slice_bytes, Ch + c_first, t0, b);
-        tma_store_3d(&maps.out, stg + (uint32_t)(slot + 2) * slice_bytes, c_first, t0, b);
-      } else if (gelu) {
-        tma_store_3d(&maps.out2, stg + (uint32_t)slot * slice_bytes, c_first, t0, b);
-        tma_store_3d(&maps.out, stg + (uint32_t)(slot + 1) * slice_bytes, c_first, t0, b);
-      } else {
-        tma_store_3d(&maps.out, stg + (uint32_t)slot * slice_bytes, c_first, t0, b);
+#pragma unroll
+      for (int hh = 0; hh < kHalves; ++hh) {
+        const int jh = jj * kHalves + hh;
+        if (jh >= groups) break;
+        const int cf = n0 + 32 * jh;
+        const uint32_t sb2 = stg + (uint32_t)(((jj % cap_iters) * kHalves + hh) * per_group) * slice_bytes;
+        if (glu) {
+          tma_store_3d(&maps.out2, sb2, cf, t0, b);
+          tma_store_3d(&maps.out2, sb2 + slice_bytes, Ch + cf, t0, b);
+          tma_store_3d(&maps.out, sb2 + 2 * slice_bytes, cf, t0, b);
+        } else if (gelu) {
+          tma_store_3d(&maps.out2, sb2, cf, t0, b);
+          tma_store_3d(&maps.out, sb2 + slice_bytes, cf, t0, b);
+        } else {
+          tma_store_3d(&maps.out, sb2, cf, t0, b);
+        }
       }
       tma_store_commit();
     }
-    slot += per_group;
   }
   if (!kPersistent && etid == 0) tma_store_wait_read();   // shared memory must stay alive until the stores have read it
 }
@@ -349,8 +367,158 @@ tc_tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const long long row = (long long)b * p.T + t;
     if (p.tma_epi) {
       // every MMA has completed, so the whole stage ring is free: it becomes the staging area of the stores
-      tap_epilogue_tma<false>(p, maps, tmem_base + ((uint32_t)(q * 32) << 16), sbias, n0, b, t0, q * 32 + lane,
-                              t < p.T, true, smem_u32(ring), (uint32_t)p.stages * stage_bytes, et);
+      tap_epilogue_tma<false, 1>(p, maps, tmem_base + ((uint32_t)(q * 32) << 16), sbias, n0, b, t0, q * 32 + lane,
+                                 t < p.T, true, smem_u32(ring), (uint32_t)p.stages * stage_bytes, et, 0);
+    } else {
+      tap_epilogue(p, tmem_base + ((uint32_t)(q * 32) << 16), sbias, n0, row, t < p.T);
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ================================================================================================ tap GEMM, halo form
+// k > 1 convolutions read every activation row `taps` times.  Here the activation tile is staged ONCE per 64-channel
+// chunk with its halo (128 + (taps-1)*dil rows) and each tap's MMA reads it through a shared-memory descriptor whose
+// start address is shifted by tap*dil rows (128 bytes each): the swizzle XOR acts on absolute shared-memory address
+// bits, so a row-shifted window of a SWIZZLE_128B tile is still a valid K-major operand.  Activation traffic from L2
+// drops by `taps`x (the kernel is L2->SM bandwidth bound: 909 MB per 320->320 conv launch at config 2).
+struct HeaderH {
+  uint64_t fullA[4];
+  uint64_t emptyA[4];
+  uint64_t fullB[8];
+  uint64_t emptyB[8];
+  uint64_t tmem_full;
+  uint32_t tmem_slot;
+  uint32_t pad;
+};
+
+__global__ void __launch_bounds__(kThreads)
+tc_tapgemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                       const __grid_constant__ TapStoreMaps maps, const TapGemmParams p, const int a_rows,
+                       const int stagesA, const int use_base_offset) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  HeaderH* hdr = reinterpret_cast<HeaderH*>(smem);
+  float* sbias = reinterpret_cast<float*>(smem + 512);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t a_slot = ((uint32_t)a_rows * 128u + 1023u) & ~1023u;
+  const uint32_t b_bytes = (uint32_t)p.NT * 128;
+  uint8_t* ringA = smem + kHeaderBytes;
+  uint8_t* ringB = ringA + (size_t)stagesA * a_slot;
+  const uint32_t ring_bytes = (uint32_t)stagesA * a_slot + (uint32_t)p.stages * b_bytes;
+  float* sbias_big = reinterpret_cast<float*>(ringA + ring_bytes);
+  if (p.NT > 128) sbias = sbias_big;
+
+  const bool glu = p.epi == MEGB200_EPI_GLU;
+  const int half = p.NT / 2;
+  const int Ch = p.N / 2;
+  const int n_tile = blockIdx.x % p.ntiles;
+  const int m_tile = blockIdx.x / p.ntiles;
+  const int b = m_tile / p.tiles_per_sample;
+  const int t0 = (m_tile % p.tiles_per_sample) * kTileM;
+  const int n0 = n_tile * (glu ? half : p.NT);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+    for (int s = 0; s < stagesA; ++s) {
+      mbar_init(smem_u32(&hdr->fullA[s]), 1);
+      mbar_init(smem_u32(&hdr->emptyA[s]), 1);
+    }
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&hdr->fullB[s]), 1);
+      mbar_init(smem_u32(&hdr->emptyB[s]), 1);
+    }
+    mbar_init(smem_u32(&hdr->tmem_full), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&hdr->tmem_slot), p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = hdr->tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int itb = 0;
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        const int sa = kc % stagesA;
+        mbar_wait(smem_u32(&hdr->emptyA[sa]), ((kc / stagesA) & 1) ^ 1);
+        const uint32_t fa = smem_u32(&hdr->fullA[sa]);
+        mbar_arrive_expect_tx(fa, (uint32_t)a_rows * 128u);
+        tma_load_3d(smem_u32(ringA + (size_t)sa * a_slot), &tmA, kc * kBlockK, t0 - (p.taps / 2) * p.dil, b, fa);
+        for (int tap = 0; tap < p.taps; ++tap, ++itb) {
+          const int sb = itb % p.stages;
+          mbar_wait(smem_u32(&hdr->emptyB[sb]), ((itb / p.stages) & 1) ^ 1);
+          const uint32_t fb = smem_u32(&hdr->fullB[sb]);
+          mbar_arrive_expect_tx(fb, b_bytes);
+          const uint32_t dstb = smem_u32(ringB + (size_t)sb * b_bytes);
+          const int kw = tap * p.Kp + kc * kBlockK;
+          if (glu) {
+            tma_load_3d(dstb, &tmW, kw, n0, 0, fb);
+            tma_load_3d(dstb + (uint32_t)half * 128, &tmW, kw, Ch + n0, 0, fb);
+          } else {
+            tma_load_3d(dstb, &tmW, kw, n0, 0, fb);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int itb = 0;
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        const int sa = kc % stagesA;
+        mbar_wait(smem_u32(&hdr->fullA[sa]), (kc / stagesA) & 1);
+        const uint32_t abase = smem_u32(ringA + (size_t)sa * a_slot);
+        for (int tap = 0; tap < p.taps; ++tap, ++itb) {
+          const int sb = itb % p.stages;
+          mbar_wait(smem_u32(&hdr->fullB[sb]), (itb / p.stages) & 1);
+          tc_fence_after();
+          const uint32_t aaddr = abase + (uint32_t)(tap * p.dil) * 128u;      // window shifted by tap*dil rows
+          uint64_t da = make_smem_desc(aaddr, 16, 1024);
+          if (use_base_offset) da |= (uint64_t)((aaddr >> 7) & 7u) << 49;
+          const uint64_t db = make_smem_desc(smem_u32(ringB + (size_t)sb * b_bytes), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)
+            umma_bf16(tmem_base, desc_advance(da, k * 32), desc_advance(db, k * 32), p.idesc, (kc | tap | k) != 0);
+          umma_commit(smem_u32(&hdr->emptyB[sb]));
+        }
+        umma_commit(smem_u32(&hdr->emptyA[sa]));
+      }
+      umma_commit(smem_u32(&hdr->tmem_full));
+    }
+  } else {
+    const int et = threadIdx.x - 64;
+    for (int i = et; i < p.NT; i += 128) {
+      int n;
+      bool ok;
+      if (glu) {
+        const int c = n0 + (i < half ? i : i - half);
+        ok = c < Ch;
+        n = (i < half) ? c : Ch + c;
+      } else {
+        n = n0 + i;
+        ok = n < p.N;
+      }
+      sbias[i] = (p.bias != nullptr && ok) ? p.bias[n] : 0.f;
+    }
+    named_bar_sync(1, 128);
+    mbar_wait(smem_u32(&hdr->tmem_full), 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int t = t0 + q * 32 + lane;
+    const long long row = (long long)b * p.T + t;
+    if (p.tma_epi) {
+      tap_epilogue_tma<false, 1>(p, maps, tmem_base + ((uint32_t)(q * 32) << 16), sbias, n0, b, t0, q * 32 + lane,
+                                 t < p.T, true, smem_u32(ringA), ring_bytes, et, 0);
     } else {
       tap_epilogue(p, tmem_base + ((uint32_t)(q * 32) << 16), sbias, n0, row, t < p.T);
     }
@@ -377,7 +545,9 @@ struct Header2 {
   uint32_t pad;
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
+constexpr int kThreadsPair = 64 + 256;   // producer warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
+
+__global__ void __launch_bounds__(kThreadsPair, 1)
 tc_tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                    const __grid_constant__ TapStoreMaps maps, const TapGemmParams p, const int total_m_tiles,
                    const int num_items) {
@@ -407,7 +577,7 @@ tc_tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&hdr->tmem_full[a]), 1);
-      mbar_init(smem_u32(&hdr->tmem_empty[a]), 8);  // 4 epilogue warps x 2 CTAs (used on the leader only)
+      mbar_init(smem_u32(&hdr->tmem_empty[a]), 16);  // 8 epilogue warps x 2 CTAs (used on the leader only)
     }
     fence_barrier_init();
   }
@@ -468,9 +638,11 @@ tc_tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
     }
   } else {
-    // ---------------- epilogue (both CTAs): each CTA drains its own 128 rows of the 256-row accumulator
+    // ---------------- epilogue (both CTAs): each CTA drains its own 128 rows of the 256-row accumulator with eight
+    // warps: warp w covers TMEM lane quarter (w & 3); the two warps of a quarter alternate over the channel groups
     const int et = threadIdx.x - 64;
     const int q = warp & 3;
+    const int h = (warp - 2) >> 2;
     int tile = 0;
     for (int item = cluster_id; item < num_items; item += num_clusters, ++tile) {
       const int acc = tile & 1;
@@ -480,7 +652,7 @@ tc_tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int t0 = (m_tile % p.tiles_per_sample) * kTileM;
       const int n0 = n_tile * (glu ? half : p.NT);
       float* sb = sbias + acc * p.NT;
-      for (int i = et; i < p.NT; i += 128) {
+      for (int i = et; i < p.NT; i += 256) {
         int n;
         bool ok;
         if (glu) {
@@ -493,18 +665,13 @@ tc_tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
         sb[i] = (p.bias != nullptr && ok) ? p.bias[n] : 0.f;
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 256);
       mbar_wait(smem_u32(&hdr->tmem_full[acc]), (tile >> 1) & 1);
       tc_fence_after();
       const int t = t0 + q * 32 + lane;
-      const long long row = (long long)b * p.T + t;
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.NT);
-      if (p.tma_epi) {
-        tap_epilogue_tma<true>(p, maps, trow, sb, n0, b, t0, q * 32 + lane, t < p.T, m_tile < total_m_tiles,
-                               smem_u32(stg), p.stg_bytes, et);
-      } else {
-        tap_epilogue(p, trow, sb, n0, row, m_tile < total_m_tiles && t < p.T);
-      }
+      tap_epilogue_tma<true, 2>(p, maps, trow, sb, n0, b, t0, q * 32 + lane, t < p.T, m_tile < total_m_tiles,
+                                smem_u32(stg), p.stg_bytes, et, h);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(smem_u32(&hdr->tmem_empty[acc]), 0);
@@ -991,7 +1158,7 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
   static const bool force_1cta = getenv("MEGB200_TAPGEMM_PAIR") == nullptr && min_items_env == nullptr;
   const long long min_items = min_items_env ? atoll(min_items_env) : 2ll * num_sms();
   const long long m_tiles_total = (long long)B * p.tiles_per_sample;
-  if (group == nullptr && G == 1 && !force_1cta && p.NT % 32 == 0 && m_tiles_total * p.ntiles >= min_items) {
+  if (group == nullptr && G == 1 && !force_1cta && p.tma_epi && p.NT % 32 == 0 && m_tiles_total * p.ntiles >= min_items) {
     // ---- CTA-pair persistent kernel
     const int half = p.NT / 2;
     const uint32_t stage2 = kTileM * 128 + half * 128;
@@ -999,9 +1166,9 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
       const uint32_t slice = epi == MEGB200_EPI_STORE_F32 ? 16384u : 8192u;
       const int per_group = glu ? 3 : (epi == MEGB200_EPI_GELU ? 2 : 1);
       const uint32_t want = (uint32_t)((glu ? half : p.NT) / 32) * per_group * slice;
-      p.stg_bytes = want > 80u * 1024 ? 80u * 1024 : want;
+      p.stg_bytes = want > 64u * 1024 ? 64u * 1024 : want;
     }
-    p.stages = pick_stages(stage2, 200 * 1024 - 2 * p.NT * 4 - p.stg_bytes, 8);
+    p.stages = pick_stages(stage2, 229000 - 2048 - 2 * p.NT * 4 - p.stg_bytes, 8);
     p.tmem_cols = tmem_cols_for(2 * p.NT);
     p.idesc = make_idesc_m(256, p.NT, 0, 0);
     CUtensorMap tmA2, tmW2;
@@ -1028,7 +1195,7 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
     if (clusters > num_items) clusters = num_items;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * clusters);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(kThreadsPair);
     cfg.dynamicSmemBytes = smem2;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -1039,6 +1206,46 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     MEGB_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_tapgemm2_kernel, tmA2, tmW2, maps, p, (int)m_tiles_total, num_items));
+    MEGB_LAUNCH_OK();
+    return 0;
+  }
+
+  // ---- halo form for k > 1 convolutions (MEGB200_TAPGEMM_HALO=0 disables, =2 also sets the descriptor base offset)
+  static const char* halo_env = getenv("MEGB200_TAPGEMM_HALO");
+  const int halo_mode = halo_env ? atoi(halo_env) : 0;
+  const int a_rows = ((kTileM + (taps - 1) * dil) + 7) / 8 * 8;
+  if (halo_mode > 0 && taps > 1 && group == nullptr && G == 1 && a_rows <= 256) {
+    const uint32_t a_slot = ((uint32_t)a_rows * 128u + 1023u) & ~1023u;
+    const uint32_t b_bytes = (uint32_t)p.NT * 128;
+    const int stagesA = 2;
+    const uint32_t budget = 112000u - (p.NT > 128 ? p.NT * 4 : 0) - stagesA * a_slot;
+    p.stages = pick_stages(b_bytes, budget, 8);
+    MEGB_CHECK_ARG(p.stages >= 2, "tc_tapgemm(halo): tile too large");
+    p.tmem_cols = tmem_cols_for(p.NT);
+    p.idesc = make_idesc(p.NT, 0, 0);
+    CUtensorMap tmAh, tmWh;
+    {
+      const uint64_t dims[3] = {(uint64_t)Ca, (uint64_t)T, (uint64_t)B};
+      const uint64_t strides[2] = {(uint64_t)Cas * 2, (uint64_t)T * Cas * 2};
+      const uint32_t box[3] = {kBlockK, (uint32_t)a_rows, 1};
+      int rc = encode_tmap_bf16(&tmAh, A, 3, dims, strides, box);
+      if (rc) return rc;
+    }
+    {
+      const uint64_t dims[3] = {(uint64_t)taps * Kp, (uint64_t)Np, 1};
+      const uint64_t strides[2] = {(uint64_t)taps * Kp * 2, (uint64_t)Np * taps * Kp * 2};
+      const uint32_t box[3] = {kBlockK, (uint32_t)(glu ? p.NT / 2 : p.NT), 1};
+      int rc = encode_tmap_bf16(&tmWh, W, 3, dims, strides, box);
+      if (rc) return rc;
+    }
+    const size_t smemh = 1024 + kHeaderBytes + (size_t)stagesA * a_slot + (size_t)p.stages * b_bytes +
+                         (p.NT > 128 ? p.NT * 4 : 0);
+    int rc = set_smem(tc_tapgemm_halo_kernel, smemh);
+    if (rc) return rc;
+    const long long blocks = (long long)B * p.tiles_per_sample * p.ntiles;
+    MEGB_CHECK_ARG(blocks > 0 && blocks < 2147483647ll, "tc_tapgemm: grid too large");
+    tc_tapgemm_halo_kernel<<<(unsigned)blocks, kThreads, smemh, st>>>(tmAh, tmWh, maps, p, a_rows, stagesA,
+                                                                      halo_mode == 2 ? 1 : 0);
     MEGB_LAUNCH_OK();
     return 0;
   }
