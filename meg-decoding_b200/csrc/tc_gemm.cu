@@ -686,6 +686,171 @@ tc_tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
 }
 
+// CTA-pair + halo: the activation tile (with halo rows) is staged once per 64-channel chunk and shared by all taps
+// (see tc_tapgemm_halo_kernel), the weight half-tiles stream through their own ring.  L2->SM traffic per 256x160 tile of
+// a 320->320 k=3 conv: 780 KB (pair) -> 460 KB.
+struct Header2H {
+  uint64_t fullA[4];
+  uint64_t emptyA[4];
+  uint64_t fullB[8];
+  uint64_t emptyB[8];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_slot;
+  uint32_t pad;
+};
+
+__global__ void __launch_bounds__(kThreadsPair, 1)
+tc_tapgemm2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                    const __grid_constant__ TapStoreMaps maps, const TapGemmParams p, const int total_m_tiles,
+                    const int num_items, const int a_rows, const int stagesA) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  Header2H* hdr = reinterpret_cast<Header2H*>(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int half = p.NT / 2;                                  // weight rows staged by each CTA
+  const uint32_t a_slot = ((uint32_t)a_rows * 128u + 1023u) & ~1023u;              // activation rows incl. halo
+  const uint32_t b_bytes = (uint32_t)half * 128;
+  uint8_t* ringA = smem + kHeaderBytes;
+  uint8_t* ringB = ringA + (size_t)stagesA * a_slot;
+  uint8_t* stg = ringB + (size_t)p.stages * b_bytes;                                 // TMA-store staging (1024-aligned)
+  float* sbias = reinterpret_cast<float*>(stg + p.stg_bytes);                        // [2][NT]: one table per acc stage
+  const bool glu = p.epi == MEGB200_EPI_GLU;
+  const int Ch = p.N / 2;
+  const int num_k = p.taps * p.kchunks;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+    for (int s = 0; s < stagesA; ++s) {
+      mbar_init(smem_u32(&hdr->fullA[s]), 1);     // the leader's producer arrives once and expects both CTAs' bytes
+      mbar_init(smem_u32(&hdr->emptyA[s]), 1);    // one multicast tcgen05.commit per use
+    }
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&hdr->fullB[s]), 1);
+      mbar_init(smem_u32(&hdr->emptyB[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&hdr->tmem_full[a]), 1);
+      mbar_init(smem_u32(&hdr->tmem_empty[a]), 16);  // 8 epilogue warps x 2 CTAs (used on the leader only)
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2sm(smem_u32(&hdr->tmem_slot), p.tmem_cols);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  cluster_sync_all();                              // barriers of both CTAs initialised before any remote traffic
+  tc_fence_after();
+  const uint32_t tmem_base = hdr->tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int ita = 0, itb = 0;
+      for (int item = cluster_id; item < num_items; item += num_clusters) {
+        const int n_tile = item % p.ntiles;
+        const int m_tile = (item / p.ntiles) * 2 + (int)rank;
+        const int b = m_tile < total_m_tiles ? m_tile / p.tiles_per_sample : 0x3fffffff;
+        const int t0 = (m_tile % p.tiles_per_sample) * kTileM;
+        const int wrow = glu ? (n_tile * half + (rank ? Ch : 0)) : (n_tile * p.NT + (int)rank * half);
+        for (int kc = 0; kc < p.kchunks; ++kc, ++ita) {
+          const int sa = ita % stagesA;
+          mbar_wait(smem_u32(&hdr->emptyA[sa]), ((ita / stagesA) & 1) ^ 1);
+          const uint32_t fa = smem_u32(&hdr->fullA[sa]);
+          if (leader) mbar_arrive_expect_tx(fa, 2u * (uint32_t)a_rows * 128u);
+          tma_load_3d_2sm(smem_u32(ringA + (size_t)sa * a_slot), &tmA, kc * kBlockK, t0 - (p.taps / 2) * p.dil, b, fa);
+          for (int tap = 0; tap < p.taps; ++tap, ++itb) {
+            const int sb = itb % p.stages;
+            mbar_wait(smem_u32(&hdr->emptyB[sb]), ((itb / p.stages) & 1) ^ 1);
+            const uint32_t fb = smem_u32(&hdr->fullB[sb]);
+            if (leader) mbar_arrive_expect_tx(fb, 2 * b_bytes);
+            tma_load_3d_2sm(smem_u32(ringB + (size_t)sb * b_bytes), &tmW, tap * p.Kp + kc * kBlockK, wrow, 0, fb);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      int ita = 0, itb = 0, tile = 0;
+      for (int item = cluster_id; item < num_items; item += num_clusters, ++tile) {
+        const int acc = tile & 1;
+        mbar_wait(smem_u32(&hdr->tmem_empty[acc]), ((tile >> 1) & 1) ^ 1);   // epilogues of both CTAs drained it
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.NT);
+        for (int kc = 0; kc < p.kchunks; ++kc, ++ita) {
+          const int sa = ita % stagesA;
+          mbar_wait(smem_u32(&hdr->fullA[sa]), (ita / stagesA) & 1);
+          const uint32_t abase = smem_u32(ringA + (size_t)sa * a_slot);
+          for (int tap = 0; tap < p.taps; ++tap, ++itb) {
+            const int sb = itb % p.stages;
+            mbar_wait(smem_u32(&hdr->fullB[sb]), (itb / p.stages) & 1);
+            tc_fence_after();
+            // tap window = the staged rows shifted by tap*dil (absolute-address swizzle keeps it a valid operand)
+            const uint64_t da = make_smem_desc(abase + (uint32_t)(tap * p.dil) * 128u, 16, 1024);
+            const uint64_t db = make_smem_desc(smem_u32(ringB + (size_t)sb * b_bytes), 16, 1024);
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              umma_bf16_2sm(d_tmem, desc_advance(da, k * 32), desc_advance(db, k * 32), p.idesc, (kc | tap | k) != 0);
+            umma_commit_2sm(smem_u32(&hdr->emptyB[sb]), 3);
+          }
+          umma_commit_2sm(smem_u32(&hdr->emptyA[sa]), 3);
+        }
+        umma_commit_2sm(smem_u32(&hdr->tmem_full[acc]), 3);                  // accumulator ready in BOTH CTAs
+      }
+    }
+  } else {
+    // ---------------- epilogue (both CTAs): each CTA drains its own 128 rows of the 256-row accumulator with eight
+    // warps: warp w covers TMEM lane quarter (w & 3); the two warps of a quarter alternate over the channel groups
+    const int et = threadIdx.x - 64;
+    const int q = warp & 3;
+    const int h = (warp - 2) >> 2;
+    int tile = 0;
+    for (int item = cluster_id; item < num_items; item += num_clusters, ++tile) {
+      const int acc = tile & 1;
+      const int n_tile = item % p.ntiles;
+      const int m_tile = (item / p.ntiles) * 2 + (int)rank;
+      const int b = m_tile / p.tiles_per_sample;
+      const int t0 = (m_tile % p.tiles_per_sample) * kTileM;
+      const int n0 = n_tile * (glu ? half : p.NT);
+      float* sb = sbias + acc * p.NT;
+      for (int i = et; i < p.NT; i += 256) {
+        int n;
+        bool ok;
+        if (glu) {
+          const int c = n0 + (i < half ? i : i - half);
+          ok = c < Ch;
+          n = (i < half) ? c : Ch + c;
+        } else {
+          n = n0 + i;
+          ok = n < p.N;
+        }
+        sb[i] = (p.bias != nullptr && ok) ? p.bias[n] : 0.f;
+      }
+      named_bar_sync(1, 256);
+      mbar_wait(smem_u32(&hdr->tmem_full[acc]), (tile >> 1) & 1);
+      tc_fence_after();
+      const int t = t0 + q * 32 + lane;
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.NT);
+      tap_epilogue_tma<true, 2>(p, maps, trow, sb, n0, b, t0, q * 32 + lane, t < p.T, m_tile < total_m_tiles,
+                                smem_u32(stg), p.stg_bytes, et, h);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(smem_u32(&hdr->tmem_empty[acc]), 0);
+    }
+  }
+  if (p.tma_epi && threadIdx.x == 64) tma_store_wait_read();
+  tc_fence_before();
+  cluster_sync_all();                              // nobody leaves while the peer may still touch its smem / TMEM
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, p.tmem_cols);
+  }
+}
+
 // ================================================================================================ weight gradient
 struct WgradParams {
   int T, M, C, taps, dil, B, kchunks /*per sample*/, ctile /*channels per CTA, multiple of 64*/, c_tiles, m_tiles;
@@ -1186,9 +1351,6 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
       int rc = encode_tmap_bf16(&tmW2, W, 3, dims, strides, box);
       if (rc) return rc;
     }
-    const size_t smem2 = 1024 + kHeaderBytes + (size_t)p.stages * stage2 + p.stg_bytes + 2 * p.NT * 4;
-    int rc = set_smem(tc_tapgemm2_kernel, smem2);
-    if (rc) return rc;
     const int m_pairs = (int)((m_tiles_total + 1) / 2);
     const int num_items = m_pairs * p.ntiles;
     int clusters = num_sms() / 2;
@@ -1196,7 +1358,6 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * clusters);
     cfg.blockDim = dim3(kThreadsPair);
-    cfg.dynamicSmemBytes = smem2;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1205,6 +1366,35 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    static const bool no_halo = getenv("MEGB200_TAPGEMM_PAIR_NOHALO") != nullptr;
+    const int a_rows2 = ((kTileM + (taps - 1) * dil) + 7) / 8 * 8;
+    if (taps > 1 && a_rows2 <= 256 && !no_halo) {
+      // halo form: activation ring (with halo rows) + weight ring
+      const uint32_t a_slot = ((uint32_t)a_rows2 * 128u + 1023u) & ~1023u;
+      const uint32_t b_half = (uint32_t)half * 128;
+      const int stagesA = 3;
+      p.stages = pick_stages(b_half, 229000 - 2048 - 2 * p.NT * 4 - p.stg_bytes - stagesA * a_slot, 8);
+      MEGB_CHECK_ARG(p.stages >= 3, "tc_tapgemm(pair, halo): tile too large");
+      CUtensorMap tmAh;
+      const uint64_t dims[3] = {(uint64_t)Ca, (uint64_t)T, (uint64_t)B};
+      const uint64_t strides[2] = {(uint64_t)Cas * 2, (uint64_t)T * Cas * 2};
+      const uint32_t box[3] = {kBlockK, (uint32_t)a_rows2, 1};
+      int rc = encode_tmap_bf16(&tmAh, A, 3, dims, strides, box);
+      if (rc) return rc;
+      const size_t smemh = 1024 + kHeaderBytes + (size_t)stagesA * a_slot + (size_t)p.stages * b_half + p.stg_bytes +
+                           2 * p.NT * 4;
+      rc = set_smem(tc_tapgemm2h_kernel, smemh);
+      if (rc) return rc;
+      cfg.dynamicSmemBytes = smemh;
+      MEGB_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_tapgemm2h_kernel, tmAh, tmW2, maps, p, (int)m_tiles_total, num_items,
+                                      a_rows2, stagesA));
+      MEGB_LAUNCH_OK();
+      return 0;
+    }
+    const size_t smem2 = 1024 + kHeaderBytes + (size_t)p.stages * stage2 + p.stg_bytes + 2 * p.NT * 4;
+    int rc = set_smem(tc_tapgemm2_kernel, smem2);
+    if (rc) return rc;
+    cfg.dynamicSmemBytes = smem2;
     MEGB_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_tapgemm2_kernel, tmA2, tmW2, maps, p, (int)m_tiles_total, num_items));
     MEGB_LAUNCH_OK();
     return 0;

@@ -11,6 +11,5 @@ print('VARIANT $tag ms/step=%.3f tapgemm=%.1f TF/s (%.3f ms/launch) wgrad=%.1f T
 run 1cta_tma      A=1
 run 1cta_direct   MEGB200_TAPGEMM_DIRECT_EPI=1
 run halo1_tma     MEGB200_TAPGEMM_HALO=1
-run halo2_tma     MEGB200_TAPGEMM_HALO=2
-run pair_tma      MEGB200_TAPGEMM_PAIR=1
-run pair_direct   MEGB200_TAPGEMM_PAIR=1 MEGB200_TAPGEMM_DIRECT_EPI=1
+run pairhalo_tma  MEGB200_TAPGEMM_PAIR=1
+run pair_tma      MEGB200_TAPGEMM_PAIR=1 MEGB200_TAPGEMM_PAIR_NOHALO=1
