@@ -36,6 +36,7 @@ __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
 struct TapGemmParams {
   int T, N, Cos, Crs, Co2s, taps, dil, Kp, kchunks, tiles_per_sample, ntiles, NT, stages, epi, debug_skip_io, tma_epi;
   uint32_t stg_bytes;   // CTA-pair kernel: dedicated staging area of the TMA-store epilogue
+  long long* dbg;       // MEGB200_DEBUG_TIMING: per-CTA clock64 stamps {start, first data, accumulator ready, end}
   uint32_t tmem_cols, idesc;
   const float* bias;
   const __nv_bfloat16* Res;
@@ -175,31 +176,47 @@ __device__ __forceinline__ void tap_epilogue_tma(const TapGemmParams& p, const T
     for (int c = 0; c < 4; ++c)
       if (n0 + 32 * h + 8 * c < p.Crs) rnext[c] = *reinterpret_cast<const uint4*>(rrow + 32 * h + 8 * c);
   }
-  if (kPersistent) {
-    // the staging area is reused every tile: the previous tile's stores must have finished reading it
-    if (etid == 0) tma_store_wait_read();
-    named_bar_sync(2, kEpiThreads);
-  }
-  for (int jj = 0; jj < iters; ++jj) {
-    if (jj > 0 && jj % cap_iters == 0) {
+  // Rounds: all channel groups that fit the staging area are converted and staged back to back; ONE proxy fence and
+  // ONE barrier per round, then a single thread issues the round's TMA stores (measured: a fence + barrier per group
+  // costs ~2500 cycles per group and made the epilogue as long as the main loop).
+  for (int jj0 = 0; jj0 < iters; jj0 += cap_iters) {
+    if (jj0 > 0 || kPersistent) {
+      // the staging area is reused: the previous stores must have finished reading it
       if (etid == 0) tma_store_wait_read();
       named_bar_sync(2, kEpiThreads);
     }
-    const int j = jj * kHalves + h;
-    const uint32_t sbase = stg + (uint32_t)(((jj % cap_iters) * kHalves + h) * per_group) * slice_bytes;
-    if (j < groups) {
+    const int jj1 = (jj0 + cap_iters < iters) ? jj0 + cap_iters : iters;
+    for (int jj = jj0; jj < jj1; ++jj) {
+      const int j = jj * kHalves + h;
+      if (j >= groups) break;
+      const uint32_t sbase = stg + (uint32_t)(((jj - jj0) * kHalves + h) * per_group) * slice_bytes;
       float o[32];
       tmem_ld32(trow + (uint32_t)(32 * j), o);
       const int c_first = n0 + 32 * j;                       // first logical output channel of this group
+      float bv[32];
+      {
+        const float4* sb4 = reinterpret_cast<const float4*>(sbias + 32 * j);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 v4 = sb4[c];
+          bv[4 * c] = v4.x; bv[4 * c + 1] = v4.y; bv[4 * c + 2] = v4.z; bv[4 * c + 3] = v4.w;
+        }
+      }
       if (glu) {
         float g[32];
         tmem_ld32(trow + (uint32_t)(half + 32 * j), g);
+        const float4* sg4 = reinterpret_cast<const float4*>(sbias + half + 32 * j);
         const bool full = c_first + 32 <= Ch;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 v4 = sg4[c];
+          g[4 * c] += v4.x; g[4 * c + 1] += v4.y; g[4 * c + 2] += v4.z; g[4 * c + 3] += v4.w;
+        }
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const bool in = full || (c_first + i) < Ch;
-          o[i] = in ? o[i] + sbias[32 * j + i] : 0.f;
-          g[i] = in ? g[i] + sbias[half + 32 * j + i] : 0.f;
+          o[i] = in ? o[i] + bv[i] : 0.f;
+          g[i] = in ? g[i] : 0.f;
         }
         stage_bf16_slice(sbase, rloc, o);
         stage_bf16_slice(sbase + slice_bytes, rloc, g);
@@ -222,8 +239,8 @@ __device__ __forceinline__ void tap_epilogue_tma(const TapGemmParams& p, const T
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float2 rf = __bfloat1622float2(rh[i]);
-          o[2 * i] = (full || c_first + 2 * i < p.N) ? o[2 * i] + sbias[32 * j + 2 * i] + rf.x : 0.f;
-          o[2 * i + 1] = (full || c_first + 2 * i + 1 < p.N) ? o[2 * i + 1] + sbias[32 * j + 2 * i + 1] + rf.y : 0.f;
+          o[2 * i] = (full || c_first + 2 * i < p.N) ? o[2 * i] + bv[2 * i] + rf.x : 0.f;
+          o[2 * i + 1] = (full || c_first + 2 * i + 1 < p.N) ? o[2 * i + 1] + bv[2 * i + 1] + rf.y : 0.f;
         }
         if (f32) {
           stage_f32_slice(sbase, rloc, o);
@@ -240,21 +257,23 @@ __device__ __forceinline__ void tap_epilogue_tma(const TapGemmParams& p, const T
     fence_proxy_async();
     named_bar_sync(2, kEpiThreads);
     if (etid == 0 && tile_valid) {
+      for (int jj = jj0; jj < jj1; ++jj) {
 #pragma unroll
-      for (int hh = 0; hh < kHalves; ++hh) {
-        const int jh = jj * kHalves + hh;
-        if (jh >= groups) break;
-        const int cf = n0 + 32 * jh;
-        const uint32_t sb2 = stg + (uint32_t)(((jj % cap_iters) * kHalves + hh) * per_group) * slice_bytes;
-        if (glu) {
-          tma_store_3d(&maps.out2, sb2, cf, t0, b);
-          tma_store_3d(&maps.out2, sb2 + slice_bytes, Ch + cf, t0, b);
-          tma_store_3d(&maps.out, sb2 + 2 * slice_bytes, cf, t0, b);
-        } else if (gelu) {
-          tma_store_3d(&maps.out2, sb2, cf, t0, b);
-          tma_store_3d(&maps.out, sb2 + slice_bytes, cf, t0, b);
-        } else {
-          tma_store_3d(&maps.out, sb2, cf, t0, b);
+        for (int hh = 0; hh < kHalves; ++hh) {
+          const int jh = jj * kHalves + hh;
+          if (jh >= groups) break;
+          const int cf = n0 + 32 * jh;
+          const uint32_t sb2 = stg + (uint32_t)(((jj - jj0) * kHalves + hh) * per_group) * slice_bytes;
+          if (glu) {
+            tma_store_3d(&maps.out2, sb2, cf, t0, b);
+            tma_store_3d(&maps.out2, sb2 + slice_bytes, Ch + cf, t0, b);
+            tma_store_3d(&maps.out, sb2 + 2 * slice_bytes, cf, t0, b);
+          } else if (gelu) {
+            tma_store_3d(&maps.out2, sb2, cf, t0, b);
+            tma_store_3d(&maps.out, sb2 + slice_bytes, cf, t0, b);
+          } else {
+            tma_store_3d(&maps.out, sb2, cf, t0, b);
+          }
         }
       }
       tma_store_commit();
@@ -287,6 +306,7 @@ tc_tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int n0 = n_tile * (glu ? half : p.NT);   // first output channel of this tile
   const int g = p.group ? p.group[b] : 0;
   const int num_k = p.taps * p.kchunks;
+  if (p.dbg != nullptr && threadIdx.x == 0) p.dbg[4 * blockIdx.x + 0] = clock64();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -332,6 +352,7 @@ tc_tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int it = 0; it < num_k; ++it) {
         const int s = it % p.stages;
         mbar_wait(smem_u32(&hdr->full[s]), (it / p.stages) & 1);
+        if (p.dbg != nullptr && it == 0) p.dbg[4 * blockIdx.x + 1] = clock64();
         tc_fence_after();
         const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
         const uint64_t da = make_smem_desc(sa, 16, 1024);
@@ -361,6 +382,7 @@ tc_tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     named_bar_sync(1, 128);
     mbar_wait(smem_u32(&hdr->tmem_full), 0);
+    if (p.dbg != nullptr && et == 0) p.dbg[4 * blockIdx.x + 2] = clock64();
     tc_fence_after();
     const int q = warp & 3;
     const int t = t0 + q * 32 + lane;
@@ -372,6 +394,7 @@ tc_tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     } else {
       tap_epilogue(p, tmem_base + ((uint32_t)(q * 32) << 16), sbias, n0, row, t < p.T);
     }
+    if (p.dbg != nullptr && et == 0) p.dbg[4 * blockIdx.x + 3] = clock64();
     tc_fence_before();
   }
   __syncthreads();
@@ -1262,6 +1285,10 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
   TapGemmParams p;
   static const bool skip_io = getenv("MEGB200_DEBUG_EPI_SKIP_IO") != nullptr;
   p.debug_skip_io = skip_io ? 1 : 0;
+  static const bool dbg_timing = getenv("MEGB200_DEBUG_TIMING") != nullptr;
+  static long long* dbg_buf = nullptr;
+  if (dbg_timing && dbg_buf == nullptr) cudaMalloc(&dbg_buf, sizeof(long long) * 4 * 65536);
+  p.dbg = nullptr;
   p.T = T; p.N = N; p.Cos = Cos; p.Crs = Crs; p.Co2s = Co2s; p.taps = taps; p.dil = dil; p.Kp = Kp; p.epi = epi;
   p.kchunks = (Ca + kBlockK - 1) / kBlockK;
   p.tiles_per_sample = (T + kTileM - 1) / kTileM;
@@ -1467,8 +1494,25 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
   if (rc) return rc;
   const long long blocks = (long long)B * p.tiles_per_sample * p.ntiles;
   MEGB_CHECK_ARG(blocks > 0 && blocks < 2147483647ll, "tc_tapgemm: grid too large");
+  if (dbg_timing && blocks <= 65536) p.dbg = dbg_buf;
   tc_tapgemm_kernel<<<(unsigned)blocks, kThreads, smem, st>>>(tmA, tmW, maps, p);
   MEGB_LAUNCH_OK();
+  if (p.dbg != nullptr) {
+    // debug only: phase durations per CTA in SM clocks (synchronises!)
+    static long long host[4 * 65536];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(host, dbg_buf, sizeof(long long) * 4 * blocks, cudaMemcpyDeviceToHost);
+    double fill_c = 0, main_c = 0, epi_c = 0, total_c = 0;
+    for (long long i = 0; i < blocks; ++i) {
+      fill_c += (double)(host[4 * i + 1] - host[4 * i + 0]);
+      main_c += (double)(host[4 * i + 2] - host[4 * i + 1]);
+      epi_c += (double)(host[4 * i + 3] - host[4 * i + 2]);
+      total_c += (double)(host[4 * i + 3] - host[4 * i + 0]);
+    }
+    fprintf(stderr, "[megb200 timing] tapgemm N=%d K=%d taps=%d epi=%d NT=%d stages=%d blocks=%lld: "
+            "start->first data %.0f, main loop %.0f, epilogue %.0f, total %.0f cycles (mean per CTA)\n",
+            N, Ca, taps, epi, p.NT, p.stages, blocks, fill_c / blocks, main_c / blocks, epi_c / blocks, total_c / blocks);
+  }
   return 0;
 }
 
