@@ -34,7 +34,7 @@ __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
 
 // ================================================================================================ tap GEMM
 struct TapGemmParams {
-  int T, N, Cos, Crs, Co2s, taps, dil, Kp, kchunks, tiles_per_sample, ntiles, NT, stages, epi, debug_skip_io, tma_epi;
+  int T, N, Cos, Crs, Co2s, taps, dil, Kp, kchunks, tiles_per_sample, ntiles, NT, n_last, stages, epi, debug_skip_io, tma_epi;
   uint32_t stg_bytes;   // CTA-pair kernel: dedicated staging area of the TMA-store epilogue
   long long* dbg;       // MEGB200_DEBUG_TIMING: per-CTA clock64 stamps {start, first data, accumulator ready, end}
   uint32_t tmem_cols, idesc;
@@ -254,8 +254,10 @@ __device__ __forceinline__ void tap_epilogue_tma(const TapGemmParams& p, const T
         }
       }
     }
+    if (!kPersistent && p.dbg != nullptr && etid == 0 && jj0 == 0) p.dbg[8 * blockIdx.x + 4] = clock64();
     fence_proxy_async();
     named_bar_sync(2, kEpiThreads);
+    if (!kPersistent && p.dbg != nullptr && etid == 0 && jj0 == 0) p.dbg[8 * blockIdx.x + 5] = clock64();
     if (etid == 0 && tile_valid) {
       for (int jj = jj0; jj < jj1; ++jj) {
 #pragma unroll
@@ -278,6 +280,7 @@ __device__ __forceinline__ void tap_epilogue_tma(const TapGemmParams& p, const T
       }
       tma_store_commit();
     }
+    if (!kPersistent && p.dbg != nullptr && etid == 0 && jj0 == 0) p.dbg[8 * blockIdx.x + 6] = clock64();
   }
   if (!kPersistent && etid == 0) tma_store_wait_read();   // shared memory must stay alive until the stores have read it
 }
@@ -306,7 +309,11 @@ tc_tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int n0 = n_tile * (glu ? half : p.NT);   // first output channel of this tile
   const int g = p.group ? p.group[b] : 0;
   const int num_k = p.taps * p.kchunks;
-  if (p.dbg != nullptr && threadIdx.x == 0) p.dbg[4 * blockIdx.x + 0] = clock64();
+  // ragged N tiling: every tile is NT wide except the last one (n_last): 320 = 256 + 64 keeps the MMA N at the widths
+  // the tensor core runs at full rate (N = 160 measured at ~60 %)
+  const int wN = (n_tile == p.ntiles - 1) ? p.n_last : p.NT;
+  const uint32_t idesc = make_idesc(wN, 0, 0);
+  if (p.dbg != nullptr && threadIdx.x == 0) p.dbg[8 * blockIdx.x + 0] = clock64();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -352,14 +359,14 @@ tc_tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int it = 0; it < num_k; ++it) {
         const int s = it % p.stages;
         mbar_wait(smem_u32(&hdr->full[s]), (it / p.stages) & 1);
-        if (p.dbg != nullptr && it == 0) p.dbg[4 * blockIdx.x + 1] = clock64();
+        if (p.dbg != nullptr && it == 0) p.dbg[8 * blockIdx.x + 1] = clock64();
         tc_fence_after();
         const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
         const uint64_t da = make_smem_desc(sa, 16, 1024);
         const uint64_t db = make_smem_desc(sa + a_bytes, 16, 1024);
 #pragma unroll
         for (int k = 0; k < kBlockK / kUmmaK; ++k)
-          umma_bf16(tmem_base, desc_advance(da, k * 32), desc_advance(db, k * 32), p.idesc, (it | k) != 0);
+          umma_bf16(tmem_base, desc_advance(da, k * 32), desc_advance(db, k * 32), idesc, (it | k) != 0);
         umma_commit(smem_u32(&hdr->empty[s]));
       }
       umma_commit(smem_u32(&hdr->tmem_full));
@@ -367,7 +374,7 @@ tc_tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else {
     // ---------------- epilogue: TMEM -> registers -> fused element-wise tail -> global (thread = one position)
     const int et = threadIdx.x - 64;
-    for (int i = et; i < p.NT; i += 128) {
+    for (int i = et; i < wN; i += 128) {
       int n;
       bool ok;
       if (glu) {
@@ -382,19 +389,21 @@ tc_tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     named_bar_sync(1, 128);
     mbar_wait(smem_u32(&hdr->tmem_full), 0);
-    if (p.dbg != nullptr && et == 0) p.dbg[4 * blockIdx.x + 2] = clock64();
+    if (p.dbg != nullptr && et == 0) p.dbg[8 * blockIdx.x + 2] = clock64();
     tc_fence_after();
     const int q = warp & 3;
     const int t = t0 + q * 32 + lane;
     const long long row = (long long)b * p.T + t;
+    TapGemmParams pe = p;
+    pe.NT = wN;
     if (p.tma_epi) {
       // every MMA has completed, so the whole stage ring is free: it becomes the staging area of the stores
-      tap_epilogue_tma<false, 1>(p, maps, tmem_base + ((uint32_t)(q * 32) << 16), sbias, n0, b, t0, q * 32 + lane,
+      tap_epilogue_tma<false, 1>(pe, maps, tmem_base + ((uint32_t)(q * 32) << 16), sbias, n0, b, t0, q * 32 + lane,
                                  t < p.T, true, smem_u32(ring), (uint32_t)p.stages * stage_bytes, et, 0);
     } else {
-      tap_epilogue(p, tmem_base + ((uint32_t)(q * 32) << 16), sbias, n0, row, t < p.T);
+      tap_epilogue(pe, tmem_base + ((uint32_t)(q * 32) << 16), sbias, n0, row, t < p.T);
     }
-    if (p.dbg != nullptr && et == 0) p.dbg[4 * blockIdx.x + 3] = clock64();
+    if (p.dbg != nullptr && et == 0) p.dbg[8 * blockIdx.x + 3] = clock64();
     tc_fence_before();
   }
   __syncthreads();
@@ -581,8 +590,10 @@ tc_tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int half = p.NT / 2;                                  // weight rows staged by each CTA
+  constexpr int kSub = 2;                                     // 64-wide k chunks per pipeline stage
   const uint32_t a_bytes = kTileM * 128, b_bytes = (uint32_t)half * 128;
-  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const uint32_t sub_bytes = a_bytes + b_bytes;
+  const uint32_t stage_bytes = kSub * sub_bytes;
   uint8_t* ring = smem + kHeaderBytes;
   uint8_t* stg = ring + (size_t)p.stages * stage_bytes;                              // TMA-store staging (1024-aligned)
   float* sbias = reinterpret_cast<float*>(stg + p.stg_bytes);                        // [2][NT]: one table per acc stage
@@ -616,6 +627,7 @@ tc_tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (warp == 0) {
     if (lane == 0) {
       int it = 0;
+      long long dbg_prod_wait = 0;
       for (int item = cluster_id; item < num_items; item += num_clusters) {
         const int n_tile = item % p.ntiles;
         const int m_tile = (item / p.ntiles) * 2 + (int)rank;
@@ -624,40 +636,67 @@ tc_tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int t0 = (m_tile % p.tiles_per_sample) * kTileM;
         // weight rows of this CTA: plain tiles split [n0, n0+half) | [n0+half, n0+NT); GLU tiles are
         // [half a-channels | their half gate channels], i.e. the leader stages the a rows and the peer the gates
-        const int wrow = glu ? (n_tile * half + (rank ? Ch : 0)) : (n_tile * p.NT + (int)rank * half);
-        for (int kit = 0; kit < num_k; ++kit, ++it) {
+        const int wN = (n_tile == p.ntiles - 1) ? p.n_last : p.NT;
+        const int wrow = glu ? (n_tile * half + (rank ? Ch : 0)) : (n_tile * p.NT + (int)rank * (wN / 2));
+        // a stage holds kSub consecutive 64-wide k chunks: one barrier round trip and one commit per 8 MMAs (the single
+        // MMA-issuing thread of the pair is issue-latency bound, measured ~630 cycles per 4-MMA stage)
+        for (int kit = 0; kit < num_k; kit += kSub, ++it) {
           const int s = it % p.stages;
+          const long long w0 = p.dbg ? clock64() : 0;
           mbar_wait(smem_u32(&hdr->empty[s]), ((it / p.stages) & 1) ^ 1);
+          if (p.dbg) dbg_prod_wait += clock64() - w0;
           const uint32_t full = smem_u32(&hdr->full[s]);
-          if (leader) mbar_arrive_expect_tx(full, 2 * stage_bytes);
-          const int tap = kit / p.kchunks, kc = kit % p.kchunks;
-          const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
-          tma_load_3d_2sm(sa, &tmA, kc * kBlockK, t0 + (tap - p.taps / 2) * p.dil, b, full);
-          tma_load_3d_2sm(sa + a_bytes, &tmW, tap * p.Kp + kc * kBlockK, wrow, 0, full);
+          const int nsub = (num_k - kit) < kSub ? (num_k - kit) : kSub;
+          if (leader) mbar_arrive_expect_tx(full, 2 * (uint32_t)nsub * sub_bytes);
+          for (int u = 0; u < nsub; ++u) {
+            const int tap = (kit + u) / p.kchunks, kc = (kit + u) % p.kchunks;
+            const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes) + (uint32_t)u * sub_bytes;
+            tma_load_3d_2sm(sa, &tmA, kc * kBlockK, t0 + (tap - p.taps / 2) * p.dil, b, full);
+            tma_load_3d_2sm(sa + a_bytes, &tmW, tap * p.Kp + kc * kBlockK, wrow, 0, full);
+          }
         }
       }
+      if (p.dbg) p.dbg[8 * blockIdx.x + 0] = dbg_prod_wait;
     }
   } else if (warp == 1) {
     if (leader && lane == 0) {
       int it = 0, tile = 0;
+      long long dbg_full_wait = 0, dbg_acc_wait = 0;
+      const long long dbg_t0 = p.dbg ? clock64() : 0;
       for (int item = cluster_id; item < num_items; item += num_clusters, ++tile) {
         const int acc = tile & 1;
+        const long long w1 = p.dbg ? clock64() : 0;
         mbar_wait(smem_u32(&hdr->tmem_empty[acc]), ((tile >> 1) & 1) ^ 1);   // epilogues of both CTAs drained it
+        if (p.dbg) dbg_acc_wait += clock64() - w1;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.NT);
-        for (int kit = 0; kit < num_k; ++kit, ++it) {
+        const int wN = ((item % p.ntiles) == p.ntiles - 1) ? p.n_last : p.NT;
+        const uint32_t idesc = make_idesc_m(256, wN, 0, 0);
+        for (int kit = 0; kit < num_k; kit += kSub, ++it) {
           const int s = it % p.stages;
+          const long long w2 = p.dbg ? clock64() : 0;
           mbar_wait(smem_u32(&hdr->full[s]), (it / p.stages) & 1);
+          if (p.dbg) dbg_full_wait += clock64() - w2;
           tc_fence_after();
-          const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
-          const uint64_t da = make_smem_desc(sa, 16, 1024);
-          const uint64_t db = make_smem_desc(sa + a_bytes, 16, 1024);
+          const int nsub = (num_k - kit) < kSub ? (num_k - kit) : kSub;
+          const uint32_t sa0 = smem_u32(ring + (size_t)s * stage_bytes);
+          for (int u = 0; u < nsub; ++u) {
+            const uint32_t sa = sa0 + (uint32_t)u * sub_bytes;
+            const uint64_t da = make_smem_desc(sa, 16, 1024);
+            const uint64_t db = make_smem_desc(sa + a_bytes, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k)
-            umma_bf16_2sm(d_tmem, desc_advance(da, k * 32), desc_advance(db, k * 32), p.idesc, (kit | k) != 0);
+            for (int kk = 0; kk < kBlockK / kUmmaK; ++kk)
+              umma_bf16_2sm(d_tmem, desc_advance(da, kk * 32), desc_advance(db, kk * 32), idesc, (kit | u | kk) != 0);
+          }
           umma_commit_2sm(smem_u32(&hdr->empty[s]), 3);                      // frees the slot in BOTH CTAs
         }
         umma_commit_2sm(smem_u32(&hdr->tmem_full[acc]), 3);                  // accumulator ready in BOTH CTAs
+      }
+      if (p.dbg) {
+        p.dbg[8 * blockIdx.x + 1] = clock64() - dbg_t0;
+        p.dbg[8 * blockIdx.x + 2] = dbg_full_wait;
+        p.dbg[8 * blockIdx.x + 3] = dbg_acc_wait;
+        p.dbg[8 * blockIdx.x + 6] = tile;
       }
     }
   } else {
@@ -667,6 +706,7 @@ tc_tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int q = warp & 3;
     const int h = (warp - 2) >> 2;
     int tile = 0;
+    long long dbg_epi_wait = 0, dbg_epi_work = 0;
     for (int item = cluster_id; item < num_items; item += num_clusters, ++tile) {
       const int acc = tile & 1;
       const int n_tile = item % p.ntiles;
@@ -674,8 +714,9 @@ tc_tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int b = m_tile / p.tiles_per_sample;
       const int t0 = (m_tile % p.tiles_per_sample) * kTileM;
       const int n0 = n_tile * (glu ? half : p.NT);
+      const int wN = (n_tile == p.ntiles - 1) ? p.n_last : p.NT;
       float* sb = sbias + acc * p.NT;
-      for (int i = et; i < p.NT; i += 256) {
+      for (int i = et; i < wN; i += 256) {
         int n;
         bool ok;
         if (glu) {
@@ -689,15 +730,25 @@ tc_tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         sb[i] = (p.bias != nullptr && ok) ? p.bias[n] : 0.f;
       }
       named_bar_sync(1, 256);
+      const long long w3 = p.dbg ? clock64() : 0;
       mbar_wait(smem_u32(&hdr->tmem_full[acc]), (tile >> 1) & 1);
+      const long long w4 = p.dbg ? clock64() : 0;
+      dbg_epi_wait += w4 - w3;
       tc_fence_after();
       const int t = t0 + q * 32 + lane;
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.NT);
-      tap_epilogue_tma<true, 2>(p, maps, trow, sb, n0, b, t0, q * 32 + lane, t < p.T, m_tile < total_m_tiles,
+      TapGemmParams pe = p;
+      pe.NT = wN;
+      tap_epilogue_tma<true, 2>(pe, maps, trow, sb, n0, b, t0, q * 32 + lane, t < p.T, m_tile < total_m_tiles,
                                 smem_u32(stg), p.stg_bytes, et, h);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(smem_u32(&hdr->tmem_empty[acc]), 0);
+      if (p.dbg) dbg_epi_work += clock64() - w4;
+    }
+    if (p.dbg && et == 0) {
+      p.dbg[8 * blockIdx.x + 4] = dbg_epi_wait;
+      p.dbg[8 * blockIdx.x + 5] = dbg_epi_work;
     }
   }
   if (p.tma_epi && threadIdx.x == 64) tma_store_wait_read();
@@ -1256,6 +1307,11 @@ tc_clip_dz_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constant
 }
 
 // ================================================================================================ host launchers
+static bool halo_mode_env_off() {
+  static const char* e = getenv("MEGB200_TAPGEMM_HALO");
+  return e == nullptr || atoi(e) == 0;
+}
+
 static int pick_stages(uint32_t stage_bytes, uint32_t budget, int max_stages) {
   int s = (int)(budget / stage_bytes);
   if (s > max_stages) s = max_stages;
@@ -1287,7 +1343,7 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
   p.debug_skip_io = skip_io ? 1 : 0;
   static const bool dbg_timing = getenv("MEGB200_DEBUG_TIMING") != nullptr;
   static long long* dbg_buf = nullptr;
-  if (dbg_timing && dbg_buf == nullptr) cudaMalloc(&dbg_buf, sizeof(long long) * 4 * 65536);
+  if (dbg_timing && dbg_buf == nullptr) cudaMalloc(&dbg_buf, sizeof(long long) * 8 * 65536);
   p.dbg = nullptr;
   p.T = T; p.N = N; p.Cos = Cos; p.Crs = Crs; p.Co2s = Co2s; p.taps = taps; p.dil = dil; p.Kp = Kp; p.epi = epi;
   p.kchunks = (Ca + kBlockK - 1) / kBlockK;
@@ -1311,15 +1367,26 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
         if (Ch % h == 0 && 2 * h <= 160) { half = h; break; }
     if (half == 0) half = Ch >= 80 ? 80 : (Ch + 15) / 16 * 16;
     p.NT = 2 * half;
+    p.n_last = p.NT;
     const int cover = Cos > Ch ? Cos : Ch;
     p.ntiles = (cover + half - 1) / half;
   } else {
     MEGB_CHECK_ARG(epi != MEGB200_EPI_GELU || (Out2 != nullptr && Co2s % 8 == 0 && Co2s >= N),
                    "tc_tapgemm: the GELU epilogue needs a pre-activation output");
-    p.NT = pick_ntile(Np);
     // output channels up to Cos must be covered so that pad channels are written as zero
     const int ncover = Cos > Np ? Cos : Np;
-    p.ntiles = (ncover + p.NT - 1) / p.NT;
+    static const bool uniform_tiles = getenv("MEGB200_TAPGEMM_UNIFORM_N") != nullptr;
+    const int cover32 = (ncover + 31) / 32 * 32;
+    if (!uniform_tiles && cover32 > 256 && halo_mode_env_off()) {
+      // ragged N tiling: 256-wide tiles plus one narrower tail (multiples of 32): 320 = 256 + 64, 640 = 256 + 256 + 128
+      p.NT = 256;
+      p.ntiles = (cover32 + 255) / 256;
+      p.n_last = cover32 - 256 * (p.ntiles - 1);
+    } else {
+      p.NT = pick_ntile(Np);
+      p.ntiles = (ncover + p.NT - 1) / p.NT;
+      p.n_last = p.NT;
+    }
     if (p.NT % 32 != 0) p.tma_epi = 0;
   }
   TapStoreMaps maps;
@@ -1395,7 +1462,7 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
     cfg.numAttrs = 1;
     static const bool no_halo = getenv("MEGB200_TAPGEMM_PAIR_NOHALO") != nullptr;
     const int a_rows2 = ((kTileM + (taps - 1) * dil) + 7) / 8 * 8;
-    if (taps > 1 && a_rows2 <= 256 && !no_halo) {
+    if (taps > 1 && a_rows2 <= 256 && !no_halo && p.n_last == p.NT) {
       // halo form: activation ring (with halo rows) + weight ring
       const uint32_t a_slot = ((uint32_t)a_rows2 * 128u + 1023u) & ~1023u;
       const uint32_t b_half = (uint32_t)half * 128;
@@ -1418,12 +1485,40 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
       MEGB_LAUNCH_OK();
       return 0;
     }
-    const size_t smem2 = 1024 + kHeaderBytes + (size_t)p.stages * stage2 + p.stg_bytes + 2 * p.NT * 4;
+    p.stages = pick_stages(2 * stage2, 229000 - 2048 - 2 * p.NT * 4 - p.stg_bytes, 8);   // two k chunks per stage
+    MEGB_CHECK_ARG(p.stages >= 2, "tc_tapgemm(pair): tile too large");
+    const size_t smem2 = 1024 + kHeaderBytes + (size_t)p.stages * 2 * stage2 + p.stg_bytes + 2 * p.NT * 4;
     int rc = set_smem(tc_tapgemm2_kernel, smem2);
     if (rc) return rc;
     cfg.dynamicSmemBytes = smem2;
+    if (dbg_timing) {
+      p.dbg = dbg_buf;
+      cudaMemsetAsync(dbg_buf, 0, sizeof(long long) * 8 * 2 * clusters, st);
+    }
     MEGB_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_tapgemm2_kernel, tmA2, tmW2, maps, p, (int)m_tiles_total, num_items));
     MEGB_LAUNCH_OK();
+    if (p.dbg != nullptr) {
+      static long long hostp[8 * 512];
+      cudaStreamSynchronize(st);
+      cudaMemcpy(hostp, dbg_buf, sizeof(long long) * 8 * 2 * clusters, cudaMemcpyDeviceToHost);
+      double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int c = 0; c < clusters; ++c) {
+        const long long* l = hostp + 8 * (2 * c);         // leader CTA of the pair
+        const long long* f = hostp + 8 * (2 * c + 1);     // follower
+        v[0] += (double)(l[0] + f[0]) / 2;                 // producer wait (empty)
+        v[1] += (double)l[1];                              // MMA loop total
+        v[2] += (double)l[2];                              // MMA wait full
+        v[3] += (double)l[3];                              // MMA wait accumulator
+        v[4] += (double)(l[4] + f[4]) / 2;                 // epilogue wait tmem_full
+        v[5] += (double)(l[5] + f[5]) / 2;                 // epilogue work
+        v[6] += (double)l[6];                              // tiles per cluster
+      }
+      for (int i = 0; i < 7; ++i) v[i] /= clusters;
+      fprintf(stderr, "[megb200 timing] pair tapgemm N=%d K=%d taps=%d epi=%d NT=%d stages=%d: per cluster %.1f tiles; MMA loop %.0f "
+              "cycles (waiting for data %.0f, for a free accumulator %.0f); per tile: MMA %.0f, epilogue work %.0f, epilogue "
+              "idle %.0f; producer waiting for free slots %.0f\n", N, Ca, taps, epi, p.NT, p.stages, v[6], v[1], v[2], v[3],
+              v[1] / v[6], v[5] / v[6], v[4] / v[6], v[0]);
+    }
     return 0;
   }
 
@@ -1499,16 +1594,24 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
   MEGB_LAUNCH_OK();
   if (p.dbg != nullptr) {
     // debug only: phase durations per CTA in SM clocks (synchronises!)
-    static long long host[4 * 65536];
+    static long long host[8 * 65536];
     cudaStreamSynchronize(st);
-    cudaMemcpy(host, dbg_buf, sizeof(long long) * 4 * blocks, cudaMemcpyDeviceToHost);
-    double fill_c = 0, main_c = 0, epi_c = 0, total_c = 0;
+    cudaMemcpy(host, dbg_buf, sizeof(long long) * 8 * blocks, cudaMemcpyDeviceToHost);
+    double fill_c = 0, main_c = 0, epi_c = 0, total_c = 0, e_stage = 0, e_bar = 0, e_issue = 0, e_wait = 0;
     for (long long i = 0; i < blocks; ++i) {
-      fill_c += (double)(host[4 * i + 1] - host[4 * i + 0]);
-      main_c += (double)(host[4 * i + 2] - host[4 * i + 1]);
-      epi_c += (double)(host[4 * i + 3] - host[4 * i + 2]);
-      total_c += (double)(host[4 * i + 3] - host[4 * i + 0]);
+      fill_c += (double)(host[8 * i + 1] - host[8 * i + 0]);
+      main_c += (double)(host[8 * i + 2] - host[8 * i + 1]);
+      epi_c += (double)(host[8 * i + 3] - host[8 * i + 2]);
+      total_c += (double)(host[8 * i + 3] - host[8 * i + 0]);
+      e_stage += (double)(host[8 * i + 4] - host[8 * i + 2]);
+      e_bar += (double)(host[8 * i + 5] - host[8 * i + 4]);
+      e_issue += (double)(host[8 * i + 6] - host[8 * i + 5]);
+      e_wait += (double)(host[8 * i + 3] - host[8 * i + 6]);
     }
+    if (p.tma_epi)
+      fprintf(stderr, "[megb200 timing]   epilogue round 0: convert+stage %.0f, fence+barrier %.0f, store issue %.0f, rest "
+              "(later rounds + wait for stores to read smem) %.0f\n", e_stage / blocks, e_bar / blocks, e_issue / blocks,
+              e_wait / blocks);
     fprintf(stderr, "[megb200 timing] tapgemm N=%d K=%d taps=%d epi=%d NT=%d stages=%d blocks=%lld: "
             "start->first data %.0f, main loop %.0f, epilogue %.0f, total %.0f cycles (mean per CTA)\n",
             N, Ca, taps, epi, p.NT, p.stages, blocks, fill_c / blocks, main_c / blocks, epi_c / blocks, total_c / blocks);
