@@ -1375,10 +1375,11 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
                    "tc_tapgemm: the GELU epilogue needs a pre-activation output");
     // output channels up to Cos must be covered so that pad channels are written as zero
     const int ncover = Cos > Np ? Cos : Np;
-    static const bool uniform_tiles = getenv("MEGB200_TAPGEMM_UNIFORM_N") != nullptr;
+    // MEGB200_TAPGEMM_RAGGED_N=1: 256-wide tiles plus one narrower tail (320 = 256 + 64).  Measured slower than uniform
+    // 160-wide tiles at config 2 (576 vs 647 TFLOP/s: the 48 KB stages leave a 2-deep ring), so it is off by default.
+    static const bool uniform_tiles = getenv("MEGB200_TAPGEMM_RAGGED_N") == nullptr;
     const int cover32 = (ncover + 31) / 32 * 32;
     if (!uniform_tiles && cover32 > 256 && halo_mode_env_off()) {
-      // ragged N tiling: 256-wide tiles plus one narrower tail (multiples of 32): 320 = 256 + 64, 640 = 256 + 256 + 128
       p.NT = 256;
       p.ntiles = (cover32 + 255) / 256;
       p.n_last = cover32 - 256 * (p.ntiles - 1);
@@ -1410,11 +1411,12 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
   }
   p.bias = bias; p.Res = (const __nv_bfloat16*)Res; p.group = group; p.Out = Out; p.Out2 = (__nv_bfloat16*)Out2;
 
-  // Kernel choice.  Measured at config 2 (profiles/): the single-CTA kernel with two co-resident CTAs per SM is currently
-  // the faster one (548 vs 498 TFLOP/s), so the CTA-pair kernel is opt-in: MEGB200_TAPGEMM_PAIR=1 enables it for large
-  // problems, MEGB200_TAPGEMM_2CTA_MIN_ITEMS=<n> additionally lowers its work threshold (the tests exercise it so).
+  // Kernel choice.  Measured at config 2 (profiles/r1_tapgemm_variants.md): the persistent CTA-pair kernel (8 epilogue
+  // warps, 128-wide k stages) reaches 647 TFLOP/s, the single-CTA kernel with two co-resident CTAs per SM 608; the pair
+  // kernel is used for large ungrouped problems.  MEGB200_TAPGEMM_1CTA=1 forces the single-CTA kernel,
+  // MEGB200_TAPGEMM_2CTA_MIN_ITEMS=<n> lowers the pair kernel's work threshold (the tests exercise it on small shapes).
   static const char* min_items_env = getenv("MEGB200_TAPGEMM_2CTA_MIN_ITEMS");
-  static const bool force_1cta = getenv("MEGB200_TAPGEMM_PAIR") == nullptr && min_items_env == nullptr;
+  static const bool force_1cta = getenv("MEGB200_TAPGEMM_1CTA") != nullptr;
   const long long min_items = min_items_env ? atoll(min_items_env) : 2ll * num_sms();
   const long long m_tiles_total = (long long)B * p.tiles_per_sample;
   if (group == nullptr && G == 1 && !force_1cta && p.tma_epi && p.NT % 32 == 0 && m_tiles_total * p.ntiles >= min_items) {
@@ -1460,7 +1462,8 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    static const bool no_halo = getenv("MEGB200_TAPGEMM_PAIR_NOHALO") != nullptr;
+    // halo form of the pair kernel: correct (tests) but measured slower (536 vs 647 TFLOP/s) -> opt-in
+    static const bool no_halo = getenv("MEGB200_TAPGEMM_PAIR_HALO") == nullptr;
     const int a_rows2 = ((kTileM + (taps - 1) * dil) + 7) / 8 * 8;
     if (taps > 1 && a_rows2 <= 256 && !no_halo && p.n_last == p.NT) {
       // halo form: activation ring (with halo rows) + weight ring
