@@ -27,7 +27,9 @@ class _ClipFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module, Y, Zi, temp, want_logits):
         eng = module._engine(Zi.dtype)
-        loss, logits, saved = eng.forward(Y, Zi, temp.detach(), module.reduction, parallel.context(), want_logits)
+        prepared = module._take_prefetched(Y, eng)
+        loss, logits, saved = eng.forward(Y, Zi, temp.detach(), module.reduction, parallel.context(), want_logits,
+                                          prepared=prepared)
         ctx.eng, ctx.saved = eng, saved
         if want_logits:
             ctx.mark_non_differentiable(logits)
@@ -50,6 +52,8 @@ class CLIPLoss(nn.Module):
             raise ValueError(f"megb200 CLIPLoss supports reduction 'mean' or 'sum', got {self.reduction!r}")
         self.temp = nn.Parameter(torch.tensor([float(args.init_temperature)]))
         self._engs = {}
+        self._prefetched = None
+        self._side_stream = None
 
     def _engine(self, dtype) -> ClipEngine:
         ops = megb200.get_ops("bf16" if dtype == torch.bfloat16 and megb200.get_precision() != "bf16_simt"
@@ -58,6 +62,39 @@ class CLIPLoss(nn.Module):
         if eng is None or eng.ops is not ops:
             eng = self._engs[id(ops)] = ClipEngine(ops)
         return eng
+
+    # ------------------------------------------------------------------ optional overlap of the target preparation
+    def prefetch_targets(self, x, dtype=None):
+        """Optional (megb200 extension, not in the reference): start packing + all-gathering the targets ``x`` on a side
+        stream.  The targets do not depend on the encoder, so calling this BEFORE ``brain_encoder(X, ...)`` overlaps the
+        transpose/cast pass and, in data parallel, the NCCL all-gather of the targets with the encoder forward.  The next
+        ``forward(x, y)`` with the same tensor picks the result up; without this call nothing changes."""
+        dev = self.temp.device
+        if dev.type != "cuda":
+            return
+        if dtype is None:
+            dtype = torch.float32 if megb200.get_precision() == "fp32" else torch.bfloat16
+        eng = self._engine(dtype)
+        Y = x.detach().to(device=dev, dtype=torch.float32).contiguous()
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(device=dev)
+        cur = torch.cuda.current_stream(dev)
+        self._side_stream.wait_stream(cur)
+        with torch.cuda.stream(self._side_stream):
+            prepared = eng.prepare_targets(Y, parallel.context())
+            done = torch.cuda.Event()
+            done.record(self._side_stream)
+        Y.record_stream(self._side_stream)
+        self._prefetched = (Y.data_ptr(), tuple(Y.shape), eng, prepared, done)
+
+    def _take_prefetched(self, Y, eng):
+        pf, self._prefetched = self._prefetched, None
+        if pf is None or pf[0] != Y.data_ptr() or pf[1] != tuple(Y.shape) or pf[2] is not eng:
+            return None
+        torch.cuda.current_stream(Y.device).wait_event(pf[4])
+        for t in pf[3]:
+            t.record_stream(torch.cuda.current_stream(Y.device))
+        return pf[3]
 
     def forward(self, x, y, fast=True, return_logits=False):
         batch_size = x.size(0)

@@ -244,21 +244,31 @@ class ClipEngine:
     def __init__(self, ops):
         self.ops = ops
 
-    def forward(self, Y, Zi, temp, reduction="mean", dist_ctx=None, want_logits=False):
+    def prepare_targets(self, Y, dist_ctx=None):
+        """Pack the (constant) targets: f32 [B,F,T] | [B,F] -> position-major rows in the activation dtype plus their
+        squared norms, all-gathered over the ranks in data parallel.  Independent of the encoder, so callers may run
+        it on a side stream while the encoder forward executes (CLIPLoss.prefetch_targets)."""
+        ops, dev = self.ops, Y.device
+        B = Y.shape[0]
+        D = Y.numel() // B
+        Yp = ops.empty(B, D, device=dev)
+        ysq = _zeros(dev, B)
+        ops.clip_prep_y(Y, Yp, ysq)
+        if dist_ctx is not None and dist_ctx.world > 1:
+            Yp, ysq = dist_ctx.all_gather_rows(Yp), dist_ctx.all_gather_rows(ysq)
+        return Yp, ysq
+
+    def forward(self, Y, Zi, temp, reduction="mean", dist_ctx=None, want_logits=False, prepared=None):
         """Y: f32 targets [B,F,T] | [B,F]; Zi: embeddings in PC layout, contiguous [B, T, F] | [B, 1, F]."""
         ops, dev = self.ops, Zi.device
         B = Zi.shape[0]
         D = Zi.numel() // B
         assert Y.numel() == B * D, f"targets {tuple(Y.shape)} and embeddings {tuple(Zi.shape)} differ in size"
-        Yp = ops.empty(B, D, device=dev)
-        ysq = _zeros(dev, B)
-        ops.clip_prep_y(Y, Yp, ysq)
+        Yp, ysq = prepared if prepared is not None else self.prepare_targets(Y, dist_ctx)
         zsq = _zeros(dev, B)
         Zf = Zi.view(B, D)
         ops.rowsumsq(Zf, zsq)
         world, rank = (dist_ctx.world, dist_ctx.rank) if dist_ctx is not None else (1, 0)
-        if world > 1:
-            Yp, ysq = dist_ctx.all_gather_rows(Yp), dist_ctx.all_gather_rows(ysq)
         Bg, off = B * world, rank * B
         raw = _zeros(dev, Bg, B)
         ops.clip_logits(Yp, Zf, raw)

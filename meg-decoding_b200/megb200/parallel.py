@@ -95,7 +95,7 @@ def allreduce_grads(params: Iterable[torch.nn.Parameter], bucket_bytes: int = 64
             chunk = flat[o:o + n]
             o += n
             if p.is_complex():
-                new = torch.view_as_complex(chunk.view(*p.shape, 2).contiguous())
+                new = torch.view_as_complex(chunk.view(*p.shape, 2).clone())
             else:
                 new = chunk.view(p.shape)
             if p.grad is None:
