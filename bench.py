@@ -274,19 +274,26 @@ def run_megb200(args):
     barrier()
     adam_ms = e0.elapsed_time(e1) / 3
 
-    # ---- end to end: host buffers in, loss out, every step
-    def e2e_step():
-        X = Xh.to(dev, non_blocking=True)
-        Y = Yh.to(dev, non_blocking=True)
-        return float(step(X, Y, subj_h))          # .item(): device -> host read of the loss, as train.py:208
+    # ---- end to end: host buffers in, loss out, every step.  Public API: megb200.data.DevicePrefetcher (pinned host
+    # batches -> device on a copy stream, two batches in flight) + the drop-in modules + loss.item() (train.py:208).
+    from megb200.data import DevicePrefetcher
 
-    e2e_step()
+    def host_batches(n):
+        for _ in range(n):
+            yield (Xh, Yh, subj_h)
+
+    def e2e_run(n):
+        last = None
+        for X, Y, subj in DevicePrefetcher(host_batches(n), dev, keep_on_host=(2,)):
+            last = float(step(X, Y, subj).detach())      # device -> host read of the loss every step
+        return last
+
+    e2e_run(2)
     barrier()
     t0 = time.perf_counter()
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     g0.record()
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_run(args.steps)
     g1.record()
     barrier()
     e2e_ms = max_over_ranks(max(g0.elapsed_time(g1), (time.perf_counter() - t0) * 1e3) / args.steps)
