@@ -60,6 +60,10 @@ int megb200_pack_x(const float* X, void* Xp, int B, int C, int T, int Cs, int dt
 int megb200_pack_weight(const float* w, void* out, int G, int O, int I, int Kt, int Np, int Kp, int mode,
                         int dtype, void* stream);
 
+/* Same packing for many weights in one launch.  `table` is a DEVICE array of n entries of ten int64:
+ * {src pointer, dst pointer, G, O, I, Kt, Np, Kp, mode, G*Np*Kt*Kp}. */
+int megb200_pack_weight_multi(const long long* table, int n, int dtype, void* stream);
+
 /* ---------------------------------------------------------------------------------------------- contractions */
 /* "tap GEMM": out[b][t][n] = sum_j sum_c A[b][t + (j - taps/2)*dil][c] * W[g][n][j*Kp + c]
  *                            (+ bias[g][n]) (+ Res[b][t][n]),   g = group[b] (0 when group == NULL),

@@ -82,6 +82,31 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
   }
 }
 
+// all conv weights of a step in ONE launch: entry e of `table` = {src, dst, G, O, I, Kt, Np, Kp, mode, total} (int64)
+template <typename T>
+__global__ void pack_weight_multi_kernel(const long long* __restrict__ table) {
+  const long long* e = table + 10 * blockIdx.y;
+  const float* w = reinterpret_cast<const float*>(e[0]);
+  T* out = reinterpret_cast<T*>(e[1]);
+  const int O = (int)e[3], I = (int)e[4], Kt = (int)e[5], Np = (int)e[6], Kp = (int)e[7], mode = (int)e[8];
+  const long long total = e[9];
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int kk = (int)(idx % ((long long)Kt * Kp));
+    const long long r = idx / ((long long)Kt * Kp);
+    const int n = (int)(r % Np);
+    const int g = (int)(r / Np);
+    const int j = kk / Kp, k = kk % Kp;
+    float v = 0.f;
+    if (mode == 0) {
+      if (n < O && k < I) v = w[(((long long)g * O + n) * I + k) * Kt + j];
+    } else {
+      if (n < I && k < O) v = w[(((long long)g * O + k) * I + n) * Kt + (Kt - 1 - j)];
+    }
+    out[idx] = from_f<T>(v);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ row-loop passes
 // One CTA owns a slab of rows; thread = (channel group of 8, row lane) and keeps its channel group for the whole
 // slab, so per-channel parameters are loaded ONCE into registers (Op::init) and the loop body is pure streaming:
@@ -618,6 +643,13 @@ int megb200_pack_weight(const float* w, void* out, int G, int O, int I, int Kt, 
   const long long total = (long long)G * Np * Kt * Kp;
   DISPATCH_DTYPE(dtype, pack_weight_kernel<DT><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
                             w, (DT*)out, G, O, I, Kt, Np, Kp, mode, total);
+                 MEGB_LAUNCH_OK(); return 0;)
+}
+
+int megb200_pack_weight_multi(const long long* table, int n, int dtype, void* stream) {
+  MEGB_CHECK_ARG(table && n > 0 && n <= 65535, "pack_weight_multi: bad arguments");
+  dim3 grid(64, n);
+  DISPATCH_DTYPE(dtype, pack_weight_multi_kernel<DT><<<grid, 256, 0, (cudaStream_t)stream>>>(table);
                  MEGB_LAUNCH_OK(); return 0;)
 }
 

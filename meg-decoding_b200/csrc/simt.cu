@@ -222,7 +222,10 @@ simt_sgemm_kernel(int transA, int transB, int M, int N, int K, float alpha, cons
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-  for (int k0 = k_begin; k0 < k_end; k0 += kSgK) {
+  // global -> register prefetch of the next k tile while the current one is multiplied (one CTA per SM at 132
+  // registers: without it every k step exposes a full global-memory latency)
+  float ra[4], rb[4];
+  auto fetch = [&](int k0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int e = tid + i * 256;
@@ -233,7 +236,7 @@ simt_sgemm_kernel(int transA, int transB, int M, int N, int K, float alpha, cons
         const int gm = m0 + m, gk = k0 + kk;
         float v = 0.f;
         if (gm < M && gk < k_end) v = transA ? Ab[(long long)gk * lda + gm] : Ab[(long long)gm * lda + gk];
-        As[kk][m] = v;
+        ra[i] = v;
       }
       {
         const int n = transB ? (e >> 3) : (e & 127);
@@ -241,10 +244,23 @@ simt_sgemm_kernel(int transA, int transB, int M, int N, int K, float alpha, cons
         const int gn = n0 + n, gk = k0 + kk;
         float v = 0.f;
         if (gn < N && gk < k_end) v = transB ? Bb[(long long)gn * ldb + gk] : Bb[(long long)gk * ldb + gn];
-        Bs[kk][n] = v;
+        rb[i] = v;
       }
     }
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + i * 256;
+      As[transA ? (e >> 7) : (e & 7)][transA ? (e & 127) : (e >> 3)] = ra[i];
+      Bs[transB ? (e & 7) : (e >> 7)][transB ? (e >> 3) : (e & 127)] = rb[i];
+    }
+  };
+  fetch(k_begin);
+  for (int k0 = k_begin; k0 < k_end; k0 += kSgK) {
+    stash();
     __syncthreads();
+    if (k0 + kSgK < k_end) fetch(k0 + kSgK);
 #pragma unroll
     for (int kk = 0; kk < kSgK; ++kk) {
       const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);

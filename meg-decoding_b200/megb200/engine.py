@@ -28,6 +28,27 @@ def _zeros(dev, *shape):
     return torch.zeros(*shape, dtype=torch.float32, device=dev)
 
 
+class _ZeroPool:
+    """One memset per pass instead of ~60 tiny ones: f32 accumulators / gradient buffers are carved out of a single
+    zero-filled allocation (256-byte aligned views).  Falls back to torch.zeros when exhausted."""
+
+    def __init__(self, dev, nfloats):
+        self.dev = dev
+        self.buf = torch.zeros(int(nfloats), dtype=torch.float32, device=dev)
+        self.off = 0
+
+    def take(self, *shape):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        n_al = (n + 63) // 64 * 64
+        if self.off + n_al > self.buf.numel():
+            return torch.zeros(*shape, dtype=torch.float32, device=self.dev)
+        v = self.buf[self.off:self.off + n].view(*shape)
+        self.off += n_al
+        return v
+
+
 class EncoderEngine:
     """BrainEncoder.forward / backward (models.py:367-383 and the modules it owns)."""
 
@@ -37,6 +58,36 @@ class EncoderEngine:
         self.seq2seq = seq2seq
         self.dil = dilations if dilations is not None else [(1, 1, 1)] * 5
         self.eps, self.momentum = eps, momentum
+        self._packed = {}        # persistent packed-weight buffers, keyed by (name, mode, device)
+        self._zp = None          # zero pool of the pass in flight
+
+    # ------------------------------------------------------------------------------------------ weight packing
+    def _conv_list(self, P):
+        """(name, weight, N, cin, taps) of every convolution on the path, in execution order."""
+        D1, D2, Fo = self.D1, self.D2, self.F
+        out = []
+        for k in range(5):
+            pk = P["blocks"][k]
+            out.append((f"b{k}.w0", pk["w0"], D2, D1 if k == 0 else D2, 3))
+            out.append((f"b{k}.w1", pk["w1"], D2, D2, 3))
+            out.append((f"b{k}.w2", pk["w2"], 2 * D2, D2, 3))
+        out.append(("wf1", P["wf1"], 2 * D2, D2, 1))
+        out.append(("wf2", P["wf2"], Fo, 2 * D2, 1))
+        return out
+
+    def _pack_all(self, P, mode, dev):
+        """Pack every conv weight for the forward (mode 0) or the data-gradient (mode 1) tap-GEMMs in one launch."""
+        items, bufs = [], {}
+        for name, w, N, cin, taps in self._conv_list(P):
+            key = (name, mode, str(dev))
+            buf = self._packed.get(key)
+            shape = (1, pad16(N), taps * pad64(cin)) if mode == 0 else (1, pad16(cin), taps * pad64(N))
+            if buf is None or tuple(buf.shape) != shape or buf.dtype != self.ops.act_dtype:
+                buf = self._packed[key] = self.ops.empty(*shape, device=dev)
+            items.append((w.view(1, N, cin, taps), buf, mode))
+            bufs[name] = buf
+        self.ops.pack_weights(items)
+        return bufs
 
     # ------------------------------------------------------------------------------------------ forward
     def forward(self, P: Dict, X: torch.Tensor, subj: torch.Tensor, mask: Optional[torch.Tensor], training: bool):
@@ -45,6 +96,8 @@ class EncoderEngine:
         D1, D2, Fo, S = self.D1, self.D2, self.F, self.S
         assert C == self.C, f"expected {self.C} sensors, got {C}"                       # models.py:233
         ctx = {"B": B, "T": T, "subj": subj, "mask": mask}
+        self._wf = self._pack_all(P, 0, dev)
+        self._zp = _ZeroPool(dev, 10 * 2 * pad64(D2) + 1024)
 
         # ---- spatial attention weights + subject chain, fp32 (models.py:204-213, 252, 269-272)
         a = _f32(dev, D1, C)
@@ -73,11 +126,11 @@ class EncoderEngine:
             pk, d = P["blocks"][k], self.dil[k]
             bc = {"x": x, "cin": cin}
             # pre-BatchNorm tensors stay in f32: the normalisation sees the unrounded convolution (+ residual)
-            u0 = self._conv(x, cin, pk["w0"], pk["b0"], D2, d[0], x if k > 0 else None, epi="store_f32")
+            u0 = self._conv(x, cin, f"b{k}.w0", pk["b0"], D2, d[0], x if k > 0 else None, epi="store_f32")
             h0, bc["bn0"] = self._bn_gelu(u0, pk, "0", training)
-            u1 = self._conv(h0, D2, pk["w1"], pk["b1"], D2, d[1], h0, epi="store_f32")
+            u1 = self._conv(h0, D2, f"b{k}.w1", pk["b1"], D2, d[1], h0, epi="store_f32")
             h1, bc["bn1"] = self._bn_gelu(u1, pk, "1", training)
-            out, v = self._conv(h1, D2, pk["w2"], pk["b2"], 2 * D2, d[2], None, epi="glu")
+            out, v = self._conv(h1, D2, f"b{k}.w2", pk["b2"], 2 * D2, d[2], None, epi="glu")
             bc.update(u0=u0, h0=h0, u1=u1, h1=h1, v=v)
             blocks.append(bc)
             x, cin = out, D2
@@ -85,8 +138,8 @@ class EncoderEngine:
         ctx["x5"] = x
 
         # ---- 1x1 head (models.py:373-374): GELU after both convs
-        q1, p1 = self._conv(x, D2, P["wf1"], P["bf1"], 2 * D2, 1, None, taps=1, epi="gelu")
-        Z, p2 = self._conv(q1, 2 * D2, P["wf2"], P["bf2"], Fo, 1, None, taps=1, epi="gelu")
+        q1, p1 = self._conv(x, D2, "wf1", P["bf1"], 2 * D2, 1, None, taps=1, epi="gelu")
+        Z, p2 = self._conv(q1, 2 * D2, "wf2", P["bf2"], Fo, 1, None, taps=1, epi="gelu")
         ctx.update(p1=p1, q1=q1, p2=p2)
         if not self.seq2seq:                                                            # models.py:382
             Zm = ops.empty(B, 1, pad8(Fo), device=dev)
@@ -94,13 +147,12 @@ class EncoderEngine:
             return Zm, ctx
         return Z, ctx
 
-    def _conv(self, x, cin, w, b, N, dil, res, taps=3, epi="store"):
-        """Conv1d (k = taps, "same") as a tap-GEMM with a fused tail.  Returns Out, or (Out, Out2) for the GELU / GLU
-        epilogues (Out2 = the pre-activation kept for backward)."""
+    def _conv(self, x, cin, wname, b, N, dil, res, taps=3, epi="store"):
+        """Conv1d (k = taps, "same") as a tap-GEMM with a fused tail on the pre-packed weight `wname`.  Returns Out, or
+        (Out, Out2) for the GELU / GLU epilogues (Out2 = the pre-activation kept for backward)."""
         ops, dev = self.ops, x.device
         B, T = x.shape[0], x.shape[1]
-        Wpk = ops.empty(1, pad16(N), taps * pad64(cin), device=dev)
-        ops.pack_weight(w.view(1, N, cin, taps), Wpk, 0)
+        Wpk = self._wf[wname]
         if epi == "store_f32":
             out = _f32(dev, B, T, pad8(N))
             ops.tapgemm(x, cin, Wpk, N, taps, dil, b, res, None, out, epi=epi)
@@ -122,7 +174,7 @@ class EncoderEngine:
         n = u.shape[0] * u.shape[1]
         sums = None
         if training:
-            sums = _zeros(dev, 2, D2)
+            sums = self._zp.take(2, D2)
             ops.bn_stats(u, D2, sums)
         st = {k: _f32(dev, D2) for k in ("scale", "shift", "mean", "rstd")}
         ops.bn_finalize(sums, pk["g" + i], pk["be" + i], pk["rm" + i], pk["rv" + i], n, self.eps, self.momentum,
@@ -140,6 +192,9 @@ class EncoderEngine:
         D1, D2, Fo, S, C = self.D1, self.D2, self.F, self.S, self.C
         n = B * T
         G: Dict = {"blocks": [dict() for _ in range(5)]}
+        self._wd = self._pack_all(P, 1, dev)
+        nparam = sum(int(w.numel()) + N for _, w, N, _, _ in self._conv_list(P))
+        self._zp = _ZeroPool(dev, nparam + S * D1 * C + S * D1 + 20 * 2 * pad64(D2) + 64 * 80)
 
         if not self.seq2seq:
             full = ops.empty(B, T, pad8(Fo), device=dev)
@@ -147,44 +202,43 @@ class EncoderEngine:
             dZ = full
         # ---- head
         # bias gradients are column sums of the tensors the element-wise backward passes write: fused there
-        dp2, G["bf2"] = ops.empty(*dZ.shape, device=dev), _zeros(dev, Fo)
+        dp2, G["bf2"] = ops.empty(*dZ.shape, device=dev), self._zp.take(Fo)
         ops.gelu_bwd(dZ, ctx["p2"], dp2, Fo, G["bf2"])
         G["wf2"] = self._wgrad(dp2, Fo, ctx["q1"], 2 * D2, 1, 1)
-        dq1 = self._dgrad(dp2, Fo, P["wf2"], 2 * D2, 1, None, taps=1)
-        dp1, G["bf1"] = ops.empty(*dq1.shape, device=dev), _zeros(dev, 2 * D2)
+        dq1 = self._dgrad(dp2, Fo, "wf2", 2 * D2, 1, None, taps=1)
+        dp1, G["bf1"] = ops.empty(*dq1.shape, device=dev), self._zp.take(2 * D2)
         ops.gelu_bwd(dq1, ctx["p1"], dp1, 2 * D2, G["bf1"])
         G["wf1"] = self._wgrad(dp1, 2 * D2, ctx["x5"], D2, 1, 1)
-        dx = self._dgrad(dp1, 2 * D2, P["wf1"], D2, 1, None, taps=1)
+        dx = self._dgrad(dp1, 2 * D2, "wf1", D2, 1, None, taps=1)
 
         # ---- conv blocks, last to first
         for k in range(4, -1, -1):
             pk, bc, d, g = P["blocks"][k], ctx["blocks"][k], self.dil[k], G["blocks"][k]
             dv = ops.empty(*bc["v"].shape, device=dev)
+            g["b2"] = self._zp.take(2 * D2)
             if D2 % 8 == 0 and bc["v"].shape[2] == 2 * D2:
-                g["b2"] = _zeros(dev, 2 * D2)
                 ops.glu_bwd(dx, bc["v"], dv, D2, g["b2"])
             else:
                 ops.glu_bwd(dx, bc["v"], dv, D2)
-                g["b2"] = _zeros(dev, 2 * D2)
                 ops.colsum(dv, 2 * D2, None, g["b2"])
             g["w2"] = self._wgrad(dv, 2 * D2, bc["h1"], D2, 3, d[2])
-            dh1 = self._dgrad(dv, 2 * D2, pk["w2"], D2, d[2], None)
+            dh1 = self._dgrad(dv, 2 * D2, f"b{k}.w2", D2, d[2], None)
             du1, g["g1"], g["be1"], g["b1"] = self._bn_gelu_bwd(dh1, bc["u1"], bc["bn1"], pk["g1"], n)
             g["w1"] = self._wgrad(du1, D2, bc["h0"], D2, 3, d[1])
-            dh0 = self._dgrad(du1, D2, pk["w1"], D2, d[1], du1)
+            dh0 = self._dgrad(du1, D2, f"b{k}.w1", D2, d[1], du1)
             du0, g["g0"], g["be0"], g["b0"] = self._bn_gelu_bwd(dh0, bc["u0"], bc["bn0"], pk["g0"], n)
             g["w0"] = self._wgrad(du0, D2, bc["x"], bc["cin"], 3, d[0])
-            dx = self._dgrad(du0, D2, pk["w0"], bc["cin"], d[0], du0 if k > 0 else None)
+            dx = self._dgrad(du0, D2, f"b{k}.w0", bc["cin"], d[0], du0 if k > 0 else None)
         dH2 = dx
 
         # ---- subject block + spatial attention, fp32 small algebra
         subj = ctx["subj"]
         order = torch.empty_like(subj)
         ops.group_order(subj, S, order)
-        dWeff = _zeros(dev, S, D1, C, 1)
+        dWeff = self._zp.take(S, D1, C, 1)
         ops.wgrad(dH2, D1, ctx["Xp"], C, 1, 1, subj, order, dWeff)
         dWeff = dWeff.view(S, D1, C)
-        dbeff = _zeros(dev, S, D1)
+        dbeff = self._zp.take(S, D1)
         ops.colsum(dH2, D1, subj, dbeff)
         dWs = _f32(dev, S, D1, D1)
         ops.matmul(dWeff, ctx["M1"], dWs, transB=True)
@@ -208,15 +262,14 @@ class EncoderEngine:
 
     def _wgrad(self, dU, M, Xin, C, taps, dil):
         ops, dev = self.ops, dU.device
-        dW = _zeros(dev, 1, M, C, taps)
+        dW = self._zp.take(1, M, C, taps)
         ops.wgrad(dU, M, Xin, C, taps, dil, None, None, dW)
         return dW.view(M, C, taps)
 
-    def _dgrad(self, dU, M, w, cin, dil, res, taps=3):
-        """dX = conv_transpose(dU): same tap-GEMM with the transposed, tap-flipped weight pack."""
+    def _dgrad(self, dU, M, wname, cin, dil, res, taps=3):
+        """dX = conv_transpose(dU): same tap-GEMM with the transposed, tap-flipped weight pack `wname`."""
         ops = self.ops
-        Wd = ops.empty(1, pad16(cin), taps * pad64(M), device=dU.device)
-        ops.pack_weight(w.view(1, M, cin, taps), Wd, 1)
+        Wd = self._wd[wname]
         out = ops.empty(dU.shape[0], dU.shape[1], pad8(cin), device=dU.device)
         ops.tapgemm(dU, M, Wd, cin, taps, dil, None, res, None, out)
         return out
@@ -224,10 +277,10 @@ class EncoderEngine:
     def _bn_gelu_bwd(self, dh, u, st, gamma, n):
         ops, dev, D2 = self.ops, dh.device, self.D2
         dy = ops.empty(*u.shape, device=dev)
-        sums2 = _zeros(dev, 2, D2)
+        sums2 = self._zp.take(2, D2)
         ops.bn_gelu_bwd_reduce(dh, u, st["scale"], st["shift"], st["mean"], st["rstd"], dy, sums2, D2)
         du = ops.empty(*u.shape, device=dev)
-        db = _zeros(dev, D2)
+        db = self._zp.take(D2)
         ops.bn_bwd_apply(dy, u, gamma, st["mean"], st["rstd"], sums2, n, du, D2, db)
         return du, sums2[1], sums2[0], db
 

@@ -21,6 +21,7 @@ _p, _i, _ll, _f, _sz = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_size_t
 SIGNATURES = {
     "megb200_pack_x": [_p, _p, _i, _i, _i, _i, _i, _p],
     "megb200_pack_weight": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "megb200_pack_weight_multi": [_p, _i, _i, _p],
     "megb200_tapgemm": [_p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p, _p, _i, _p, _i, _i, _p, _i, _p, _i, _i, _i, _p],
     "megb200_wgrad": [_p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _p, _sz, _i, _i, _p],
     "megb200_group_order": [_p, _i, _i, _p, _p],

@@ -103,6 +103,28 @@ class CudaOps:
         assert out.shape[0] == G and out.shape[2] == Kt * Kp
         L.call("megb200_pack_weight", w.data_ptr(), out.data_ptr(), G, O, I, Kt, Np, Kp, mode, self.dt, self._stream())
 
+    def pack_weights(self, items):
+        """items: list of (w f32 [G,O,I,Kt], out [G,Np,Kt*Kp], mode).  One launch for all of them; the descriptor table
+        is cached while the tensors' addresses stay the same (parameters are updated in place by the optimizer)."""
+        key = tuple((w.data_ptr(), o.data_ptr(), m) for w, o, m in items)
+        cached = getattr(self, "_pack_tables", None)
+        if cached is None:
+            cached = self._pack_tables = {}
+        tab = cached.get(key)
+        if tab is None:
+            rows = []
+            for w, o, m in items:
+                self._chk_f32(w)
+                self._chk_act(o)
+                G, O, I, Kt = w.shape
+                Np, Kp = o.shape[1], o.shape[2] // Kt
+                assert o.shape[0] == G and o.shape[2] == Kt * Kp
+                rows.append([w.data_ptr(), o.data_ptr(), G, O, I, Kt, Np, Kp, m, G * Np * Kt * Kp])
+            if len(cached) > 64:
+                cached.clear()
+            tab = cached[key] = torch.tensor(rows, dtype=torch.int64).to(items[0][0].device)
+        L.call("megb200_pack_weight_multi", tab.data_ptr(), len(items), self.dt, self._stream())
+
     # ------------------------------------------------------------------ contractions
     def tapgemm(self, A, Ca, W, N, taps, dil, bias, Res, group, Out, epi="store", Out2=None):
         """epi: "store" | "store_f32" (Out is f32: pre-BatchNorm tensors) | "gelu" (Out2 = pre-activation, Out =

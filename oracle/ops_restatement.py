@@ -48,6 +48,10 @@ class TorchOps:
         else:
             o4[:, :I, :, :O] = self._r(w.flip(3).permute(0, 2, 3, 1))
 
+    def pack_weights(self, items):
+        for w, out, mode in items:
+            self.pack_weight(w, out, mode)
+
     # ------------------------------------------------------------------ contractions
     def tapgemm(self, A, Ca, W, N, taps, dil, bias, Res, group, Out, epi="store", Out2=None):
         B, T, _ = A.shape
