@@ -113,7 +113,7 @@ __global__ void pack_weight_multi_kernel(const long long* __restrict__ table) {
 // 16/32-byte vector loads and stores, no parameter traffic.  Op::row() consumes one 8-vector, may write outputs, and
 // may add into up to two per-channel accumulators that end in one global atomic per channel per CTA.
 template <class Op>
-__global__ void __launch_bounds__(256) rowloop_kernel(Op op, long long rows, long long rows_per_block, int C, int Cs,
+__global__ void __launch_bounds__(256, 3) rowloop_kernel(Op op, long long rows, long long rows_per_block, int C, int Cs,
                                                       const int32_t* __restrict__ group, int Tn,
                                                       float* __restrict__ out0, float* __restrict__ out1) {
   extern __shared__ float sm[];  // [2][Cs] when the op reduces
@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(256) rowloop_kernel(Op op, long long rows, lon
       op.init(g * 8);
 #pragma unroll 2
       for (long long r = r0 + lane_r; r < r1; r += R) op.row(r, g * 8, a0, a1);
+      op.finish(g * 8, a0, a1);
       if (Op::kAcc > 0) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -164,6 +165,7 @@ struct StatsOp {
   const T* u;
   int Cs;
   __device__ __forceinline__ void init(int) {}
+  __device__ __forceinline__ void finish(int, float (&)[8], float (&)[8]) const {}
   __device__ __forceinline__ void row(long long r, int c0, float (&a0)[8], float (&a1)[8]) const {
     float x[8];
     load8(u + r * Cs + c0, x);
@@ -181,6 +183,7 @@ struct ColsumOp {
   const T* u;
   int Cs;
   __device__ __forceinline__ void init(int) {}
+  __device__ __forceinline__ void finish(int, float (&)[8], float (&)[8]) const {}
   __device__ __forceinline__ void row(long long r, int c0, float (&a0)[8], float (&a1)[8]) const {
     float x[8];
     load8(u + r * Cs + c0, x);
@@ -206,16 +209,19 @@ struct BnGeluOp {
       sh[i] = in ? shift[c0 + i] : 0.f;
     }
   }
+  __device__ __forceinline__ void finish(int, float (&)[8], float (&)[8]) const {}
   __device__ __forceinline__ void row(long long r, int c0, float (&a0)[8], float (&a1)[8]) const {
     float x[8], o[8];
     load8(u + r * Cs + c0, x);
+    // pad channels have scale = shift = 0 (init): gelu(0) = 0, so no per-element predicate is needed
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = (c0 + i < C) ? gelu_t<T>(fmaf(x[i], sc[i], sh[i])) : 0.f;
+    for (int i = 0; i < 8; ++i) o[i] = gelu_t<T>(fmaf(x[i], sc[i], sh[i]));
     store8(h + r * Cs + c0, o);
   }
 };
 
-// dY = dH * gelu'(y), y = scale*u + shift; accumulates sum dY and sum dY*xhat
+// dY = dH * gelu'(y), y = scale*u + shift; accumulates sum dY and sum dY*xhat.  Per element the loop only forms
+// sum d and sum d*u; xhat = (u - mean)*rstd is folded in once per thread at the end (finish()).
 template <typename TU, typename T>
 struct BnGeluBwdOp {
   static constexpr int kAcc = 2;
@@ -224,15 +230,13 @@ struct BnGeluBwdOp {
   T* dy;
   const float *scale, *shift, *mean, *rstd;
   int Cs, C;
-  float sc[8], sh[8], mu[8], rs[8];
+  float sc[8], sh[8];
   __device__ __forceinline__ void init(int c0) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const bool in = c0 + i < C;
       sc[i] = in ? scale[c0 + i] : 0.f;
       sh[i] = in ? shift[c0 + i] : 0.f;
-      mu[i] = in ? mean[c0 + i] : 0.f;
-      rs[i] = in ? rstd[c0 + i] : 0.f;
     }
   }
   __device__ __forceinline__ void row(long long r, int c0, float (&a0)[8], float (&a1)[8]) const {
@@ -241,15 +245,19 @@ struct BnGeluBwdOp {
     load8(u + r * Cs + c0, x);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      float d = 0.f;
-      if (c0 + i < C) {
-        d = round_to<T>(g[i] * gelu_grad_t<T>(fmaf(x[i], sc[i], sh[i])));
-        a0[i] += d;
-        a1[i] += d * (x[i] - mu[i]) * rs[i];
-      }
+      const float d = g[i] * gelu_grad_t<T>(fmaf(x[i], sc[i], sh[i]));   // pad channels: dH = 0 -> d = 0
+      a0[i] += d;
+      a1[i] = fmaf(d, x[i], a1[i]);
       o[i] = d;
     }
     store8(dy + r * Cs + c0, o);
+  }
+  __device__ __forceinline__ void finish(int c0, float (&a0)[8], float (&a1)[8]) const {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = c0 + i;
+      a1[i] = (c < C) ? (a1[i] - mean[c] * a0[i]) * rstd[c] : 0.f;       // sum d*(u - mean)*rstd
+    }
   }
 };
 
@@ -278,6 +286,7 @@ struct BnBwdApplyOp {
       }
     }
   }
+  __device__ __forceinline__ void finish(int, float (&)[8], float (&)[8]) const {}
   __device__ __forceinline__ void row(long long r, int c0, float (&a0)[8], float (&a1)[8]) const {
     float g[8], x[8], o[8];
     load8(dy + r * Cs + c0, g);
@@ -300,13 +309,14 @@ struct GeluBwdOp {
   T* dp;
   int Cs, C;
   __device__ __forceinline__ void init(int) {}
+  __device__ __forceinline__ void finish(int, float (&)[8], float (&)[8]) const {}
   __device__ __forceinline__ void row(long long r, int c0, float (&a0)[8], float (&a1)[8]) const {
     float g[8], x[8], o[8];
     load8(dq + r * Cs + c0, g);
     load8(p + r * Cs + c0, x);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      o[i] = (c0 + i < C) ? round_to<T>(g[i] * gelu_grad_t<T>(x[i])) : 0.f;
+      o[i] = g[i] * gelu_grad_t<T>(x[i]);            // pad channels: dQ = 0
       a0[i] += o[i];
     }
     store8(dp + r * Cs + c0, o);
@@ -323,6 +333,7 @@ struct GluBwdOp {
   T* dV;
   int Vs, Os, C;
   __device__ __forceinline__ void init(int) {}
+  __device__ __forceinline__ void finish(int, float (&)[8], float (&)[8]) const {}
   __device__ __forceinline__ void row(long long r, int c0, float (&a0)[8], float (&a1)[8]) const {
     if (c0 >= C) return;
     float d[8], a[8], g[8], da[8], dg[8];

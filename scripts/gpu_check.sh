@@ -40,7 +40,7 @@ for s in ${stages}; do
                       run ncu_launches 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off \
                           --csv --log-file gpurun_out/launches.csv python bench.py --ncu-step --warmup 3 ;;
     ncu_full)         run ncu_plain2 300 python bench.py --ncu-step --warmup 3 &&
-                      run ncu_full 1200 ncu --set full --clock-control none --import-source on --profile-from-start off \
+                      run ncu_full 1200 ncu --set full --clock-control none --import-source on --profile-from-start off --kernel-name-base demangled \
                           -k regex:"${NCU_KERNEL:-tc_tapgemm}" -s "${NCU_SKIP:-8}" -c "${NCU_COUNT:-2}" -f -o gpurun_out/prof_${NCU_TAG:-tapgemm} \
                           python bench.py --ncu-step --warmup 3 ;;
     all_gpu_tests)    run all_gpu_tests 1800 ${PT} tests ;;
