@@ -245,7 +245,8 @@ struct BnGeluBwdOp {
     load8(u + r * Cs + c0, x);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float d = g[i] * gelu_grad_t<T>(fmaf(x[i], sc[i], sh[i]));   // pad channels: dH = 0 -> d = 0
+      float d = g[i] * gelu_grad_t<T>(fmaf(x[i], sc[i], sh[i]));
+      if (c0 + 8 > C && c0 + i >= C) d = 0.f;        // only the last, partial channel group pays for the mask
       a0[i] += d;
       a1[i] = fmaf(d, x[i], a1[i]);
       o[i] = d;
@@ -316,7 +317,8 @@ struct GeluBwdOp {
     load8(p + r * Cs + c0, x);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      o[i] = g[i] * gelu_grad_t<T>(x[i]);            // pad channels: dQ = 0
+      o[i] = g[i] * gelu_grad_t<T>(x[i]);
+      if (c0 + 8 > C && c0 + i >= C) o[i] = 0.f;     // only the last, partial channel group pays for the mask
       a0[i] += o[i];
     }
     store8(dp + r * Cs + c0, o);

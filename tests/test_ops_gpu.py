@@ -312,7 +312,9 @@ def test_glu_gelu_timemean(dtype, C):
     ops.gelu_bwd(gd, Pd, dP, C, db)
     ref.gelu_bwd(g, P, dPr, C, dbr)
     _close(dP, dPr, dtype, "gelu_bwd")
-    _close(db, dP.float().cpu()[:, :, :C].sum((0, 1)), torch.float32, "gelu_bwd dbias", atol_scale=20)
+    # the fused column sums are taken before the rounding of dP: compare with one rounding of slack in bf16
+    _close(db, dP.float().cpu()[:, :, :C].sum((0, 1)), torch.float32, "gelu_bwd dbias",
+           atol_scale=20 if dtype == torch.float32 else 400)
     Fs = pad8(C)
     Zm, Zmr = ops.empty(B, 1, Fs, device=DEV), ref.empty(B, 1, Fs, device="cpu")
     ops.time_mean(Pd, Zm, C)
