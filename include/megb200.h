@@ -71,10 +71,13 @@ int megb200_pack_weight_multi(const long long* table, int n, int dtype, void* st
  * 1x1 chain pre-multiplied into one grouped GEMM keyed by subject index (models.py:220,269-272), Conv1d k=3
  * forward (models.py:310-319), its data gradient (flipped/transposed pack), and the 1x1 head convs
  * (models.py:373-374).  N = logical output channels; channels N..Cos-1 of Out are written as zero.  `epilogue`
- * is one of MEGB200_EPI_*; Out2/Co2s are used by the GELU and GLU epilogues only. */
+ * is one of MEGB200_EPI_*; Out2/Co2s are used by the GELU and GLU epilogues only.  `stats` (optional, f32 epilogue
+ * only): sums[2][N] += (sum, sum of squares) over all positions of Out — the train-mode BatchNorm statistics of
+ * models.py:291,299, reduced in the epilogue instead of a separate pass (same result as megb200_bn_stats). */
 int megb200_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int N, int Np, int Kp, int taps,
                     int dil, const float* bias, const void* Res, int Crs, const int32_t* group, int G,
-                    int epilogue, void* Out, int Cos, void* Out2, int Co2s, int dtype, int backend, void* stream);
+                    int epilogue, void* Out, int Cos, void* Out2, int Co2s, float* stats, int dtype, int backend,
+                    void* stream);
 
 /* Weight gradient: dW[g][m][c][j] += sum_{b: group[b]==g} sum_t dU[b][t][m] * Xin[b][t + (j - taps/2)*dil][c]
  * (f32, nn.Conv1d layout [G][M][C][taps]; accumulated — caller zeroes).  Replaces autograd's

@@ -107,7 +107,7 @@ int encode_tmap(CUtensorMap* map, const void* base, int elem_bytes, int swizzle_
 
 int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int N, int Np, int Kp, int taps, int dil,
                const float* bias, const void* Res, int Crs, const int32_t* group, int G, int epi, void* Out, int Cos,
-               void* Out2, int Co2s, cudaStream_t st);
+               void* Out2, int Co2s, float* stats, int* stats_fused, cudaStream_t st);
 int tc_wgrad(const void* dU, int M, int Ms, const void* Xin, int C, int Cs, int B, int T, int taps, int dil,
              const int32_t* group, const int32_t* order, int G, float* dW, float* workspace, size_t ws_bytes,
              cudaStream_t st);
@@ -167,7 +167,8 @@ int megb200_group_order(const int32_t* group, int B, int G, int32_t* order, void
 
 int megb200_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int N, int Np, int Kp, int taps,
                     int dil, const float* bias, const void* Res, int Crs, const int32_t* group, int G, int epilogue,
-                    void* Out, int Cos, void* Out2, int Co2s, int dtype, int backend, void* stream) {
+                    void* Out, int Cos, void* Out2, int Co2s, float* stats, int dtype, int backend, void* stream) {
+  MEGB_CHECK_ARG(stats == nullptr || epilogue == MEGB200_EPI_STORE_F32, "tapgemm: statistics need the f32 epilogue");
   MEGB_CHECK_ARG(A && W && Out && B > 0 && T > 0 && Ca > 0 && N > 0 && taps >= 1 && (taps & 1) && dil >= 1 && G >= 1,
                  "tapgemm: bad arguments");
   MEGB_CHECK_ARG(epilogue >= MEGB200_EPI_STORE && epilogue <= MEGB200_EPI_GLU, "tapgemm: unknown epilogue %d", epilogue);
@@ -184,17 +185,24 @@ int megb200_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W,
       set_last_error("tapgemm: the tensor-core engine needs bf16 activations");
       return MEGB200_ERR_UNSUPPORTED;
     }
-    return tc::tc_tapgemm(A, B, T, Ca, Cas, W, N, Np, Kp, taps, dil, bias, Res, Crs, group, G, epilogue, Out, Cos, Out2,
-                          Co2s, st);
+    int fused = 0;
+    int rc = tc::tc_tapgemm(A, B, T, Ca, Cas, W, N, Np, Kp, taps, dil, bias, Res, Crs, group, G, epilogue, Out, Cos,
+                            Out2, Co2s, stats, &fused, st);
+    if (rc != 0 || stats == nullptr || fused) return rc;
+    return megb200_bn_stats(Out, (long long)B * T, N, Cos, stats, MEGB200_F32, stream);   // kernel variant without fusion
   }
   MEGB_CHECK_ARG(backend == MEGB200_SIMT, "tapgemm: unknown backend %d", backend);
+  int rc;
   if (dtype == MEGB200_F32)
-    return simt_tapgemm<float>(A, B, T, Ca, Cas, W, N, Np, Kp, taps, dil, bias, Res, Crs, group, epilogue, Out, Cos,
-                               Out2, Co2s, st);
-  if (dtype == MEGB200_BF16)
-    return simt_tapgemm<__nv_bfloat16>(A, B, T, Ca, Cas, W, N, Np, Kp, taps, dil, bias, Res, Crs, group, epilogue, Out,
-                                       Cos, Out2, Co2s, st);
-  MEGB_CHECK_ARG(false, "tapgemm: unknown dtype %d", dtype);
+    rc = simt_tapgemm<float>(A, B, T, Ca, Cas, W, N, Np, Kp, taps, dil, bias, Res, Crs, group, epilogue, Out, Cos, Out2,
+                             Co2s, st);
+  else if (dtype == MEGB200_BF16)
+    rc = simt_tapgemm<__nv_bfloat16>(A, B, T, Ca, Cas, W, N, Np, Kp, taps, dil, bias, Res, Crs, group, epilogue, Out,
+                                     Cos, Out2, Co2s, st);
+  else
+    MEGB_CHECK_ARG(false, "tapgemm: unknown dtype %d", dtype);
+  if (rc != 0 || stats == nullptr) return rc;
+  return megb200_bn_stats(Out, (long long)B * T, N, Cos, stats, MEGB200_F32, stream);
 }
 
 int megb200_wgrad(const void* dU, int M, int Ms, const void* Xin, int C, int Cs, int B, int T, int taps, int dil,

@@ -36,6 +36,7 @@ __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
 struct TapGemmParams {
   int T, N, Cos, Crs, Co2s, taps, dil, Kp, kchunks, tiles_per_sample, ntiles, NT, n_last, stages, epi, debug_skip_io, tma_epi;
   uint32_t stg_bytes;   // CTA-pair kernel: dedicated staging area of the TMA-store epilogue
+  float* stats;         // optional BatchNorm statistics sums[2][N] (sum, sum of squares) fused into the f32 epilogue
   long long* dbg;       // MEGB200_DEBUG_TIMING: per-CTA clock64 stamps {start, first data, accumulator ready, end}
   uint32_t tmem_cols, idesc;
   const float* bias;
@@ -153,7 +154,11 @@ __device__ __forceinline__ void stage_f32_slice(uint32_t base, int rloc, const f
 template <bool kPersistent, int kHalves>
 __device__ __forceinline__ void tap_epilogue_tma(const TapGemmParams& p, const TapStoreMaps& maps, uint32_t trow,
                                                  const float* sbias, int n0, int b, int t0, int rloc, bool row_valid,
-                                                 bool tile_valid, uint32_t stg, uint32_t stg_bytes, int etid, int h) {
+                                                 bool tile_valid, uint32_t stg, uint32_t stg_bytes, int etid, int h,
+                                                 float* sstat = nullptr, int sstat_base = 0, int sstat_stride = 0) {
+  // sstat (optional, f32 epilogue only): shared-memory table [2][sstat_stride] of per-channel (sum, sum of squares)
+  // accumulators, indexed by channel - sstat_base; the BatchNorm batch statistics are reduced here from the staged
+  // f32 tile instead of a separate pass over the 118 MB tensor.
   constexpr int kEpiThreads = 128 * kHalves;
   const bool glu = p.epi == MEGB200_EPI_GLU;
   const bool gelu = p.epi == MEGB200_EPI_GELU;
@@ -258,6 +263,35 @@ __device__ __forceinline__ void tap_epilogue_tma(const TapGemmParams& p, const T
     fence_proxy_async();
     named_bar_sync(2, kEpiThreads);
     if (!kPersistent && p.dbg != nullptr && etid == 0 && jj0 == 0) p.dbg[8 * blockIdx.x + 5] = clock64();
+    if (f32 && sstat != nullptr && tile_valid) {
+      // column sums of the staged slices: warp = block of rows, lane = channel (conflict-free swizzled reads)
+      constexpr int kRowsPer = 128 / (kEpiThreads / 32);
+      const int c = etid & 31, r0 = (etid >> 5) * kRowsPer;
+      for (int jj = jj0; jj < jj1; ++jj) {
+#pragma unroll
+        for (int hh = 0; hh < kHalves; ++hh) {
+          const int jh = jj * kHalves + hh;
+          if (jh >= groups) break;
+          const uint32_t sb2 = stg + (uint32_t)(((jj - jj0) * kHalves + hh) * per_group) * slice_bytes;
+          float su = 0.f, sq = 0.f;
+#pragma unroll 4
+          for (int r = r0; r < r0 + kRowsPer; ++r) {
+            if (t0 + r < p.T) {
+              float v;
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v)
+                           : "r"(sb2 + (uint32_t)r * 128u + ((((uint32_t)c >> 2) ^ ((uint32_t)r & 7u)) << 4) + ((uint32_t)c & 3u) * 4u));
+              su += v;
+              sq = fmaf(v, v, sq);
+            }
+          }
+          const int ch = n0 + 32 * jh + c - sstat_base;
+          if (ch < sstat_stride) {
+            atomicAdd(&sstat[ch], su);
+            atomicAdd(&sstat[sstat_stride + ch], sq);
+          }
+        }
+      }
+    }
     if (etid == 0 && tile_valid) {
       for (int jj = jj0; jj < jj1; ++jj) {
 #pragma unroll
@@ -298,6 +332,7 @@ tc_tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint8_t* ring = smem + kHeaderBytes;
   float* sbias_big = reinterpret_cast<float*>(ring + (size_t)p.stages * stage_bytes);
   if (p.NT > 128) sbias = sbias_big;
+  float* sstat = sbias_big + (p.NT > 128 ? p.NT : 0);      // [2][NT] BatchNorm partial sums of this tile
 
   const bool glu = p.epi == MEGB200_EPI_GLU;
   const int half = p.NT / 2;          // GLU: the tile is [half "a" channels | the matching half gate channels]
@@ -374,6 +409,8 @@ tc_tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else {
     // ---------------- epilogue: TMEM -> registers -> fused element-wise tail -> global (thread = one position)
     const int et = threadIdx.x - 64;
+    if (p.stats != nullptr)
+      for (int i = et; i < 2 * p.NT; i += 128) sstat[i] = 0.f;
     for (int i = et; i < wN; i += 128) {
       int n;
       bool ok;
@@ -399,7 +436,18 @@ tc_tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (p.tma_epi) {
       // every MMA has completed, so the whole stage ring is free: it becomes the staging area of the stores
       tap_epilogue_tma<false, 1>(pe, maps, tmem_base + ((uint32_t)(q * 32) << 16), sbias, n0, b, t0, q * 32 + lane,
-                                 t < p.T, true, smem_u32(ring), (uint32_t)p.stages * stage_bytes, et, 0);
+                                 t < p.T, true, smem_u32(ring), (uint32_t)p.stages * stage_bytes, et, 0,
+                                 p.stats != nullptr ? sstat : nullptr, n0, p.NT);
+      if (p.stats != nullptr) {
+        named_bar_sync(2, 128);
+        for (int i = et; i < wN; i += 128) {
+          const int n = n0 + i;
+          if (n < p.N) {
+            atomicAdd(&p.stats[n], sstat[i]);
+            atomicAdd(&p.stats[p.N + n], sstat[p.NT + i]);
+          }
+        }
+      }
     } else {
       tap_epilogue(pe, tmem_base + ((uint32_t)(q * 32) << 16), sbias, n0, row, t < p.T);
     }
@@ -597,6 +645,7 @@ tc_tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   uint8_t* ring = smem + kHeaderBytes;
   uint8_t* stg = ring + (size_t)p.stages * stage_bytes;                              // TMA-store staging (1024-aligned)
   float* sbias = reinterpret_cast<float*>(stg + p.stg_bytes);                        // [2][NT]: one table per acc stage
+  float* sstat = sbias + 2 * p.NT;                 // [2][Cos] BatchNorm partial sums of all tiles of this CTA
   const bool glu = p.epi == MEGB200_EPI_GLU;
   const int Ch = p.N / 2;
   const int num_k = p.taps * p.kchunks;
@@ -705,6 +754,8 @@ tc_tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int et = threadIdx.x - 64;
     const int q = warp & 3;
     const int h = (warp - 2) >> 2;
+    if (p.stats != nullptr)
+      for (int i = et; i < 2 * p.Cos; i += 256) sstat[i] = 0.f;      // visible after the first named barrier below
     int tile = 0;
     long long dbg_epi_wait = 0, dbg_epi_work = 0;
     for (int item = cluster_id; item < num_items; item += num_clusters, ++tile) {
@@ -740,11 +791,18 @@ tc_tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       TapGemmParams pe = p;
       pe.NT = wN;
       tap_epilogue_tma<true, 2>(pe, maps, trow, sb, n0, b, t0, q * 32 + lane, t < p.T, m_tile < total_m_tiles,
-                                smem_u32(stg), p.stg_bytes, et, h);
+                                smem_u32(stg), p.stg_bytes, et, h, p.stats != nullptr ? sstat : nullptr, 0, p.Cos);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(smem_u32(&hdr->tmem_empty[acc]), 0);
       if (p.dbg) dbg_epi_work += clock64() - w4;
+    }
+    if (p.stats != nullptr) {
+      named_bar_sync(2, 256);
+      for (int i = et; i < p.N; i += 256) {
+        atomicAdd(&p.stats[i], sstat[i]);
+        atomicAdd(&p.stats[p.N + i], sstat[p.Cos + i]);
+      }
     }
     if (p.dbg && et == 0) {
       p.dbg[8 * blockIdx.x + 4] = dbg_epi_wait;
@@ -1334,7 +1392,8 @@ static int set_smem(K kernel, size_t bytes) {
 
 int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int N, int Np, int Kp, int taps, int dil,
                const float* bias, const void* Res, int Crs, const int32_t* group, int G, int epi, void* Out, int Cos,
-               void* Out2, int Co2s, cudaStream_t st) {
+               void* Out2, int Co2s, float* stats, int* stats_fused, cudaStream_t st) {
+  *stats_fused = 0;
   MEGB_CHECK_ARG(Cas % 8 == 0 && Cos % 8 == 0 && (Res == nullptr || Crs % 8 == 0), "tc_tapgemm: strides must be multiples of 8");
   MEGB_CHECK_ARG(Kp % 64 == 0 && Np % 16 == 0 && Np >= N, "tc_tapgemm: Kp %% 64 and Np %% 16 required (Kp=%d Np=%d)", Kp, Np);
   const bool glu = epi == MEGB200_EPI_GLU;
@@ -1410,6 +1469,9 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
     }
   }
   p.bias = bias; p.Res = (const __nv_bfloat16*)Res; p.group = group; p.Out = Out; p.Out2 = (__nv_bfloat16*)Out2;
+  // BatchNorm statistics ride on the f32 TMA-store epilogue (single-CTA and pair kernels, not the halo forms)
+  const bool fuse_stats = stats != nullptr && epi == MEGB200_EPI_STORE_F32 && p.tma_epi && halo_mode_env_off();
+  p.stats = fuse_stats ? stats : nullptr;
 
   // Kernel choice.  Measured at config 2 (profiles/r1_tapgemm_variants.md): the persistent CTA-pair kernel (8 epilogue
   // warps, 128-wide k stages) reaches 647 TFLOP/s, the single-CTA kernel with two co-resident CTAs per SM 608; the pair
@@ -1466,6 +1528,7 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
     static const bool no_halo = getenv("MEGB200_TAPGEMM_PAIR_HALO") == nullptr;
     const int a_rows2 = ((kTileM + (taps - 1) * dil) + 7) / 8 * 8;
     if (taps > 1 && a_rows2 <= 256 && !no_halo && p.n_last == p.NT) {
+      p.stats = nullptr;
       // halo form: activation ring (with halo rows) + weight ring
       const uint32_t a_slot = ((uint32_t)a_rows2 * 128u + 1023u) & ~1023u;
       const uint32_t b_half = (uint32_t)half * 128;
@@ -1488,9 +1551,9 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
       MEGB_LAUNCH_OK();
       return 0;
     }
-    p.stages = pick_stages(2 * stage2, 229000 - 2048 - 2 * p.NT * 4 - p.stg_bytes, 8);   // two k chunks per stage
+    p.stages = pick_stages(2 * stage2, 229000 - 2048 - 2 * p.NT * 4 - 2 * Cos * 4 - p.stg_bytes, 8);   // two k chunks per stage
     MEGB_CHECK_ARG(p.stages >= 2, "tc_tapgemm(pair): tile too large");
-    const size_t smem2 = 1024 + kHeaderBytes + (size_t)p.stages * 2 * stage2 + p.stg_bytes + 2 * p.NT * 4;
+    const size_t smem2 = 1024 + kHeaderBytes + (size_t)p.stages * 2 * stage2 + p.stg_bytes + 2 * p.NT * 4 + 2 * Cos * 4;
     int rc = set_smem(tc_tapgemm2_kernel, smem2);
     if (rc) return rc;
     cfg.dynamicSmemBytes = smem2;
@@ -1500,6 +1563,7 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
     }
     MEGB_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_tapgemm2_kernel, tmA2, tmW2, maps, p, (int)m_tiles_total, num_items));
     MEGB_LAUNCH_OK();
+    *stats_fused = fuse_stats ? 1 : 0;
     if (p.dbg != nullptr) {
       static long long hostp[8 * 512];
       cudaStreamSynchronize(st);
@@ -1530,6 +1594,7 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
   const int halo_mode = halo_env ? atoi(halo_env) : 0;
   const int a_rows = ((kTileM + (taps - 1) * dil) + 7) / 8 * 8;
   if (halo_mode > 0 && taps > 1 && group == nullptr && G == 1 && a_rows <= 256) {
+    p.stats = nullptr;
     const uint32_t a_slot = ((uint32_t)a_rows * 128u + 1023u) & ~1023u;
     const uint32_t b_bytes = (uint32_t)p.NT * 128;
     const int stagesA = 2;
@@ -1566,7 +1631,7 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
   }
 
   const uint32_t stage_bytes = kTileM * 128 + p.NT * 128;
-  p.stages = pick_stages(stage_bytes, 112000 - (p.NT > 128 ? p.NT * 4 : 0), 6);
+  p.stages = pick_stages(stage_bytes, 112000 - (p.NT > 128 ? p.NT * 4 : 0) - 2 * p.NT * 4, 6);
   MEGB_CHECK_ARG(p.stages >= 2, "tc_tapgemm: tile too large for the stage ring");
   p.tmem_cols = tmem_cols_for(p.NT);
   p.idesc = make_idesc(p.NT, 0, 0);
@@ -1587,7 +1652,7 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
     int rc = encode_tmap_bf16(&tmW, W, 3, dims, strides, box);
     if (rc) return rc;
   }
-  const size_t smem = 1024 + kHeaderBytes + (size_t)p.stages * stage_bytes + (p.NT > 128 ? p.NT * 4 : 0);
+  const size_t smem = 1024 + kHeaderBytes + (size_t)p.stages * stage_bytes + (p.NT > 128 ? p.NT * 4 : 0) + 2 * p.NT * 4;
   int rc = set_smem(tc_tapgemm_kernel, smem);
   if (rc) return rc;
   const long long blocks = (long long)B * p.tiles_per_sample * p.ntiles;
@@ -1595,6 +1660,7 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
   if (dbg_timing && blocks <= 65536) p.dbg = dbg_buf;
   tc_tapgemm_kernel<<<(unsigned)blocks, kThreads, smem, st>>>(tmA, tmW, maps, p);
   MEGB_LAUNCH_OK();
+  *stats_fused = p.stats != nullptr ? 1 : 0;
   if (p.dbg != nullptr) {
     // debug only: phase durations per CTA in SM clocks (synchronises!)
     static long long host[8 * 65536];

@@ -126,10 +126,13 @@ class EncoderEngine:
             pk, d = P["blocks"][k], self.dil[k]
             bc = {"x": x, "cin": cin}
             # pre-BatchNorm tensors stay in f32: the normalisation sees the unrounded convolution (+ residual)
-            u0 = self._conv(x, cin, f"b{k}.w0", pk["b0"], D2, d[0], x if k > 0 else None, epi="store_f32")
-            h0, bc["bn0"] = self._bn_gelu(u0, pk, "0", training)
-            u1 = self._conv(h0, D2, f"b{k}.w1", pk["b1"], D2, d[1], h0, epi="store_f32")
-            h1, bc["bn1"] = self._bn_gelu(u1, pk, "1", training)
+            # (the train-mode batch statistics ride on the conv epilogue: sums[2][D2])
+            s0 = self._zp.take(2, D2) if training else None
+            u0 = self._conv(x, cin, f"b{k}.w0", pk["b0"], D2, d[0], x if k > 0 else None, epi="store_f32", stats=s0)
+            h0, bc["bn0"] = self._bn_gelu(u0, pk, "0", training, s0)
+            s1 = self._zp.take(2, D2) if training else None
+            u1 = self._conv(h0, D2, f"b{k}.w1", pk["b1"], D2, d[1], h0, epi="store_f32", stats=s1)
+            h1, bc["bn1"] = self._bn_gelu(u1, pk, "1", training, s1)
             out, v = self._conv(h1, D2, f"b{k}.w2", pk["b2"], 2 * D2, d[2], None, epi="glu")
             bc.update(u0=u0, h0=h0, u1=u1, h1=h1, v=v)
             blocks.append(bc)
@@ -147,7 +150,7 @@ class EncoderEngine:
             return Zm, ctx
         return Z, ctx
 
-    def _conv(self, x, cin, wname, b, N, dil, res, taps=3, epi="store"):
+    def _conv(self, x, cin, wname, b, N, dil, res, taps=3, epi="store", stats=None):
         """Conv1d (k = taps, "same") as a tap-GEMM with a fused tail on the pre-packed weight `wname`.  Returns Out, or
         (Out, Out2) for the GELU / GLU epilogues (Out2 = the pre-activation kept for backward)."""
         ops, dev = self.ops, x.device
@@ -155,7 +158,7 @@ class EncoderEngine:
         Wpk = self._wf[wname]
         if epi == "store_f32":
             out = _f32(dev, B, T, pad8(N))
-            ops.tapgemm(x, cin, Wpk, N, taps, dil, b, res, None, out, epi=epi)
+            ops.tapgemm(x, cin, Wpk, N, taps, dil, b, res, None, out, epi=epi, stats=stats)
             return out
         if epi == "glu":
             out, v = ops.empty(B, T, pad8(N // 2), device=dev), ops.empty(B, T, pad8(N), device=dev)
@@ -169,13 +172,9 @@ class EncoderEngine:
         ops.tapgemm(x, cin, Wpk, N, taps, dil, b, res, None, out)
         return out
 
-    def _bn_gelu(self, u, pk, i, training):
+    def _bn_gelu(self, u, pk, i, training, sums):
         ops, dev, D2 = self.ops, u.device, self.D2
         n = u.shape[0] * u.shape[1]
-        sums = None
-        if training:
-            sums = self._zp.take(2, D2)
-            ops.bn_stats(u, D2, sums)
         st = {k: _f32(dev, D2) for k in ("scale", "shift", "mean", "rstd")}
         ops.bn_finalize(sums, pk["g" + i], pk["be" + i], pk["rm" + i], pk["rv" + i], n, self.eps, self.momentum,
                         training, st["scale"], st["shift"], st["mean"], st["rstd"])

@@ -22,7 +22,7 @@ SIGNATURES = {
     "megb200_pack_x": [_p, _p, _i, _i, _i, _i, _i, _p],
     "megb200_pack_weight": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "megb200_pack_weight_multi": [_p, _i, _i, _p],
-    "megb200_tapgemm": [_p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p, _p, _i, _p, _i, _i, _p, _i, _p, _i, _i, _i, _p],
+    "megb200_tapgemm": [_p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p, _p, _i, _p, _i, _i, _p, _i, _p, _i, _p, _i, _i, _p],
     "megb200_wgrad": [_p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p, _p, _sz, _i, _i, _p],
     "megb200_group_order": [_p, _i, _i, _p, _p],
     "megb200_colsum": [_p, _i, _i, _i, _i, _p, _i, _p, _i, _p],

@@ -126,7 +126,7 @@ class CudaOps:
         L.call("megb200_pack_weight_multi", tab.data_ptr(), len(items), self.dt, self._stream())
 
     # ------------------------------------------------------------------ contractions
-    def tapgemm(self, A, Ca, W, N, taps, dil, bias, Res, group, Out, epi="store", Out2=None):
+    def tapgemm(self, A, Ca, W, N, taps, dil, bias, Res, group, Out, epi="store", Out2=None, stats=None):
         """epi: "store" | "store_f32" (Out is f32: pre-BatchNorm tensors) | "gelu" (Out2 = pre-activation, Out =
         gelu) | "glu" (N = 2*Ch; Out2 = V [.., 2Ch], Out = GLU(V) [.., Ch])."""
         code = {"store": L.EPI_STORE, "store_f32": L.EPI_STORE_F32, "gelu": L.EPI_GELU, "glu": L.EPI_GLU}[epi]
@@ -135,7 +135,8 @@ class CudaOps:
             self._chk_f32(Out)
         else:
             self._chk_act(Out)
-        self._chk_f32(bias)
+        self._chk_f32(bias, stats)
+        assert stats is None or (epi == "store_f32" and stats.numel() == 2 * N)
         B, T, Cas = A.shape
         G, Np, Ktot = W.shape
         Kp = Ktot // taps
@@ -150,7 +151,7 @@ class CudaOps:
         ev = self._prof_begin()
         L.call("megb200_tapgemm", A.data_ptr(), B, T, Ca, Cas, W.data_ptr(), N, Np, Kp, taps, dil, _ptr(bias),
                _ptr(Res), 0 if Res is None else Res.shape[2], _ptr(group), G, code, Out.data_ptr(), Out.shape[2],
-               _ptr(Out2), 0 if Out2 is None else Out2.shape[2], self.dt, self.be, self._stream())
+               _ptr(Out2), 0 if Out2 is None else Out2.shape[2], _ptr(stats), self.dt, self.be, self._stream())
         self._prof_end(ev, "tapgemm", 2.0 * B * T * N * taps * Ca)
 
     def group_order(self, group, G, order):

@@ -53,7 +53,7 @@ class TorchOps:
             self.pack_weight(w, out, mode)
 
     # ------------------------------------------------------------------ contractions
-    def tapgemm(self, A, Ca, W, N, taps, dil, bias, Res, group, Out, epi="store", Out2=None):
+    def tapgemm(self, A, Ca, W, N, taps, dil, bias, Res, group, Out, epi="store", Out2=None, stats=None):
         B, T, _ = A.shape
         G, Np, Ktot = W.shape
         Kp = Ktot // taps
@@ -80,6 +80,8 @@ class TorchOps:
             Out[:, :, :N] = self._r(acc)
         elif epi == "store_f32":
             Out[:, :, :N] = acc
+            if stats is not None:
+                self.bn_stats(Out, N, stats.view(2, N))
         elif epi == "gelu":
             Out2.zero_()
             Out2[:, :, :N] = self._r(acc)

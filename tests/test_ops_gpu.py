@@ -106,6 +106,7 @@ EPI_CASES = [
     # B, T, Ca, N, taps, epi
     (2, 40, 32, 32, 3, "store_f32"),
     (2, 360, 320, 320, 3, "store_f32"),
+    (5, 200, 320, 320, 3, "store_f32"),      # odd number of M tiles: the CTA-pair kernel's last pair is half empty
     (2, 40, 32, 64, 3, "glu"),              # D2 = 32
     (2, 360, 320, 640, 3, "glu"),           # D2 = 320: tile = 80 a-channels + 80 gates
     (3, 130, 32, 64, 1, "gelu"),
@@ -136,9 +137,13 @@ def test_tapgemm_fused_epilogues(dtype, backend, case):
     else:
         Out, Outr = ops.empty(B, T, pad8(N), device=DEV), ref.empty(B, T, pad8(N), device="cpu")
         Out2, Out2r = ops.empty(B, T, pad8(N), device=DEV), ref.empty(B, T, pad8(N), device="cpu")
-    ops.tapgemm(Ad, Ca, W.to(DEV), N, taps, 1, bias.to(DEV), Resd, None, Out, epi=epi, Out2=Out2)
-    ref.tapgemm(A, Ca, W, N, taps, 1, bias, Res, None, Outr, epi=epi, Out2=Out2r)
+    stats = torch.zeros(2, N, device=DEV) if epi == "store_f32" else None
+    statsr = torch.zeros(2, N) if epi == "store_f32" else None
+    ops.tapgemm(Ad, Ca, W.to(DEV), N, taps, 1, bias.to(DEV), Resd, None, Out, epi=epi, Out2=Out2, stats=stats)
+    ref.tapgemm(A, Ca, W, N, taps, 1, bias, Res, None, Outr, epi=epi, Out2=Out2r, stats=statsr)
     torch.cuda.synchronize()
+    if stats is not None:      # BatchNorm batch statistics fused into the epilogue
+        _close(stats, statsr, torch.float32, f"tapgemm fused BN statistics {backend}", atol_scale=50)
     _close(Out, Outr, torch.float32 if epi == "store_f32" else dtype, f"tapgemm {epi} Out {backend}",
            atol_scale=5 if epi == "store_f32" else 1)
     if Out2 is not None:
