@@ -245,11 +245,17 @@ struct BnGeluBwdOp {
     load8(u + r * Cs + c0, x);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      float d = g[i] * gelu_grad_t<T>(fmaf(x[i], sc[i], sh[i]));
-      if (c0 + 8 > C && c0 + i >= C) d = 0.f;        // only the last, partial channel group pays for the mask
-      a0[i] += d;
-      a1[i] = fmaf(d, x[i], a1[i]);
-      o[i] = d;
+      o[i] = g[i] * gelu_grad_t<T>(fmaf(x[i], sc[i], sh[i]));
+    }
+    if (c0 + 8 > C) {                                 // only the last, partial channel group pays for the mask
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (c0 + i >= C) o[i] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      a0[i] += o[i];
+      a1[i] = fmaf(o[i], x[i], a1[i]);
     }
     store8(dy + r * Cs + c0, o);
   }
@@ -318,9 +324,14 @@ struct GeluBwdOp {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       o[i] = g[i] * gelu_grad_t<T>(x[i]);
-      if (c0 + 8 > C && c0 + i >= C) o[i] = 0.f;     // only the last, partial channel group pays for the mask
-      a0[i] += o[i];
     }
+    if (c0 + 8 > C) {                                 // only the last, partial channel group pays for the mask
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (c0 + i >= C) o[i] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a0[i] += o[i];
     store8(dp + r * Cs + c0, o);
   }
 };
