@@ -174,6 +174,12 @@ int megb200_clip_ce_finish(const float* L, const float* row_lse, const float* co
 int megb200_clip_dz(const void* coef, int ldc, const void* Yp, const void* Z, const float* cvec, const float* gscale,
                     void* dZ, int By, int Bz, long long D, int dtype, int backend, void* stream);
 
+/* Top-k retrieval metric (the reference's Classifier, models.py:403-460; "next" row N1): given the f32 dot-product
+ * matrix raw[By][Bz] (rows speech, columns brain) and the squared brain norms, rank[r] = number of brain embeddings
+ * more similar (cosine) to speech row off + r than the matching one.  top-1 = mean(rank == 0), top-10 = mean(rank < 10).
+ * Integer output, bit-exact given raw. */
+int megb200_retrieval_rank(const float* raw, const float* zsq, int32_t* rank, int By, int Bz, int off, void* stream);
+
 /* ---------------------------------------------------------------------------------------------- misc */
 /* d[i] = s[i] cast between f32 and the activation dtype (n elements) */
 int megb200_cast(const void* src, void* dst, long long n, int src_dtype, int dst_dtype, void* stream);

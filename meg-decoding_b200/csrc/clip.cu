@@ -123,6 +123,25 @@ __global__ void clip_finish_kernel(const float* __restrict__ L, const float* __r
   }
 }
 
+// Retrieval rank of the matching brain embedding for every speech row (the reference's Classifier, models.py:403-460,
+// computes the full cosine matrix in an O(B^2) Python loop and then argmax / topk): rank[r] = number of brains j whose
+// cosine similarity to speech row off + r exceeds that of the matching brain r.  One warp per row; |y_i| is common to a
+// row and drops out of the comparison.
+__global__ void clip_rank_kernel(const float* __restrict__ raw, const float* __restrict__ zsq,
+                                 int32_t* __restrict__ rank, int Bz, int off, int rows) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float* rr = raw + (long long)(off + warp) * Bz;
+  const float own = rr[warp] * rsqrtf(zsq[warp]);
+  int cnt = 0;
+  for (int j = lane; j < Bz; j += 32)
+    if (j != warp && rr[j] * rsqrtf(zsq[j]) > own) ++cnt;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0) rank[warp] = cnt;
+}
+
 }  // namespace megb200
 
 using namespace megb200;
@@ -159,6 +178,13 @@ int megb200_clip_ce_finish(const float* L, const float* row_lse, const float* co
                                                               (__nv_bfloat16*)coef, ldc, cvec, By, Bz);
   else
     MEGB_CHECK_ARG(false, "clip_ce_finish: unknown dtype");
+  MEGB_LAUNCH_OK();
+  return 0;
+}
+
+int megb200_retrieval_rank(const float* raw, const float* zsq, int32_t* rank, int By, int Bz, int off, void* stream) {
+  MEGB_CHECK_ARG(raw && zsq && rank && By > 0 && Bz > 0 && off >= 0 && off + Bz <= By, "retrieval_rank: bad arguments");
+  clip_rank_kernel<<<(Bz * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(raw, zsq, rank, Bz, off, Bz);
   MEGB_LAUNCH_OK();
   return 0;
 }

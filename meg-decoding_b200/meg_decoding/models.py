@@ -249,23 +249,42 @@ class BrainEncoder(nn.Module):
 
 
 class Classifier(nn.Module):
-    """models.py:386-460 — top-1 / top-10 retrieval accuracy of speech segments against brain embeddings.
-
-    Metric only (no grad).  "Next" row N1 of the scope table: restated here without the reference's O(B^2) Python loop.
-    """
+    """models.py:386-460 — top-1 / top-10 retrieval accuracy: for every speech segment, is the matching brain embedding
+    the most (one of the 10 most) cosine-similar among the batch?  Metric only (``no_grad``), called every step
+    (train.py:205-206).  "Next" row N1 of the scope table: the reference's O(B^2) Python loop of dot products becomes the
+    tcgen05 logits contraction plus one rank kernel (megb200_retrieval_rank); same return values."""
 
     def __init__(self, args):
         super().__init__()
-        self.batch_size = getattr(args, "batch_size", None) if not isinstance(args, dict) else args.get("batch_size")
+        self.factor = 1
+        try:
+            self.normalize_image_features = args.get("normalize_image_features", False) if hasattr(args, "get") else \
+                getattr(args, "normalize_image_features", False)
+        except Exception:
+            self.normalize_image_features = False
+        self._eng = None
 
     @torch.no_grad()
-    def forward(self, Z: torch.Tensor, Y: torch.Tensor, test=False):
-        B = Z.size(0)
-        z = Z.reshape(B, -1).float()
-        y = Y.reshape(B, -1).float()
-        sim = (y / y.norm(dim=-1, keepdim=True)) @ (z / z.norm(dim=-1, keepdim=True)).T
-        t = torch.arange(B, device=sim.device)
-        top1 = (sim.argmax(dim=1) == t).float().mean().item()
-        k = min(10, B)
-        top10 = (sim.topk(k, dim=1).indices == t[:, None]).any(dim=1).float().mean().item()
-        return top1, top10
+    def forward(self, Z: torch.Tensor, Y: torch.Tensor, test=False, top_k=None):
+        from megb200.engine import ClipEngine
+        batch_size = Z.size(0)
+        z = Z.detach()
+        if z.dtype not in (torch.bfloat16, torch.float32):
+            z = z.float()
+        if z.dim() == 3:
+            Zi = z.permute(0, 2, 1)
+            if not Zi.is_contiguous():
+                Zi = Zi.contiguous()
+        else:
+            Zi = z.contiguous().unsqueeze(1)
+        ops = megb200.get_ops("bf16" if Zi.dtype == torch.bfloat16 and megb200.get_precision() != "bf16_simt"
+                              else ("bf16_simt" if Zi.dtype == torch.bfloat16 else "fp32"))
+        if self._eng is None or self._eng.ops is not ops:
+            self._eng = ClipEngine(ops)
+        Yf = Y.detach().to(device=Zi.device, dtype=torch.float32).contiguous()
+        rank = self._eng.retrieval_ranks(Yf, Zi)
+        top1 = (rank == 0).float().mean().item()
+        top10 = (rank < min(10, batch_size)).float().mean().item()
+        if top_k is None:
+            return top1, top10
+        return top1, top10, (rank < min(int(top_k), batch_size)).float().mean().item()

@@ -348,6 +348,22 @@ class ClipEngine:
         ctx = dict(coef=coef, Yp=Yp, Zf=Zf, cvec=cvec, dtemp=out2[1:2], shape=Zi.shape)
         return loss.view(()), (Lg if want_logits else None), ctx
 
+    def retrieval_ranks(self, Y, Zi):
+        """Rank of the matching brain embedding among all brains of the batch for every speech segment (cosine
+        similarity; the reference's Classifier, models.py:403-460).  Returns int32 [B]."""
+        ops, dev = self.ops, Zi.device
+        B = Zi.shape[0]
+        D = Zi.numel() // B
+        Yp, _ = self.prepare_targets(Y, None)
+        zsq = _zeros(dev, B)
+        Zf = Zi.view(B, D)
+        ops.rowsumsq(Zf, zsq)
+        raw = _zeros(dev, B, B)
+        ops.clip_logits(Yp, Zf, raw)
+        rank = torch.empty(B, dtype=torch.int32, device=dev)
+        ops.retrieval_rank(raw, zsq, rank, 0)
+        return rank
+
     def backward(self, ctx, gscale):
         """gscale: f32 [1] upstream gradient of the (scalar) loss.  Returns (dZ in PC layout, dtemp f32 [1])."""
         ops = self.ops

@@ -332,6 +332,13 @@ class CudaOps:
         L.call("megb200_clip_dz", coef.data_ptr(), coef.shape[1], Yp.data_ptr(), Z.data_ptr(), cvec.data_ptr(), gscale.data_ptr(),
                dZ.data_ptr(), By, Bz, Z.numel() // Bz, self.dt, self.be, self._stream())
 
+    def retrieval_rank(self, raw, zsq, rank, off=0):
+        self._chk_f32(raw, zsq)
+        assert rank.dtype == torch.int32 and rank.is_cuda
+        By, Bz = raw.shape
+        L.call("megb200_retrieval_rank", raw.data_ptr(), zsq.data_ptr(), rank.data_ptr(), By, Bz, int(off),
+               self._stream())
+
     def cast(self, src, dst):
         code = {torch.float32: L.F32, torch.bfloat16: L.BF16}
         assert src.is_contiguous() and dst.is_contiguous() and src.numel() == dst.numel()

@@ -248,5 +248,11 @@ class TorchOps:
         r = coef[:, :By].float() @ Yp.float().reshape(By, -1) - Z.float().reshape(Z.shape[0], -1) * cvec[:, None]
         dZ.copy_(self._r(gscale * r).view(dZ.shape))
 
+    def retrieval_rank(self, raw, zsq, rank, off=0):
+        Bz = raw.shape[1]
+        sim = raw[off:off + Bz] / torch.sqrt(zsq)[None, :]
+        own = sim.diagonal()
+        rank.copy_(((sim > own[:, None]).sum(1)).to(torch.int32))
+
     def cast(self, src, dst):
         dst.copy_(src.to(dst.dtype))

@@ -104,3 +104,20 @@ def test_one_sided_dp_loss_equals_global(torch_ops):
     full = R.clip_loss(Y, Z, temp)
     parts = R.clip_loss_one_sided(Y, list(Z.chunk(world)), temp)
     assert abs(float(sum(parts)) - float(full)) < 1e-6
+
+
+def test_classifier_matches_oracle_topk(torch_ops):
+    """N1: Classifier (top-1 / top-10 retrieval accuracy, models.py:403-460) on the logits + rank path."""
+    from meg_decoding.models import Classifier
+    from oracle import restatement as R
+    g = torch.Generator().manual_seed(5)
+    B, Fo, T = 24, 16, 6
+    Y = torch.randn(B, Fo, T, generator=g)
+    Z = 0.6 * Y + torch.randn(B, Fo, T, generator=g)          # correlated: accuracies strictly between 0 and 1
+    clf = Classifier(synth.Args(normalize_image_features=False))
+    top1, top10 = clf(Z, Y)
+    r1, r10 = R.topk_accuracy(Z, Y, k=10)
+    assert abs(top1 - r1) < 1e-6 and abs(top10 - r10) < 1e-6
+    assert 0.0 < top1 <= top10 <= 1.0
+    t1, t10, t3 = clf(Z, Y, top_k=3)
+    assert abs(t3 - R.topk_accuracy(Z, Y, k=3)[1]) < 1e-6

@@ -150,3 +150,20 @@ def test_bf16_is_the_default_precision_and_output_is_bf16():
     with torch.no_grad():
         Z = enc(X, subj)
     assert Z.dtype == torch.bfloat16 and Z.shape == (cfg.B, cfg.F, cfg.T)
+
+
+def test_classifier_topk_matches_oracle(mode):
+    """N1: the retrieval metric (models.py:403-460) from the tcgen05 logits + the rank kernel; integer ranks."""
+    from meg_decoding.models import Classifier
+    from oracle import restatement as R
+    g = torch.Generator().manual_seed(9)
+    B, Fo, T = 64, 64, 40
+    Y = torch.randn(B, Fo, T, generator=g)
+    Z = 0.15 * Y + torch.randn(B, Fo, T, generator=g)
+    clf = Classifier(synth.Args(normalize_image_features=False))
+    dt = torch.float32 if mode == "fp32" else torch.bfloat16
+    Zd = Z.to(DEV).to(dt)
+    top1, top10 = clf(Zd, Y.to(DEV))
+    r1, r10 = R.topk_accuracy(Zd.float().cpu(), Y, k=10)
+    print(f"[parity] classifier {mode}: top1 {top1:.3f} (oracle {r1:.3f}) top10 {top10:.3f} (oracle {r10:.3f})")
+    assert abs(top1 - r1) <= 1.0 / B + 1e-6 and abs(top10 - r10) <= 1.0 / B + 1e-6   # near-ties may flip one rank in bf16
