@@ -159,7 +159,7 @@ def test_classifier_topk_matches_oracle(mode):
     g = torch.Generator().manual_seed(9)
     B, Fo, T = 64, 64, 40
     Y = torch.randn(B, Fo, T, generator=g)
-    Z = 0.15 * Y + torch.randn(B, Fo, T, generator=g)
+    Z = 0.03 * Y + torch.randn(B, Fo, T, generator=g)       # weak coupling: accuracies strictly inside (0, 1)
     clf = Classifier(synth.Args(normalize_image_features=False))
     dt = torch.float32 if mode == "fp32" else torch.bfloat16
     Zd = Z.to(DEV).to(dt)
