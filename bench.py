@@ -274,7 +274,7 @@ def run_megb200(args):
     if "tapgemm" in kern and kern["tapgemm"][1] > 0:
         fl, tms, n = kern["tapgemm"]
         ach = fl / (tms * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "kernel": "tc_tapgemm_kernel (conv fwd + dgrad + 1x1 + subject GEMM)",
+        roofline = {"bound": "tensor", "kernel": "tc_tapgemm2_kernel + tc_tapgemm_kernel (conv fwd + dgrad, 1x1 heads, grouped subject GEMM)",
                     "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                     "frac": ach / peaks["bf16_sustained"], "traffic": traffic,
                     "traffic_source": "profiles/r1_tapgemm2_ncu.json: mean dram read+write bytes per captured launch "
