@@ -10,7 +10,9 @@ on the host cores (bounded sample).  `--impl reference` times that CPU port alon
 PyTorch; /root/reference does not exist on the GPU box, so its pinned restatement is what runs).
 """
 import argparse
+import gc
 import json
+import math
 import os
 import statistics
 import sys
@@ -47,13 +49,21 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz, self.err = index, [], set(), False, None, None
-
-    def run(self):
-        try:
+        self.h = None
+        try:       # import + NVML init on the caller's thread, BEFORE the timed region (the import holds the GIL for ms)
             import pynvml
             pynvml.nvmlInit()
-            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+
+    def run(self):
+        if self.h is None:
+            return
+        try:
+            import pynvml
+            h = self.h
             while not self.stop_flag:
                 self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
                 try:
@@ -240,12 +250,16 @@ def run_megb200(args):
     except (ValueError, IndexError):
         pass
     sampler = ClockSampler(nvml_index)
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    gc.collect()
+    gc.disable()                 # no collector pauses on the enqueueing thread inside the timed regions
     barrier()
+    sampler.start()
     ev0.record()
+    th0 = time.perf_counter()
     for _ in range(args.steps):
         loss = step(Xd, Yd, subj_h)
+    host_ms = (time.perf_counter() - th0) * 1e3 / args.steps      # host time to ENQUEUE a step (no sync inside)
     ev1.record()
     barrier()
     clocks = sampler.result()
@@ -299,30 +313,64 @@ def run_megb200(args):
 
     # ---- end to end: host buffers in, loss out, every step.  Public API: megb200.data.DevicePrefetcher (pinned host
     # batches -> device on a copy stream, two batches in flight) + the drop-in modules + loss.item() (train.py:208).
-    from megb200.data import DevicePrefetcher
+    from megb200.data import AsyncScalarReader, DevicePrefetcher
 
     def host_batches(n):
         for _ in range(n):
             yield (Xh, Yh, subj_h)
 
-    def e2e_run(n):
-        last = None
-        for X, Y, subj in DevicePrefetcher(host_batches(n), dev, keep_on_host=(2,)):
-            last = float(step(X, Y, subj).detach())      # device -> host read of the loss every step
-        return last
+    prefetcher = DevicePrefetcher(host_batches(0), dev, keep_on_host=(2,))
+    PRIME = 2
+    fill = {}
 
-    e2e_run(2)
+    def e2e_time(lag):
+        # ONE continuous run of PRIME + K + PRIME steps; the K steps in the middle are timed, so the window is the
+        # pipeline's steady state and holds K steps, K batch copies (of the batches two ahead) and K loss reads.
+        # lag = 0: `loss.item()` after every step, the reference's loop (train.py:208); lag = 1: the same read
+        # pipelined one step behind (megb200.data.AsyncScalarReader) so the stream never drains between steps.
+        n = PRIME + args.steps + PRIME
+        reader = AsyncScalarReader(dev, lag=lag)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        got, t0, t1 = [], 0.0, 0.0
+        barrier()
+        ta = time.perf_counter()
+        for i, (X, Y, subj) in enumerate(prefetcher.reset(host_batches(n))):
+            if i == PRIME:
+                g0.record()
+                t0 = time.perf_counter()
+            v = reader.push(step(X, Y, subj))            # device -> host read of the loss, every step
+            if v is not None:
+                got.append(v)
+            if i == PRIME + args.steps - 1:
+                g1.record()
+                t1 = time.perf_counter()
+        got += reader.drain()
+        barrier()
+        fill[lag] = (time.perf_counter() - ta) * 1e3 / n      # whole run incl. the first batch's exposed copy
+        assert len(got) == n and all(math.isfinite(v) for v in got)
+        return max_over_ranks(max(g0.elapsed_time(g1), (t1 - t0) * 1e3) / args.steps)
+
+    e2e_time(1)
+    # three repetitions of the K-step loop each (PCIe traffic makes single runs noisy); the median is reported
+    sync_runs = [e2e_time(0) for _ in range(3)]
+    pipe_runs = [e2e_time(1) for _ in range(3)]
+    e2e_sync_ms, e2e_ms = statistics.median(sync_runs), statistics.median(pipe_runs)
+    # the H2D copy of one batch on its own (nothing else running): the floor PCIe sets for the end-to-end step
     barrier()
-    t0 = time.perf_counter()
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    g0.record()
-    e2e_run(args.steps)
-    g1.record()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(3):
+        Xd.copy_(Xh, non_blocking=True)
+        Yd.copy_(Yh, non_blocking=True)
+    c1.record()
     barrier()
-    e2e_ms = max_over_ranks(max(g0.elapsed_time(g1), (time.perf_counter() - t0) * 1e3) / args.steps)
+    h2d_alone_ms = c0.elapsed_time(c1) / 3
     h2d = Xh.numel() * 4 + Yh.numel() * 4 + subj_h.numel() * 4
     e2e = {"value": B * world / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-           "ms_per_step": e2e_ms}
+           "ms_per_step": e2e_ms, "loss_read": "every step, pipelined one step behind (AsyncScalarReader)",
+           "window": "K steps in the steady state of one continuous run (2 priming steps before, 2 after)",
+           "ms_per_step_sync_read": e2e_sync_ms, "runs_ms": pipe_runs, "runs_ms_sync_read": sync_runs,
+           "ms_per_step_whole_run_incl_fill": fill.get(1), "h2d_alone_ms": h2d_alone_ms, "h2d_alone_GBps": h2d / (h2d_alone_ms * 1e-3) / 1e9}
 
     flops_step = B * synth.encoder_flops_per_sample(cfg) + synth.clip_flops(cfg, B, B * world)
     line = {
@@ -333,7 +381,7 @@ def run_megb200(args):
         "roofline": roofline,
         "step_tflops": flops_step / (ms * 1e-3) / 1e12,
         "step_frac_of_peak": flops_step / (ms * 1e-3) / 1e12 / peaks["bf16_sustained"],
-        "adam_ms": adam_ms, "loss": loss_value, "precision": args.precision,
+        "adam_ms": adam_ms, "host_enqueue_ms_per_step": host_ms, "loss": loss_value, "precision": args.precision,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         Bs = min(B, args.cpu_sample)

@@ -818,9 +818,9 @@ tc_tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
 }
 
-// CTA-pair + halo: the activation tile (with halo rows) is staged once per 64-channel chunk and shared by all taps
-// (see tc_tapgemm_halo_kernel), the weight half-tiles stream through their own ring.  L2->SM traffic per 256x160 tile of
-// a 320->320 k=3 conv: 780 KB (pair) -> 460 KB.
+// CTA-pair + halo (the default for k > 1): the activation rows (with halo) of a 64-channel chunk are staged once and
+// shared by all taps (see tc_tapgemm_halo_kernel); the same stage carries the weight half-tiles of all taps, so one
+// barrier round trip feeds taps*4 MMAs.  L2->SM traffic per 256x160 tile of a 320->320 k=3 conv: 780 KB (pair) -> 460 KB.
 struct Header2H {
   uint64_t fullA[4];
   uint64_t emptyA[4];
@@ -845,10 +845,13 @@ tc_tapgemm2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int half = p.NT / 2;                                  // weight rows staged by each CTA
   const uint32_t a_slot = ((uint32_t)a_rows * 128u + 1023u) & ~1023u;              // activation rows incl. halo
   const uint32_t b_bytes = (uint32_t)half * 128;
+  // one stage = the activation rows (with halo) of a 64-channel chunk + the weight half-tiles of ALL taps for that
+  // chunk: one barrier round trip and one commit per taps*4 MMAs
+  const uint32_t stage_bytes = a_slot + (uint32_t)p.taps * b_bytes;
   uint8_t* ringA = smem + kHeaderBytes;
-  uint8_t* ringB = ringA + (size_t)stagesA * a_slot;
-  uint8_t* stg = ringB + (size_t)p.stages * b_bytes;                                 // TMA-store staging (1024-aligned)
+  uint8_t* stg = ringA + (size_t)stagesA * stage_bytes;                              // TMA-store staging (1024-aligned)
   float* sbias = reinterpret_cast<float*>(stg + p.stg_bytes);                        // [2][NT]: one table per acc stage
+  float* sstat = sbias + 2 * p.NT;                 // [2][Cos] BatchNorm partial sums of all tiles of this CTA
   const bool glu = p.epi == MEGB200_EPI_GLU;
   const int Ch = p.N / 2;
   const int num_k = p.taps * p.kchunks;
@@ -860,10 +863,6 @@ tc_tapgemm2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int s = 0; s < stagesA; ++s) {
       mbar_init(smem_u32(&hdr->fullA[s]), 1);     // the leader's producer arrives once and expects both CTAs' bytes
       mbar_init(smem_u32(&hdr->emptyA[s]), 1);    // one multicast tcgen05.commit per use
-    }
-    for (int s = 0; s < p.stages; ++s) {
-      mbar_init(smem_u32(&hdr->fullB[s]), 1);
-      mbar_init(smem_u32(&hdr->emptyB[s]), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&hdr->tmem_full[a]), 1);
@@ -882,7 +881,7 @@ tc_tapgemm2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0) {
     if (lane == 0) {
-      int ita = 0, itb = 0;
+      int ita = 0;
       for (int item = cluster_id; item < num_items; item += num_clusters) {
         const int n_tile = item % p.ntiles;
         const int m_tile = (item / p.ntiles) * 2 + (int)rank;
@@ -893,21 +892,17 @@ tc_tapgemm2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const int sa = ita % stagesA;
           mbar_wait(smem_u32(&hdr->emptyA[sa]), ((ita / stagesA) & 1) ^ 1);
           const uint32_t fa = smem_u32(&hdr->fullA[sa]);
-          if (leader) mbar_arrive_expect_tx(fa, 2u * (uint32_t)a_rows * 128u);
-          tma_load_3d_2sm(smem_u32(ringA + (size_t)sa * a_slot), &tmA, kc * kBlockK, t0 - (p.taps / 2) * p.dil, b, fa);
-          for (int tap = 0; tap < p.taps; ++tap, ++itb) {
-            const int sb = itb % p.stages;
-            mbar_wait(smem_u32(&hdr->emptyB[sb]), ((itb / p.stages) & 1) ^ 1);
-            const uint32_t fb = smem_u32(&hdr->fullB[sb]);
-            if (leader) mbar_arrive_expect_tx(fb, 2 * b_bytes);
-            tma_load_3d_2sm(smem_u32(ringB + (size_t)sb * b_bytes), &tmW, tap * p.Kp + kc * kBlockK, wrow, 0, fb);
-          }
+          if (leader) mbar_arrive_expect_tx(fa, 2u * ((uint32_t)a_rows * 128u + (uint32_t)p.taps * b_bytes));
+          const uint32_t sbase = smem_u32(ringA + (size_t)sa * stage_bytes);
+          tma_load_3d_2sm(sbase, &tmA, kc * kBlockK, t0 - (p.taps / 2) * p.dil, b, fa);
+          for (int tap = 0; tap < p.taps; ++tap)
+            tma_load_3d_2sm(sbase + a_slot + (uint32_t)tap * b_bytes, &tmW, tap * p.Kp + kc * kBlockK, wrow, 0, fa);
         }
       }
     }
   } else if (warp == 1) {
     if (leader && lane == 0) {
-      int ita = 0, itb = 0, tile = 0;
+      int ita = 0, tile = 0;
       for (int item = cluster_id; item < num_items; item += num_clusters, ++tile) {
         const int acc = tile & 1;
         mbar_wait(smem_u32(&hdr->tmem_empty[acc]), ((tile >> 1) & 1) ^ 1);   // epilogues of both CTAs drained it
@@ -916,18 +911,15 @@ tc_tapgemm2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int kc = 0; kc < p.kchunks; ++kc, ++ita) {
           const int sa = ita % stagesA;
           mbar_wait(smem_u32(&hdr->fullA[sa]), (ita / stagesA) & 1);
-          const uint32_t abase = smem_u32(ringA + (size_t)sa * a_slot);
-          for (int tap = 0; tap < p.taps; ++tap, ++itb) {
-            const int sb = itb % p.stages;
-            mbar_wait(smem_u32(&hdr->fullB[sb]), (itb / p.stages) & 1);
-            tc_fence_after();
+          tc_fence_after();
+          const uint32_t abase = smem_u32(ringA + (size_t)sa * stage_bytes);
+          for (int tap = 0; tap < p.taps; ++tap) {
             // tap window = the staged rows shifted by tap*dil (absolute-address swizzle keeps it a valid operand)
             const uint64_t da = make_smem_desc(abase + (uint32_t)(tap * p.dil) * 128u, 16, 1024);
-            const uint64_t db = make_smem_desc(smem_u32(ringB + (size_t)sb * b_bytes), 16, 1024);
+            const uint64_t db = make_smem_desc(abase + a_slot + (uint32_t)tap * b_bytes, 16, 1024);
 #pragma unroll
-            for (int k = 0; k < kBlockK / kUmmaK; ++k)
-              umma_bf16_2sm(d_tmem, desc_advance(da, k * 32), desc_advance(db, k * 32), p.idesc, (kc | tap | k) != 0);
-            umma_commit_2sm(smem_u32(&hdr->emptyB[sb]), 3);
+            for (int kk = 0; kk < kBlockK / kUmmaK; ++kk)
+              umma_bf16_2sm(d_tmem, desc_advance(da, kk * 32), desc_advance(db, kk * 32), p.idesc, (kc | tap | kk) != 0);
           }
           umma_commit_2sm(smem_u32(&hdr->emptyA[sa]), 3);
         }
@@ -941,6 +933,8 @@ tc_tapgemm2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int q = warp & 3;
     const int h = (warp - 2) >> 2;
     int tile = 0;
+    if (p.stats != nullptr)
+      for (int i = et; i < 2 * p.Cos; i += 256) sstat[i] = 0.f;      // visible after the first named barrier below
     for (int item = cluster_id; item < num_items; item += num_clusters, ++tile) {
       const int acc = tile & 1;
       const int n_tile = item % p.ntiles;
@@ -968,10 +962,17 @@ tc_tapgemm2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int t = t0 + q * 32 + lane;
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.NT);
       tap_epilogue_tma<true, 2>(p, maps, trow, sb, n0, b, t0, q * 32 + lane, t < p.T, m_tile < total_m_tiles,
-                                smem_u32(stg), p.stg_bytes, et, h);
+                                smem_u32(stg), p.stg_bytes, et, h, p.stats != nullptr ? sstat : nullptr, 0, p.Cos);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(smem_u32(&hdr->tmem_empty[acc]), 0);
+    }
+    if (p.stats != nullptr) {
+      named_bar_sync(2, 256);
+      for (int i = et; i < p.N; i += 256) {
+        atomicAdd(&p.stats[i], sstat[i]);
+        atomicAdd(&p.stats[p.N + i], sstat[p.Cos + i]);
+      }
     }
   }
   if (p.tma_epi && threadIdx.x == 64) tma_store_wait_read();
@@ -1524,31 +1525,33 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    // halo form of the pair kernel: correct (tests) but measured slower (536 vs 647 TFLOP/s) -> opt-in
-    static const bool no_halo = getenv("MEGB200_TAPGEMM_PAIR_HALO") == nullptr;
+    // halo form of the pair kernel, default for k > 1 (653 vs 599 TFLOP/s on the same box, r1_tapgemm_variants.md);
+    // MEGB200_TAPGEMM_PAIR_HALO=0 selects the plain pair kernel
+    static const char* ph_env = getenv("MEGB200_TAPGEMM_PAIR_HALO");
+    static const bool no_halo = ph_env != nullptr && atoi(ph_env) == 0;
     const int a_rows2 = ((kTileM + (taps - 1) * dil) + 7) / 8 * 8;
     if (taps > 1 && a_rows2 <= 256 && !no_halo && p.n_last == p.NT) {
-      p.stats = nullptr;
       // halo form: activation ring (with halo rows) + weight ring
       const uint32_t a_slot = ((uint32_t)a_rows2 * 128u + 1023u) & ~1023u;
       const uint32_t b_half = (uint32_t)half * 128;
-      const int stagesA = 3;
-      p.stages = pick_stages(b_half, 229000 - 2048 - 2 * p.NT * 4 - p.stg_bytes - stagesA * a_slot, 8);
-      MEGB_CHECK_ARG(p.stages >= 3, "tc_tapgemm(pair, halo): tile too large");
+      const uint32_t stage_h = a_slot + (uint32_t)taps * b_half;
+      const int stagesA = pick_stages(stage_h, 229000 - 2048 - 2 * p.NT * 4 - 2 * Cos * 4 - p.stg_bytes, 4);
+      MEGB_CHECK_ARG(stagesA >= 2, "tc_tapgemm(pair, halo): tile too large");
+      p.stages = stagesA;
       CUtensorMap tmAh;
       const uint64_t dims[3] = {(uint64_t)Ca, (uint64_t)T, (uint64_t)B};
       const uint64_t strides[2] = {(uint64_t)Cas * 2, (uint64_t)T * Cas * 2};
       const uint32_t box[3] = {kBlockK, (uint32_t)a_rows2, 1};
       int rc = encode_tmap_bf16(&tmAh, A, 3, dims, strides, box);
       if (rc) return rc;
-      const size_t smemh = 1024 + kHeaderBytes + (size_t)stagesA * a_slot + (size_t)p.stages * b_half + p.stg_bytes +
-                           2 * p.NT * 4;
+      const size_t smemh = 1024 + kHeaderBytes + (size_t)stagesA * stage_h + p.stg_bytes + 2 * p.NT * 4 + 2 * Cos * 4;
       rc = set_smem(tc_tapgemm2h_kernel, smemh);
       if (rc) return rc;
       cfg.dynamicSmemBytes = smemh;
       MEGB_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_tapgemm2h_kernel, tmAh, tmW2, maps, p, (int)m_tiles_total, num_items,
                                       a_rows2, stagesA));
       MEGB_LAUNCH_OK();
+      *stats_fused = fuse_stats ? 1 : 0;
       return 0;
     }
     p.stages = pick_stages(2 * stage2, 229000 - 2048 - 2 * p.NT * 4 - 2 * Cos * 4 - p.stg_bytes, 8);   // two k chunks per stage

@@ -13,49 +13,121 @@ class DevicePrefetcher:
     pass through) and yields the same tuples with the tensors resident on ``device``.
 
     Copies are issued on a dedicated stream from pinned memory (tensors that are not pinned are pinned once per batch),
-    ``depth`` batches ahead; the consumer's stream waits on the copy's event, and the buffers are tied to the consumer
-    stream with ``record_stream`` so the caching allocator cannot recycle them early.
+    ``depth`` batches ahead, into a fixed ring of ``depth + 1`` device buffer sets allocated on first use — the caching
+    allocator is never involved in steady state, so a host that runs ahead of the device (no per-step sync) cannot
+    trigger a cudaMalloc.  The consumer's stream waits on the copy's event; a slot is overwritten only after the
+    consumer stream has passed the point where the NEXT batch was requested, so a yielded batch is valid until the
+    following ``next()`` call plus the work already enqueued on the consumer stream (clone it to keep it longer).
     """
 
     def __init__(self, batches: Iterable[Sequence], device, keep_on_host: Sequence[int] = (), depth: int = 2):
-        self.it: Iterator = iter(batches)
         self.device = torch.device(device)
         self.keep = set(keep_on_host)
         self.depth = max(1, depth)
         self.stream = torch.cuda.Stream(device=self.device)
+        self.ring = [dict() for _ in range(self.depth + 1)]       # slot -> {(position, shape, dtype): device buffer}
+        self.released = [None] * (self.depth + 1)                 # slot -> event: consumer is done with the slot
+        self.n_issued = 0
         self.queue = []
+        self.current = None
+        self.reset(batches)
+
+    def reset(self, batches: Iterable[Sequence]) -> "DevicePrefetcher":
+        """Start over on a new iterable (next epoch), keeping the device ring."""
+        self._release_current()
+        self.queue.clear()
+        self.it: Iterator = iter(batches)
         for _ in range(self.depth):
             self._issue()
+        return self
+
+    def _release_current(self):
+        if self.current is not None:               # the batch handed out last time is done once the stream gets here
+            rel = torch.cuda.Event()
+            rel.record(torch.cuda.current_stream(self.device))
+            self.released[self.current] = rel
+            self.current = None
 
     def _issue(self):
         try:
             batch = next(self.it)
         except StopIteration:
             return
+        slot = self.n_issued % len(self.ring)
+        self.n_issued += 1
         out = []
         with torch.cuda.stream(self.stream):
+            if self.released[slot] is not None:
+                self.stream.wait_event(self.released[slot])
+                self.released[slot] = None
             for i, t in enumerate(batch):
                 if not torch.is_tensor(t) or i in self.keep:
                     out.append(t)
                     continue
                 if not t.is_pinned():
                     t = t.pin_memory()
-                out.append(t.to(self.device, non_blocking=True))
+                key = (i, tuple(t.shape), t.dtype)
+                buf = self.ring[slot].get(key)
+                if buf is None:
+                    buf = self.ring[slot][key] = torch.empty(t.shape, dtype=t.dtype, device=self.device)
+                buf.copy_(t, non_blocking=True)
+                out.append(buf)
             ev = torch.cuda.Event()
             ev.record(self.stream)
-        self.queue.append((out, ev))
+        self.queue.append((out, ev, slot))
 
     def __iter__(self):
         return self
 
     def __next__(self):
+        cur = torch.cuda.current_stream(self.device)
+        self._release_current()
         if not self.queue:
             raise StopIteration
-        out, ev = self.queue.pop(0)
-        cur = torch.cuda.current_stream(self.device)
+        out, ev, slot = self.queue.pop(0)
         cur.wait_event(ev)
-        for t in out:
-            if torch.is_tensor(t) and t.is_cuda:
-                t.record_stream(cur)
+        self.current = slot
         self._issue()
         return tuple(out)
+
+
+class AsyncScalarReader:
+    """Pipelined device -> host read of one scalar per step (the loss the reference logs with ``loss.item()``,
+    train.py:208).  ``push(t)`` enqueues a copy of ``t`` into a pinned slot behind the step's kernels and returns the value
+    pushed ``lag`` steps earlier (None for the first ``lag`` calls), so the host never drains the stream between steps and
+    step i+1 is enqueued while step i still runs; ``drain()`` returns the values still in flight.  Every step's value
+    reaches the host — ``lag`` steps late.
+    """
+
+    def __init__(self, device, lag: int = 1):
+        self.device = torch.device(device)
+        self.lag = max(0, int(lag))
+        self.cuda = self.device.type == "cuda"
+        self.slots = [torch.empty(1, dtype=torch.float32, pin_memory=self.cuda) for _ in range(self.lag + 1)]
+        self.pending = []          # (slot index, event)
+        self.n = 0
+
+    def push(self, t: torch.Tensor):
+        i = self.n % len(self.slots)
+        self.n += 1
+        self.slots[i].copy_(t.detach().reshape(1).to(torch.float32), non_blocking=True)
+        ev = None
+        if self.cuda:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+        self.pending.append((i, ev))
+        if len(self.pending) > self.lag:
+            return self._pop()
+        return None
+
+    def _pop(self) -> float:
+        i, ev = self.pending.pop(0)
+        if ev is not None:
+            ev.synchronize()
+        return float(self.slots[i][0])
+
+    def drain(self):
+        out = []
+        while self.pending:
+            out.append(self._pop())
+        return out

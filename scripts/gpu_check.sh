@@ -23,8 +23,8 @@ for s in ${stages}; do
     tc_all)           run tc_all 600 ${PT} tests/test_ops_gpu.py -k "tc" ;;
     tc_halo1)         MEGB200_TAPGEMM_HALO=1 run tc_halo1 600 ${PT} tests/test_ops_gpu.py -k "tapgemm and tc" ;;
     tc_halo2)         MEGB200_TAPGEMM_HALO=2 run tc_halo2 600 ${PT} tests/test_ops_gpu.py -k "tapgemm and tc" ;;
-    tc_pair)          MEGB200_TAPGEMM_2CTA_MIN_ITEMS=1 run tc_pair 600 ${PT} tests/test_ops_gpu.py -k "tapgemm and tc" ;;
-    tc_pairhalo)      MEGB200_TAPGEMM_2CTA_MIN_ITEMS=1 MEGB200_TAPGEMM_PAIR_HALO=1 run tc_pairhalo 600 ${PT} tests/test_ops_gpu.py -k "tapgemm and tc" ;;
+    tc_pair)          MEGB200_TAPGEMM_2CTA_MIN_ITEMS=1 MEGB200_TAPGEMM_PAIR_HALO=0 run tc_pair 600 ${PT} tests/test_ops_gpu.py -k "tapgemm and tc" ;;
+    tc_pairhalo)      MEGB200_TAPGEMM_2CTA_MIN_ITEMS=1 run tc_pairhalo 600 ${PT} tests/test_ops_gpu.py -k "tapgemm and tc" ;;
     tc_1cta)          MEGB200_TAPGEMM_1CTA=1 run tc_1cta 600 ${PT} tests/test_ops_gpu.py -k "tapgemm and tc" ;;
     parity_pair)      MEGB200_TAPGEMM_2CTA_MIN_ITEMS=1 run parity_pair 600 ${PT} -s tests/test_parity_gpu.py -k "bf16 and not bf16_simt and not full_size and not default" ;;
     tc_wgrad)         run tc_wgrad 300 ${PT} tests/test_ops_gpu.py -k "wgrad and tc" ;;

@@ -121,3 +121,17 @@ def test_classifier_matches_oracle_topk(torch_ops):
     assert 0.0 < top1 <= top10 <= 1.0
     t1, t10, t3 = clf(Z, Y, top_k=3)
     assert abs(t3 - R.topk_accuracy(Z, Y, k=3)[1]) < 1e-6
+
+
+def test_async_scalar_reader_returns_every_value_in_order():
+    from megb200.data import AsyncScalarReader
+    for lag in (0, 1, 3):
+        r = AsyncScalarReader("cpu", lag=lag)
+        got = []
+        for i in range(7):
+            v = r.push(torch.tensor(float(i) + 0.5))
+            assert (v is None) == (i < lag)
+            if v is not None:
+                got.append(v)
+        got += r.drain()
+        assert got == [i + 0.5 for i in range(7)]
