@@ -109,9 +109,29 @@ __global__ void pack_weight_multi_kernel(const long long* __restrict__ table) {
 
 // ------------------------------------------------------------------------------------------ row-loop passes
 // One CTA owns a slab of rows; thread = (channel group of 8, row lane) and keeps its channel group for the whole
-// slab, so per-channel parameters are loaded ONCE into registers (Op::init) and the loop body is pure streaming:
-// 16/32-byte vector loads and stores, no parameter traffic.  Op::row() consumes one 8-vector, may write outputs, and
-// may add into up to two per-channel accumulators that end in one global atomic per channel per CTA.
+// slab, so per-channel parameters are loaded ONCE into registers (Op::init) and the loop body is pure streaming.
+// Op::row() consumes one 8-vector per input stream, may write outputs, and may add into up to two per-channel
+// accumulators that end in one global atomic per channel per CTA.
+//
+// An Op names its input streams (base pointer + row pitch in bytes; a row slab of a stream is one contiguous range of
+// memory).  The staged kernel moves those slabs HBM -> shared memory with 1-D bulk copies (cp.async.bulk, one elected
+// producer thread, mbarrier ring of `stages` slabs), so the depth of the memory pipeline is set by the ring, not by
+// registers/occupancy, and the consumer warps spend their issue slots on math, LDS and the output stores only.
+// Measured with ncu before this form (direct per-thread LDG, 24 warps/SM): 34-48 % of DRAM peak, top stall
+// long_scoreboard.  The direct kernel remains for grouped reductions and very wide rows.
+constexpr int kRowConsumers = 256;
+
+template <class Op>
+__device__ __forceinline__ void rowloop_flush(const Op&, int C, int Cs, const int32_t* group, int Tn, long long r0,
+                                              float* sm0, float* sm1, float* out0, float* out1, int tid, int nthr) {
+  long long obase = 0;
+  if (group != nullptr) obase = (long long)group[r0 / Tn] * C;
+  if (out0 != nullptr)
+    for (int c = tid; c < C; c += nthr) atomicAdd(&out0[obase + c], sm0[c]);
+  if (Op::kAcc > 1 && out1 != nullptr)
+    for (int c = tid; c < C; c += nthr) atomicAdd(&out1[obase + c], sm1[c]);
+}
+
 template <class Op>
 __global__ void __launch_bounds__(256, 3) rowloop_kernel(Op op, long long rows, long long rows_per_block, int C, int Cs,
                                                       const int32_t* __restrict__ group, int Tn,
@@ -130,6 +150,9 @@ __global__ void __launch_bounds__(256, 3) rowloop_kernel(Op op, long long rows, 
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   long long r1 = r0 + rows_per_block;
   if (r1 > rows) r1 = rows;
+  const uint8_t* b0 = static_cast<const uint8_t*>(op.in_base(0));
+  const uint8_t* b1 = static_cast<const uint8_t*>(op.in_base(Op::kIn - 1));
+  const long long p0 = op.in_pitch(0), p1 = op.in_pitch(Op::kIn - 1);
   if (lane_r < R) {
     for (int g = lane_g; g < cg; g += W) {
       float a0[8], a1[8];
@@ -137,7 +160,7 @@ __global__ void __launch_bounds__(256, 3) rowloop_kernel(Op op, long long rows, 
       for (int i = 0; i < 8; ++i) a0[i] = a1[i] = 0.f;
       op.init(g * 8);
 #pragma unroll 2
-      for (long long r = r0 + lane_r; r < r1; r += R) op.row(r, g * 8, a0, a1);
+      for (long long r = r0 + lane_r; r < r1; r += R) op.row(b0 + r * p0, b1 + r * p1, r, g * 8, a0, a1);
       op.finish(g * 8, a0, a1);
       if (Op::kAcc > 0) {
 #pragma unroll
@@ -150,25 +173,141 @@ __global__ void __launch_bounds__(256, 3) rowloop_kernel(Op op, long long rows, 
   }
   if (Op::kAcc > 0) {
     __syncthreads();
-    long long obase = 0;
-    if (group != nullptr) obase = (long long)group[r0 / Tn] * C;
-    if (out0 != nullptr)
-      for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(&out0[obase + c], sm0[c]);
-    if (Op::kAcc > 1 && out1 != nullptr)
-      for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(&out1[obase + c], sm1[c]);
+    rowloop_flush(op, C, Cs, group, Tn, r0, sm0, sm1, out0, out1, threadIdx.x, blockDim.x);
+  }
+}
+
+// ---- staged form
+__device__ __forceinline__ uint32_t rs_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void rs_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void rs_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void rs_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void rs_mbar_wait(uint32_t bar, uint32_t parity) {
+  // bounded: a lost copy must surface as a launch failure, never as a hung GPU
+  for (uint32_t spins = 0;; ++spins) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (spins > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void rs_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+constexpr int kRowMaxStages = 8;
+
+template <class Op>
+__global__ void __launch_bounds__(kRowConsumers + 32, 2)
+rowstage_kernel(Op op, long long rows, long long rows_per_block, int slab_rows, int stages, int C, int Cs,
+                float* __restrict__ out0, float* __restrict__ out1) {
+  extern __shared__ __align__(128) uint8_t rs_smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(rs_smem);
+  uint64_t* empty = full + kRowMaxStages;
+  uint8_t* ring = rs_smem + 128;
+  const uint32_t p0 = (uint32_t)op.in_pitch(0), p1 = Op::kIn > 1 ? (uint32_t)op.in_pitch(1) : 0u;
+  const uint32_t stage_bytes = (uint32_t)slab_rows * (p0 + p1);
+  float* sm0 = reinterpret_cast<float*>(ring + (size_t)stages * stage_bytes);
+  float* sm1 = sm0 + Cs;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      rs_mbar_init(rs_smem_u32(&full[s]), 1);
+      rs_mbar_init(rs_smem_u32(&empty[s]), kRowConsumers / 32);     // one arrival per consumer warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (Op::kAcc > 0)
+    for (int i = threadIdx.x; i < 2 * Cs; i += blockDim.x) sm0[i] = 0.f;
+  __syncthreads();
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > rows) r1 = rows;
+  const int nslabs = r1 > r0 ? (int)((r1 - r0 + slab_rows - 1) / slab_rows) : 0;
+
+  if (warp == kRowConsumers / 32) {
+    if (lane == 0) {
+      const uint8_t* b0 = static_cast<const uint8_t*>(op.in_base(0));
+      const uint8_t* b1 = static_cast<const uint8_t*>(op.in_base(Op::kIn - 1));
+      for (int i = 0; i < nslabs; ++i) {
+        const int s = i % stages;
+        rs_mbar_wait(rs_smem_u32(&empty[s]), ((i / stages) & 1) ^ 1);
+        const long long rs = r0 + (long long)i * slab_rows;
+        const uint32_t n = (uint32_t)((r1 - rs) < slab_rows ? (r1 - rs) : slab_rows);
+        const uint32_t fb = rs_smem_u32(&full[s]);
+        const uint32_t dst = rs_smem_u32(ring + (size_t)s * stage_bytes);
+        rs_mbar_expect_tx(fb, n * (p0 + p1));
+        rs_bulk_load(dst, b0 + rs * p0, n * p0, fb);
+        if (Op::kIn > 1) rs_bulk_load(dst + (uint32_t)slab_rows * p0, b1 + rs * p1, n * p1, fb);
+      }
+    }
+  } else {
+    const int cg = Cs >> 3;                          // <= 256 on this path (launcher)
+    const int R = kRowConsumers / cg;
+    const int lane_g = threadIdx.x % cg, lane_r = threadIdx.x / cg;
+    const bool active = lane_r < R;
+    float a0[8], a1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a0[i] = a1[i] = 0.f;
+    op.init(lane_g * 8);
+    for (int i = 0; i < nslabs; ++i) {
+      const int s = i % stages;
+      rs_mbar_wait(rs_smem_u32(&full[s]), (i / stages) & 1);
+      const long long rs = r0 + (long long)i * slab_rows;
+      const int n = (int)((r1 - rs) < slab_rows ? (r1 - rs) : slab_rows);
+      const uint8_t* s0 = ring + (size_t)s * stage_bytes;
+      const uint8_t* s1 = Op::kIn > 1 ? s0 + (size_t)slab_rows * p0 : s0;
+      if (active) {
+#pragma unroll 2
+        for (int rr = lane_r; rr < n; rr += R) op.row(s0 + (size_t)rr * p0, s1 + (size_t)rr * p1, rs + rr, lane_g * 8, a0, a1);
+      }
+      __syncwarp();
+      if (lane == 0) rs_mbar_arrive(rs_smem_u32(&empty[s]));
+    }
+    if (active) {
+      op.finish(lane_g * 8, a0, a1);
+      if (Op::kAcc > 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          atomicAdd(&sm0[lane_g * 8 + i], a0[i]);
+          if (Op::kAcc > 1) atomicAdd(&sm1[lane_g * 8 + i], a1[i]);
+        }
+      }
+    }
+  }
+  if (Op::kAcc > 0) {
+    __syncthreads();
+    rowloop_flush(op, C, Cs, nullptr, 1, r0, sm0, sm1, out0, out1, threadIdx.x, blockDim.x);
   }
 }
 
 template <typename T>
 struct StatsOp {
-  static constexpr int kAcc = 2;
+  static constexpr int kAcc = 2, kIn = 1;
   const T* u;
   int Cs;
+  __host__ __device__ __forceinline__ const void* in_base(int) const { return u; }
+  __host__ __device__ __forceinline__ long long in_pitch(int) const { return (long long)Cs * sizeof(T); }
   __device__ __forceinline__ void init(int) {}
   __device__ __forceinline__ void finish(int, float (&)[8], float (&)[8]) const {}
-  __device__ __forceinline__ void row(long long r, int c0, float (&a0)[8], float (&a1)[8]) const {
+  __device__ __forceinline__ void row(const void* pu, const void*, long long, int c0, float (&a0)[8],
+                                      float (&a1)[8]) const {
     float x[8];
-    load8(u + r * Cs + c0, x);
+    load8(static_cast<const T*>(pu) + c0, x);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       a0[i] += x[i];
@@ -179,14 +318,17 @@ struct StatsOp {
 
 template <typename T>
 struct ColsumOp {
-  static constexpr int kAcc = 1;
+  static constexpr int kAcc = 1, kIn = 1;
   const T* u;
   int Cs;
+  __host__ __device__ __forceinline__ const void* in_base(int) const { return u; }
+  __host__ __device__ __forceinline__ long long in_pitch(int) const { return (long long)Cs * sizeof(T); }
   __device__ __forceinline__ void init(int) {}
   __device__ __forceinline__ void finish(int, float (&)[8], float (&)[8]) const {}
-  __device__ __forceinline__ void row(long long r, int c0, float (&a0)[8], float (&a1)[8]) const {
+  __device__ __forceinline__ void row(const void* pu, const void*, long long, int c0, float (&a0)[8],
+                                      float (&a1)[8]) const {
     float x[8];
-    load8(u + r * Cs + c0, x);
+    load8(static_cast<const T*>(pu) + c0, x);
 #pragma unroll
     for (int i = 0; i < 8; ++i) a0[i] += x[i];
   }
@@ -195,12 +337,14 @@ struct ColsumOp {
 // H = gelu(scale*U + shift)
 template <typename TU, typename T>
 struct BnGeluOp {
-  static constexpr int kAcc = 0;
+  static constexpr int kAcc = 0, kIn = 1;
   const TU* u;
   T* h;
   const float *scale, *shift;
   int Cs, C;
   float sc[8], sh[8];
+  __host__ __device__ __forceinline__ const void* in_base(int) const { return u; }
+  __host__ __device__ __forceinline__ long long in_pitch(int) const { return (long long)Cs * sizeof(TU); }
   __device__ __forceinline__ void init(int c0) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -210,9 +354,10 @@ struct BnGeluOp {
     }
   }
   __device__ __forceinline__ void finish(int, float (&)[8], float (&)[8]) const {}
-  __device__ __forceinline__ void row(long long r, int c0, float (&a0)[8], float (&a1)[8]) const {
+  __device__ __forceinline__ void row(const void* pu, const void*, long long r, int c0, float (&a0)[8],
+                                      float (&a1)[8]) const {
     float x[8], o[8];
-    load8(u + r * Cs + c0, x);
+    load8(static_cast<const TU*>(pu) + c0, x);
     // pad channels have scale = shift = 0 (init): gelu(0) = 0, so no per-element predicate is needed
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = gelu_t<T>(fmaf(x[i], sc[i], sh[i]));
@@ -224,13 +369,15 @@ struct BnGeluOp {
 // sum d and sum d*u; xhat = (u - mean)*rstd is folded in once per thread at the end (finish()).
 template <typename TU, typename T>
 struct BnGeluBwdOp {
-  static constexpr int kAcc = 2;
+  static constexpr int kAcc = 2, kIn = 2;
   const T* dh;
   const TU* u;
   T* dy;
   const float *scale, *shift, *mean, *rstd;
   int Cs, C;
   float sc[8], sh[8];
+  __host__ __device__ __forceinline__ const void* in_base(int k) const { return k == 0 ? (const void*)dh : (const void*)u; }
+  __host__ __device__ __forceinline__ long long in_pitch(int k) const { return (long long)Cs * (k == 0 ? sizeof(T) : sizeof(TU)); }
   __device__ __forceinline__ void init(int c0) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -239,10 +386,11 @@ struct BnGeluBwdOp {
       sh[i] = in ? shift[c0 + i] : 0.f;
     }
   }
-  __device__ __forceinline__ void row(long long r, int c0, float (&a0)[8], float (&a1)[8]) const {
+  __device__ __forceinline__ void row(const void* pd, const void* pu, long long r, int c0, float (&a0)[8],
+                                      float (&a1)[8]) const {
     float g[8], x[8], o[8];
-    load8(dh + r * Cs + c0, g);
-    load8(u + r * Cs + c0, x);
+    load8(static_cast<const T*>(pd) + c0, g);
+    load8(static_cast<const TU*>(pu) + c0, x);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       o[i] = g[i] * gelu_grad_t<T>(fmaf(x[i], sc[i], sh[i]));
@@ -271,7 +419,7 @@ struct BnGeluBwdOp {
 // dU = gamma*rstd*(dY - s0/n - xhat*s1/n) = A*dY + Bc*U + Cc per channel; accumulates sum dU (the conv bias gradient)
 template <typename TU, typename T>
 struct BnBwdApplyOp {
-  static constexpr int kAcc = 1;
+  static constexpr int kAcc = 1, kIn = 2;
   const T* dy;
   const TU* u;
   T* du;
@@ -279,6 +427,8 @@ struct BnBwdApplyOp {
   float inv_n;
   int Cs, C;
   float ca[8], cb[8], cc[8];
+  __host__ __device__ __forceinline__ const void* in_base(int k) const { return k == 0 ? (const void*)dy : (const void*)u; }
+  __host__ __device__ __forceinline__ long long in_pitch(int k) const { return (long long)Cs * (k == 0 ? sizeof(T) : sizeof(TU)); }
   __device__ __forceinline__ void init(int c0) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -294,10 +444,11 @@ struct BnBwdApplyOp {
     }
   }
   __device__ __forceinline__ void finish(int, float (&)[8], float (&)[8]) const {}
-  __device__ __forceinline__ void row(long long r, int c0, float (&a0)[8], float (&a1)[8]) const {
+  __device__ __forceinline__ void row(const void* pd, const void* pu, long long r, int c0, float (&a0)[8],
+                                      float (&a1)[8]) const {
     float g[8], x[8], o[8];
-    load8(dy + r * Cs + c0, g);
-    load8(u + r * Cs + c0, x);
+    load8(static_cast<const T*>(pd) + c0, g);
+    load8(static_cast<const TU*>(pu) + c0, x);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       o[i] = round_to<T>(fmaf(ca[i], g[i], fmaf(cb[i], x[i], cc[i])));
@@ -310,17 +461,20 @@ struct BnBwdApplyOp {
 // dP = dQ * gelu'(P); accumulates sum dP (bias gradient of the 1x1 head convs)
 template <typename T>
 struct GeluBwdOp {
-  static constexpr int kAcc = 1;
+  static constexpr int kAcc = 1, kIn = 2;
   const T* dq;
   const T* p;
   T* dp;
   int Cs, C;
+  __host__ __device__ __forceinline__ const void* in_base(int k) const { return k == 0 ? dq : p; }
+  __host__ __device__ __forceinline__ long long in_pitch(int) const { return (long long)Cs * sizeof(T); }
   __device__ __forceinline__ void init(int) {}
   __device__ __forceinline__ void finish(int, float (&)[8], float (&)[8]) const {}
-  __device__ __forceinline__ void row(long long r, int c0, float (&a0)[8], float (&a1)[8]) const {
+  __device__ __forceinline__ void row(const void* pd, const void* pp, long long r, int c0, float (&a0)[8],
+                                      float (&a1)[8]) const {
     float g[8], x[8], o[8];
-    load8(dq + r * Cs + c0, g);
-    load8(p + r * Cs + c0, x);
+    load8(static_cast<const T*>(pd) + c0, g);
+    load8(static_cast<const T*>(pp) + c0, x);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       o[i] = g[i] * gelu_grad_t<T>(x[i]);
@@ -340,19 +494,22 @@ struct GeluBwdOp {
 // Requires C % 8 == 0 (the launcher falls back to the scalar kernel otherwise).
 template <typename T>
 struct GluBwdOp {
-  static constexpr int kAcc = 2;
+  static constexpr int kAcc = 2, kIn = 2;
   const T* dout;
   const T* V;
   T* dV;
   int Vs, Os, C;
+  __host__ __device__ __forceinline__ const void* in_base(int k) const { return k == 0 ? dout : V; }
+  __host__ __device__ __forceinline__ long long in_pitch(int k) const { return (long long)(k == 0 ? Os : Vs) * sizeof(T); }
   __device__ __forceinline__ void init(int) {}
   __device__ __forceinline__ void finish(int, float (&)[8], float (&)[8]) const {}
-  __device__ __forceinline__ void row(long long r, int c0, float (&a0)[8], float (&a1)[8]) const {
+  __device__ __forceinline__ void row(const void* pd, const void* pv, long long r, int c0, float (&a0)[8],
+                                      float (&a1)[8]) const {
     if (c0 >= C) return;
     float d[8], a[8], g[8], da[8], dg[8];
-    load8(dout + r * Os + c0, d);
-    load8(V + r * Vs + c0, a);
-    load8(V + r * Vs + C + c0, g);
+    load8(static_cast<const T*>(pd) + c0, d);
+    load8(static_cast<const T*>(pv) + c0, a);
+    load8(static_cast<const T*>(pv) + C + c0, g);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float s = sigmoid_f(g[i]);
@@ -366,10 +523,44 @@ struct GluBwdOp {
   }
 };
 
+static bool rowloop_direct_env() {
+  static const bool v = getenv("MEGB200_ROWLOOP_DIRECT") != nullptr;
+  return v;
+}
+
 template <class Op>
 static int launch_rowloop(Op op, long long rows, int C, int Cs, const int32_t* group, int Tn, float* out0,
                           float* out1, cudaStream_t st) {
   MEGB_CHECK_ARG(Cs % 8 == 0 && Cs >= C && Cs <= 4096, "rowloop: bad channel stride %d (C=%d)", Cs, C);
+  if (rows < 1) return 0;
+  // ---- staged form: ungrouped, row fits the 256 consumer threads, inputs 16-byte aligned (bulk-copy rule)
+  const long long pitch_sum = op.in_pitch(0) + (Op::kIn > 1 ? op.in_pitch(1) : 0);
+  const bool aligned = (((uintptr_t)op.in_base(0) | (uintptr_t)op.in_base(Op::kIn - 1) | (uintptr_t)op.in_pitch(0) |
+                         (uintptr_t)op.in_pitch(Op::kIn - 1)) & 15) == 0;
+  if (group == nullptr && Cs <= 8 * kRowConsumers && aligned && pitch_sum <= 24 * 1024 && !rowloop_direct_env()) {
+    const int R = kRowConsumers / (Cs >> 3);
+    int slab_rows = (int)(24 * 1024 / pitch_sum) / R * R;          // ~24 KB per stage, whole row-lane rounds
+    if (slab_rows < R) slab_rows = R;
+    const long long stage_bytes = (long long)slab_rows * pitch_sum;
+    const size_t acc_bytes = Op::kAcc > 0 ? 2 * Cs * sizeof(float) : 0;
+    int stages = (int)((100 * 1024 - 128 - (long long)acc_bytes) / stage_bytes);
+    if (stages > kRowMaxStages) stages = kRowMaxStages;
+    if (stages >= 2) {
+      long long blocks = (long long)num_sms() * 2;                  // one resident wave (2 CTAs per SM)
+      long long rpb = (rows + blocks - 1) / blocks;
+      if (rpb < slab_rows) rpb = slab_rows;
+      blocks = (rows + rpb - 1) / rpb;
+      const size_t smem = 128 + (size_t)stages * stage_bytes + acc_bytes;
+      static bool attr_set = false;   // per instantiation
+      if (!attr_set) {
+        MEGB_CUDA_OK(cudaFuncSetAttribute(rowstage_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, 101 * 1024));
+        attr_set = true;
+      }
+      rowstage_kernel<Op><<<(int)blocks, kRowConsumers + 32, smem, st>>>(op, rows, rpb, slab_rows, stages, C, Cs, out0, out1);
+      MEGB_LAUNCH_OK();
+      return 0;
+    }
+  }
   long long rpb;
   if (group != nullptr) {
     rpb = Tn;
@@ -379,7 +570,6 @@ static int launch_rowloop(Op op, long long rows, int C, int Cs, const int32_t* g
     if (rpb < 16) rpb = 16;
   }
   long long blocks = (rows + rpb - 1) / rpb;
-  if (blocks < 1) return 0;
   const size_t smem = Op::kAcc > 0 ? 2 * Cs * sizeof(float) : 0;
   rowloop_kernel<Op><<<(int)blocks, 256, smem, st>>>(op, rows, rpb, C, Cs, group, Tn, out0, out1);
   MEGB_LAUNCH_OK();
