@@ -198,49 +198,53 @@ simt_wgrad_kernel(const T* __restrict__ dU, int M, int Ms, const T* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------ small f32 GEMM
-// 128x128x8 tile, 256 threads, 8x8 outputs per thread from two float4 shared loads per operand and k (FMA-bound, not
-// LDS-bound); optional split-K with f32 atomics when the output has too few tiles to fill the machine (e.g. the
-// (270 x C) reductions over all subjects, K = S*270).
-constexpr int kSgM = 128, kSgN = 128, kSgK = 8, kSgPad = 4;
+// (16*TM)x(16*TM)x8 tile, 256 threads, TMxTM outputs per thread.  TM = 8 (128x128: two float4 shared loads per operand
+// and k, FMA-bound) for problems with enough tiles to fill the machine; TM = 4 (64x64) for the subject-chain products
+// whose whole output is a few 128-tiles (270 x 208: 6) -- there the time is one CTA's serial k loop, so the launcher
+// trades tile efficiency for parallelism and adds deterministic split-K through the workspace.
+constexpr int kSgPad = 4;
 
+template <int TM, int kSgK>
 __global__ void __launch_bounds__(256)
 simt_sgemm_kernel(int transA, int transB, int M, int N, int K, float alpha, const float* __restrict__ A, int lda,
                   long long sA, const float* __restrict__ Bm, int ldb, long long sB, float beta,
                   float* __restrict__ Cm, int ldc, long long sC, int splits, int kchunk, float* __restrict__ part) {
-  __shared__ __align__(16) float As[kSgK][kSgM + kSgPad];
-  __shared__ __align__(16) float Bs[kSgK][kSgN + kSgPad];
+  constexpr int kTile = 16 * TM;                 // rows and columns per CTA
+  constexpr int kPer = kTile * kSgK / 256;       // operand elements per thread and k step
+  __shared__ __align__(16) float As[kSgK][kTile + kSgPad];
+  __shared__ __align__(16) float Bs[kSgK][kTile + kSgPad];
   const int batch = blockIdx.z / splits, split = blockIdx.z % splits;
-  const int m0 = blockIdx.x * kSgM, n0 = blockIdx.y * kSgN;
+  const int m0 = blockIdx.x * kTile, n0 = blockIdx.y * kTile;
   const float* Ab = A + batch * sA;
   const float* Bb = Bm + batch * sB;
   float* Cb = Cm + batch * sC;
   const int k_begin = split * kchunk;
   const int k_end = min(K, k_begin + kchunk);
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  float acc[8][8];
+  float acc[TM][TM];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < TM; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-  // global -> register prefetch of the next k tile while the current one is multiplied (one CTA per SM at 132
-  // registers: without it every k step exposes a full global-memory latency)
-  float ra[4], rb[4];
+    for (int j = 0; j < TM; ++j) acc[i][j] = 0.f;
+  // global -> register prefetch of the next k tile while the current one is multiplied (without it every k step
+  // exposes a full global-memory latency)
+  float ra[kPer], rb[kPer];
   auto fetch = [&](int k0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < kPer; ++i) {
       const int e = tid + i * 256;
       {
         // transposed A is m-contiguous in memory, plain A is k-contiguous: keep the fast index on the lanes
-        const int m = transA ? (e & 127) : (e >> 3);
-        const int kk = transA ? (e >> 7) : (e & 7);
+        const int m = transA ? (e % kTile) : (e / kSgK);
+        const int kk = transA ? (e / kTile) : (e % kSgK);
         const int gm = m0 + m, gk = k0 + kk;
         float v = 0.f;
         if (gm < M && gk < k_end) v = transA ? Ab[(long long)gk * lda + gm] : Ab[(long long)gm * lda + gk];
         ra[i] = v;
       }
       {
-        const int n = transB ? (e >> 3) : (e & 127);
-        const int kk = transB ? (e & 7) : (e >> 7);
+        const int n = transB ? (e / kSgK) : (e % kTile);
+        const int kk = transB ? (e % kSgK) : (e / kTile);
         const int gn = n0 + n, gk = k0 + kk;
         float v = 0.f;
         if (gn < N && gk < k_end) v = transB ? Bb[(long long)gn * ldb + gk] : Bb[(long long)gk * ldb + gn];
@@ -250,10 +254,10 @@ simt_sgemm_kernel(int transA, int transB, int M, int N, int K, float alpha, cons
   };
   auto stash = [&]() {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < kPer; ++i) {
       const int e = tid + i * 256;
-      As[transA ? (e >> 7) : (e & 7)][transA ? (e & 127) : (e >> 3)] = ra[i];
-      Bs[transB ? (e & 7) : (e >> 7)][transB ? (e >> 3) : (e & 127)] = rb[i];
+      As[transA ? (e / kTile) : (e % kSgK)][transA ? (e % kTile) : (e / kSgK)] = ra[i];
+      Bs[transB ? (e % kSgK) : (e / kTile)][transB ? (e / kSgK) : (e % kTile)] = rb[i];
     }
   };
   fetch(k_begin);
@@ -263,26 +267,28 @@ simt_sgemm_kernel(int transA, int transB, int M, int N, int K, float alpha, cons
     if (k0 + kSgK < k_end) fetch(k0 + kSgK);
 #pragma unroll
     for (int kk = 0; kk < kSgK; ++kk) {
-      const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);
-      const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
-      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 8]);
-      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 8 + 4]);
-      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float a[TM], b[TM];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int v = 0; v < TM / 4; ++v) {
+        const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * TM + 4 * v]);
+        const float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tx * TM + 4 * v]);
+        a[4 * v] = av.x; a[4 * v + 1] = av.y; a[4 * v + 2] = av.z; a[4 * v + 3] = av.w;
+        b[4 * v] = bv.x; b[4 * v + 1] = bv.y; b[4 * v + 2] = bv.z; b[4 * v + 3] = bv.w;
+      }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TM; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int m = m0 + ty * 8 + i;
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + ty * TM + i;
     if (m >= M) continue;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int n = n0 + tx * 8 + j;
+    for (int j = 0; j < TM; ++j) {
+      const int n = n0 + tx * TM + j;
       if (n >= N) continue;
       float* dst = Cb + (long long)m * ldc + n;
       if (splits > 1) {
@@ -463,27 +469,36 @@ extern "C" int megb200_sgemm(int transA, int transB, int M, int N, int K, float 
                              long long strideA, const float* Bm, int ldb, long long strideB, float beta, float* C,
                              int ldc, long long strideC, int batch, float* workspace, size_t ws_bytes, void* stream) {
   MEGB_CHECK_ARG(A && Bm && C && M > 0 && N > 0 && K > 0 && batch > 0, "sgemm: bad arguments");
-  const int mt = (M + kSgM - 1) / kSgM, nt = (N + kSgN - 1) / kSgN;
-  MEGB_CHECK_ARG(nt <= 65535, "sgemm: N too large");
   cudaStream_t st = (cudaStream_t)stream;
-  // split-K (through the workspace, deterministic) when the output has too few tiles to fill the machine and K is long
+  // tile: 64 unless the problem is large (the hot path's products are all small: at most 7290 x 270 x 208); the 64-tile
+  // kernel co-resides 6-8 CTAs per SM, which hides the k loop's global-load latency
+  const long long tiles64 = (long long)((M + 63) / 64) * ((N + 63) / 64) * batch;
+  const int tile = tiles64 >= 16ll * num_sms() ? 128 : 64;
+  const int mt = (M + tile - 1) / tile, nt = (N + tile - 1) / tile;
+  MEGB_CHECK_ARG(nt <= 65535, "sgemm: N too large");
+  // split-K (through the workspace, deterministic: fixed k ranges, summed in order) until about six CTAs per SM exist
   int splits = 1;
   const long long tiles = (long long)mt * nt * batch;
   const long long per_split = (long long)batch * M * N;
-  if (workspace != nullptr && tiles < num_sms() && K >= 512) {
-    splits = (int)((num_sms() + tiles - 1) / tiles);
-    if (splits > K / 128) splits = K / 128;
+  if (workspace != nullptr && tiles < 6ll * num_sms() && K >= 32) {
+    splits = (int)((6ll * num_sms() + tiles - 1) / tiles);
+    if (splits > K / 32) splits = K / 32;
     const long long fit = (long long)(ws_bytes / sizeof(float)) / per_split;
     if (splits > fit) splits = (int)fit;
     if (splits < 1) splits = 1;
   }
   int kchunk = (K + splits - 1) / splits;
-  kchunk = (kchunk + kSgK - 1) / kSgK * kSgK;
+  const int bk = tile == 128 ? 8 : 32;       // k elements per step: long steps amortise the global-load round trip
+  kchunk = (kchunk + bk - 1) / bk * bk;
   splits = (K + kchunk - 1) / kchunk;
   MEGB_CHECK_ARG((long long)batch * splits <= 65535, "sgemm: batch too large");
   dim3 grid(mt, nt, batch * splits);
-  simt_sgemm_kernel<<<grid, 256, 0, st>>>(transA, transB, M, N, K, alpha, A, lda, strideA, Bm, ldb, strideB, beta, C,
-                                          ldc, strideC, splits, kchunk, workspace);
+  if (tile == 128)
+    simt_sgemm_kernel<8, 8><<<grid, 256, 0, st>>>(transA, transB, M, N, K, alpha, A, lda, strideA, Bm, ldb, strideB, beta, C,
+                                               ldc, strideC, splits, kchunk, workspace);
+  else
+    simt_sgemm_kernel<4, 32><<<grid, 256, 0, st>>>(transA, transB, M, N, K, alpha, A, lda, strideA, Bm, ldb, strideB, beta, C,
+                                               ldc, strideC, splits, kchunk, workspace);
   MEGB_LAUNCH_OK();
   if (splits > 1) {
     long long blocks = (per_split + 255) / 256;

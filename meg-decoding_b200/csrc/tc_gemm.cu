@@ -107,7 +107,7 @@ __device__ __forceinline__ void tap_epilogue(const TapGemmParams& p, uint32_t tr
         } else if (p.epi == MEGB200_EPI_GELU) {
           if (c0 < p.Co2s) store8(prow + c0, o);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = (c0 + i < p.N) ? gelu_t<__nv_bfloat16>(o[i]) : 0.f;
+          for (int i = 0; i < 8; ++i) o[i] = gelu_t<__nv_bfloat16>(o[i]);     // out-of-range channels are 0; gelu(0) = 0
           store8(orow + c0, o);
         } else {
           store8(orow + c0, o);
@@ -184,11 +184,22 @@ __device__ __forceinline__ void tap_epilogue_tma(const TapGemmParams& p, const T
   // Rounds: all channel groups that fit the staging area are converted and staged back to back; ONE proxy fence and
   // ONE barrier per round, then a single thread issues the round's TMA stores (measured: a fence + barrier per group
   // costs ~2500 cycles per group and made the epilogue as long as the main loop).
+  const bool dbgp = kPersistent && p.dbg != nullptr && etid == 0;
+  long long dt0 = dbgp ? clock64() : 0;
+  auto dbg_phase = [&](int slot) {
+    if (dbgp) {
+      const long long t = clock64();
+      p.dbg[16 * blockIdx.x + 8 + slot] += t - dt0;
+      dt0 = t;
+    }
+  };
   for (int jj0 = 0; jj0 < iters; jj0 += cap_iters) {
     if (jj0 > 0 || kPersistent) {
       // the staging area is reused: the previous stores must have finished reading it
-      if (etid == 0) tma_store_wait_read();
+      if ((etid & 31) == 0) tma_store_wait_read();
+      dbg_phase(0);
       named_bar_sync(2, kEpiThreads);
+      dbg_phase(1);
     }
     const int jj1 = (jj0 + cap_iters < iters) ? jj0 + cap_iters : iters;
     for (int jj = jj0; jj < jj1; ++jj) {
@@ -252,71 +263,91 @@ __device__ __forceinline__ void tap_epilogue_tma(const TapGemmParams& p, const T
         } else if (gelu) {
           stage_bf16_slice(sbase, rloc, o);                                   // pre-activation P
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = (full || c_first + i < p.N) ? gelu_t<__nv_bfloat16>(o[i]) : 0.f;
+          for (int i = 0; i < 32; ++i) o[i] = gelu_t<__nv_bfloat16>(o[i]);   // out-of-range channels are already 0 and gelu(0) = 0;
+          // a per-element predicate here compiled to 32 serialised branches (2900 cycles per group)
           stage_bf16_slice(sbase + slice_bytes, rloc, o);                     // Q = gelu(P)
         } else {
           stage_bf16_slice(sbase, rloc, o);
         }
       }
     }
-    if (!kPersistent && p.dbg != nullptr && etid == 0 && jj0 == 0) p.dbg[8 * blockIdx.x + 4] = clock64();
+    if (!kPersistent && p.dbg != nullptr && etid == 0 && jj0 == 0) p.dbg[16 * blockIdx.x + 4] = clock64();
+    dbg_phase(2);
     fence_proxy_async();
     named_bar_sync(2, kEpiThreads);
-    if (!kPersistent && p.dbg != nullptr && etid == 0 && jj0 == 0) p.dbg[8 * blockIdx.x + 5] = clock64();
+    dbg_phase(3);
+    if (!kPersistent && p.dbg != nullptr && etid == 0 && jj0 == 0) p.dbg[16 * blockIdx.x + 5] = clock64();
     if (f32 && sstat != nullptr && tile_valid) {
-      // column sums of the staged slices: warp = block of rows, lane = channel (conflict-free swizzled reads)
-      constexpr int kRowsPer = 128 / (kEpiThreads / 32);
-      const int c = etid & 31, r0 = (etid >> 5) * kRowsPer;
-      for (int jj = jj0; jj < jj1; ++jj) {
-#pragma unroll
-        for (int hh = 0; hh < kHalves; ++hh) {
-          const int jh = jj * kHalves + hh;
-          if (jh >= groups) break;
-          const uint32_t sb2 = stg + (uint32_t)(((jj - jj0) * kHalves + hh) * per_group) * slice_bytes;
-          float su = 0.f, sq = 0.f;
+      // column sums of the staged slices: ONE warp owns a slice (so the table update needs no atomics).  Each LDS.128
+      // covers 4 rows x 8 chunks (conflict-free under the 128 B swizzle); a lane keeps 4 channels of every 4th row and
+      // the four row-lanes are folded with two shuffle steps.  (Earlier forms: every warp read 16 rows of every slice
+      // and met in 8-way shared atomics -- 6000 cycles per tile; two warps per slice with 2-way atomics -- 3500.)
+      constexpr int kWarps = kEpiThreads / 32;
+      const int l = etid & 31, chunk = l & 7, rsub = l >> 3;
+      const int nslots = (jj1 - jj0) * kHalves;
+      int rows_valid = p.T - t0;
+      if (rows_valid > 128) rows_valid = 128;
+      for (int slot = etid >> 5; slot < nslots; slot += kWarps) {
+        const int jh = jj0 * kHalves + slot;
+        if (jh >= groups) break;
+        const uint32_t sb2 = stg + (uint32_t)(slot * per_group) * slice_bytes;
+        float su[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
-          for (int r = r0; r < r0 + kRowsPer; ++r) {
-            if (t0 + r < p.T) {
-              float v;
-              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v)
-                           : "r"(sb2 + (uint32_t)r * 128u + ((((uint32_t)c >> 2) ^ ((uint32_t)r & 7u)) << 4) + ((uint32_t)c & 3u) * 4u));
-              su += v;
-              sq = fmaf(v, v, sq);
-            }
-          }
-          const int ch = n0 + 32 * jh + c - sstat_base;
-          if (ch < sstat_stride) {
-            atomicAdd(&sstat[ch], su);
-            atomicAdd(&sstat[sstat_stride + ch], sq);
-          }
+        for (int r = rsub; r < rows_valid; r += 4) {
+          float4 v;
+          asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+              : "r"(sb2 + (uint32_t)r * 128u + ((((uint32_t)chunk) ^ ((uint32_t)r & 7u)) << 4)));
+          su[0] += v.x; su[1] += v.y; su[2] += v.z; su[3] += v.w;
+          sq[0] = fmaf(v.x, v.x, sq[0]); sq[1] = fmaf(v.y, v.y, sq[1]);
+          sq[2] = fmaf(v.z, v.z, sq[2]); sq[3] = fmaf(v.w, v.w, sq[3]);
         }
-      }
-    }
-    if (etid == 0 && tile_valid) {
-      for (int jj = jj0; jj < jj1; ++jj) {
 #pragma unroll
-        for (int hh = 0; hh < kHalves; ++hh) {
-          const int jh = jj * kHalves + hh;
-          if (jh >= groups) break;
-          const int cf = n0 + 32 * jh;
-          const uint32_t sb2 = stg + (uint32_t)(((jj - jj0) * kHalves + hh) * per_group) * slice_bytes;
-          if (glu) {
-            tma_store_3d(&maps.out2, sb2, cf, t0, b);
-            tma_store_3d(&maps.out2, sb2 + slice_bytes, Ch + cf, t0, b);
-            tma_store_3d(&maps.out, sb2 + 2 * slice_bytes, cf, t0, b);
-          } else if (gelu) {
-            tma_store_3d(&maps.out2, sb2, cf, t0, b);
-            tma_store_3d(&maps.out, sb2 + slice_bytes, cf, t0, b);
-          } else {
-            tma_store_3d(&maps.out, sb2, cf, t0, b);
-          }
+        for (int k = 0; k < 4; ++k) {
+          su[k] += __shfl_xor_sync(0xffffffffu, su[k], 8);
+          sq[k] += __shfl_xor_sync(0xffffffffu, sq[k], 8);
+          su[k] += __shfl_xor_sync(0xffffffffu, su[k], 16);
+          sq[k] += __shfl_xor_sync(0xffffffffu, sq[k], 16);
+        }
+        if (rsub == 0) {
+          const int ch0 = n0 + 32 * jh + 4 * chunk - sstat_base;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (ch0 + k < sstat_stride) {
+              sstat[ch0 + k] += su[k];
+              sstat[sstat_stride + ch0 + k] += sq[k];
+            }
         }
       }
-      tma_store_commit();
     }
-    if (!kPersistent && p.dbg != nullptr && etid == 0 && jj0 == 0) p.dbg[8 * blockIdx.x + 6] = clock64();
+    dbg_phase(4);
+    if ((etid & 31) == 0 && tile_valid) {
+      // one elected lane per warp issues the stores of "its" slices (a single issuing thread spent ~380 cycles per
+      // store, 1900 per tile); the bulk group is per thread, so the same lanes wait for it before the area is reused
+      const int nslots = (jj1 - jj0) * kHalves;
+      bool any = false;
+      for (int slot = etid >> 5; slot < nslots; slot += kEpiThreads / 32) {
+        const int jh = jj0 * kHalves + slot;
+        if (jh >= groups) break;
+        const int cf = n0 + 32 * jh;
+        const uint32_t sb2 = stg + (uint32_t)(slot * per_group) * slice_bytes;
+        if (glu) {
+          tma_store_3d(&maps.out2, sb2, cf, t0, b);
+          tma_store_3d(&maps.out2, sb2 + slice_bytes, Ch + cf, t0, b);
+          tma_store_3d(&maps.out, sb2 + 2 * slice_bytes, cf, t0, b);
+        } else if (gelu) {
+          tma_store_3d(&maps.out2, sb2, cf, t0, b);
+          tma_store_3d(&maps.out, sb2 + slice_bytes, cf, t0, b);
+        } else {
+          tma_store_3d(&maps.out, sb2, cf, t0, b);
+        }
+        any = true;
+      }
+      if (any) tma_store_commit();
+    }
+    dbg_phase(5);
+    if (!kPersistent && p.dbg != nullptr && etid == 0 && jj0 == 0) p.dbg[16 * blockIdx.x + 6] = clock64();
   }
-  if (!kPersistent && etid == 0) tma_store_wait_read();   // shared memory must stay alive until the stores have read it
+  if (!kPersistent && (etid & 31) == 0) tma_store_wait_read();   // shared memory must stay alive until the stores have read it
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -348,7 +379,7 @@ tc_tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // the tensor core runs at full rate (N = 160 measured at ~60 %)
   const int wN = (n_tile == p.ntiles - 1) ? p.n_last : p.NT;
   const uint32_t idesc = make_idesc(wN, 0, 0);
-  if (p.dbg != nullptr && threadIdx.x == 0) p.dbg[8 * blockIdx.x + 0] = clock64();
+  if (p.dbg != nullptr && threadIdx.x == 0) p.dbg[16 * blockIdx.x + 0] = clock64();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -394,7 +425,7 @@ tc_tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int it = 0; it < num_k; ++it) {
         const int s = it % p.stages;
         mbar_wait(smem_u32(&hdr->full[s]), (it / p.stages) & 1);
-        if (p.dbg != nullptr && it == 0) p.dbg[8 * blockIdx.x + 1] = clock64();
+        if (p.dbg != nullptr && it == 0) p.dbg[16 * blockIdx.x + 1] = clock64();
         tc_fence_after();
         const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
         const uint64_t da = make_smem_desc(sa, 16, 1024);
@@ -426,7 +457,7 @@ tc_tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     named_bar_sync(1, 128);
     mbar_wait(smem_u32(&hdr->tmem_full), 0);
-    if (p.dbg != nullptr && et == 0) p.dbg[8 * blockIdx.x + 2] = clock64();
+    if (p.dbg != nullptr && et == 0) p.dbg[16 * blockIdx.x + 2] = clock64();
     tc_fence_after();
     const int q = warp & 3;
     const int t = t0 + q * 32 + lane;
@@ -451,7 +482,7 @@ tc_tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     } else {
       tap_epilogue(pe, tmem_base + ((uint32_t)(q * 32) << 16), sbias, n0, row, t < p.T);
     }
-    if (p.dbg != nullptr && et == 0) p.dbg[8 * blockIdx.x + 3] = clock64();
+    if (p.dbg != nullptr && et == 0) p.dbg[16 * blockIdx.x + 3] = clock64();
     tc_fence_before();
   }
   __syncthreads();
@@ -705,7 +736,7 @@ tc_tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           }
         }
       }
-      if (p.dbg) p.dbg[8 * blockIdx.x + 0] = dbg_prod_wait;
+      if (p.dbg) p.dbg[16 * blockIdx.x + 0] = dbg_prod_wait;
     }
   } else if (warp == 1) {
     if (leader && lane == 0) {
@@ -742,10 +773,10 @@ tc_tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         umma_commit_2sm(smem_u32(&hdr->tmem_full[acc]), 3);                  // accumulator ready in BOTH CTAs
       }
       if (p.dbg) {
-        p.dbg[8 * blockIdx.x + 1] = clock64() - dbg_t0;
-        p.dbg[8 * blockIdx.x + 2] = dbg_full_wait;
-        p.dbg[8 * blockIdx.x + 3] = dbg_acc_wait;
-        p.dbg[8 * blockIdx.x + 6] = tile;
+        p.dbg[16 * blockIdx.x + 1] = clock64() - dbg_t0;
+        p.dbg[16 * blockIdx.x + 2] = dbg_full_wait;
+        p.dbg[16 * blockIdx.x + 3] = dbg_acc_wait;
+        p.dbg[16 * blockIdx.x + 6] = tile;
       }
     }
   } else {
@@ -805,11 +836,11 @@ tc_tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
     }
     if (p.dbg && et == 0) {
-      p.dbg[8 * blockIdx.x + 4] = dbg_epi_wait;
-      p.dbg[8 * blockIdx.x + 5] = dbg_epi_work;
+      p.dbg[16 * blockIdx.x + 4] = dbg_epi_wait;
+      p.dbg[16 * blockIdx.x + 5] = dbg_epi_work;
     }
   }
-  if (p.tma_epi && threadIdx.x == 64) tma_store_wait_read();
+  if (p.tma_epi && warp >= 2 && lane == 0) tma_store_wait_read();
   tc_fence_before();
   cluster_sync_all();                              // nobody leaves while the peer may still touch its smem / TMEM
   if (warp == 1) {
@@ -882,6 +913,7 @@ tc_tapgemm2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0) {
     if (lane == 0) {
       int ita = 0;
+      long long dbg_prod_wait = 0;
       for (int item = cluster_id; item < num_items; item += num_clusters) {
         const int n_tile = item % p.ntiles;
         const int m_tile = (item / p.ntiles) * 2 + (int)rank;
@@ -890,7 +922,9 @@ tc_tapgemm2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int wrow = glu ? (n_tile * half + (rank ? Ch : 0)) : (n_tile * p.NT + (int)rank * half);
         for (int kc = 0; kc < p.kchunks; ++kc, ++ita) {
           const int sa = ita % stagesA;
+          const long long w0 = p.dbg ? clock64() : 0;
           mbar_wait(smem_u32(&hdr->emptyA[sa]), ((ita / stagesA) & 1) ^ 1);
+          if (p.dbg) dbg_prod_wait += clock64() - w0;
           const uint32_t fa = smem_u32(&hdr->fullA[sa]);
           if (leader) mbar_arrive_expect_tx(fa, 2u * ((uint32_t)a_rows * 128u + (uint32_t)p.taps * b_bytes));
           const uint32_t sbase = smem_u32(ringA + (size_t)sa * stage_bytes);
@@ -899,18 +933,25 @@ tc_tapgemm2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tma_load_3d_2sm(sbase + a_slot + (uint32_t)tap * b_bytes, &tmW, tap * p.Kp + kc * kBlockK, wrow, 0, fa);
         }
       }
+      if (p.dbg) p.dbg[16 * blockIdx.x + 0] = dbg_prod_wait;
     }
   } else if (warp == 1) {
     if (leader && lane == 0) {
       int ita = 0, tile = 0;
+      long long dbg_full_wait = 0, dbg_acc_wait = 0;
+      const long long dbg_t0 = p.dbg ? clock64() : 0;
       for (int item = cluster_id; item < num_items; item += num_clusters, ++tile) {
         const int acc = tile & 1;
+        const long long w1 = p.dbg ? clock64() : 0;
         mbar_wait(smem_u32(&hdr->tmem_empty[acc]), ((tile >> 1) & 1) ^ 1);   // epilogues of both CTAs drained it
+        if (p.dbg) dbg_acc_wait += clock64() - w1;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.NT);
         for (int kc = 0; kc < p.kchunks; ++kc, ++ita) {
           const int sa = ita % stagesA;
+          const long long w2 = p.dbg ? clock64() : 0;
           mbar_wait(smem_u32(&hdr->fullA[sa]), (ita / stagesA) & 1);
+          if (p.dbg) dbg_full_wait += clock64() - w2;
           tc_fence_after();
           const uint32_t abase = smem_u32(ringA + (size_t)sa * stage_bytes);
           for (int tap = 0; tap < p.taps; ++tap) {
@@ -925,6 +966,12 @@ tc_tapgemm2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         umma_commit_2sm(smem_u32(&hdr->tmem_full[acc]), 3);                  // accumulator ready in BOTH CTAs
       }
+      if (p.dbg) {
+        p.dbg[16 * blockIdx.x + 1] = clock64() - dbg_t0;
+        p.dbg[16 * blockIdx.x + 2] = dbg_full_wait;
+        p.dbg[16 * blockIdx.x + 3] = dbg_acc_wait;
+        p.dbg[16 * blockIdx.x + 6] = tile;
+      }
     }
   } else {
     // ---------------- epilogue (both CTAs): each CTA drains its own 128 rows of the 256-row accumulator with eight
@@ -933,6 +980,7 @@ tc_tapgemm2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int q = warp & 3;
     const int h = (warp - 2) >> 2;
     int tile = 0;
+    long long dbg_epi_wait = 0, dbg_epi_work = 0;
     if (p.stats != nullptr)
       for (int i = et; i < 2 * p.Cos; i += 256) sstat[i] = 0.f;      // visible after the first named barrier below
     for (int item = cluster_id; item < num_items; item += num_clusters, ++tile) {
@@ -957,7 +1005,10 @@ tc_tapgemm2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         sb[i] = (p.bias != nullptr && ok) ? p.bias[n] : 0.f;
       }
       named_bar_sync(1, 256);
+      const long long w3 = p.dbg ? clock64() : 0;
       mbar_wait(smem_u32(&hdr->tmem_full[acc]), (tile >> 1) & 1);
+      const long long w4 = p.dbg ? clock64() : 0;
+      dbg_epi_wait += w4 - w3;
       tc_fence_after();
       const int t = t0 + q * 32 + lane;
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.NT);
@@ -966,6 +1017,11 @@ tc_tapgemm2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(smem_u32(&hdr->tmem_empty[acc]), 0);
+      if (p.dbg) dbg_epi_work += clock64() - w4;
+    }
+    if (p.dbg && et == 0) {
+      p.dbg[16 * blockIdx.x + 4] = dbg_epi_wait;
+      p.dbg[16 * blockIdx.x + 5] = dbg_epi_work;
     }
     if (p.stats != nullptr) {
       named_bar_sync(2, 256);
@@ -975,7 +1031,7 @@ tc_tapgemm2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   }
-  if (p.tma_epi && threadIdx.x == 64) tma_store_wait_read();
+  if (p.tma_epi && warp >= 2 && lane == 0) tma_store_wait_read();
   tc_fence_before();
   cluster_sync_all();                              // nobody leaves while the peer may still touch its smem / TMEM
   if (warp == 1) {
@@ -1403,7 +1459,7 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
   p.debug_skip_io = skip_io ? 1 : 0;
   static const bool dbg_timing = getenv("MEGB200_DEBUG_TIMING") != nullptr;
   static long long* dbg_buf = nullptr;
-  if (dbg_timing && dbg_buf == nullptr) cudaMalloc(&dbg_buf, sizeof(long long) * 8 * 65536);
+  if (dbg_timing && dbg_buf == nullptr) cudaMalloc(&dbg_buf, sizeof(long long) * 16 * 65536);
   p.dbg = nullptr;
   p.T = T; p.N = N; p.Cos = Cos; p.Crs = Crs; p.Co2s = Co2s; p.taps = taps; p.dil = dil; p.Kp = Kp; p.epi = epi;
   p.kchunks = (Ca + kBlockK - 1) / kBlockK;
@@ -1525,11 +1581,43 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    auto report_pair_timing = [&](const char* which) {
+      static long long hostp[16 * 512];
+      cudaStreamSynchronize(st);
+      cudaMemcpy(hostp, dbg_buf, sizeof(long long) * 16 * 2 * clusters, cudaMemcpyDeviceToHost);
+      double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int c = 0; c < clusters; ++c) {
+        const long long* l = hostp + 16 * (2 * c);         // leader CTA of the pair
+        const long long* f = hostp + 16 * (2 * c + 1);     // follower
+        v[0] += (double)(l[0] + f[0]) / 2;                 // producer wait (empty)
+        v[1] += (double)l[1];                              // MMA loop total
+        v[2] += (double)l[2];                              // MMA wait full
+        v[3] += (double)l[3];                              // MMA wait accumulator
+        v[4] += (double)(l[4] + f[4]) / 2;                 // epilogue wait tmem_full
+        v[5] += (double)(l[5] + f[5]) / 2;                 // epilogue work
+        v[6] += (double)l[6];                              // tiles per cluster
+      }
+      double ph[6] = {0, 0, 0, 0, 0, 0};
+      for (int c = 0; c < clusters; ++c)
+        for (int i = 0; i < 6; ++i) ph[i] += (double)hostp[16 * (2 * c) + 8 + i];
+      for (int i = 0; i < 7; ++i) v[i] /= clusters;
+      for (int i = 0; i < 6; ++i) ph[i] /= clusters * v[6];
+      fprintf(stderr, "[megb200 timing]   epilogue thread 0 per tile: wait stores-read %.0f, barrier %.0f, tmem->convert->stage %.0f, "
+              "fence+barrier %.0f, stats %.0f, store issue %.0f\n", ph[0], ph[1], ph[2], ph[3], ph[4], ph[5]);
+      fprintf(stderr, "[megb200 timing] %s tapgemm N=%d K=%d taps=%d epi=%d NT=%d stages=%d: per cluster %.1f tiles; MMA loop %.0f "
+              "cycles (waiting for data %.0f, for a free accumulator %.0f); per tile: MMA %.0f, epilogue work %.0f, epilogue "
+              "idle %.0f; producer waiting for free slots %.0f\n", which, N, Ca, taps, epi, p.NT, p.stages, v[6], v[1], v[2], v[3],
+              v[1] / v[6], v[5] / v[6], v[4] / v[6], v[0]);
+    };
     // halo form of the pair kernel, default for k > 1 (653 vs 599 TFLOP/s on the same box, r1_tapgemm_variants.md);
     // MEGB200_TAPGEMM_PAIR_HALO=0 selects the plain pair kernel
     static const char* ph_env = getenv("MEGB200_TAPGEMM_PAIR_HALO");
     static const bool no_halo = ph_env != nullptr && atoi(ph_env) == 0;
     const int a_rows2 = ((kTileM + (taps - 1) * dil) + 7) / 8 * 8;
+    if (dbg_timing) {
+      p.dbg = dbg_buf;
+      cudaMemsetAsync(dbg_buf, 0, sizeof(long long) * 16 * 2 * clusters, st);
+    }
     if (taps > 1 && a_rows2 <= 256 && !no_halo && p.n_last == p.NT) {
       // halo form: activation ring (with halo rows) + weight ring
       const uint32_t a_slot = ((uint32_t)a_rows2 * 128u + 1023u) & ~1023u;
@@ -1552,6 +1640,7 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
                                       a_rows2, stagesA));
       MEGB_LAUNCH_OK();
       *stats_fused = fuse_stats ? 1 : 0;
+      if (p.dbg != nullptr) report_pair_timing("pair+halo");
       return 0;
     }
     p.stages = pick_stages(2 * stage2, 229000 - 2048 - 2 * p.NT * 4 - 2 * Cos * 4 - p.stg_bytes, 8);   // two k chunks per stage
@@ -1560,35 +1649,10 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
     int rc = set_smem(tc_tapgemm2_kernel, smem2);
     if (rc) return rc;
     cfg.dynamicSmemBytes = smem2;
-    if (dbg_timing) {
-      p.dbg = dbg_buf;
-      cudaMemsetAsync(dbg_buf, 0, sizeof(long long) * 8 * 2 * clusters, st);
-    }
     MEGB_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_tapgemm2_kernel, tmA2, tmW2, maps, p, (int)m_tiles_total, num_items));
     MEGB_LAUNCH_OK();
     *stats_fused = fuse_stats ? 1 : 0;
-    if (p.dbg != nullptr) {
-      static long long hostp[8 * 512];
-      cudaStreamSynchronize(st);
-      cudaMemcpy(hostp, dbg_buf, sizeof(long long) * 8 * 2 * clusters, cudaMemcpyDeviceToHost);
-      double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      for (int c = 0; c < clusters; ++c) {
-        const long long* l = hostp + 8 * (2 * c);         // leader CTA of the pair
-        const long long* f = hostp + 8 * (2 * c + 1);     // follower
-        v[0] += (double)(l[0] + f[0]) / 2;                 // producer wait (empty)
-        v[1] += (double)l[1];                              // MMA loop total
-        v[2] += (double)l[2];                              // MMA wait full
-        v[3] += (double)l[3];                              // MMA wait accumulator
-        v[4] += (double)(l[4] + f[4]) / 2;                 // epilogue wait tmem_full
-        v[5] += (double)(l[5] + f[5]) / 2;                 // epilogue work
-        v[6] += (double)l[6];                              // tiles per cluster
-      }
-      for (int i = 0; i < 7; ++i) v[i] /= clusters;
-      fprintf(stderr, "[megb200 timing] pair tapgemm N=%d K=%d taps=%d epi=%d NT=%d stages=%d: per cluster %.1f tiles; MMA loop %.0f "
-              "cycles (waiting for data %.0f, for a free accumulator %.0f); per tile: MMA %.0f, epilogue work %.0f, epilogue "
-              "idle %.0f; producer waiting for free slots %.0f\n", N, Ca, taps, epi, p.NT, p.stages, v[6], v[1], v[2], v[3],
-              v[1] / v[6], v[5] / v[6], v[4] / v[6], v[0]);
-    }
+    if (p.dbg != nullptr) report_pair_timing("pair");
     return 0;
   }
 
@@ -1666,19 +1730,19 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
   *stats_fused = p.stats != nullptr ? 1 : 0;
   if (p.dbg != nullptr) {
     // debug only: phase durations per CTA in SM clocks (synchronises!)
-    static long long host[8 * 65536];
+    static long long host[16 * 65536];
     cudaStreamSynchronize(st);
-    cudaMemcpy(host, dbg_buf, sizeof(long long) * 8 * blocks, cudaMemcpyDeviceToHost);
+    cudaMemcpy(host, dbg_buf, sizeof(long long) * 16 * blocks, cudaMemcpyDeviceToHost);
     double fill_c = 0, main_c = 0, epi_c = 0, total_c = 0, e_stage = 0, e_bar = 0, e_issue = 0, e_wait = 0;
     for (long long i = 0; i < blocks; ++i) {
-      fill_c += (double)(host[8 * i + 1] - host[8 * i + 0]);
-      main_c += (double)(host[8 * i + 2] - host[8 * i + 1]);
-      epi_c += (double)(host[8 * i + 3] - host[8 * i + 2]);
-      total_c += (double)(host[8 * i + 3] - host[8 * i + 0]);
-      e_stage += (double)(host[8 * i + 4] - host[8 * i + 2]);
-      e_bar += (double)(host[8 * i + 5] - host[8 * i + 4]);
-      e_issue += (double)(host[8 * i + 6] - host[8 * i + 5]);
-      e_wait += (double)(host[8 * i + 3] - host[8 * i + 6]);
+      fill_c += (double)(host[16 * i + 1] - host[16 * i + 0]);
+      main_c += (double)(host[16 * i + 2] - host[16 * i + 1]);
+      epi_c += (double)(host[16 * i + 3] - host[16 * i + 2]);
+      total_c += (double)(host[16 * i + 3] - host[16 * i + 0]);
+      e_stage += (double)(host[16 * i + 4] - host[16 * i + 2]);
+      e_bar += (double)(host[16 * i + 5] - host[16 * i + 4]);
+      e_issue += (double)(host[16 * i + 6] - host[16 * i + 5]);
+      e_wait += (double)(host[16 * i + 3] - host[16 * i + 6]);
     }
     if (p.tma_epi)
       fprintf(stderr, "[megb200 timing]   epilogue round 0: convert+stage %.0f, fence+barrier %.0f, store issue %.0f, rest "
@@ -1774,7 +1838,9 @@ int tc_clip_logits(const void* Yp, const void* Zp, float* raw, int By, int Bz, l
   p.i_tiles = (By + kTileM - 1) / kTileM;
   p.kchunks_total = (int)((D + kBlockK - 1) / kBlockK);
   const long long tiles = (long long)p.i_tiles * j_tiles;
-  long long splits = ((long long)num_sms() + tiles - 1) / tiles;
+  // split-K so that the grid is ONE wave: floor, not ceil -- 16 i-tiles (8 ranks) x ceil(148/16) = 160 CTAs ran as two
+  // waves, the second 8 % full
+  long long splits = (long long)num_sms() / tiles;
   if (splits > p.kchunks_total) splits = p.kchunks_total;
   if (splits < 1) splits = 1;
   p.kchunks_per_cta = (int)((p.kchunks_total + splits - 1) / splits);
