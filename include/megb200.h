@@ -124,10 +124,23 @@ int megb200_bn_finalize(const float* sums, const float* gamma, const float* beta
 /* H = gelu(scale*U + shift)   (models.py:314,317) */
 int megb200_bn_gelu(const void* U, const float* scale, const float* shift, void* H, long long rows, int C, int Cs,
                     int u_dtype, int dtype, void* stream);
-/* dY = dH * gelu'(scale*U+shift); sums2[0][c] += sum dY, sums2[1][c] += sum dY*xhat, xhat = (U-mean)*rstd */
+/* Training-mode BatchNorm1d + GELU in one launch (models.py:311-317 with nn.BatchNorm1d in train()): scale/shift come
+ * from the batch sums (sums[0][c] = sum U, sums[1][c] = sum U^2 over `count` rows); also writes scale/shift/mean/rstd
+ * for the backward pass and applies the momentum update of running_mean / running_var (unbiased variance). */
+int megb200_bn_gelu_train(const void* U, const float* sums, const float* gamma, const float* beta, float* running_mean,
+                          float* running_var, long long count, float eps, float momentum, float* scale, float* shift,
+                          float* mean, float* rstd, void* H, long long rows, int C, int Cs, int u_dtype, int dtype,
+                          void* stream);
+/* dY = dH * gelu'(scale*U+shift); sums2[0][c] += sum dY, sums2[1][c] += sum dY*xhat, xhat = (U-mean)*rstd.
+ * dY may be NULL (sums only) when megb200_bn_gelu_bwd_apply follows. */
 int megb200_bn_gelu_bwd_reduce(const void* dH, const void* U, const float* scale, const float* shift,
                                const float* mean, const float* rstd, void* dY, float* sums2, long long rows, int C,
                                int Cs, int u_dtype, int dtype, void* stream);
+/* dU = gamma*rstd * (dY - sums2[0]/n - xhat * sums2[1]/n) with dY = dH * gelu'(scale*U+shift) recomputed on the fly
+ * (SURVEY appendix A3); dbias as in megb200_bn_bwd_apply (may be NULL). */
+int megb200_bn_gelu_bwd_apply(const void* dH, const void* U, const float* scale, const float* shift, const float* gamma,
+                              const float* mean, const float* rstd, const float* sums2, long long count, void* dU,
+                              float* dbias, long long rows, int C, int Cs, int u_dtype, int dtype, void* stream);
 /* dU = gamma*rstd * (dY - sums2[0]/n - xhat * sums2[1]/n)   (SURVEY appendix A3);
  * dbias[c] += sum dU (the gradient of the conv bias in front of the BatchNorm; may be NULL) */
 int megb200_bn_bwd_apply(const void* dY, const void* U, const float* gamma, const float* mean, const float* rstd,

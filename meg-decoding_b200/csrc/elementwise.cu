@@ -166,6 +166,7 @@ __global__ void __launch_bounds__(256, 3) rowloop_kernel(Op op, long long rows, 
 #pragma unroll
       for (int i = 0; i < 8; ++i) a0[i] = a1[i] = 0.f;
       op.init(g * 8);
+      if (Op::kPublish && blockIdx.x == 0 && lane_r == 0) op.publish(g * 8);
 #pragma unroll 2
       for (long long r = r0 + lane_r; r < r1; r += R) op.row(b0 + r * p0, b1 + r * p1, r, g * 8, a0, a1);
       op.finish(g * 8, a0, a1);
@@ -271,6 +272,7 @@ rowstage_kernel(Op op, long long rows, long long rows_per_block, int slab_rows, 
 #pragma unroll
     for (int i = 0; i < 8; ++i) a0[i] = a1[i] = 0.f;
     op.init(lane_g * 8);
+    if (Op::kPublish && blockIdx.x == 0 && lane_r == 0) op.publish(lane_g * 8);
     for (int i = 0; i < nslabs; ++i) {
       const int s = i % stages;
       rs_mbar_wait(rs_smem_u32(&full[s]), (i / stages) & 1);
@@ -305,10 +307,12 @@ rowstage_kernel(Op op, long long rows, long long rows_per_block, int slab_rows, 
 template <typename T>
 struct StatsOp {
   static constexpr int kAcc = 2, kIn = 1;
+  static constexpr bool kPublish = false;
   const T* u;
   int Cs;
   __host__ __device__ __forceinline__ const void* in_base(int) const { return u; }
   __host__ __device__ __forceinline__ long long in_pitch(int) const { return (long long)Cs * sizeof(T); }
+  __device__ __forceinline__ void publish(int) const {}
   __device__ __forceinline__ void init(int) {}
   __device__ __forceinline__ void finish(int, float (&)[8], float (&)[8]) const {}
   __device__ __forceinline__ void row(const void* pu, const void*, long long, int c0, float (&a0)[8],
@@ -326,10 +330,12 @@ struct StatsOp {
 template <typename T>
 struct ColsumOp {
   static constexpr int kAcc = 1, kIn = 1;
+  static constexpr bool kPublish = false;
   const T* u;
   int Cs;
   __host__ __device__ __forceinline__ const void* in_base(int) const { return u; }
   __host__ __device__ __forceinline__ long long in_pitch(int) const { return (long long)Cs * sizeof(T); }
+  __device__ __forceinline__ void publish(int) const {}
   __device__ __forceinline__ void init(int) {}
   __device__ __forceinline__ void finish(int, float (&)[8], float (&)[8]) const {}
   __device__ __forceinline__ void row(const void* pu, const void*, long long, int c0, float (&a0)[8],
@@ -345,6 +351,7 @@ struct ColsumOp {
 template <typename TU, typename T>
 struct BnGeluOp {
   static constexpr int kAcc = 0, kIn = 1;
+  static constexpr bool kPublish = false;
   const TU* u;
   T* h;
   const float *scale, *shift;
@@ -352,6 +359,7 @@ struct BnGeluOp {
   float sc[8], sh[8];
   __host__ __device__ __forceinline__ const void* in_base(int) const { return u; }
   __host__ __device__ __forceinline__ long long in_pitch(int) const { return (long long)Cs * sizeof(TU); }
+  __device__ __forceinline__ void publish(int) const {}
   __device__ __forceinline__ void init(int c0) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -377,6 +385,7 @@ struct BnGeluOp {
 template <typename TU, typename T>
 struct BnGeluBwdOp {
   static constexpr int kAcc = 2, kIn = 2;
+  static constexpr bool kPublish = false;
   const T* dh;
   const TU* u;
   T* dy;
@@ -385,6 +394,7 @@ struct BnGeluBwdOp {
   float sc[8], sh[8];
   __host__ __device__ __forceinline__ const void* in_base(int k) const { return k == 0 ? (const void*)dh : (const void*)u; }
   __host__ __device__ __forceinline__ long long in_pitch(int k) const { return (long long)Cs * (k == 0 ? sizeof(T) : sizeof(TU)); }
+  __device__ __forceinline__ void publish(int) const {}
   __device__ __forceinline__ void init(int c0) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -412,7 +422,7 @@ struct BnGeluBwdOp {
       a0[i] += o[i];
       a1[i] = fmaf(o[i], x[i], a1[i]);
     }
-    store8(dy + r * Cs + c0, o);
+    if (dy != nullptr) store8(dy + r * Cs + c0, o);
   }
   __device__ __forceinline__ void finish(int c0, float (&a0)[8], float (&a1)[8]) const {
 #pragma unroll
@@ -427,6 +437,7 @@ struct BnGeluBwdOp {
 template <typename TU, typename T>
 struct BnBwdApplyOp {
   static constexpr int kAcc = 1, kIn = 2;
+  static constexpr bool kPublish = false;
   const T* dy;
   const TU* u;
   T* du;
@@ -436,6 +447,7 @@ struct BnBwdApplyOp {
   float ca[8], cb[8], cc[8];
   __host__ __device__ __forceinline__ const void* in_base(int k) const { return k == 0 ? (const void*)dy : (const void*)u; }
   __host__ __device__ __forceinline__ long long in_pitch(int k) const { return (long long)Cs * (k == 0 ? sizeof(T) : sizeof(TU)); }
+  __device__ __forceinline__ void publish(int) const {}
   __device__ __forceinline__ void init(int c0) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -465,16 +477,127 @@ struct BnBwdApplyOp {
   }
 };
 
+// Training-mode BatchNorm + GELU in ONE launch: every thread derives scale/shift of its 8 channels from the batch sums
+// (a handful of flops), block 0 also publishes scale/shift/mean/rstd for the backward pass and updates the running
+// statistics (nn.BatchNorm1d: momentum update with the unbiased variance).  Replaces bn_finalize + bn_gelu: the tiny
+// finalize launch cost ~8 us of dependent-launch bubble per BatchNorm.
+template <typename TU, typename T>
+struct BnGeluTrainOp {
+  static constexpr int kAcc = 0, kIn = 1;
+  static constexpr bool kPublish = true;
+  const TU* u;
+  T* h;
+  const float *sums, *gamma, *beta;
+  float *rm, *rv, *scale, *shift, *mean, *rstd;
+  float count, eps, momentum;
+  int Cs, C;
+  float sc[8], sh[8];
+  __host__ __device__ __forceinline__ const void* in_base(int) const { return u; }
+  __host__ __device__ __forceinline__ long long in_pitch(int) const { return (long long)Cs * sizeof(TU); }
+  __device__ __forceinline__ void stats(int c, float& m, float& var, float& rs) const {
+    m = sums[c] / count;
+    var = fmaxf(sums[C + c] / count - m * m, 0.f);
+    rs = rsqrtf(var + eps);
+  }
+  __device__ __forceinline__ void init(int c0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = c0 + i;
+      sc[i] = sh[i] = 0.f;
+      if (c < C) {
+        float m, var, rs;
+        stats(c, m, var, rs);
+        sc[i] = gamma[c] * rs;
+        sh[i] = beta[c] - m * sc[i];
+      }
+    }
+  }
+  __device__ __forceinline__ void publish(int c0) const {
+    for (int i = 0; i < 8; ++i) {
+      const int c = c0 + i;
+      if (c >= C) break;
+      float m, var, rs;
+      stats(c, m, var, rs);
+      const float unbiased = count > 1.f ? var * count / (count - 1.f) : var;
+      rm[c] = (1.f - momentum) * rm[c] + momentum * m;
+      rv[c] = (1.f - momentum) * rv[c] + momentum * unbiased;
+      scale[c] = sc[i];
+      shift[c] = sh[i];
+      mean[c] = m;
+      rstd[c] = rs;
+    }
+  }
+  __device__ __forceinline__ void finish(int, float (&)[8], float (&)[8]) const {}
+  __device__ __forceinline__ void row(const void* pu, const void*, long long r, int c0, float (&a0)[8],
+                                      float (&a1)[8]) const {
+    float x[8], o[8];
+    load8(static_cast<const TU*>(pu) + c0, x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = gelu_t<T>(fmaf(x[i], sc[i], sh[i]));
+    store8(h + r * Cs + c0, o);
+  }
+};
+
+// Second backward pass with the GELU derivative recomputed: dU = A*(dH*gelu'(scale*U+shift)) + Bc*U + Cc.  Reads dH
+// and U (the same bytes the two-tensor form read) so the reduce pass no longer has to WRITE dY (59 MB per BatchNorm).
+template <typename TU, typename T>
+struct BnGeluBwdApplyOp {
+  static constexpr int kAcc = 1, kIn = 2;
+  static constexpr bool kPublish = false;
+  const T* dh;
+  const TU* u;
+  T* du;
+  const float *scale, *shift, *gamma, *mean, *rstd, *sums2;
+  float inv_n;
+  int Cs, C;
+  float sc[8], sh[8], ca[8], cb[8], cc[8];
+  __host__ __device__ __forceinline__ const void* in_base(int k) const { return k == 0 ? (const void*)dh : (const void*)u; }
+  __host__ __device__ __forceinline__ long long in_pitch(int k) const { return (long long)Cs * (k == 0 ? sizeof(T) : sizeof(TU)); }
+  __device__ __forceinline__ void publish(int) const {}
+  __device__ __forceinline__ void init(int c0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = c0 + i;
+      if (c < C) {
+        const float rsd = rstd[c], A = gamma[c] * rsd;
+        sc[i] = scale[c];
+        sh[i] = shift[c];
+        ca[i] = A;
+        cb[i] = -A * rsd * sums2[C + c] * inv_n;
+        cc[i] = -A * sums2[c] * inv_n - cb[i] * mean[c];
+      } else {
+        sc[i] = sh[i] = ca[i] = cb[i] = cc[i] = 0.f;
+      }
+    }
+  }
+  __device__ __forceinline__ void finish(int, float (&)[8], float (&)[8]) const {}
+  __device__ __forceinline__ void row(const void* pd, const void* pu, long long r, int c0, float (&a0)[8],
+                                      float (&a1)[8]) const {
+    float g[8], x[8], o[8];
+    load8(static_cast<const T*>(pd) + c0, g);
+    load8(static_cast<const TU*>(pu) + c0, x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float dy = g[i] * gelu_grad_t<T>(fmaf(x[i], sc[i], sh[i]));
+      o[i] = round_to<T>(fmaf(ca[i], dy, fmaf(cb[i], x[i], cc[i])));     // pad channels: all coefficients 0
+      a0[i] += o[i];
+    }
+    store8(du + r * Cs + c0, o);
+  }
+};
+
 // dP = dQ * gelu'(P); accumulates sum dP (bias gradient of the 1x1 head convs)
 template <typename T>
 struct GeluBwdOp {
   static constexpr int kAcc = 1, kIn = 2;
+  static constexpr bool kPublish = false;
   const T* dq;
   const T* p;
   T* dp;
   int Cs, C;
   __host__ __device__ __forceinline__ const void* in_base(int k) const { return k == 0 ? dq : p; }
   __host__ __device__ __forceinline__ long long in_pitch(int) const { return (long long)Cs * sizeof(T); }
+  __device__ __forceinline__ void publish(int) const {}
   __device__ __forceinline__ void init(int) {}
   __device__ __forceinline__ void finish(int, float (&)[8], float (&)[8]) const {}
   __device__ __forceinline__ void row(const void* pd, const void* pp, long long r, int c0, float (&a0)[8],
@@ -502,12 +625,14 @@ struct GeluBwdOp {
 template <typename T>
 struct GluBwdOp {
   static constexpr int kAcc = 2, kIn = 2;
+  static constexpr bool kPublish = false;
   const T* dout;
   const T* V;
   T* dV;
   int Vs, Os, C;
   __host__ __device__ __forceinline__ const void* in_base(int k) const { return k == 0 ? dout : V; }
   __host__ __device__ __forceinline__ long long in_pitch(int k) const { return (long long)(k == 0 ? Os : Vs) * sizeof(T); }
+  __device__ __forceinline__ void publish(int) const {}
   __device__ __forceinline__ void init(int) {}
   __device__ __forceinline__ void finish(int, float (&)[8], float (&)[8]) const {}
   __device__ __forceinline__ void row(const void* pd, const void* pv, long long r, int c0, float (&a0)[8],
@@ -907,10 +1032,35 @@ int megb200_bn_gelu(const void* U, const float* scale, const float* shift, void*
                                                            (cudaStream_t)stream);))
 }
 
+int megb200_bn_gelu_train(const void* U, const float* sums, const float* gamma, const float* beta, float* running_mean,
+                          float* running_var, long long count, float eps, float momentum, float* scale, float* shift,
+                          float* mean, float* rstd, void* H, long long rows, int C, int Cs, int u_dtype, int dtype,
+                          void* stream) {
+  MEGB_CHECK_ARG(U && H && sums && gamma && beta && running_mean && running_var && scale && shift && mean && rstd,
+                 "bn_gelu_train: null argument");
+  MEGB_CHECK_ARG(rows > 0 && count > 0 && Cs % 8 == 0 && Cs >= C, "bn_gelu_train: bad arguments");
+  DISPATCH_U(u_dtype, DISPATCH_DTYPE(dtype, BnGeluTrainOp<TU, DT> op{(const TU*)U, (DT*)H, sums, gamma, beta, running_mean,
+                                                                    running_var, scale, shift, mean, rstd, (float)count,
+                                                                    eps, momentum, Cs, C};
+                                     return launch_rowloop(op, rows, C, Cs, nullptr, 1, nullptr, nullptr,
+                                                           (cudaStream_t)stream);))
+}
+
+int megb200_bn_gelu_bwd_apply(const void* dH, const void* U, const float* scale, const float* shift, const float* gamma,
+                              const float* mean, const float* rstd, const float* sums2, long long count, void* dU,
+                              float* dbias, long long rows, int C, int Cs, int u_dtype, int dtype, void* stream) {
+  MEGB_CHECK_ARG(dH && U && dU && scale && shift && gamma && mean && rstd && sums2, "bn_gelu_bwd_apply: null argument");
+  MEGB_CHECK_ARG(rows > 0 && count > 0 && Cs % 8 == 0, "bn_gelu_bwd_apply: bad arguments");
+  DISPATCH_U(u_dtype,
+             DISPATCH_DTYPE(dtype, BnGeluBwdApplyOp<TU, DT> op{(const DT*)dH, (const TU*)U, (DT*)dU, scale, shift, gamma, mean,
+                                                              rstd, sums2, 1.f / (float)count, Cs, C};
+                            return launch_rowloop(op, rows, C, Cs, nullptr, 1, dbias, nullptr, (cudaStream_t)stream);))
+}
+
 int megb200_bn_gelu_bwd_reduce(const void* dH, const void* U, const float* scale, const float* shift,
                                const float* mean, const float* rstd, void* dY, float* sums2, long long rows, int C,
                                int Cs, int u_dtype, int dtype, void* stream) {
-  MEGB_CHECK_ARG(dH && U && dY && sums2 && rows > 0, "bn_gelu_bwd_reduce: bad arguments");
+  MEGB_CHECK_ARG(dH && U && sums2 && rows > 0, "bn_gelu_bwd_reduce: bad arguments");   // dY may be NULL
   DISPATCH_U(u_dtype,
              DISPATCH_DTYPE(dtype, BnGeluBwdOp<TU, DT> op{(const DT*)dH, (const TU*)U, (DT*)dY, scale, shift, mean, rstd, Cs, C};
                             return launch_rowloop(op, rows, C, Cs, nullptr, 1, sums2, sums2 + C, (cudaStream_t)stream);))

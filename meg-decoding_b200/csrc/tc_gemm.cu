@@ -189,8 +189,8 @@ __device__ __forceinline__ void tap_epilogue_tma(const TapGemmParams& p, const T
   auto dbg_phase = [&](int slot) {
     if (dbgp) {
       const long long t = clock64();
-      p.dbg[16 * blockIdx.x + 8 + slot] += t - dt0;
-      dt0 = t;
+      atomicAdd(reinterpret_cast<unsigned long long*>(&p.dbg[16 * blockIdx.x + 8 + slot]), (unsigned long long)(t - dt0));
+      dt0 = clock64();
     }
   };
   for (int jj0 = 0; jj0 < iters; jj0 += cap_iters) {
@@ -277,6 +277,33 @@ __device__ __forceinline__ void tap_epilogue_tma(const TapGemmParams& p, const T
     named_bar_sync(2, kEpiThreads);
     dbg_phase(3);
     if (!kPersistent && p.dbg != nullptr && etid == 0 && jj0 == 0) p.dbg[16 * blockIdx.x + 5] = clock64();
+    // the stores are issued BEFORE the statistics pass: both only read the staging area, so the TMA engine drains it
+    // while the warps reduce it
+    if ((etid & 31) == 0 && tile_valid) {
+      // one elected lane per warp issues the stores of "its" slices (a single issuing thread spent ~380 cycles per
+      // store, 1900 per tile); the bulk group is per thread, so the same lanes wait for it before the area is reused
+      const int nslots = (jj1 - jj0) * kHalves;
+      bool any = false;
+      for (int slot = etid >> 5; slot < nslots; slot += kEpiThreads / 32) {
+        const int jh = jj0 * kHalves + slot;
+        if (jh >= groups) break;
+        const int cf = n0 + 32 * jh;
+        const uint32_t sb2 = stg + (uint32_t)(slot * per_group) * slice_bytes;
+        if (glu) {
+          tma_store_3d(&maps.out2, sb2, cf, t0, b);
+          tma_store_3d(&maps.out2, sb2 + slice_bytes, Ch + cf, t0, b);
+          tma_store_3d(&maps.out, sb2 + 2 * slice_bytes, cf, t0, b);
+        } else if (gelu) {
+          tma_store_3d(&maps.out2, sb2, cf, t0, b);
+          tma_store_3d(&maps.out, sb2 + slice_bytes, cf, t0, b);
+        } else {
+          tma_store_3d(&maps.out, sb2, cf, t0, b);
+        }
+        any = true;
+      }
+      if (any) tma_store_commit();
+    }
+    dbg_phase(4);
     if (f32 && sstat != nullptr && tile_valid) {
       // column sums of the staged slices: ONE warp owns a slice (so the table update needs no atomics).  Each LDS.128
       // covers 4 rows x 8 chunks (conflict-free under the 128 B swizzle); a lane keeps 4 channels of every 4th row and
@@ -318,31 +345,6 @@ __device__ __forceinline__ void tap_epilogue_tma(const TapGemmParams& p, const T
             }
         }
       }
-    }
-    dbg_phase(4);
-    if ((etid & 31) == 0 && tile_valid) {
-      // one elected lane per warp issues the stores of "its" slices (a single issuing thread spent ~380 cycles per
-      // store, 1900 per tile); the bulk group is per thread, so the same lanes wait for it before the area is reused
-      const int nslots = (jj1 - jj0) * kHalves;
-      bool any = false;
-      for (int slot = etid >> 5; slot < nslots; slot += kEpiThreads / 32) {
-        const int jh = jj0 * kHalves + slot;
-        if (jh >= groups) break;
-        const int cf = n0 + 32 * jh;
-        const uint32_t sb2 = stg + (uint32_t)(slot * per_group) * slice_bytes;
-        if (glu) {
-          tma_store_3d(&maps.out2, sb2, cf, t0, b);
-          tma_store_3d(&maps.out2, sb2 + slice_bytes, Ch + cf, t0, b);
-          tma_store_3d(&maps.out, sb2 + 2 * slice_bytes, cf, t0, b);
-        } else if (gelu) {
-          tma_store_3d(&maps.out2, sb2, cf, t0, b);
-          tma_store_3d(&maps.out, sb2 + slice_bytes, cf, t0, b);
-        } else {
-          tma_store_3d(&maps.out, sb2, cf, t0, b);
-        }
-        any = true;
-      }
-      if (any) tma_store_commit();
     }
     dbg_phase(5);
     if (!kPersistent && p.dbg != nullptr && etid == 0 && jj0 == 0) p.dbg[16 * blockIdx.x + 6] = clock64();
@@ -1136,14 +1138,23 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__
           const uint64_t da = make_smem_desc(sa, atom_bytes, 1024);
           const uint64_t db0 = make_smem_desc(sa + a_bytes, atom_bytes, 1024);
           const uint64_t db1 = make_smem_desc(sa + a_bytes + (uint32_t)(p.n0_cols / 64) * atom_bytes, atom_bytes, 1024);
-#pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+          auto issue = [&](int k) {
             const uint32_t acc = (!fresh || k != 0) ? 1u : 0u;
             umma_bf16(tmem_base, desc_advance(da, k * kUmmaK * 128), desc_advance(db0, k * kUmmaK * 128), p.idesc0,
                       acc);
             if (p.n1_cols > 0)
               umma_bf16(tmem_base + (uint32_t)p.n0_cols, desc_advance(da, k * kUmmaK * 128),
                         desc_advance(db1, k * kUmmaK * 128), p.idesc1, acc);
+          };
+          // the last chunk of a sample holds T - kc*64 real positions; the rest is TMA zero fill of dU, so k steps
+          // past it add nothing (T = 360: 3 of 4 steps in the sixth chunk).  Full chunks keep the unrolled issue loop.
+          const int rem = p.T - kc * kBlockK;
+          if (rem >= kBlockK) {
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) issue(k);
+          } else {
+            const int ksteps = (rem + kUmmaK - 1) / kUmmaK;
+            for (int k = 0; k < ksteps; ++k) issue(k);
           }
           fresh = false;
           umma_commit(smem_u32(&hdr->empty[s]));
@@ -1603,7 +1614,7 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
       for (int i = 0; i < 7; ++i) v[i] /= clusters;
       for (int i = 0; i < 6; ++i) ph[i] /= clusters * v[6];
       fprintf(stderr, "[megb200 timing]   epilogue thread 0 per tile: wait stores-read %.0f, barrier %.0f, tmem->convert->stage %.0f, "
-              "fence+barrier %.0f, stats %.0f, store issue %.0f\n", ph[0], ph[1], ph[2], ph[3], ph[4], ph[5]);
+              "fence+barrier %.0f, store issue %.0f, stats %.0f\n", ph[0], ph[1], ph[2], ph[3], ph[4], ph[5]);
       fprintf(stderr, "[megb200 timing] %s tapgemm N=%d K=%d taps=%d epi=%d NT=%d stages=%d: per cluster %.1f tiles; MMA loop %.0f "
               "cycles (waiting for data %.0f, for a free accumulator %.0f); per tile: MMA %.0f, epilogue work %.0f, epilogue "
               "idle %.0f; producer waiting for free slots %.0f\n", which, N, Ca, taps, epi, p.NT, p.stages, v[6], v[1], v[2], v[3],

@@ -32,6 +32,8 @@ SIGNATURES = {
     "megb200_bn_stats": [_p, _ll, _i, _i, _p, _i, _p],
     "megb200_bn_finalize": [_p, _p, _p, _p, _p, _ll, _f, _f, _i, _p, _p, _p, _p, _i, _p],
     "megb200_bn_gelu": [_p, _p, _p, _p, _ll, _i, _i, _i, _i, _p],
+    "megb200_bn_gelu_train": [_p, _p, _p, _p, _p, _p, _ll, _f, _f, _p, _p, _p, _p, _p, _ll, _i, _i, _i, _i, _p],
+    "megb200_bn_gelu_bwd_apply": [_p, _p, _p, _p, _p, _p, _p, _p, _ll, _p, _p, _ll, _i, _i, _i, _i, _p],
     "megb200_bn_gelu_bwd_reduce": [_p, _p, _p, _p, _p, _p, _p, _p, _ll, _i, _i, _i, _i, _p],
     "megb200_bn_bwd_apply": [_p, _p, _p, _p, _p, _p, _ll, _p, _p, _ll, _i, _i, _i, _i, _p],
     "megb200_glu": [_p, _p, _ll, _i, _i, _i, _i, _p],

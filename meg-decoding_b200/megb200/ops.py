@@ -233,14 +233,35 @@ class CudaOps:
         L.call("megb200_bn_gelu", U.data_ptr(), scale.data_ptr(), shift.data_ptr(), H.data_ptr(), rows, C, U.shape[2],
                self._udt(U), self.dt, self._stream())
 
+    def bn_gelu_train(self, U, sums, gamma, beta, rm, rv, count, eps, momentum, scale, shift, mean, rstd, H, C):
+        """Training-mode BatchNorm + GELU in one launch (bn_finalize + bn_gelu; also updates rm / rv)."""
+        self._chk_f32(sums, gamma, beta, rm, rv, scale, shift, mean, rstd)
+        self._chk_act(H)
+        assert H.shape == U.shape
+        rows = U.shape[0] * U.shape[1]
+        L.call("megb200_bn_gelu_train", U.data_ptr(), sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(), rm.data_ptr(),
+               rv.data_ptr(), int(count), float(eps), float(momentum), scale.data_ptr(), shift.data_ptr(),
+               mean.data_ptr(), rstd.data_ptr(), H.data_ptr(), rows, C, U.shape[2], self._udt(U), self.dt, self._stream())
+
     def bn_gelu_bwd_reduce(self, dH, U, scale, shift, mean, rstd, dY, sums2, C):
+        """dY may be None: only the two per-channel sums are formed (bn_gelu_bwd_apply recomputes dY)."""
         self._chk_act(dH, dY)
         self._chk_f32(sums2)
-        assert dH.shape == U.shape == dY.shape
+        assert dH.shape == U.shape and (dY is None or dY.shape == U.shape)
         rows = U.shape[0] * U.shape[1]
         L.call("megb200_bn_gelu_bwd_reduce", dH.data_ptr(), U.data_ptr(), scale.data_ptr(), shift.data_ptr(),
-               mean.data_ptr(), rstd.data_ptr(), dY.data_ptr(), sums2.data_ptr(), rows, C, U.shape[2], self._udt(U),
+               mean.data_ptr(), rstd.data_ptr(), _ptr(dY), sums2.data_ptr(), rows, C, U.shape[2], self._udt(U),
                self.dt, self._stream())
+
+    def bn_gelu_bwd_apply(self, dH, U, scale, shift, gamma, mean, rstd, sums2, count, dU, C, dbias=None):
+        """bn_bwd_apply with dY = dH * gelu'(scale*U + shift) recomputed instead of read."""
+        self._chk_act(dH, dU)
+        self._chk_f32(dbias)
+        assert dH.shape == U.shape == dU.shape
+        rows = U.shape[0] * U.shape[1]
+        L.call("megb200_bn_gelu_bwd_apply", dH.data_ptr(), U.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+               gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), sums2.data_ptr(), int(count), dU.data_ptr(),
+               _ptr(dbias), rows, C, U.shape[2], self._udt(U), self.dt, self._stream())
 
     def bn_bwd_apply(self, dY, U, gamma, mean, rstd, sums2, count, dU, C, dbias=None):
         """dbias (f32 [C], accumulated): column sums of dU = gradient of the conv bias in front of the BatchNorm."""

@@ -85,23 +85,15 @@ def allreduce_grads(params: Iterable[torch.nn.Parameter], bucket_bytes: int = 64
             return
         views = []
         for p in bucket:
-            g = p.grad if p.grad is not None else torch.zeros_like(p)
+            if p.grad is None:          # absent on this rank: contribute zeros, receive the other ranks' sum
+                p.grad = torch.zeros_like(p)
+            g = p.grad
+            if not g.is_contiguous():
+                g = p.grad = g.contiguous()
             views.append(torch.view_as_real(g).reshape(-1) if g.is_complex() else g.reshape(-1))
-        flat = torch.cat(views)
+        flat = torch.cat(views)                                    # one gather kernel
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=_CTX.group)
-        o = 0
-        for p, v in zip(bucket, views):
-            n = v.numel()
-            chunk = flat[o:o + n]
-            o += n
-            if p.is_complex():
-                new = torch.view_as_complex(chunk.view(*p.shape, 2).clone())
-            else:
-                new = chunk.view(p.shape)
-            if p.grad is None:
-                p.grad = new.clone()
-            else:
-                p.grad.copy_(new)
+        torch._foreach_copy_(views, list(flat.split([v.numel() for v in views])))   # one multi-tensor scatter
         bucket, size = [], 0
 
     for p in plist:

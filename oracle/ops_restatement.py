@@ -163,13 +163,28 @@ class TorchOps:
         H.zero_()
         H[:, :, :C] = self._r(F.gelu(U[:, :, :C].float() * scale + shift))
 
+    def bn_gelu_train(self, U, sums, gamma, beta, rm, rv, count, eps, momentum, scale, shift, mean, rstd, H, C):
+        self.bn_finalize(sums, gamma, beta, rm, rv, count, eps, momentum, True, scale, shift, mean, rstd)
+        self.bn_gelu(U, scale, shift, H, C)
+
+    def bn_gelu_bwd_apply(self, dH, U, scale, shift, gamma, mean, rstd, sums2, count, dU, C, dbias=None):
+        u = U[:, :, :C].float()
+        dy = dH[:, :, :C].float() * _gelu_grad(u * scale + shift)
+        xh = (u - mean) * rstd
+        du = gamma * rstd * (dy - sums2[0] / count - xh * sums2[1] / count)
+        dU.zero_()
+        dU[:, :, :C] = self._r(du)
+        if dbias is not None:
+            dbias += dU[:, :, :C].float().sum((0, 1))
+
     def bn_gelu_bwd_reduce(self, dH, U, scale, shift, mean, rstd, dY, sums2, C):
         u = U[:, :, :C].float()
         gp = _gelu_grad(u * scale + shift)
-        dy = self._r(dH[:, :, :C].float() * gp).float()
+        dy = self._r(dH[:, :, :C].float() * gp).float() if dY is not None else dH[:, :, :C].float() * gp
         xh = (u - mean) * rstd
-        dY.zero_()
-        dY[:, :, :C] = self._r(dy)
+        if dY is not None:
+            dY.zero_()
+            dY[:, :, :C] = self._r(dy)
         sums2[0] += dy.sum((0, 1))
         sums2[1] += (dy * xh).sum((0, 1))
 

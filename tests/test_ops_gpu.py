@@ -284,6 +284,31 @@ def test_batchnorm_gelu_chain(dtype, u_f32, shape):
             # fused conv-bias gradient = column sums of the dU just written (analytically ~0: compare absolutely)
             want = dU.float().cpu()[:, :, :C].sum((0, 1))
             assert float((db.cpu() - want).abs().max()) <= 1e-3 * float(dU.float().abs().max()) * (n ** 0.5)
+            # --- fused forms used by the engine: one-launch train-mode BN+GELU, reduce without dY, apply with recompute
+            rm2, rv2 = _rand(gen, C, scale=0.1), torch.rand(C, generator=gen) + 0.5
+            rm2d, rv2d = rm2.to(DEV), rv2.to(DEV)
+            st2 = {k: torch.full((C,), float("nan"), device=DEV) for k in st}
+            H2 = ops.empty(B, T, pad8(C), device=DEV)
+            ops.bn_gelu_train(Ud, sums, gamma.to(DEV), beta.to(DEV), rm2d, rv2d, n, 1e-5, 0.1, st2["scale"], st2["shift"],
+                              st2["mean"], st2["rstd"], H2, C)
+            str2 = {k: torch.empty(C) for k in st}
+            ref.bn_finalize(sums.cpu(), gamma, beta, rm2, rv2, n, 1e-5, 0.1, 1, str2["scale"], str2["shift"], str2["mean"],
+                            str2["rstd"])
+            for k in st:
+                _close(st2[k], str2[k], torch.float32, f"bn_gelu_train {k}", atol_scale=20)
+            _close(rm2d, rm2, torch.float32, "bn_gelu_train running_mean", atol_scale=20)
+            _close(rv2d, rv2, torch.float32, "bn_gelu_train running_var", atol_scale=20)
+            _close(H2, Hr, dtype, "bn_gelu_train H")
+            s3 = torch.zeros(2, C, device=DEV)
+            ops.bn_gelu_bwd_reduce(dHd, Ud, st["scale"], st["shift"], st["mean"], st["rstd"], None, s3, C)
+            assert torch.equal(s3, s2), "the sums must not depend on whether dY is written"
+            dU2, dU2r = ops.empty(B, T, pad8(C), device=DEV), ref.empty(B, T, pad8(C), device="cpu")
+            db2 = torch.zeros(C, device=DEV)
+            ops.bn_gelu_bwd_apply(dHd, Ud, st["scale"], st["shift"], gamma.to(DEV), st["mean"], st["rstd"], s2, n, dU2, C, db2)
+            ref.bn_gelu_bwd_apply(dH, U, stc["scale"], stc["shift"], gamma, stc["mean"], stc["rstd"], s2.cpu(), n, dU2r, C)
+            _close(dU2, dU2r, dtype, "bn_gelu_bwd_apply")
+            want2 = dU2.float().cpu()[:, :, :C].sum((0, 1))
+            assert float((db2.cpu() - want2).abs().max()) <= 1e-3 * float(dU2.float().abs().max()) * (n ** 0.5)
 
 
 @pytest.mark.parametrize("dtype", EW_DTYPES)
