@@ -15,35 +15,60 @@ static inline int ew_grid(long long work_items, int threads) {
 }
 
 // ------------------------------------------------------------------------------------------ transpose-pack
-// in f32 [B][C][T] -> out [B][T][Cs] (+ optional per-sample sum of squares of the unrounded input)
+// in f32 [B][C][T] -> out [B][T][Cs] (+ optional per-sample sum of squares of the unrounded input).
+// 64 (channels) x 64 (positions) tile, 256 threads: a warp reads one channel row as 32 x 8 B = 256 contiguous bytes and
+// writes one position row as 32 x (2 channels) = 128 B of bf16 (256 B of f32), so both sides move whole 128 B lines.
+// (The first form used 32 x 32 tiles and 2-byte stores: half-line writes, 3.4 TB/s on the 566 MB target pack.)
+constexpr int kTpTile = 64;
+
 template <typename T>
-__global__ void transpose_pack_kernel(const float* __restrict__ in, T* __restrict__ out, float* __restrict__ sq,
-                                      int B, int C, int Tn, int Cs) {
-  __shared__ float tile[32][33];
+__global__ void __launch_bounds__(256) transpose_pack_kernel(const float* __restrict__ in, T* __restrict__ out,
+                                                             float* __restrict__ sq, int B, int C, int Tn, int Cs) {
+  __shared__ float tile[kTpTile][kTpTile + 1];
   __shared__ float red[8];
   const int b = blockIdx.z;
-  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  const int t0 = blockIdx.x * kTpTile, c0 = blockIdx.y * kTpTile;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool t_vec = (Tn & 1) == 0 && (reinterpret_cast<uintptr_t>(in) & 7) == 0;   // 8-byte loads: even rows, aligned base
   float ss = 0.f;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int c = c0 + ty + 8 * i, t = t0 + tx;
-    float v = 0.f;
-    if (c < C && t < Tn) v = in[((long long)b * C + c) * Tn + t];
-    tile[ty + 8 * i][tx] = v;
-    ss += v * v;
+  for (int i = 0; i < 8; ++i) {
+    const int cl = warp + 8 * i, c = c0 + cl, t = t0 + 2 * lane;
+    float v0 = 0.f, v1 = 0.f;
+    if (c < C) {
+      const float* src = in + ((long long)b * C + c) * Tn + t;
+      if (t_vec && t + 1 < Tn) {
+        const float2 v = *reinterpret_cast<const float2*>(src);
+        v0 = v.x;
+        v1 = v.y;
+      } else {
+        if (t < Tn) v0 = src[0];
+        if (t + 1 < Tn) v1 = src[1];
+      }
+    }
+    tile[cl][2 * lane] = v0;
+    tile[cl][2 * lane + 1] = v1;
+    ss = fmaf(v0, v0, fmaf(v1, v1, ss));
   }
   __syncthreads();
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int t = t0 + ty + 8 * i, c = c0 + tx;
-    if (t < Tn && c < Cs) out[((long long)b * Tn + t) * Cs + c] = from_f<T>(tile[tx][ty + 8 * i]);
+  for (int i = 0; i < 8; ++i) {
+    const int tl = warp + 8 * i, t = t0 + tl, c = c0 + 2 * lane;
+    if (t < Tn && c < Cs) {          // Cs is even (multiple of 8), so c + 1 < Cs too; channels >= C were read as 0
+      T* dst = out + ((long long)b * Tn + t) * Cs + c;
+      const float a0 = tile[2 * lane][tl], a1 = tile[2 * lane + 1][tl];
+      if constexpr (sizeof(T) == 2) {
+        *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(a0, a1);
+      } else {
+        *reinterpret_cast<float2*>(dst) = make_float2(a0, a1);
+      }
+    }
   }
   if (sq != nullptr) {
     ss = warp_sum(ss);
-    if (tx == 0) red[ty] = ss;
+    if (lane == 0) red[warp] = ss;
     __syncthreads();
-    if (ty == 0 && tx == 0) {
+    if (threadIdx.x == 0) {
       float s = 0.f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) s += red[i];
@@ -55,8 +80,8 @@ __global__ void transpose_pack_kernel(const float* __restrict__ in, T* __restric
 template <typename T>
 static int launch_transpose_pack(const float* in, void* out, float* sq, int B, int C, int Tn, int Cs,
                                  cudaStream_t st) {
-  dim3 grid((Tn + 31) / 32, (Cs + 31) / 32, B), block(32, 8);
-  transpose_pack_kernel<T><<<grid, block, 0, st>>>(in, (T*)out, sq, B, C, Tn, Cs);
+  dim3 grid((Tn + kTpTile - 1) / kTpTile, (Cs + kTpTile - 1) / kTpTile, B);
+  transpose_pack_kernel<T><<<grid, 256, 0, st>>>(in, (T*)out, sq, B, C, Tn, Cs);
   MEGB_LAUNCH_OK();
   return 0;
 }
@@ -281,6 +306,7 @@ rowstage_kernel(Op op, long long rows, long long rows_per_block, int slab_rows, 
       const uint8_t* s0 = ring + (size_t)s * stage_bytes;
       const uint8_t* s1 = Op::kIn > 1 ? s0 + (size_t)slab_rows * p0 : s0;
       if (active) {
+        // two rows in flight per thread; three resident CTAs per SM without unrolling measured 3-7 % slower
 #pragma unroll 2
         for (int rr = lane_r; rr < n; rr += R) op.row(s0 + (size_t)rr * p0, s1 + (size_t)rr * p1, rs + rr, lane_g * 8, a0, a1);
       }
@@ -675,7 +701,7 @@ static int launch_rowloop(Op op, long long rows, int C, int Cs, const int32_t* g
     if (slab_rows < R) slab_rows = R;
     const long long stage_bytes = (long long)slab_rows * pitch_sum;
     const size_t acc_bytes = Op::kAcc > 0 ? 2 * Cs * sizeof(float) : 0;
-    int stages = (int)((100 * 1024 - 128 - (long long)acc_bytes) / stage_bytes);
+    int stages = (int)((100 * 1024 - 128 - (long long)acc_bytes) / stage_bytes);      // two CTAs per SM
     if (stages > kRowMaxStages) stages = kRowMaxStages;
     if (stages >= 2) {
       long long blocks = (long long)num_sms() * 2;                  // one resident wave (2 CTAs per SM)

@@ -233,10 +233,11 @@ class BrainEncoder(nn.Module):
             # models.py:236 — one centre per forward call from the global NumPy RNG unless pinned
             c = self.drop_center if self.drop_center is not None else int(np.random.randint(C))
             mask = sa.drop_masks[c]
+            nbt = []
             for k in range(5):
                 cb = getattr(self.conv_blocks, f"conv{k}")
-                cb.batchnorm0.num_batches_tracked += 1
-                cb.batchnorm1.num_batches_tracked += 1
+                nbt += [cb.batchnorm0.num_batches_tracked, cb.batchnorm1.num_batches_tracked]
+            torch._foreach_add_(nbt, 1)            # one launch for the ten counters instead of ten
         params = self._param_list()
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
             Zi = _EncoderFn.apply(self, X, subj, mask, present, *params)
