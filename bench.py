@@ -295,11 +295,43 @@ def run_megb200(args):
                                       "(ncu --set full, config 2)" if traffic else None,
                     "peak_source": peaks["source"] + " sustained",
                     "launches_per_step": n // args.steps, "avg_launch_ms": tms / n,
-                    "share_of_step": tms / args.steps / ms}
+                    "share_of_step": tms / args.steps / ms}      # share of the EAGER timed region the events were taken in
         if "wgrad" in kern:
             fl2, t2, n2 = kern["wgrad"]
             roofline["wgrad"] = {"achieved": fl2 / (t2 * 1e-3) / 1e12, "launches_per_step": n2 // args.steps,
                                  "avg_launch_ms": t2 / n2, "share_of_step": t2 / args.steps / ms}
+
+    # ---- the same K steps replayed from a CUDA graph (megb200.graph.GraphedTrainStep: the step recorded once through
+    # the same C-ABI launches).  One cudaGraphLaunch per step, so the number does not depend on how fast this host can
+    # enqueue ~145 launches; it is the headline `value` when it is available (single rank), the eager loop above stays
+    # in the line as `ms_per_step_eager` and is where the per-launch roofline events were taken.
+    graph_ms, graph_note, eager_ms = None, None, ms
+    if world == 1 and not args.no_graph:
+        try:
+            from megb200.graph import GraphedTrainStep
+            gstep = GraphedTrainStep(enc, lossf, Xd, Yd, subj_h, drop_center=enc.drop_center)
+            for _ in range(3):
+                gstep()
+            barrier()
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            q0.record()
+            for _ in range(args.steps):
+                gloss = gstep()
+            q1.record()
+            barrier()
+            graph_ms = q0.elapsed_time(q1) / args.steps
+            gl = float(gloss)
+            if not math.isfinite(gl) or abs(gl - loss_value) > 0.05 * abs(loss_value):
+                graph_note, graph_ms = f"graph loss {gl} disagrees with eager {loss_value}", None
+            else:
+                launches = gstep.launches_per_step
+        except Exception as e:          # capture is an optimisation of the launch path, never a different compute path
+            graph_note = f"capture failed: {type(e).__name__}: {e}"[:200]
+            if os.environ.get("MEGB200_GRAPH_DEBUG"):
+                import traceback
+                traceback.print_exc()
+    if graph_ms is not None:
+        ms = graph_ms
 
     # ---- optimizer step, reported separately
     barrier()
@@ -381,6 +413,8 @@ def run_megb200(args):
         "roofline": roofline,
         "step_tflops": flops_step / (ms * 1e-3) / 1e12,
         "step_frac_of_peak": flops_step / (ms * 1e-3) / 1e12 / peaks["bf16_sustained"],
+        "launch_path": "cuda_graph" if graph_ms is not None else "eager", "ms_per_step_eager": eager_ms,
+        "ms_per_step_graph": graph_ms, "graph_note": graph_note,
         "adam_ms": adam_ms, "host_enqueue_ms_per_step": host_ms, "loss": loss_value, "precision": args.precision,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -407,6 +441,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "bf16_simt"])
     ap.add_argument("--cpu-sample", type=int, default=32, help="samples per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time only the eager launch path")
     ap.add_argument("--ncu-step", action="store_true", help="run one step inside cudaProfilerStart/Stop and exit")
     args = ap.parse_args()
     if args.impl == "reference":

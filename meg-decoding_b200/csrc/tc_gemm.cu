@@ -13,6 +13,8 @@
 
 #include "tc_common.cuh"
 
+#include <mutex>
+
 namespace megb200 {
 namespace tc {
 
@@ -1210,19 +1212,27 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__
   }
 }
 
-// partial[slot][tap][M][C] -> dW[m][c][tap] += sum_slot
+// partial[slot][tap][M][C] -> dW[m][c][tap] += sum_slot.  Thread = one (m, c): coalesced slot reads (all independent,
+// unrolled for memory-level parallelism) and one contiguous run of `taps` floats written per thread.
 __global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dW, int slots, int taps, int M,
                                     int C) {
-  const long long n = (long long)taps * M * C;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n;
+  const long long mc = (long long)M * C;
+  const long long n = (long long)taps * mc;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < mc;
        idx += (long long)gridDim.x * blockDim.x) {
-    float s = 0.f;
-    for (int k = 0; k < slots; ++k) s += part[(long long)k * n + idx];
-    const int c = (int)(idx % C);
-    const long long r = idx / C;
-    const int m = (int)(r % M);
-    const int tap = (int)(r / M);
-    dW[((long long)m * C + c) * taps + tap] += s;
+    for (int tap = 0; tap < taps; ++tap) {
+      const float* src = part + (long long)tap * mc + idx;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      int k = 0;
+      for (; k + 4 <= slots; k += 4) {
+        s0 += src[(long long)k * n];
+        s1 += src[(long long)(k + 1) * n];
+        s2 += src[(long long)(k + 2) * n];
+        s3 += src[(long long)(k + 3) * n];
+      }
+      for (; k < slots; ++k) s0 += src[(long long)k * n];
+      dW[idx * taps + tap] += (s0 + s1) + (s2 + s3);
+    }
   }
 }
 
@@ -1323,7 +1333,7 @@ tc_clip_logits_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_cons
 
 // ================================================================================================ CLIP dZ
 struct DzParams {
-  int By, Bz, NT /*d columns per CTA, multiple of 64*/, stages, kchunks;
+  int By, Bz, NT /*d columns per CTA, multiple of 64*/, stages, kchunks, swap_grid;
   long long D;
   uint32_t tmem_cols, idesc;
   const __nv_bfloat16* Z;
@@ -1344,8 +1354,9 @@ tc_clip_dz_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constant
   const uint32_t b_bytes = (uint32_t)(p.NT / 64) * atom_bytes;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   uint8_t* ring = smem + kHeaderBytes;
-  const long long d0 = (long long)blockIdx.x * p.NT;
-  const int j0 = blockIdx.y * kTileM;
+  // blockIdx.x = j tile (fastest) when the launcher could swap: CTAs sharing a Y tile run together (L2 hit on the re-read)
+  const long long d0 = (long long)(p.swap_grid ? blockIdx.y : blockIdx.x) * p.NT;
+  const int j0 = (p.swap_grid ? blockIdx.x : blockIdx.y) * kTileM;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmC);
@@ -1426,6 +1437,143 @@ tc_clip_dz_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constant
   }
 }
 
+// Small-K form of the dZ contraction (K = By <= 512: the single-GPU step and 2-GPU jobs).  There the kernel is bound by
+// the Y / Z / dZ streams (566 MB at config 2), not by the MMAs, so everything that touches global memory is a TMA tile:
+// the Z tile of the CTA is fetched into swizzled shared memory while the k loop runs, the epilogue rewrites it IN PLACE
+// (thread = row: 16-byte swizzled chunks) and one thread stores it back with TMA.  The first form read Z and wrote dZ
+// with per-thread 32-byte global accesses strided by D (2.4 TB/s).  128 x 128 tiles, 96 KB: two CTAs per SM overlap
+// one's epilogue with the other's loads.
+struct DzSmallHeader {
+  uint64_t full[4];
+  uint64_t empty[4];
+  uint64_t tmem_full;
+  uint64_t zfull;
+  uint32_t tmem_slot;
+  uint32_t pad;
+};
+
+__global__ void __launch_bounds__(kThreads)
+tc_clip_dz_small_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmY,
+                        const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmDZ,
+                        const DzParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  DzSmallHeader* hdr = reinterpret_cast<DzSmallHeader*>(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kNT = 128;
+  const uint32_t atom_bytes = kBlockK * 128;                // 64 k-rows x 128 B (= 64 d columns)
+  const uint32_t a_bytes = kTileM * 128;                    // coef tile: 128 j rows x 64 k
+  const uint32_t b_bytes = (kNT / 64) * atom_bytes;
+  const uint32_t stage_bytes = a_bytes + b_bytes;           // 32 KB
+  uint8_t* ring = smem + kHeaderBytes;
+  uint8_t* zt = ring + (size_t)p.stages * stage_bytes;      // Z / dZ tile: 2 slices of [128 rows][64 cols] bf16
+  const uint32_t zslice = kTileM * 128;
+  // blockIdx.x = j tile (fastest): the CTAs that share a Y tile are scheduled together, so its second read is an L2 hit
+  const long long d0 = (long long)blockIdx.y * kNT;
+  const int j0 = blockIdx.x * kTileM;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmC);
+    tma_prefetch_desc(&tmY);
+    tma_prefetch_desc(&tmZ);
+    tma_prefetch_desc(&tmDZ);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&hdr->full[s]), 1);
+      mbar_init(smem_u32(&hdr->empty[s]), 1);
+    }
+    mbar_init(smem_u32(&hdr->tmem_full), 1);
+    mbar_init(smem_u32(&hdr->zfull), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&hdr->tmem_slot), kNT);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = hdr->tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t zf = smem_u32(&hdr->zfull);
+      mbar_arrive_expect_tx(zf, 2 * zslice);
+      tma_load_2d(smem_u32(zt), &tmZ, (int)d0, j0, zf);
+      tma_load_2d(smem_u32(zt) + zslice, &tmZ, (int)d0 + 64, j0, zf);
+      for (int it = 0; it < p.kchunks; ++it) {
+        const int s = it % p.stages;
+        mbar_wait(smem_u32(&hdr->empty[s]), ((it / p.stages) & 1) ^ 1);
+        const uint32_t full = smem_u32(&hdr->full[s]);
+        mbar_arrive_expect_tx(full, stage_bytes);
+        const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
+        tma_load_2d(sa, &tmC, it * kBlockK, j0, full);                                    // coef[j][i]: K-major
+        for (int a = 0; a < kNT / 64; ++a)                                                // Y[i][d]: MN-major
+          tma_load_2d(sa + a_bytes + a * atom_bytes, &tmY, (int)(d0 + a * 64), it * kBlockK, full);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int it = 0; it < p.kchunks; ++it) {
+        const int s = it % p.stages;
+        mbar_wait(smem_u32(&hdr->full[s]), (it / p.stages) & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
+        const uint64_t da = make_smem_desc(sa, 16, 1024);
+        const uint64_t db = make_smem_desc(sa + a_bytes, atom_bytes, 1024);
+#pragma unroll
+        for (int k = 0; k < kBlockK / kUmmaK; ++k)
+          umma_bf16(tmem_base, desc_advance(da, k * 32), desc_advance(db, k * kUmmaK * 128), p.idesc, (it | k) != 0);
+        umma_commit(smem_u32(&hdr->empty[s]));
+      }
+      umma_commit(smem_u32(&hdr->tmem_full));
+    }
+  } else {
+    const int q = warp & 3;
+    const int rloc = q * 32 + lane;                 // row of the tile = TMEM lane
+    const int j = j0 + rloc;
+    const float cj = j < p.Bz ? p.cvec[j] : 0.f;
+    const float gs = p.gscale[0];
+    mbar_wait(smem_u32(&hdr->zfull), 0);
+    mbar_wait(smem_u32(&hdr->tmem_full), 0);
+    tc_fence_after();
+    const uint32_t sw = (uint32_t)rloc & 7u;
+#pragma unroll
+    for (int g = 0; g < kNT / 32; ++g) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 32), v);
+      const uint32_t rowaddr = smem_u32(zt) + (uint32_t)(g >> 1) * zslice + (uint32_t)rloc * 128u;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t addr = rowaddr + ((((uint32_t)(g & 1) * 4u + (uint32_t)c) ^ sw) << 4);
+        uint4 zz;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(zz.x), "=r"(zz.y), "=r"(zz.z), "=r"(zz.w) : "r"(addr));
+        const __nv_bfloat162* zh = reinterpret_cast<const __nv_bfloat162*>(&zz);
+        uint32_t o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 zf2 = __bfloat1622float2(zh[e]);
+          o[e] = pack_bf16x2(gs * (v[8 * c + 2 * e] - zf2.x * cj), gs * (v[8 * c + 2 * e + 1] - zf2.y * cj));
+        }
+        st_shared_v4(addr, o[0], o[1], o[2], o[3]);
+      }
+    }
+    tc_fence_before();
+    fence_proxy_async();
+    named_bar_sync(1, 128);
+    if (threadIdx.x == 64) {
+      tma_store_2d(&tmDZ, smem_u32(zt), (int)d0, j0);
+      tma_store_2d(&tmDZ, smem_u32(zt) + zslice, (int)d0 + 64, j0);
+      tma_store_commit();
+      tma_store_wait_read();
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kNT);
+  }
+}
+
 // ================================================================================================ host launchers
 static bool halo_mode_env_off() {
   static const char* e = getenv("MEGB200_TAPGEMM_HALO");
@@ -1446,9 +1594,26 @@ static int pick_ntile(int Np) {
   return (((Np + tiles - 1) / tiles) + 15) / 16 * 16;
 }
 
+// Raises the kernel's dynamic shared-memory limit when needed.  The attribute only ever grows and is remembered per
+// kernel (and device), so steady-state launches -- and launches recorded into a CUDA graph after a warm-up step -- make
+// no attribute call at all.
 template <class K>
 static int set_smem(K kernel, size_t bytes) {
+  struct Entry { const void* fn; int dev; size_t bytes; };
+  static Entry table[64];
+  static int used = 0;
+  static std::mutex mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  const void* fn = reinterpret_cast<const void*>(kernel);
+  std::lock_guard<std::mutex> lock(mu);
+  Entry* e = nullptr;
+  for (int i = 0; i < used; ++i)
+    if (table[i].fn == fn && table[i].dev == dev) e = &table[i];
+  if (e != nullptr && bytes <= e->bytes) return 0;
   MEGB_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  if (e == nullptr && used < 64) e = &table[used++], e->fn = fn, e->dev = dev, e->bytes = 0;
+  if (e != nullptr) e->bytes = bytes;
   return 0;
 }
 
@@ -1825,9 +1990,9 @@ int tc_wgrad(const void* dU, int M, int Ms, const void* Xin, int C, int Cs, int 
   tc_wgrad_kernel<<<grid, kThreads, smem, st>>>(tmU, tmX, p);
   MEGB_LAUNCH_OK();
   if (p.mode == 0) {
-    long long blocks = (slot_elems + 255) / 256;
-    if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-    wgrad_reduce_kernel<<<(int)blocks, 256, 0, st>>>(workspace, dW, splits, taps, M, C);
+    long long blocks = ((long long)M * C + 127) / 128;
+    if (blocks > num_sms() * 16) blocks = num_sms() * 16;
+    wgrad_reduce_kernel<<<(int)blocks, 128, 0, st>>>(workspace, dW, splits, taps, M, C);
     MEGB_LAUNCH_OK();
   }
   return 0;
@@ -1885,6 +2050,48 @@ int tc_clip_dz(const void* coef, int ldc, const void* Yp, const void* Z, const f
   MEGB_CHECK_ARG(D % 16 == 0 && ldc % 8 == 0, "tc_clip_dz: D %% 16 and ldc %% 8 required (D=%lld ldc=%d)", D, ldc);
   DzParams p;
   p.By = By; p.Bz = Bz; p.D = D;
+  static const bool no_small = getenv("MEGB200_CLIP_DZ_LARGE") != nullptr;
+  if (By <= 512 && D >= 128 && D % 64 == 0 && (D + 127) / 128 <= 65535 && !no_small) {
+    // stream-bound regime: TMA-staged Z / dZ tiles, 128 x 128 tiles, two CTAs per SM
+    p.NT = 128;
+    p.swap_grid = 1;
+    p.kchunks = (By + kBlockK - 1) / kBlockK;
+    p.stages = 2;
+    p.tmem_cols = 128;
+    p.idesc = make_idesc(128, 0, 1);
+    p.Z = (const __nv_bfloat16*)Z; p.cvec = cvec; p.gscale = gscale; p.dZ = (__nv_bfloat16*)dZ;
+    CUtensorMap tmC, tmY, tmZ, tmDZ;
+    {
+      const uint64_t dims[2] = {(uint64_t)By, (uint64_t)Bz};
+      const uint64_t strides[1] = {(uint64_t)ldc * 2};
+      const uint32_t box[2] = {kBlockK, kTileM};
+      int rc = encode_tmap_bf16(&tmC, coef, 2, dims, strides, box);
+      if (rc) return rc;
+    }
+    {
+      const uint64_t dims[2] = {(uint64_t)D, (uint64_t)By};
+      const uint64_t strides[1] = {(uint64_t)D * 2};
+      const uint32_t box[2] = {64, kBlockK};
+      int rc = encode_tmap_bf16(&tmY, Yp, 2, dims, strides, box);
+      if (rc) return rc;
+    }
+    {
+      const uint64_t dims[2] = {(uint64_t)D, (uint64_t)Bz};
+      const uint64_t strides[1] = {(uint64_t)D * 2};
+      const uint32_t box[2] = {64, kTileM};
+      int rc = encode_tmap_bf16(&tmZ, Z, 2, dims, strides, box);
+      if (rc) return rc;
+      rc = encode_tmap_bf16(&tmDZ, dZ, 2, dims, strides, box);
+      if (rc) return rc;
+    }
+    const size_t smem = 1024 + kHeaderBytes + (size_t)p.stages * (kTileM * 128 + 2 * kBlockK * 128) + 2 * kTileM * 128;
+    int rc = set_smem(tc_clip_dz_small_kernel, smem);
+    if (rc) return rc;
+    dim3 grid((Bz + kTileM - 1) / kTileM, (unsigned)((D + 127) / 128));
+    tc_clip_dz_small_kernel<<<grid, kThreads, smem, st>>>(tmC, tmY, tmZ, tmDZ, p);
+    MEGB_LAUNCH_OK();
+    return 0;
+  }
   p.NT = D >= 256 ? 256 : (int)((D + 63) / 64 * 64);
   p.kchunks = (By + kBlockK - 1) / kBlockK;
   const uint32_t stage_bytes = kTileM * 128 + (p.NT / 64) * kBlockK * 128;
@@ -1912,7 +2119,9 @@ int tc_clip_dz(const void* coef, int ldc, const void* Yp, const void* Z, const f
   if (rc) return rc;
   const long long dt = (D + p.NT - 1) / p.NT;
   MEGB_CHECK_ARG(dt < 2147483647ll, "tc_clip_dz: grid too large");
+  p.swap_grid = dt <= 65535 ? 1 : 0;
   dim3 grid((unsigned)dt, (Bz + kTileM - 1) / kTileM);
+  if (p.swap_grid) grid = dim3((Bz + kTileM - 1) / kTileM, (unsigned)dt);
   tc_clip_dz_kernel<<<grid, kThreads, smem, st>>>(tmC, tmY, p);
   MEGB_LAUNCH_OK();
   return 0;

@@ -232,7 +232,10 @@ class BrainEncoder(nn.Module):
         if self.training:
             # models.py:236 — one centre per forward call from the global NumPy RNG unless pinned
             c = self.drop_center if self.drop_center is not None else int(np.random.randint(C))
-            mask = sa.drop_masks[c]
+            if torch.is_tensor(c):      # device-resident centre (megb200.graph: the step is replayed from a CUDA graph)
+                mask = sa.drop_masks.index_select(0, c.reshape(1).to(torch.int64)).reshape(-1)
+            else:
+                mask = sa.drop_masks[c]
             nbt = []
             for k in range(5):
                 cb = getattr(self.conv_blocks, f"conv{k}")

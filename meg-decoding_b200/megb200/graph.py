@@ -1,0 +1,183 @@
+"""One training step replayed from a CUDA graph.
+
+The hot path launches ~145 kernels per step through the C-ABI; enqueueing them from Python costs 5-7 ms of host time
+against ~8.6 ms of device time at the Gwilliams shape, so a busy host (or a faster GPU step) makes the loop launch
+bound.  ``GraphedTrainStep`` records ``zero grads -> BrainEncoder.forward -> CLIPLoss -> backward`` once -- the same
+kernels, launched through the same C-ABI calls while the stream is capturing -- and replays the recording: one
+``cudaGraphLaunch`` per step.
+
+What makes the step capturable (nothing in it may depend on host values that change between steps):
+  * inputs live in static device buffers that ``__call__`` refills (``copy_`` from pinned or device memory);
+  * the subject indices are a device tensor (the drop-in module routes on the device; no subject's gradient is None);
+  * the spatial-dropout centre (models.py:236 draws one per forward call) is a device scalar the mask is gathered by,
+    refilled before every replay from the same NumPy RNG the reference uses;
+  * tensor maps, packed-weight tables and shared-memory attributes are created by the warm-up steps, so the captured
+    region contains kernel launches and memsets only.
+
+Data parallel: the step is captured per rank WITHOUT the collectives (use the eager path when
+``megb200.parallel.context()`` is set).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import os
+
+import numpy as np
+import torch
+
+from . import lib, parallel
+
+__all__ = ["GraphedTrainStep"]
+
+
+class GraphedTrainStep:
+    def __init__(self, encoder, loss_fn, X, Y, subject_idxs, drop_center: Optional[int] = None, warmup: int = 3):
+        if parallel.context() is not None:
+            raise RuntimeError("GraphedTrainStep captures a single-rank step; use the eager modules in data parallel")
+        self.enc, self.lossf = encoder, loss_fn
+        dev = next(encoder.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("GraphedTrainStep needs the modules on a CUDA device")
+        self.dev = dev
+        self.C = int(X.shape[1])
+        self.S = int(encoder.num_subjects)
+        self.X = torch.empty(tuple(X.shape), dtype=torch.float32, device=dev)
+        self.Y = torch.empty(tuple(Y.shape), dtype=torch.float32, device=dev)
+        self.subj = torch.zeros(int(X.shape[0]), dtype=torch.int32, device=dev)
+        self.center = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._one = torch.ones(1, dtype=torch.float32, device=dev)
+        self.params = [p for p in list(encoder.parameters()) + list(loss_fn.parameters()) if p.requires_grad]
+        self._user_center = encoder.drop_center
+        self.load(X, Y, subject_idxs, drop_center)
+
+        # warm-up on a side stream (torch's capture recipe); module buffers (BatchNorm running statistics, counters) are
+        # restored afterwards so that building the graph has no side effect on the model
+        saved = {k: v.clone() for k, v in list(encoder.named_buffers()) + list(loss_fn.named_buffers())}
+        encoder.drop_center = self.center
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(max(1, warmup)):
+                    self._step_eager()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            for p in self.params:
+                p.grad = None
+            n0 = lib.launch_count()
+            self.graph = torch.cuda.CUDAGraph()
+            undo = self._arm_capture_probe() if os.environ.get("MEGB200_GRAPH_DEBUG") else None
+            try:
+                with torch.cuda.graph(self.graph):
+                    self.loss = self._step_eager()
+            finally:
+                if undo:
+                    undo()
+            self.launches_per_step = lib.launch_count() - n0       # megb200 kernels recorded into the graph
+            # the gradient tensors the recording writes; re-attached after every replay in case the caller dropped them
+            # (optimizer.zero_grad(set_to_none=True), an eager step in between, ...)
+            self._static_grads = [p.grad for p in self.params]
+        finally:
+            encoder.drop_center = self._user_center
+        with torch.no_grad():
+            for k, v in list(encoder.named_buffers()) + list(loss_fn.named_buffers()):
+                v.copy_(saved[k])
+
+    @staticmethod
+    def _arm_capture_probe():
+        """MEGB200_GRAPH_DEBUG=1: report the first megb200 op after which the stream is no longer capturing."""
+        import sys
+
+        import megb200
+        ops = megb200.get_ops()
+        seen = {"n": 0, "bad": False}
+        saved = {}
+
+        def wrap(name, fn):
+            def w(*a, **k):
+                r = fn(*a, **k)
+                seen["n"] += 1
+                if not seen["bad"]:
+                    try:
+                        ok = torch.cuda.is_current_stream_capturing()
+                    except Exception as e:      # an invalidated capture raises here
+                        ok = repr(e)[:120]
+                    if ok is not True:
+                        seen["bad"] = True
+                        print(f"[megb200.graph] capture broken after op #{seen['n']} {name}: {ok}", file=sys.stderr, flush=True)
+                return r
+            return w
+
+        for name in dir(ops):
+            if not name.startswith("_") and callable(getattr(ops, name)):
+                saved[name] = getattr(ops, name)
+                setattr(ops, name, wrap(name, saved[name]))
+
+        def undo():
+            for name in saved:
+                try:
+                    delattr(ops, name)
+                except AttributeError:
+                    pass
+        return undo
+
+    def _step_eager(self):
+        """zero grads -> forward -> CLIP loss -> backward, WITHOUT the autograd engine: the drop-in modules wrap exactly
+        these engine calls in two autograd nodes (models.py::_EncoderFn, loss.py::_ClipFn); calling the engines directly
+        records the same kernels but keeps the autograd worker thread and its end-of-backward stream synchronisation
+        (which touches the legacy stream when an earlier eager step left gradient accumulators alive) out of the capture."""
+        enc, lossf = self.enc, self.lossf
+        with torch.no_grad():
+            sa = enc.subject_block.spatial_attention
+            mask = None
+            if enc.training:
+                mask = sa.drop_masks.index_select(0, self.center).reshape(-1)
+                nbt = []
+                for k in range(5):
+                    cb = getattr(enc.conv_blocks, f"conv{k}")
+                    nbt += [cb.batchnorm0.num_batches_tracked, cb.batchnorm1.num_batches_tracked]
+                torch._foreach_add_(nbt, 1)
+            params = enc._param_list()
+            P = enc._param_dict(params)
+            eng = enc._engine()
+            Zi, saved = eng.forward(P, self.X, self.subj, mask, enc.training)
+            Fs, Fo = Zi.shape[2], enc.F
+            Zl = Zi if Fs == Fo else Zi[:, :, :Fo].contiguous()
+            ceng = lossf._engine(Zl.dtype)
+            loss, _, csaved = ceng.forward(self.Y, Zl, lossf.temp.detach(), lossf.reduction, None, False)
+            dZ, dtemp = ceng.backward(csaved, self._one)
+            if Fs != Fo:
+                dZ = torch.nn.functional.pad(dZ, (0, Fs - Fo))
+            G = eng.backward(P, saved, dZ.contiguous())
+            for p, g in zip(params, enc._grad_list(G, None)):
+                p.grad = g if g.shape == p.shape else g.reshape(p.shape)
+            lossf.temp.grad = dtemp.reshape(lossf.temp.shape)
+        return loss.detach()
+
+    def load(self, X, Y, subject_idxs, drop_center: Optional[int] = None):
+        """Refill the static inputs (async on the current stream; pinned host tensors do not block)."""
+        self.X.copy_(X, non_blocking=True)
+        self.Y.copy_(Y, non_blocking=True)
+        s = torch.as_tensor(subject_idxs)
+        if not s.is_cuda:
+            if s.numel() and (int(s.max()) >= self.S or int(s.min()) < -self.S):
+                raise IndexError("index {} is out of range".format(int(s.max())))      # ModuleList semantics
+            s = torch.where(s < 0, s + self.S, s)
+        self.subj.copy_(s.to(torch.int32), non_blocking=True)
+        if self.enc.training:
+            c = drop_center if drop_center is not None else self._user_center
+            if c is None:
+                c = int(np.random.randint(self.C))                                       # models.py:236
+            self.center.fill_(int(c))
+
+    def __call__(self, X=None, Y=None, subject_idxs=None, drop_center: Optional[int] = None):
+        """Run one step on a new batch (or on the batch already loaded when called without arguments).  Returns the
+        loss as a device scalar that the NEXT call overwrites; parameter ``.grad`` tensors are rewritten in place."""
+        if X is not None:
+            self.load(X, Y, subject_idxs, drop_center)
+        self.graph.replay()
+        for p, g in zip(self.params, self._static_grads):
+            if p.grad is not g:
+                p.grad = g
+        return self.loss

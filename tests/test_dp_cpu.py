@@ -50,7 +50,9 @@ def _worker(rank, world, port, q):
         zc = torch.nn.Parameter(torch.zeros(2, dtype=torch.cfloat))
         zc.grad = torch.full((2,), complex(rank + 1, 1.0), dtype=torch.cfloat)
         parallel.allreduce_grads([extra, zc])
-        q.put((rank, float(loss), Zl.grad.clone(), lossf.temp.grad.clone(), extra.grad.clone(), zc.grad.clone()))
+        # plain numpy payloads: torch tensors travel through the queue as shared-memory handles that die with this process
+        q.put((rank, float(loss.detach()), Zl.grad.numpy().copy(), lossf.temp.grad.numpy().copy(),
+               extra.grad.numpy().copy(), zc.grad.numpy().copy()))
         center = parallel.share_drop_center(5 + rank, "cpu")
         assert center == 5
     finally:
@@ -72,7 +74,7 @@ def test_two_rank_clip_matches_single_process():
     res = {}
     for _ in range(world):
         r = q.get(timeout=150)
-        res[r[0]] = r[1:]
+        res[r[0]] = (r[1],) + tuple(torch.from_numpy(a) for a in r[2:])
     for p in procs:
         p.join(timeout=30)
         assert p.exitcode == 0

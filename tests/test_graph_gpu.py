@@ -1,0 +1,63 @@
+"""GPU tier: a training step replayed from a CUDA graph (megb200.graph) must reproduce the eager step — it is the same
+kernel sequence — for every new batch, subject assignment and spatial-dropout centre.  Not bit for bit: the BatchNorm
+sums are f32 atomics whose order differs run to run, and a flipped last bit moves a few bf16 roundings downstream."""
+import pytest
+import torch
+
+import megb200
+from megb200 import synth
+from megb200.graph import GraphedTrainStep
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _eager(enc, lossf, X, Y, subj, center):
+    for p in list(enc.parameters()) + list(lossf.parameters()):
+        p.grad = None
+    enc.drop_center = center
+    loss = lossf(Y, enc(X, subj))
+    loss.backward()
+    grads = {k: v.grad.clone() for k, v in list(enc.named_parameters()) + list(lossf.named_parameters()) if v.grad is not None}
+    return loss.detach().clone(), grads
+
+
+@pytest.mark.parametrize("name", ["narrow", "tiny_static"])
+def test_graph_replay_equals_eager_step(name):
+    megb200.set_precision("bf16")
+    cfg = synth.get_config(name)
+    enc, lossf = H.make_modules(cfg, DEV)
+    enc.train()
+    state0 = {k: v.clone() for k, v in enc.state_dict().items()}
+    X, Y, subj = H.make_inputs(cfg, DEV)
+    step = GraphedTrainStep(enc, lossf, X, Y, subj, drop_center=synth.drop_center(cfg))
+    assert step.launches_per_step > 20
+    for k, v in enc.state_dict().items():
+        assert torch.equal(v, state0[k]), f"building the graph changed {k}"
+    gen = torch.Generator().manual_seed(3)
+    for it in range(3):
+        Xn = torch.randn(X.shape, generator=gen)
+        Yn = torch.randn(Y.shape, generator=gen)
+        sn = torch.randint(0, cfg.num_subjects, (cfg.B,), generator=gen, dtype=torch.int32)
+        center = int(torch.randint(0, cfg.C, (1,), generator=gen))
+        bufs = {k: v.clone() for k, v in enc.named_buffers()}
+        loss_g = step(Xn.pin_memory(), Yn.pin_memory(), sn, drop_center=center).clone()
+        grads_g = {k: v.grad.clone() for k, v in list(enc.named_parameters()) + list(lossf.named_parameters())}
+        bufs_g = {k: v.clone() for k, v in enc.named_buffers()}
+        with torch.no_grad():                       # rewind the BatchNorm statistics and redo the step eagerly
+            for k, v in enc.named_buffers():
+                v.copy_(bufs[k])
+        loss_e, grads_e = _eager(enc, lossf, Xn.to(DEV), Yn.to(DEV), sn.to(DEV), center)
+        enc.drop_center = None
+        # run-to-run spread of the eager bf16 step itself is ~5e-4 on these tiny batches (atomic order -> bf16 roundings)
+        assert abs(float(loss_g) - float(loss_e)) <= 3e-3 * abs(float(loss_e)), (it, float(loss_g), float(loss_e))
+        for k, g in grads_e.items():
+            if not k.endswith("bias") or "final" in k:       # conv biases in front of a BatchNorm have ~0 gradient
+                a, b = (torch.view_as_real(t) if t.is_complex() else t for t in (grads_g[k], g))
+                if b.numel() == 1:        # the temperature gradient is a small difference of large sums
+                    assert abs(float(a) - float(b)) <= 0.15 * abs(float(b)) + 5e-3, (it, k, float(a), float(b))
+                else:
+                    assert H.rel_fro(a, b) <= 5e-2, (it, k, H.rel_fro(a, b))
+        for k, v in enc.named_buffers():
+            assert H.rel_fro(bufs_g[k].float(), v.float()) <= 1e-2, (it, k)      # late-layer batch means inherit the bf16 spread
