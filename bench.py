@@ -303,13 +303,30 @@ def run_megb200(args):
 
     # ---- the same K steps replayed from a CUDA graph (megb200.graph.GraphedTrainStep: the step recorded once through
     # the same C-ABI launches).  One cudaGraphLaunch per step, so the number does not depend on how fast this host can
-    # enqueue ~145 launches; it is the headline `value` when it is available (single rank), the eager loop above stays
+    # enqueue ~145 launches; it is the headline `value` when it is available, the eager loop above stays
     # in the line as `ms_per_step_eager` and is where the per-launch roofline events were taken.
     graph_ms, graph_note, eager_ms = None, None, ms
-    if world == 1 and not args.no_graph:
+    use_graph = not args.no_graph and (world == 1 or os.environ.get("MEGB200_BENCH_DP_GRAPH", "1") != "0")
+    if use_graph:
+        gstep, ok = None, 1
         try:
             from megb200.graph import GraphedTrainStep
             gstep = GraphedTrainStep(enc, lossf, Xd, Yd, subj_h, drop_center=enc.drop_center)
+        except Exception as e:          # capture is an optimisation of the launch path, never a different compute path
+            graph_note, ok = f"capture failed: {type(e).__name__}: {e}"[:200], 0
+            if os.environ.get("MEGB200_GRAPH_DEBUG"):
+                import traceback
+                traceback.print_exc()
+        if world > 1:                   # all ranks replay or none does: the recording contains collectives
+            flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ok = int(flag.item())
+            if not ok and graph_note is None:
+                graph_note = "capture failed on another rank"
+        if not ok:
+            gstep = None
+    if use_graph and gstep is not None:
+        try:
             for _ in range(3):
                 gstep()
             barrier()
@@ -319,17 +336,19 @@ def run_megb200(args):
                 gloss = gstep()
             q1.record()
             barrier()
-            graph_ms = q0.elapsed_time(q1) / args.steps
+            graph_ms = max_over_ranks(q0.elapsed_time(q1) / args.steps)
             gl = float(gloss)
             if not math.isfinite(gl) or abs(gl - loss_value) > 0.05 * abs(loss_value):
                 graph_note, graph_ms = f"graph loss {gl} disagrees with eager {loss_value}", None
             else:
                 launches = gstep.launches_per_step
-        except Exception as e:          # capture is an optimisation of the launch path, never a different compute path
-            graph_note = f"capture failed: {type(e).__name__}: {e}"[:200]
-            if os.environ.get("MEGB200_GRAPH_DEBUG"):
-                import traceback
-                traceback.print_exc()
+        except Exception as e:
+            graph_note, graph_ms = f"replay failed: {type(e).__name__}: {e}"[:200], None
+        if world > 1:                   # one verdict for all ranks
+            flag = torch.tensor([1 if graph_ms is not None else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                graph_ms = None
     if graph_ms is not None:
         ms = graph_ms
 
@@ -355,7 +374,9 @@ def run_megb200(args):
     PRIME = 2
     fill = {}
 
-    def e2e_time(lag):
+    gstep_ok = graph_ms is not None
+
+    def e2e_time(lag, fn=None):
         # ONE continuous run of PRIME + K + PRIME steps; the K steps in the middle are timed, so the window is the
         # pipeline's steady state and holds K steps, K batch copies (of the batches two ahead) and K loss reads.
         # lag = 0: `loss.item()` after every step, the reference's loop (train.py:208); lag = 1: the same read
@@ -370,7 +391,7 @@ def run_megb200(args):
             if i == PRIME:
                 g0.record()
                 t0 = time.perf_counter()
-            v = reader.push(step(X, Y, subj))            # device -> host read of the loss, every step
+            v = reader.push((fn or step)(X, Y, subj))    # device -> host read of the loss, every step
             if v is not None:
                 got.append(v)
             if i == PRIME + args.steps - 1:
@@ -387,6 +408,18 @@ def run_megb200(args):
     sync_runs = [e2e_time(0) for _ in range(3)]
     pipe_runs = [e2e_time(1) for _ in range(3)]
     e2e_sync_ms, e2e_ms = statistics.median(sync_runs), statistics.median(pipe_runs)
+    e2e_eager_ms, e2e_path, graph_runs = e2e_ms, "eager", None
+    if gstep_ok:
+        # same loop with the step replayed from the CUDA graph: the prefetched device batch is copied into the graph's
+        # static inputs (device -> device, inside the timed window), then one cudaGraphLaunch
+        try:
+            e2e_time(1, gstep)
+            graph_runs = [e2e_time(1, gstep) for _ in range(3)]
+            gsync = statistics.median([e2e_time(0, gstep) for _ in range(3)])
+            if statistics.median(graph_runs) < e2e_ms:
+                e2e_ms, e2e_sync_ms, e2e_path = statistics.median(graph_runs), min(gsync, e2e_sync_ms), "cuda_graph"
+        except Exception as e:
+            graph_note = f"graph e2e failed: {type(e).__name__}: {e}"[:200]
     # the H2D copy of one batch on its own (nothing else running): the floor PCIe sets for the end-to-end step
     barrier()
     c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -401,7 +434,8 @@ def run_megb200(args):
     e2e = {"value": B * world / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
            "ms_per_step": e2e_ms, "loss_read": "every step, pipelined one step behind (AsyncScalarReader)",
            "window": "K steps in the steady state of one continuous run (2 priming steps before, 2 after)",
-           "ms_per_step_sync_read": e2e_sync_ms, "runs_ms": pipe_runs, "runs_ms_sync_read": sync_runs,
+           "ms_per_step_sync_read": e2e_sync_ms, "launch_path": e2e_path, "ms_per_step_eager": e2e_eager_ms,
+           "runs_ms_graph": graph_runs, "runs_ms": pipe_runs, "runs_ms_sync_read": sync_runs,
            "ms_per_step_whole_run_incl_fill": fill.get(1), "h2d_alone_ms": h2d_alone_ms, "h2d_alone_GBps": h2d / (h2d_alone_ms * 1e-3) / 1e9}
 
     flops_step = B * synth.encoder_flops_per_sample(cfg) + synth.clip_flops(cfg, B, B * world)
@@ -426,7 +460,21 @@ def run_megb200(args):
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
+        # Teardown order matters: a CUDA graph that holds NCCL kernels must be destroyed BEFORE the communicator
+        # (destroy_process_group otherwise waits forever on it -- measured: the job printed its line and then hung).
+        barrier()
+        gstep = None          # noqa: F841  (drops the recording)
+        prefetcher = None     # noqa: F841
+        gc.enable()
+        gc.collect()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        backstop = threading.Timer(20.0, lambda: os._exit(0))      # never let teardown outlive the measurement
+        backstop.daemon = True
+        backstop.start()
         dist.destroy_process_group()
+        backstop.cancel()
     return 0
 
 

@@ -14,8 +14,11 @@ What makes the step capturable (nothing in it may depend on host values that cha
   * tensor maps, packed-weight tables and shared-memory attributes are created by the warm-up steps, so the captured
     region contains kernel launches and memsets only.
 
-Data parallel: the step is captured per rank WITHOUT the collectives (use the eager path when
-``megb200.parallel.context()`` is set).
+Data parallel (``megb200.parallel.init()`` done): the recording includes the hot path's collectives -- the all-gather
+of the packed targets on a forked side stream (it overlaps the encoder forward inside the graph), the two all-reduces
+of the softmax partials and the SUM all-reduce of the gradients -- captured in ``thread_local`` error mode because the
+NCCL watchdog thread polls events while the stream captures.  Every rank must build the step at the same point of the
+program (the warm-up steps run real collectives).
 """
 from __future__ import annotations
 
@@ -33,8 +36,7 @@ __all__ = ["GraphedTrainStep"]
 
 class GraphedTrainStep:
     def __init__(self, encoder, loss_fn, X, Y, subject_idxs, drop_center: Optional[int] = None, warmup: int = 3):
-        if parallel.context() is not None:
-            raise RuntimeError("GraphedTrainStep captures a single-rank step; use the eager modules in data parallel")
+        self.dist = parallel.context()
         self.enc, self.lossf = encoder, loss_fn
         dev = next(encoder.parameters()).device
         if dev.type != "cuda":
@@ -49,6 +51,7 @@ class GraphedTrainStep:
         self._one = torch.ones(1, dtype=torch.float32, device=dev)
         self.params = [p for p in list(encoder.parameters()) + list(loss_fn.parameters()) if p.requires_grad]
         self._user_center = encoder.drop_center
+        self._side = torch.cuda.Stream(device=dev) if self.dist is not None else None
         self.load(X, Y, subject_idxs, drop_center)
 
         # warm-up on a side stream (torch's capture recipe); module buffers (BatchNorm running statistics, counters) are
@@ -69,7 +72,8 @@ class GraphedTrainStep:
             self.graph = torch.cuda.CUDAGraph()
             undo = self._arm_capture_probe() if os.environ.get("MEGB200_GRAPH_DEBUG") else None
             try:
-                with torch.cuda.graph(self.graph):
+                mode = {} if self.dist is None else {"capture_error_mode": "thread_local"}
+                with torch.cuda.graph(self.graph, **mode):
                     self.loss = self._step_eager()
             finally:
                 if undo:
@@ -141,11 +145,21 @@ class GraphedTrainStep:
             params = enc._param_list()
             P = enc._param_dict(params)
             eng = enc._engine()
+            ceng = lossf._engine(eng.ops.act_dtype)
+            prepared = None
+            if self.dist is not None:
+                # fork: pack + all-gather the targets while the encoder forward runs (joined before the logits)
+                cur = torch.cuda.current_stream(self.dev)
+                self._side.wait_stream(cur)
+                with torch.cuda.stream(self._side):
+                    prepared = ceng.prepare_targets(self.Y, self.dist)
             Zi, saved = eng.forward(P, self.X, self.subj, mask, enc.training)
             Fs, Fo = Zi.shape[2], enc.F
             Zl = Zi if Fs == Fo else Zi[:, :, :Fo].contiguous()
-            ceng = lossf._engine(Zl.dtype)
-            loss, _, csaved = ceng.forward(self.Y, Zl, lossf.temp.detach(), lossf.reduction, None, False)
+            if self.dist is not None:
+                torch.cuda.current_stream(self.dev).wait_stream(self._side)
+            loss, _, csaved = ceng.forward(self.Y, Zl, lossf.temp.detach(), lossf.reduction, self.dist, False,
+                                           prepared=prepared)
             dZ, dtemp = ceng.backward(csaved, self._one)
             if Fs != Fo:
                 dZ = torch.nn.functional.pad(dZ, (0, Fs - Fo))
@@ -153,6 +167,8 @@ class GraphedTrainStep:
             for p, g in zip(params, enc._grad_list(G, None)):
                 p.grad = g if g.shape == p.shape else g.reshape(p.shape)
             lossf.temp.grad = dtemp.reshape(lossf.temp.shape)
+            if self.dist is not None:
+                parallel.allreduce_grads(self.params)           # part of the recording: replay returns summed gradients
         return loss.detach()
 
     def load(self, X, Y, subject_idxs, drop_center: Optional[int] = None):
