@@ -277,7 +277,7 @@ def run_megb200(args):
     peaks = measured_peaks()
     roofline = None
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1_tapgemm2_ncu.json")
+    tpath = os.path.join(ROOT, "profiles", "r1_tapgemm2h_ncu.json")
     if os.path.exists(tpath):
         try:
             ls = [e for e in json.load(open(tpath))["launches"] if "dram_read_bytes" in e]
@@ -288,10 +288,10 @@ def run_megb200(args):
     if "tapgemm" in kern and kern["tapgemm"][1] > 0:
         fl, tms, n = kern["tapgemm"]
         ach = fl / (tms * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "kernel": "tc_tapgemm2_kernel + tc_tapgemm_kernel (conv fwd + dgrad, 1x1 heads, grouped subject GEMM)",
+        roofline = {"bound": "tensor", "kernel": "tc_tapgemm2h_kernel (k=3 convs fwd + dgrad: 29 of 35 launches) + tc_tapgemm2_kernel (1x1 heads) + tc_tapgemm_kernel (grouped subject GEMM, ragged N)",
                     "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                     "frac": ach / peaks["bf16_sustained"], "traffic": traffic,
-                    "traffic_source": "profiles/r1_tapgemm2_ncu.json: mean dram read+write bytes per captured launch "
+                    "traffic_source": "profiles/r1_tapgemm2h_ncu.json: mean dram read+write bytes per captured launch "
                                       "(ncu --set full, config 2)" if traffic else None,
                     "peak_source": peaks["source"] + " sustained",
                     "launches_per_step": n // args.steps, "avg_launch_ms": tms / n,
