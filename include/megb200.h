@@ -194,6 +194,13 @@ int megb200_clip_dz(const void* coef, int ldc, const void* Yp, const void* Z, co
 int megb200_retrieval_rank(const float* raw, const float* zsq, int32_t* rank, int By, int Bz, int off, void* stream);
 
 /* ---------------------------------------------------------------------------------------------- misc */
+/* "Next" row N4: torch.optim.Adam (train.py:160-162: Adam over the encoder's and the loss's parameters) for all tensors in one
+ * launch.  table (device): n rows of 6 int64 = {param, grad, exp_avg, exp_avg_sq pointers (f32; a complex tensor counts as
+ * 2*numel floats), numel, pointer to the tensor's int64 step counter (device; read for the bias corrections 1-beta^(count+1),
+ * then incremented)}.  Per-tensor counters because torch does not advance a parameter whose grad is None.  weight_decay is
+ * the L2 form (added to the gradient), amsgrad is not supported -- the reference uses neither. */
+int megb200_adam_multi(const long long* table, int n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                       void* stream);
 /* d[i] = s[i] cast between f32 and the activation dtype (n elements) */
 int megb200_cast(const void* src, void* dst, long long n, int src_dtype, int dst_dtype, void* stream);
 #ifdef __cplusplus

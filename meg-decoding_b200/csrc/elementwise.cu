@@ -4,6 +4,8 @@
 // channel per CTA.  Bound: HBM bandwidth; algorithmic bytes are stated per op in DESIGN.md.
 #include "common.cuh"
 
+#include <math.h>
+
 namespace megb200 {
 
 static inline int ew_grid(long long work_items, int threads) {
@@ -1165,6 +1167,87 @@ int megb200_rowsumsq(const void* Z, float* sq, int B, long long D, int dtype, vo
   dim3 grid(chunks, B);
   DISPATCH_DTYPE(dtype, rowsumsq_kernel<DT><<<grid, 256, 0, (cudaStream_t)stream>>>((const DT*)Z, sq, D, chunks);
                  MEGB_LAUNCH_OK(); return 0;)
+}
+
+// ------------------------------------------------------------------------------------------ multi-tensor Adam ("next" row N4)
+// torch.optim.Adam (train.py:160-162) over all parameter tensors in ONE launch (+ a one-block counter bump).  table: n rows
+// of 6 int64 = {param, grad, exp_avg, exp_avg_sq (device pointers, f32; complex tensors as 2*numel floats), numel,
+// pointer to the tensor's own int64 step counter}.  torch keeps the step count PER PARAMETER (a tensor whose grad was
+// None -- a subject absent from the batch -- does not advance), so the bias corrections are formed on the device from
+// each row's counter.  blockIdx.y = tensor, the blocks of a row stride over its elements (float4 when the four pointers
+// are 16-byte aligned).  HBM-bound: 7 floats of traffic per element (read p, g, m, v; write p, m, v).
+struct AdamHyper {
+  float lr, beta1, beta2, eps, weight_decay;
+};
+
+__device__ __forceinline__ void adam_update(float& p, float g, float& m, float& v, const AdamHyper& h, float step_size,
+                                            float inv_sqrt_bc2) {
+  g = fmaf(h.weight_decay, p, g);                           // L2 form (torch.optim.Adam, not AdamW)
+  m = fmaf(1.f - h.beta1, g - m, m);                        // exp_avg.lerp_(grad, 1 - beta1), as torch
+  v = fmaf(h.beta2, v, (1.f - h.beta2) * g * g);
+  const float denom = sqrtf(v) * inv_sqrt_bc2 + h.eps;
+  p -= step_size * (m / denom);
+}
+
+__global__ void __launch_bounds__(256) adam_multi_kernel(const long long* __restrict__ table, const AdamHyper h) {
+  const long long* e = table + 6 * blockIdx.y;
+  float* p = reinterpret_cast<float*>(e[0]);
+  const float* g = reinterpret_cast<const float*>(e[1]);
+  float* m = reinterpret_cast<float*>(e[2]);
+  float* v = reinterpret_cast<float*>(e[3]);
+  const long long n = e[4];
+  const double t = (double)(*reinterpret_cast<const long long*>(e[5]) + 1);      // this update's 1-based step
+  const float step_size = (float)((double)h.lr / (1.0 - pow((double)h.beta1, t)));
+  const float inv_sqrt_bc2 = (float)(1.0 / sqrt(1.0 - pow((double)h.beta2, t)));
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long nthr = (long long)gridDim.x * blockDim.x;
+  const bool vec = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0;
+  long long done = 0;
+  if (vec) {
+    const long long n4 = n >> 2;
+#pragma unroll 2
+    for (long long i = tid; i < n4; i += nthr) {
+      float4 pp = reinterpret_cast<float4*>(p)[i];
+      const float4 gg = reinterpret_cast<const float4*>(g)[i];
+      float4 mm = reinterpret_cast<float4*>(m)[i];
+      float4 vv = reinterpret_cast<float4*>(v)[i];
+      adam_update(pp.x, gg.x, mm.x, vv.x, h, step_size, inv_sqrt_bc2);
+      adam_update(pp.y, gg.y, mm.y, vv.y, h, step_size, inv_sqrt_bc2);
+      adam_update(pp.z, gg.z, mm.z, vv.z, h, step_size, inv_sqrt_bc2);
+      adam_update(pp.w, gg.w, mm.w, vv.w, h, step_size, inv_sqrt_bc2);
+      reinterpret_cast<float4*>(p)[i] = pp;
+      reinterpret_cast<float4*>(m)[i] = mm;
+      reinterpret_cast<float4*>(v)[i] = vv;
+    }
+    done = n4 << 2;
+  }
+  for (long long i = done + tid; i < n; i += nthr) {
+    float pp = p[i], mm = m[i], vv = v[i];
+    adam_update(pp, g[i], mm, vv, h, step_size, inv_sqrt_bc2);
+    p[i] = pp;
+    m[i] = mm;
+    v[i] = vv;
+  }
+}
+
+// after the update: advance the counters of the tensors that took part (separate launch = no race with their readers)
+__global__ void adam_bump_kernel(const long long* __restrict__ table, int n) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n) *reinterpret_cast<long long*>(table[6 * r + 5]) += 1;
+}
+
+int megb200_adam_multi(const long long* table, int n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                       void* stream) {
+  MEGB_CHECK_ARG(table && n > 0 && n <= 65535, "adam_multi: bad arguments");
+  MEGB_CHECK_ARG(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f, "adam_multi: bad hyper-parameters");
+  AdamHyper h;
+  h.lr = lr; h.beta1 = beta1; h.beta2 = beta2; h.eps = eps; h.weight_decay = weight_decay;
+  dim3 grid(32, n);        // largest tensor of the path: 655 k elements = 20 float4 per thread
+  adam_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(table, h);
+  MEGB_LAUNCH_OK();
+  adam_bump_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(table, n);
+  MEGB_LAUNCH_OK();
+  return 0;
 }
 
 int megb200_cast(const void* src, void* dst, long long n, int src_dtype, int dst_dtype, void* stream) {
