@@ -194,6 +194,13 @@ int megb200_clip_dz(const void* coef, int ldc, const void* Yp, const void* Z, co
 int megb200_retrieval_rank(const float* raw, const float* zsq, int32_t* rank, int By, int Bz, int off, void* stream);
 
 /* ---------------------------------------------------------------------------------------------- misc */
+/* "Next" row N2: the batch collator of the reference (Gwilliams2022Collator.forward, gwilliams2022.py:653-662) on the device.
+ * X, Out: f32 [rows][T] with rows = B*C (Out may alias X).  Per row: subtract the mean of the first baseline_len samples
+ * (baseline_correction_single, preproc_utils.py:128-142), then sklearn RobustScaler over time -- (x - median) / (q75 - q25),
+ * numpy linear-interpolated quantiles, a scale below 10 eps becomes 1 (scaleAndClamp, preproc_utils.py:69-90) -- then, if
+ * clamp != 0, clamp to [-clamp_lim, clamp_lim].  1 <= baseline_len <= T <= 4096. */
+int megb200_robust_scale(const float* X, float* Out, long long rows, int T, int baseline_len, float clamp_lim, int clamp,
+                         void* stream);
 /* "Next" row N4: torch.optim.Adam (train.py:160-162: Adam over the encoder's and the loss's parameters) for all tensors in one
  * launch.  table (device): n rows of 6 int64 = {param, grad, exp_avg, exp_avg_sq pointers (f32; a complex tensor counts as
  * 2*numel floats), numel, pointer to the tensor's int64 step counter (device; read for the bias corrections 1-beta^(count+1),

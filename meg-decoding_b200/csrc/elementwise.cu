@@ -1169,6 +1169,112 @@ int megb200_rowsumsq(const void* Z, float* sq, int B, long long D, int dtype, vo
                  MEGB_LAUNCH_OK(); return 0;)
 }
 
+// ------------------------------------------------------------------------------------------ collator ("next" row N2)
+// Gwilliams2022Collator (gwilliams2022.py:653-662) on the device: per (sample, channel) row of T time steps
+//   x <- x - mean(x[:L])                                  baseline_correction_single, preproc_utils.py:128-142
+//   x <- (x - median) / (q75 - q25), IQR < 10 eps -> 1    sklearn RobustScaler via scaleAndClamp, preproc_utils.py:69-90
+//   x <- clamp(x, -lim, lim)
+// One CTA per row: the row is sorted in shared memory by a bitonic network over P = next power of two >= T slots (+inf
+// padding), the three order statistics are read off with numpy's linear interpolation (virtual index q (T-1), lerp in
+// double), and the row is rewritten from the unsorted copy.  Integer/compare work on 1.4 KB rows; bound by the
+// barrier-separated network stages (45 for T = 360), several CTAs per SM.
+__global__ void robust_scale_kernel(const float* __restrict__ X, float* __restrict__ Out, long long rows, int T, int P,
+                                    int L, float lim, int clamp) {
+  extern __shared__ float rs_buf[];      // [P] sort buffer, [T] unsorted baseline-corrected copy
+  float* srt = rs_buf;
+  float* raw = rs_buf + P;
+  __shared__ float red[32];
+  __shared__ float s_med;
+  __shared__ double s_q[2];
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const float* x = X + row * T;
+    float part = 0.f;
+    for (int i = tid; i < T; i += nthr) {
+      const float v = x[i];
+      raw[i] = v;
+      if (i < L) part += v;
+    }
+    part = warp_sum(part);
+    if ((tid & 31) == 0) red[tid >> 5] = part;
+    __syncthreads();
+    float base = 0.f;
+    for (int w = 0; w < (nthr + 31) / 32; ++w) base += red[w];
+    base /= (float)L;
+    for (int i = tid; i < P; i += nthr) {
+      float v = INFINITY;
+      if (i < T) {
+        v = raw[i] - base;
+        raw[i] = v;
+      }
+      srt[i] = v;
+    }
+    __syncthreads();
+    for (int k = 2; k <= P; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int c = tid; c < (P >> 1); c += nthr) {
+          const int i = ((c & ~(j - 1)) << 1) | (c & (j - 1));
+          const int ip = i | j;
+          const float a = srt[i], b = srt[ip];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) {
+            srt[i] = b;
+            srt[ip] = a;
+          }
+        }
+        __syncthreads();
+      }
+    }
+    if (tid < 3) {
+      if (tid == 1) {
+        // np.nanmedian of an f32 column: middle element, or the f32 mean of the middle pair -> center_ stays f32
+        s_med = (T & 1) ? srt[(T - 1) >> 1] : __fmul_rn(__fadd_rn(srt[(T >> 1) - 1], srt[T >> 1]), 0.5f);
+      } else {
+        // np.nanpercentile, method "linear": virtual index q*(T-1); numpy returns f64 for f32 input (its _lerp runs in
+        // double: a + (b-a)*g, or b - (b-a)*(1-g) when g >= 0.5), so scale_ = q75 - q25 is a double
+        const double vi = (tid == 0 ? 0.25 : 0.75) * (double)(T - 1);
+        int lo = (int)floor(vi);
+        if (lo > T - 1) lo = T - 1;
+        const int hi = lo + 1 < T ? lo + 1 : T - 1;
+        const double g = vi - (double)lo;
+        const double a = (double)srt[lo], b = (double)srt[hi];
+        const double d = b - a;
+        s_q[tid >> 1] = g >= 0.5 ? b - d * (1.0 - g) : a + d * g;
+      }
+    }
+    __syncthreads();
+    const float med = s_med;
+    double scale = s_q[1] - s_q[0];
+    if (scale < 10.0 * 2.220446049250313e-16) scale = 1.0;       // sklearn _handle_zeros_in_scale (eps of the f64 scale)
+    float* o = Out + row * T;
+    for (int i = tid; i < T; i += nthr) {
+      // transform(): X -= center_ (f32), X /= scale_ (f32 array / f64 scale, rounded back to f32)
+      float v = (float)((double)(raw[i] - med) / scale);
+      if (clamp) v = fminf(fmaxf(v, -lim), lim);
+      o[i] = v;
+    }
+    __syncthreads();
+  }
+}
+
+int megb200_robust_scale(const float* X, float* Out, long long rows, int T, int baseline_len, float clamp_lim, int clamp,
+                         void* stream) {
+  MEGB_CHECK_ARG(X && Out && rows > 0 && T >= 1 && T <= 4096, "robust_scale: bad arguments (1 <= T <= 4096)");
+  MEGB_CHECK_ARG(baseline_len >= 1 && baseline_len <= T, "robust_scale: baseline_len must be in [1, T]");
+  int P = 2;
+  while (P < T) P <<= 1;
+  int threads = P / 2;
+  if (threads < 32) threads = 32;
+  if (threads > 512) threads = 512;
+  const size_t smem = (size_t)(P + T) * sizeof(float);
+  long long blocks = rows;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  robust_scale_kernel<<<(int)blocks, threads, smem, (cudaStream_t)stream>>>(X, Out, rows, T, P, baseline_len, clamp_lim, clamp);
+  MEGB_LAUNCH_OK();
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------ multi-tensor Adam ("next" row N4)
 // torch.optim.Adam (train.py:160-162) over all parameter tensors in ONE launch (+ a one-block counter bump).  table: n rows
 // of 6 int64 = {param, grad, exp_avg, exp_avg_sq (device pointers, f32; complex tensors as 2*numel floats), numel,

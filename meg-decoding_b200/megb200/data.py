@@ -91,6 +91,42 @@ class DevicePrefetcher:
         return tuple(out)
 
 
+def robust_scale_(X: torch.Tensor, baseline_len: int, clamp_lim: float = 20.0, clamp: bool = True) -> torch.Tensor:
+    """In-place device form of the reference collator's brain-data transform ("next" row N2): baseline correction,
+    per-(sample, channel) RobustScaler over time, clamp.  X: contiguous f32 CUDA tensor [..., T]."""
+    from . import lib
+    if not (X.is_cuda and X.dtype == torch.float32 and X.is_contiguous()):
+        raise RuntimeError("robust_scale_: contiguous f32 CUDA tensor expected")
+    T = X.shape[-1]
+    with torch.cuda.device(X.device):
+        lib.call("megb200_robust_scale", X.data_ptr(), X.data_ptr(), X.numel() // T, T, int(baseline_len), float(clamp_lim),
+                 int(bool(clamp)), torch._C._cuda_getCurrentRawStream(X.device.index))
+    return X
+
+
+class DeviceCollator:
+    """``Gwilliams2022Collator`` (gwilliams2022.py:639-662) with the arithmetic on the GPU: same constructor argument
+    (``args.preprocs``: brain_resample_rate, baseline_len_sec, clamp, clamp_lim) and the same ``batch -> (X, Y,
+    subject_idx)`` contract, but X comes back resident on ``device`` (f32 [B, C, T]) — use it as the DataLoader's
+    ``collate_fn`` with ``num_workers=0`` or call it on the collated CPU batch in the training loop.  The reference
+    spends one sklearn ``RobustScaler`` fit per sample on CPU workers here."""
+
+    def __init__(self, args, device="cuda"):
+        pre = args.preprocs
+        self.baseline_len_samp = int(pre["brain_resample_rate"] * pre["baseline_len_sec"])
+        self.clamp, self.clamp_lim = bool(pre["clamp"]), float(pre["clamp_lim"])
+        self.device = torch.device(device)
+
+    def __call__(self, batch):
+        X = torch.stack([item[0] for item in batch]).to(torch.float32)
+        Y = torch.stack([item[1] for item in batch])
+        subject_idx = torch.IntTensor([item[2] for item in batch])
+        X = X.pin_memory().to(self.device, non_blocking=True) if not X.is_cuda else X.contiguous()
+        return robust_scale_(X, self.baseline_len_samp, self.clamp_lim, self.clamp), Y, subject_idx
+
+    forward = __call__
+
+
 class AsyncScalarReader:
     """Pipelined device -> host read of one scalar per step (the loss the reference logs with ``loss.item()``,
     train.py:208).  ``push(t)`` enqueues a copy of ``t`` into a pinned slot behind the step's kernels and returns the value
