@@ -301,7 +301,8 @@ def test_batchnorm_gelu_chain(dtype, u_f32, shape):
             _close(H2, Hr, dtype, "bn_gelu_train H")
             s3 = torch.zeros(2, C, device=DEV)
             ops.bn_gelu_bwd_reduce(dHd, Ud, st["scale"], st["shift"], st["mean"], st["rstd"], None, s3, C)
-            assert torch.equal(s3, s2), "the sums must not depend on whether dY is written"
+            # same arithmetic either way; the per-channel atomics commute only up to f32 rounding
+            _close(s3, s2.cpu(), torch.float32, "bn_gelu_bwd_reduce sums without dY", atol_scale=20)
             dU2, dU2r = ops.empty(B, T, pad8(C), device=DEV), ref.empty(B, T, pad8(C), device="cpu")
             db2 = torch.zeros(C, device=DEV)
             ops.bn_gelu_bwd_apply(dHd, Ud, st["scale"], st["shift"], gamma.to(DEV), st["mean"], st["rstd"], s2, n, dU2, C, db2)
