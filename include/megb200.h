@@ -194,6 +194,17 @@ int megb200_clip_dz(const void* coef, int ldc, const void* Yp, const void* Z, co
 int megb200_retrieval_rank(const float* raw, const float* zsq, int32_t* rank, int By, int Bz, int off, void* stream);
 
 /* ---------------------------------------------------------------------------------------------- misc */
+/* "Next" row N3: Gwilliams2022DatasetBase.__getitem__ / segment_to_task (gwilliams2022.py:130-152) for a batch, recordings
+ * resident in HBM.  n_rec recordings (session keys) x n_tasks tasks; slot = rec*n_tasks + task.
+ *   rec_base[slot]  device pointer of the f32 [C][rec_len[slot]] recording;  onsets[onset_off[slot] + k] = onset (samples) of
+ *   the k-th segment of that task in that recording;  nseg_accum = cumsum(num_segments_foreach_task) (int64 [n_tasks]);
+ *   seg[b] = speech-segment id, rec[b] = recording drawn for sample b (the reference draws it with np.random.choice, :134).
+ * out: f32 [B][C][T]; index_out: int64 [B][3] = {task, i_in_task, onset} (bit-exact with the reference's integers);
+ * *error (device int, OR-ed): 1 = segment id / recording index out of range, 2 = window outside its recording (zero-filled). */
+int megb200_gather_segments(const long long* rec_base, const long long* rec_len, const long long* onset_off,
+                            const long long* onsets, const long long* nseg_accum, int n_rec, int n_tasks,
+                            const long long* seg, const int* rec, int B, int C, int T, float* out, long long* index_out,
+                            int* error, void* stream);
 /* "Next" row N2: the batch collator of the reference (Gwilliams2022Collator.forward, gwilliams2022.py:653-662) on the device.
  * X, Out: f32 [rows][T] with rows = B*C (Out may alias X).  Per row: subtract the mean of the first baseline_len samples
  * (baseline_correction_single, preproc_utils.py:128-142), then sklearn RobustScaler over time -- (x - median) / (q75 - q25),

@@ -1169,6 +1169,77 @@ int megb200_rowsumsq(const void* Z, float* sq, int B, long long D, int dtype, vo
                  MEGB_LAUNCH_OK(); return 0;)
 }
 
+// ------------------------------------------------------------------------------------------ segment gather ("next" row N3)
+// Gwilliams2022DatasetBase.__getitem__ / segment_to_task (gwilliams2022.py:130-152) for a whole batch: recordings stay
+// resident in HBM, a batch is B windows of (C, T) gathered by integer-exact index arithmetic.
+//   task      = searchsorted(cumsum(num_segments_foreach_task), i + 1)   (left)
+//   i_in_task = i - cumsum[task - 1]
+//   onset     = onsets[onset_off[rec * n_tasks + task] + i_in_task]
+//   out[b]    = recording(rec, task)[:, onset : onset + T]
+// index_out[b] = {task, i_in_task, onset}; *error is set when a segment id or a window falls outside its table /
+// recording (the reference would raise or return a short slice): such windows are zero-filled.
+__global__ void segment_index_kernel(const long long* __restrict__ nseg_accum, int n_tasks,
+                                     const long long* __restrict__ onset_off, const long long* __restrict__ onsets,
+                                     const long long* __restrict__ rec_len, const long long* __restrict__ seg,
+                                     const int* __restrict__ rec, int n_rec, int B, int T, long long* __restrict__ index_out,
+                                     int* __restrict__ error) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const long long i = seg[b];
+  const int r = rec[b];
+  long long task = -1, iit = -1, onset = -1;
+  if (i >= 0 && i < nseg_accum[n_tasks - 1] && r >= 0 && r < n_rec) {
+    int t = 0;
+    while (t < n_tasks && nseg_accum[t] < i + 1) ++t;             // np.searchsorted(accum, i + 1), side = "left"
+    task = t;
+    iit = i - (t > 0 ? nseg_accum[t - 1] : 0);
+    const long long slot = (long long)r * n_tasks + t;
+    onset = onsets[onset_off[slot] + iit];
+    if (onset < 0 || onset + T > rec_len[slot]) {
+      atomicOr(error, 2);
+      onset = -1;
+    }
+  } else {
+    atomicOr(error, 1);
+  }
+  index_out[3 * b + 0] = task;
+  index_out[3 * b + 1] = iit;
+  index_out[3 * b + 2] = onset;
+}
+
+__global__ void segment_copy_kernel(const long long* __restrict__ rec_base, const long long* __restrict__ rec_len,
+                                    const int* __restrict__ rec, int n_tasks, const long long* __restrict__ index,
+                                    int C, int T, float* __restrict__ out) {
+  // blockIdx.x = (b, c) row; threads stride over the T samples of the window (contiguous in both source and output)
+  const long long row = blockIdx.x;
+  const int b = (int)(row / C), c = (int)(row % C);
+  const long long task = index[3 * b], onset = index[3 * b + 2];
+  float* o = out + row * T;
+  if (task < 0 || onset < 0) {
+    for (int t = threadIdx.x; t < T; t += blockDim.x) o[t] = 0.f;
+    return;
+  }
+  const long long slot = (long long)rec[b] * n_tasks + task;
+  const float* src = reinterpret_cast<const float*>(rec_base[slot]) + (long long)c * rec_len[slot] + onset;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) o[t] = src[t];
+}
+
+int megb200_gather_segments(const long long* rec_base, const long long* rec_len, const long long* onset_off,
+                            const long long* onsets, const long long* nseg_accum, int n_rec, int n_tasks,
+                            const long long* seg, const int* rec, int B, int C, int T, float* out, long long* index_out,
+                            int* error, void* stream) {
+  MEGB_CHECK_ARG(rec_base && rec_len && onset_off && onsets && nseg_accum && seg && rec && out && index_out && error,
+                 "gather_segments: null argument");
+  MEGB_CHECK_ARG(n_rec > 0 && n_tasks > 0 && B > 0 && C > 0 && T > 0, "gather_segments: bad sizes");
+  cudaStream_t st = (cudaStream_t)stream;
+  segment_index_kernel<<<(B + 127) / 128, 128, 0, st>>>(nseg_accum, n_tasks, onset_off, onsets, rec_len, seg, rec, n_rec, B, T,
+                                                      index_out, error);
+  MEGB_LAUNCH_OK();
+  segment_copy_kernel<<<(unsigned)((long long)B * C), 128, 0, st>>>(rec_base, rec_len, rec, n_tasks, index_out, C, T, out);
+  MEGB_LAUNCH_OK();
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------ collator ("next" row N2)
 // Gwilliams2022Collator (gwilliams2022.py:653-662) on the device: per (sample, channel) row of T time steps
 //   x <- x - mean(x[:L])                                  baseline_correction_single, preproc_utils.py:128-142

@@ -127,6 +127,74 @@ class DeviceCollator:
     forward = __call__
 
 
+class DeviceSegmentStore:
+    """The Gwilliams datasets' ``__getitem__`` (gwilliams2022.py:130-143) for whole batches with the recordings resident
+    in HBM ("next" row N3): ``recordings[key][f"task{t}"]`` = f32 (C, length), ``meg_onsets[key][f"task{t}"]`` = integer
+    onsets, ``num_segments_foreach_task`` and ``valid_subjects`` exactly as the reference dataset object holds them.
+
+    ``gather(seg_ids, rng=np.random)`` draws one recording key per sample like the reference
+    (``np.random.choice(list(self.X.keys()))``) — or takes explicit ``rec`` indices — and returns
+    ``(X [B, C, T] on the device, subject_idx int32 [B] on the host, index int64 [B, 3] = task / i_in_task / onset)``.
+    """
+
+    def __init__(self, recordings, meg_onsets, num_segments_foreach_task, valid_subjects, seq_len_samp, device="cuda"):
+        import numpy as np
+        self.device = torch.device(device)
+        self.keys = list(recordings.keys())
+        self.n_tasks = len(num_segments_foreach_task)
+        self.T = int(seq_len_samp)
+        vs = np.asarray(valid_subjects)
+        self.subject_of_rec = np.array([int(np.where(vs == k.split("_")[0])[0][0]) for k in self.keys], dtype=np.int32)
+        self._rec = []                                   # keeps the device recordings alive
+        base, length, off, ons = [], [], [], []
+        self.C = None
+        for k in self.keys:
+            for t in range(self.n_tasks):
+                a = torch.as_tensor(np.ascontiguousarray(recordings[k][f"task{t}"]), dtype=torch.float32).to(self.device)
+                self.C = a.shape[0] if self.C is None else self.C
+                assert a.dim() == 2 and a.shape[0] == self.C, "all recordings must have the same channel count"
+                self._rec.append(a)
+                base.append(a.data_ptr())
+                length.append(a.shape[1])
+                o = np.asarray(meg_onsets[k][f"task{t}"], dtype=np.int64)
+                assert len(o) == int(num_segments_foreach_task[t]), "one onset per segment of the task"
+                off.append(sum(len(x) for x in ons))
+                ons.append(o)
+        i64 = dict(dtype=torch.int64, device=self.device)
+        self.rec_base, self.rec_len = torch.tensor(base, **i64), torch.tensor(length, **i64)
+        self.onset_off, self.onsets = torch.tensor(off, **i64), torch.as_tensor(np.concatenate(ons)).to(self.device)
+        self.nseg_accum = torch.as_tensor(np.cumsum(np.asarray(num_segments_foreach_task, dtype=np.int64))).to(self.device)
+        self.error = torch.zeros(1, dtype=torch.int32, device=self.device)
+
+    def gather(self, seg_ids, rec=None, rng=None, check: bool = True):
+        import numpy as np
+        from . import lib
+        seg = torch.as_tensor(seg_ids, dtype=torch.int64)
+        B = seg.numel()
+        if rec is None:
+            rng = rng if rng is not None else np.random
+            rec = np.array([self.keys.index(str(rng.choice(self.keys))) for _ in range(B)], dtype=np.int32)
+        rec = np.asarray(rec, dtype=np.int32)
+        out = torch.empty(B, self.C, self.T, dtype=torch.float32, device=self.device)
+        index = torch.empty(B, 3, dtype=torch.int64, device=self.device)
+        seg_d, rec_d = seg.to(self.device), torch.from_numpy(rec).to(self.device)
+        self.error.zero_()
+        with torch.cuda.device(self.device):
+            lib.call("megb200_gather_segments", self.rec_base.data_ptr(), self.rec_len.data_ptr(), self.onset_off.data_ptr(),
+                     self.onsets.data_ptr(), self.nseg_accum.data_ptr(), len(self.keys), self.n_tasks, seg_d.data_ptr(),
+                     rec_d.data_ptr(), B, self.C, self.T, out.data_ptr(), index.data_ptr(), self.error.data_ptr(),
+                     torch._C._cuda_getCurrentRawStream(self.device.index))
+        if check:
+            e = int(self.error.item())
+            if e & 1:
+                raise IndexError("segment id or recording index out of range")          # the reference raises IndexError too
+            if e & 2:
+                raise ValueError("a segment window runs past the end of its recording")  # torch.stack would fail downstream
+        valid = (rec >= 0) & (rec < len(self.keys))
+        subj = np.where(valid, self.subject_of_rec[np.clip(rec, 0, len(self.keys) - 1)], -1).astype(np.int32)
+        return out, torch.from_numpy(subj), index
+
+
 class AsyncScalarReader:
     """Pipelined device -> host read of one scalar per step (the loss the reference logs with ``loss.item()``,
     train.py:208).  ``push(t)`` enqueues a copy of ``t`` into a pinned slot behind the step's kernels and returns the value

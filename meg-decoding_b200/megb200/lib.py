@@ -49,6 +49,7 @@ SIGNATURES = {
     "megb200_clip_ce_finish": [_p, _p, _p, _p, _p, _p, _i, _f, _p, _p, _i, _p, _i, _i, _i, _p],
     "megb200_clip_dz": [_p, _i, _p, _p, _p, _p, _p, _i, _i, _ll, _i, _i, _p],
     "megb200_retrieval_rank": [_p, _p, _p, _i, _i, _i, _p],
+    "megb200_gather_segments": [_p, _p, _p, _p, _p, _i, _i, _p, _p, _i, _i, _i, _p, _p, _p, _p],
     "megb200_robust_scale": [_p, _p, _ll, _i, _i, _f, _i, _p],
     "megb200_adam_multi": [_p, _i, _f, _f, _f, _f, _f, _p],
     "megb200_cast": [_p, _p, _ll, _i, _i, _p],
