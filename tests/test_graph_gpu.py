@@ -23,9 +23,24 @@ def _eager(enc, lossf, X, Y, subj, center):
     return loss.detach().clone(), grads
 
 
+# precision -> (loss rel, gradient rel-Frobenius, buffer rel-Frobenius).  The f32 check mode is the tight comparison (only
+# f32 atomics reorder); in bf16 a flipped rounding moves whole activations on these 4-6 sample batches, so the bounds
+# there only have to catch structural errors (a stale mask or batch gives O(1) differences).
+TOL = {"fp32": (1e-4, 2e-3, 1e-4), "bf16": (1e-2, 0.15, 2e-2)}
+
+
+@pytest.fixture(autouse=True)
+def _restore_precision():
+    old = megb200.get_precision()
+    yield
+    megb200.set_precision(old)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
 @pytest.mark.parametrize("name", ["narrow", "tiny_static"])
-def test_graph_replay_equals_eager_step(name):
-    megb200.set_precision("bf16")
+def test_graph_replay_equals_eager_step(name, precision):
+    megb200.set_precision(precision)
+    tl, tg, tb = TOL[precision]
     cfg = synth.get_config(name)
     enc, lossf = H.make_modules(cfg, DEV)
     enc.train()
@@ -51,13 +66,14 @@ def test_graph_replay_equals_eager_step(name):
         loss_e, grads_e = _eager(enc, lossf, Xn.to(DEV), Yn.to(DEV), sn.to(DEV), center)
         enc.drop_center = None
         # run-to-run spread of the eager bf16 step itself is ~5e-4 on these tiny batches (atomic order -> bf16 roundings)
-        assert abs(float(loss_g) - float(loss_e)) <= 3e-3 * abs(float(loss_e)), (it, float(loss_g), float(loss_e))
+        assert abs(float(loss_g) - float(loss_e)) <= tl * abs(float(loss_e)), (it, float(loss_g), float(loss_e))
         for k, g in grads_e.items():
             if not k.endswith("bias") or "final" in k:       # conv biases in front of a BatchNorm have ~0 gradient
                 a, b = (torch.view_as_real(t) if t.is_complex() else t for t in (grads_g[k], g))
                 if b.numel() == 1:        # the temperature gradient is a small difference of large sums
-                    assert abs(float(a) - float(b)) <= 0.15 * abs(float(b)) + 5e-3, (it, k, float(a), float(b))
+                    assert abs(float(a) - float(b)) <= 2 * tg * abs(float(b)) + (5e-3 if precision == "bf16" else 1e-5), \
+                        (it, k, float(a), float(b))
                 else:
-                    assert H.rel_fro(a, b) <= 5e-2, (it, k, H.rel_fro(a, b))
+                    assert H.rel_fro(a, b) <= tg, (it, k, H.rel_fro(a, b))
         for k, v in enc.named_buffers():
-            assert H.rel_fro(bufs_g[k].float(), v.float()) <= 1e-2, (it, k)      # late-layer batch means inherit the bf16 spread
+            assert H.rel_fro(bufs_g[k].float(), v.float()) <= tb, (it, k)      # late-layer batch means inherit the bf16 spread
