@@ -173,6 +173,8 @@ __device__ __forceinline__ void tap_epilogue_tma(const TapGemmParams& p, const T
   const int iters = (groups + kHalves - 1) / kHalves;
   int cap_iters = (int)(stg_bytes / slice_bytes) / (per_group * kHalves);   // iterations whose slices fit at once
   if (cap_iters < 1) cap_iters = 1;
+  // an odd group count leaves the last iteration half empty: when every slice of the tile fits, it is ONE round
+  if ((uint32_t)(groups * per_group) * slice_bytes <= stg_bytes) cap_iters = iters;
   const long long row = (long long)b * p.T + t0 + rloc;
   const __nv_bfloat16* rrow = (p.Res != nullptr && row_valid && tile_valid) ? p.Res + row * p.Crs + n0 : nullptr;
   uint4 rnext[4];
@@ -1712,11 +1714,23 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
     // ---- CTA-pair persistent kernel
     const int half = p.NT / 2;
     const uint32_t stage2 = kTileM * 128 + half * 128;
+    // Staging area of the TMA-store epilogue: 64 KB, or the whole tile (one staging round per tile instead of two: the
+    // f32 and GELU epilogues of a 160-channel tile need 80 KB) when that costs no pipeline stage.  kSmemMax = the
+    // 227 KB a block may opt into.
+    constexpr uint32_t kSmemMax = 232448;
+    uint32_t want_stg = 0;
+    auto grow_staging = [&](uint32_t stage_bytes, uint32_t tables, int max_stages) {
+      const int now = pick_stages(stage_bytes, kSmemMax - 2048 - tables - p.stg_bytes, max_stages);
+      if (want_stg > p.stg_bytes && want_stg <= 96u * 1024 &&
+          pick_stages(stage_bytes, kSmemMax - 2048 - tables - want_stg, max_stages) == now)
+        p.stg_bytes = want_stg;
+      return pick_stages(stage_bytes, kSmemMax - 2048 - tables - p.stg_bytes, max_stages);
+    };
     if (p.tma_epi) {
       const uint32_t slice = epi == MEGB200_EPI_STORE_F32 ? 16384u : 8192u;
       const int per_group = glu ? 3 : (epi == MEGB200_EPI_GELU ? 2 : 1);
-      const uint32_t want = (uint32_t)((glu ? half : p.NT) / 32) * per_group * slice;
-      p.stg_bytes = want > 64u * 1024 ? 64u * 1024 : want;
+      want_stg = (uint32_t)((glu ? half : p.NT) / 32) * per_group * slice;
+      p.stg_bytes = want_stg > 64u * 1024 ? 64u * 1024 : want_stg;
     }
     p.stages = pick_stages(stage2, 229000 - 2048 - 2 * p.NT * 4 - p.stg_bytes, 8);
     p.tmem_cols = tmem_cols_for(2 * p.NT);
@@ -1793,7 +1807,7 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
       const uint32_t a_slot = ((uint32_t)a_rows2 * 128u + 1023u) & ~1023u;
       const uint32_t b_half = (uint32_t)half * 128;
       const uint32_t stage_h = a_slot + (uint32_t)taps * b_half;
-      const int stagesA = pick_stages(stage_h, 229000 - 2048 - 2 * p.NT * 4 - 2 * Cos * 4 - p.stg_bytes, 4);
+      const int stagesA = grow_staging(stage_h, 2 * p.NT * 4 + 2 * Cos * 4, 4);
       MEGB_CHECK_ARG(stagesA >= 2, "tc_tapgemm(pair, halo): tile too large");
       p.stages = stagesA;
       CUtensorMap tmAh;
@@ -1813,7 +1827,7 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
       if (p.dbg != nullptr) report_pair_timing("pair+halo");
       return 0;
     }
-    p.stages = pick_stages(2 * stage2, 229000 - 2048 - 2 * p.NT * 4 - 2 * Cos * 4 - p.stg_bytes, 8);   // two k chunks per stage
+    p.stages = grow_staging(2 * stage2, 2 * p.NT * 4 + 2 * Cos * 4, 8);   // two k chunks per stage
     MEGB_CHECK_ARG(p.stages >= 2, "tc_tapgemm(pair): tile too large");
     const size_t smem2 = 1024 + kHeaderBytes + (size_t)p.stages * 2 * stage2 + p.stg_bytes + 2 * p.NT * 4 + 2 * Cos * 4;
     int rc = set_smem(tc_tapgemm2_kernel, smem2);
