@@ -1957,7 +1957,7 @@ int tc_wgrad(const void* dU, int M, int Ms, const void* Xin, int C, int Cs, int 
   p.m_tiles = (M + kTileM - 1) / kTileM;
   p.tmem_cols = tmem_cols_for(p.ctile);
   const uint32_t stage_bytes = 2 * kBlockK * 128 + (p.ctile / 64) * kBlockK * 128;
-  p.stages = pick_stages(stage_bytes, 200 * 1024, 6);
+  p.stages = pick_stages(stage_bytes, 232448 - 2048, 6);       // all of the 227 KB a block may opt into (one CTA per SM)
   MEGB_CHECK_ARG(p.stages >= 2, "tc_wgrad: tile too large");
   p.group = group; p.order = order;
   const long long base = (long long)p.m_tiles * p.c_tiles * taps;
