@@ -1965,7 +1965,10 @@ int tc_wgrad(const void* dU, int M, int Ms, const void* Xin, int C, int Cs, int 
   int splits;
   if (group == nullptr) {
     p.mode = 0;
-    splits = (int)((num_sms() + base - 1) / base);
+    // ONE wave: floor, not ceil.  (ceil gave 15 x 10 = 150 CTAs for the 320->640 layers and 16 x 10 = 160 for the 640->1024
+    // head on 148 SMs at one CTA per SM: a second wave of 2 / 12 CTAs doubled those launches -- seen in the ncu grid sizes.)
+    splits = (int)(num_sms() / base);
+    if (splits < 1) splits = 1;
     if (splits > B) splits = B;
     const long long max_slots = (long long)(ws_bytes / sizeof(float)) / slot_elems;
     if (splits > max_slots) splits = (int)max_slots;
@@ -1974,7 +1977,7 @@ int tc_wgrad(const void* dU, int M, int Ms, const void* Xin, int C, int Cs, int 
   } else {
     MEGB_CHECK_ARG(order != nullptr, "tc_wgrad: grouped mode needs the group-sorted sample order");
     p.mode = 1;
-    splits = (int)((num_sms() + base - 1) / base);
+    splits = (int)(num_sms() / base);
     if (splits > B) splits = B;
     if (splits < 1) splits = 1;
     p.out = dW;
