@@ -517,7 +517,7 @@ struct HeaderH {
 __global__ void __launch_bounds__(kThreads)
 tc_tapgemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                        const __grid_constant__ TapStoreMaps maps, const TapGemmParams p, const int a_rows,
-                       const int stagesA, const int use_base_offset) {
+                       const int stagesA) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   HeaderH* hdr = reinterpret_cast<HeaderH*>(smem);
@@ -601,7 +601,6 @@ tc_tapgemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           tc_fence_after();
           const uint32_t aaddr = abase + (uint32_t)(tap * p.dil) * 128u;      // window shifted by tap*dil rows
           uint64_t da = make_smem_desc(aaddr, 16, 1024);
-          if (use_base_offset) da |= (uint64_t)((aaddr >> 7) & 7u) << 49;
           const uint64_t db = make_smem_desc(smem_u32(ringB + (size_t)sb * b_bytes), 16, 1024);
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k)
@@ -1840,7 +1839,9 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
     return 0;
   }
 
-  // ---- halo form for k > 1 convolutions (MEGB200_TAPGEMM_HALO=0 disables, =2 also sets the descriptor base offset)
+  // ---- single-CTA halo form for k > 1 convolutions, opt-in (MEGB200_TAPGEMM_HALO=1).  The row-shifted descriptor uses
+  // base_offset = 0: the swizzle is a function of the absolute shared-memory address (setting the field gave wrong
+  // results, profiles/r1_tapgemm_variants.md)
   static const char* halo_env = getenv("MEGB200_TAPGEMM_HALO");
   const int halo_mode = halo_env ? atoi(halo_env) : 0;
   const int a_rows = ((kTileM + (taps - 1) * dil) + 7) / 8 * 8;
@@ -1875,8 +1876,7 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
     if (rc) return rc;
     const long long blocks = (long long)B * p.tiles_per_sample * p.ntiles;
     MEGB_CHECK_ARG(blocks > 0 && blocks < 2147483647ll, "tc_tapgemm: grid too large");
-    tc_tapgemm_halo_kernel<<<(unsigned)blocks, kThreads, smemh, st>>>(tmAh, tmWh, maps, p, a_rows, stagesA,
-                                                                      halo_mode == 2 ? 1 : 0);
+    tc_tapgemm_halo_kernel<<<(unsigned)blocks, kThreads, smemh, st>>>(tmAh, tmWh, maps, p, a_rows, stagesA);
     MEGB_LAUNCH_OK();
     return 0;
   }

@@ -22,7 +22,6 @@ for s in ${stages}; do
     tc_tapgemm)       run tc_tapgemm 300 ${PT} tests/test_ops_gpu.py -k "tapgemm and tc" ;;
     tc_all)           run tc_all 600 ${PT} tests/test_ops_gpu.py -k "tc" ;;
     tc_halo1)         MEGB200_TAPGEMM_HALO=1 run tc_halo1 600 ${PT} tests/test_ops_gpu.py -k "tapgemm and tc" ;;
-    tc_halo2)         MEGB200_TAPGEMM_HALO=2 run tc_halo2 600 ${PT} tests/test_ops_gpu.py -k "tapgemm and tc" ;;
     tc_pair)          MEGB200_TAPGEMM_2CTA_MIN_ITEMS=1 MEGB200_TAPGEMM_PAIR_HALO=0 run tc_pair 600 ${PT} tests/test_ops_gpu.py -k "tapgemm and tc" ;;
     tc_pairhalo)      MEGB200_TAPGEMM_2CTA_MIN_ITEMS=1 run tc_pairhalo 600 ${PT} tests/test_ops_gpu.py -k "tapgemm and tc" ;;
     tc_1cta)          MEGB200_TAPGEMM_1CTA=1 run tc_1cta 600 ${PT} tests/test_ops_gpu.py -k "tapgemm and tc" ;;

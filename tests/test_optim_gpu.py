@@ -8,10 +8,10 @@ from megb200 import synth
 from megb200.optim import Adam
 from tests import helpers as H
 
-pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+@pytest.mark.gpu
 @pytest.mark.parametrize("wd", [0.0, 0.01])
 def test_adam_matches_torch_adam(wd):
     cfg = synth.get_config("narrow")
@@ -41,7 +41,7 @@ def test_adam_matches_torch_adam(wd):
     assert worst <= 2e-6
 
 
-def test_adam_rejects_cpu_parameters():
+def test_adam_rejects_cpu_parameters():          # CPU tier: the product path has no CPU fallback
     p = torch.nn.Parameter(torch.zeros(4))
     p.grad = torch.ones(4)
     with pytest.raises(RuntimeError):
