@@ -88,40 +88,52 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
-def cpu_reference_step_time(cfg, B_sample, steps, warmup, threads=None):
-    """fwd + CLIPLoss + bwd of the oracle port (fp32, all host threads) on a B_sample-sized slice of the workload."""
+def cpu_reference_step_time(cfg, B_sample, steps, warmup, threads=None, seed=0, keep_first=False):
+    """fwd + CLIPLoss + bwd of the oracle port (fp32, all host threads) on the first B_sample samples of the workload's
+    batch.  Returns the per-step times; with keep_first also (Z, loss) of the first step (weights at their initial
+    values: the parity reference of the bench line)."""
     from megb200 import synth
     from oracle import restatement as R
     if threads:
         torch.set_num_threads(threads)
     P = R.state_to_torch(synth.make_state(cfg), requires_grad=True)
     temp = torch.tensor([float(cfg.init_temperature)], requires_grad=True)
-    X, Y, subj = synth.make_batch(cfg, 0, B=B_sample)
+    X, Y, subj = synth.make_batch(cfg, seed, B=B_sample)
     X, Y, subj = torch.from_numpy(X), torch.from_numpy(Y), torch.from_numpy(subj)
     loc = synth.sensor_locations(cfg.C)
     center = synth.drop_center(cfg)
-    times = []
+    times, first = [], None
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        R.train_step(P, temp, X, Y, subj, loc, K=cfg.K, d_drop=cfg.d_drop, seq2seq=cfg.seq2seq, drop_center=center)
+        Z, loss, _ = R.train_step(P, temp, X, Y, subj, loc, K=cfg.K, d_drop=cfg.d_drop, seq2seq=cfg.seq2seq,
+                                  drop_center=center)
         dt = time.perf_counter() - t0
+        if i == 0 and keep_first:
+            first = (Z, float(loss))
+        del Z, loss
         if i >= warmup:
             times.append(dt)
-    return times
+    return (times, first) if keep_first else times
 
 
 def run_reference(args):
+    """The reference arm: the reference's own CPU implementation of the path (its pinned port, oracle/restatement.py --
+    /root/reference does not exist on the GPU box and is not pip-installable) on the box's host cores, at the FULL batch
+    of the config, with the requested warm-up and step counts."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     from megb200 import synth
     cfg = synth.get_config(args.config)
+    if args.batch:
+        cfg["B"] = args.batch
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    B_sample = min(cfg.B, args.cpu_sample)
-    # keep the whole run within a few minutes: probe one step, shrink the sample if needed
+    B_sample = min(cfg.B, args.cpu_sample) if args.cpu_sample > 0 else cfg.B
+    # safety net only: the whole run must end within a few minutes even on a slow host (a B=256 step is ~3 s on the
+    # B200 box); the sample that was actually timed is stated in the line
     probe = cpu_reference_step_time(cfg, B_sample, 1, 0)[0]
-    budget = 150.0
+    budget = 280.0
     while B_sample > 8 and probe * (args.steps + args.warmup) > budget:
         B_sample //= 2
         probe = cpu_reference_step_time(cfg, B_sample, 1, 0)[0]
@@ -134,8 +146,9 @@ def run_reference(args):
         "dtype": "f32", "data": "synthetic",
         "config": workload_config(cfg, 1, cfg.B),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{B_sample} of {cfg.B} samples per step (same shapes), fwd+CLIP+bwd, fp32, "
-                                   f"oracle/restatement.py pinned to the reference by tests/golden"},
+                         "sample": f"{B_sample} of {cfg.B} samples per step (same shapes), {args.warmup} warm-up + "
+                                   f"{args.steps} timed steps, fwd+CLIP+bwd, fp32, oracle/restatement.py pinned to the "
+                                   f"reference by tests/golden"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -214,22 +227,31 @@ def run_megb200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # warm-up: at least W (>= 3) steps, and keep going until ~1 s has passed so that clocks, the caching allocator and
-    # NCCL channels are in steady state before anything is timed
-    n_warm = 0
-    for _ in range(max(args.warmup, 3)):            # includes one-time costs (module load, allocator growth)
-        loss = step(Xd, Yd, subj_h)
-        n_warm += 1
+    # parity step: the very first step, weights at their initial values; its loss / embeddings are compared with the
+    # CPU oracle's first step on the same inputs further down (the `parity` object of the line)
+    for p in params:
+        p.grad = None
+    Z0 = enc(Xd, subj_h)
+    loss0 = lossf(Yd, Z0)
+    loss0.backward()
+    parity_gpu = (Z0.detach().float().cpu(), float(loss0.detach()))
+    del Z0, loss0
+
+    # priming (setup, not warm-up): ~1 s of steps so that clocks, the caching allocator and NCCL channels are in steady
+    # state; then EXACTLY max(W, 3) warm-up steps, then the K timed steps.  No optimizer step is taken before the timed
+    # regions: the timed weights are the initial weights, so `loss` in the line is comparable with the oracle's.
+    n_prime = 0
     torch.cuda.synchronize()
     t_warm = time.perf_counter()
-    while time.perf_counter() - t_warm < 1.0 and n_warm < 400:
+    while (time.perf_counter() - t_warm < 1.0 and n_prime < 400) or n_prime < 2:
         loss = step(Xd, Yd, subj_h)
-        n_warm += 1
-        if n_warm % 4 == 0:
+        n_prime += 1
+        if n_prime % 4 == 0:
             torch.cuda.synchronize()
     barrier()
-    for _ in range(2):                       # Adam's lazy state init must not land in any timed region
-        opt.step()
+    n_warm = max(args.warmup, 3)
+    for _ in range(n_warm):
+        loss = step(Xd, Yd, subj_h)
     barrier()
 
     if args.ncu_step:
@@ -278,23 +300,40 @@ def run_megb200(args):
         k[2] += 1
     peaks = measured_peaks()
     roofline = None
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1_tapgemm2h_ncu.json")
-    if os.path.exists(tpath):
+    # DRAM traffic of the dominant kernel comes from an `ncu --set full` capture (never taken inside this run: profiling
+    # replays kernels).  It is only quoted while the kernel sources are the ones the capture was taken on (source hash
+    # stored by scripts/ncu_extract.py); a stale capture reads as null.
+    traffic, traffic_src, tensor_pipe_pct = None, None, None
+    import glob
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    try:
+        from ncu_extract import source_sha
+        cur_sha = source_sha()
+    except Exception:
+        cur_sha = None
+    for tpath in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_tapgemm2h_ncu.json")), reverse=True):
         try:
-            ls = [e for e in json.load(open(tpath))["launches"] if "dram_read_bytes" in e]
+            d = json.load(open(tpath))
+            if d.get("source_sha") is None or d.get("source_sha") != cur_sha:
+                traffic_src = f"{os.path.basename(tpath)} is stale (kernel sources changed since the capture)"
+                continue
+            ls = [e for e in d["launches"] if "dram_read_bytes" in e]
             if ls:
                 traffic = sum(e["dram_read_bytes"] + e["dram_write_bytes"] for e in ls) / len(ls)
+                tp = [e["tensor_pipe_active_pct"] for e in ls if "tensor_pipe_active_pct" in e]
+                tensor_pipe_pct = sum(tp) / len(tp) if tp else None
+                traffic_src = (f"profiles/{os.path.basename(tpath)}: mean dram read+write bytes per captured launch "
+                               f"(ncu --set full, config 2, same kernel sources: {cur_sha})")
+                break
         except Exception:
-            traffic = None
+            continue
     if "tapgemm" in kern and kern["tapgemm"][1] > 0:
         fl, tms, n = kern["tapgemm"]
         ach = fl / (tms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "kernel": "tc_tapgemm2h_kernel (k=3 convs fwd + dgrad: 29 of 35 launches) + tc_tapgemm2_kernel (1x1 heads) + tc_tapgemm_kernel (grouped subject GEMM, ragged N)",
                     "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                     "frac": ach / peaks["bf16_sustained"], "traffic": traffic,
-                    "traffic_source": "profiles/r1_tapgemm2h_ncu.json: mean dram read+write bytes per captured launch "
-                                      "(ncu --set full, config 2)" if traffic else None,
+                    "traffic_source": traffic_src, "ncu_tensor_pipe_active_pct": tensor_pipe_pct,
                     "peak_source": peaks["source"] + " sustained",
                     "launches_per_step": n // args.steps, "avg_launch_ms": tms / n,
                     "share_of_step": tms / args.steps / ms}      # share of the EAGER timed region the events were taken in
@@ -354,7 +393,10 @@ def run_megb200(args):
     if graph_ms is not None:
         ms = graph_ms
 
-    # ---- optimizer step, reported separately
+    # ---- optimizer step, reported separately; taken AFTER the timed regions so they see the initial weights
+    barrier()
+    for _ in range(2):                       # Adam's lazy state init must not land in its own timed region
+        opt.step()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -452,7 +494,7 @@ def run_megb200(args):
     flops_step = B * synth.encoder_flops_per_sample(cfg) + synth.clip_flops(cfg, B, B * world)
     line = {
         "metric": METRIC, "value": B * world / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": n_warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "warmup": n_warm, "priming_steps": n_prime, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16" if args.precision.startswith("bf16") else "f32", "data": "synthetic",
         "config": workload_config(cfg, world, B), "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "roofline": roofline,
@@ -463,11 +505,25 @@ def run_megb200(args):
         "adam_ms": adam_ms, "adam_ms_torch_optim": adam_torch_ms, "host_enqueue_ms_per_step": host_ms, "loss": loss_value, "precision": args.precision,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        Bs = min(B, args.cpu_sample)
-        times = cpu_reference_step_time(cfg, Bs, 2, 1, threads=os.cpu_count())
+        # CPU leg: the oracle port at the FULL batch (a B=256 step is ~3 s on the box's cores): 1 warm-up + 2 timed steps.
+        # Its first step (initial weights, same inputs) is the reference of the `parity` object.
+        Bs = min(B, args.cpu_sample) if args.cpu_sample > 0 else B
+        times, first = cpu_reference_step_time(cfg, Bs, 2, 1, threads=os.cpu_count(), seed=rank, keep_first=True)
         v = Bs / (sum(times) / len(times))
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                                 "sample": f"{Bs} of {B} samples per step, 1 warm-up + 2 timed steps, fwd+CLIP+bwd fp32"}
+        if Bs == B:
+            Zr, lr = first
+            zg, lg = parity_gpu
+            zerr = float((zg.double() - Zr.double()).norm() / Zr.double().norm())
+            tol = 2e-2 if args.precision.startswith("bf16") else 1e-3
+            line["parity"] = {"loss_rel": abs(lg - lr) / abs(lr), "z_rel": zerr, "loss": lg, "loss_oracle": lr,
+                              "tolerance": tol, "ok": bool(zerr <= tol and abs(lg - lr) / abs(lr) <= tol),
+                              "config": f"{cfg.name} B={B}: first step at the initial weights (the timed steps run on the "
+                                        f"same weights) vs oracle/restatement.py on the host CPU, same inputs; "
+                                        f"z_rel = ||Z - Z_ref||_F / ||Z_ref||_F"}
+        else:
+            line["parity"] = {"skipped": f"CPU sample {Bs} < batch {B}"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -498,7 +554,7 @@ def main():
     ap.add_argument("--config", default="gwilliams")
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (default: the config's)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "bf16_simt"])
-    ap.add_argument("--cpu-sample", type=int, default=32, help="samples per CPU-baseline step")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="samples per CPU-baseline step (0 = the full batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time only the eager launch path")
     ap.add_argument("--ncu-step", action="store_true", help="run one step inside cudaProfilerStart/Stop and exit")

@@ -47,6 +47,18 @@ const char* megb200_last_error(void);
 /* number of kernels this library has launched in this process (for the bench's gpu_launches claim) */
 long long megb200_launch_count(void);
 
+/* Kernel-variant selection (host-side, process-wide; takes effect at the next launch).  The library picks between
+ * several hand-written forms of one contraction by problem size (e.g. the persistent CTA-pair tap-GEMM from 2 x #SM work
+ * items up); these switches let a caller -- the test-suite -- force each form on any shape.  Names:
+ *   "tapgemm_pair_min_items" (-1 = default), "tapgemm_force_1cta", "tapgemm_pair_halo", "tapgemm_halo",
+ *   "tapgemm_ragged_n", "tapgemm_direct_epi", "clip_dz_large", "rowloop_direct", "wgrad_splits" (0 = automatic).
+ * Read-only (written by the launchers, for tests): "last_tapgemm_kernel" (0 single CTA, 1 CTA pair, 2 CTA pair + halo,
+ * 3 single CTA + halo), "last_clip_dz_kernel" (0 small-K, 1 large-K), "last_wgrad_splits".
+ * Initial values come from the MEGB200_* environment variables.  Results never depend on the variant beyond f32
+ * summation order.  Returns MEGB200_ERR_ARG for an unknown name; get returns -(2^62) then. */
+int megb200_set_option(const char* name, long long value);
+long long megb200_get_option(const char* name);
+
 /* ---------------------------------------------------------------------------------------------- packing */
 /* X f32 [B][C][T] (NCW, as the collator delivers it: gwilliams2022.py:654-662) -> PC [B][T][Cs]; pad
  * channels C..Cs-1 are written as zero. */

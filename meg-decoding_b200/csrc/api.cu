@@ -1,6 +1,8 @@
 // C-ABI entry points that dispatch between the two contraction engines, plus library-level plumbing
 // (error string, SM count, TMA descriptor encoding through the runtime-resolved driver entry point).
 #include <stdarg.h>
+#include <stddef.h>
+#include <stdlib.h>
 
 #include "tc_common.cuh"
 
@@ -17,6 +19,50 @@ void set_last_error(const char* fmt, ...) {
 
 static unsigned long long g_launches = 0;
 void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
+
+static long long env_ll(const char* name, long long dflt) {
+  const char* e = getenv(name);
+  return e != nullptr ? atoll(e) : dflt;
+}
+
+Options& options() {
+  static Options o = {
+      env_ll("MEGB200_TAPGEMM_2CTA_MIN_ITEMS", -1),
+      getenv("MEGB200_TAPGEMM_1CTA") != nullptr ? 1 : 0,
+      (int)env_ll("MEGB200_TAPGEMM_PAIR_HALO", 1),
+      (int)env_ll("MEGB200_TAPGEMM_HALO", 0),
+      getenv("MEGB200_TAPGEMM_RAGGED_N") != nullptr ? 1 : 0,
+      getenv("MEGB200_TAPGEMM_DIRECT_EPI") != nullptr ? 1 : 0,
+      getenv("MEGB200_CLIP_DZ_LARGE") != nullptr ? 1 : 0,
+      getenv("MEGB200_ROWLOOP_DIRECT") != nullptr ? 1 : 0,
+      (int)env_ll("MEGB200_WGRAD_SPLITS", 0),
+      -1, -1, -1,
+  };
+  return o;
+}
+
+struct OptionEntry { const char* name; int kind; /* 0 = long long, 1 = int */ size_t off; };
+static const OptionEntry kOptionTable[] = {
+    {"tapgemm_pair_min_items", 0, offsetof(Options, tapgemm_pair_min_items)},
+    {"tapgemm_force_1cta", 1, offsetof(Options, tapgemm_force_1cta)},
+    {"tapgemm_pair_halo", 1, offsetof(Options, tapgemm_pair_halo)},
+    {"tapgemm_halo", 1, offsetof(Options, tapgemm_halo)},
+    {"tapgemm_ragged_n", 1, offsetof(Options, tapgemm_ragged_n)},
+    {"tapgemm_direct_epi", 1, offsetof(Options, tapgemm_direct_epi)},
+    {"clip_dz_large", 1, offsetof(Options, clip_dz_large)},
+    {"rowloop_direct", 1, offsetof(Options, rowloop_direct)},
+    {"wgrad_splits", 1, offsetof(Options, wgrad_splits)},
+    {"last_tapgemm_kernel", 1, offsetof(Options, last_tapgemm_kernel)},
+    {"last_clip_dz_kernel", 1, offsetof(Options, last_clip_dz_kernel)},
+    {"last_wgrad_splits", 1, offsetof(Options, last_wgrad_splits)},
+};
+
+static const OptionEntry* find_option(const char* name) {
+  if (name == nullptr) return nullptr;
+  for (const OptionEntry& e : kOptionTable)
+    if (strcmp(e.name, name) == 0) return &e;
+  return nullptr;
+}
 
 int num_sms() {
   static int cached[64] = {0};
@@ -157,6 +203,26 @@ extern "C" {
 int megb200_version(void) { return MEGB200_VERSION; }
 const char* megb200_last_error(void) { return g_err; }
 long long megb200_launch_count(void) { return (long long)__atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
+int megb200_set_option(const char* name, long long value) {
+  const OptionEntry* e = find_option(name);
+  MEGB_CHECK_ARG(e != nullptr, "set_option: unknown option '%s'", name ? name : "(null)");
+  char* base = reinterpret_cast<char*>(&options());
+  if (e->kind == 0) *reinterpret_cast<long long*>(base + e->off) = value;
+  else *reinterpret_cast<int*>(base + e->off) = (int)value;
+  return 0;
+}
+
+long long megb200_get_option(const char* name) {
+  const OptionEntry* e = find_option(name);
+  if (e == nullptr) {
+    set_last_error("get_option: unknown option '%s'", name ? name : "(null)");
+    return -(1ll << 62);
+  }
+  const char* base = reinterpret_cast<const char*>(&options());
+  return e->kind == 0 ? *reinterpret_cast<const long long*>(base + e->off)
+                      : (long long)*reinterpret_cast<const int*>(base + e->off);
+}
 
 int megb200_group_order(const int32_t* group, int B, int G, int32_t* order, void* stream) {
   MEGB_CHECK_ARG(group && order && B > 0 && G > 0 && G < 8192, "group_order: bad arguments");

@@ -44,6 +44,25 @@ void set_last_error(const char* fmt, ...);
 int num_sms();
 void count_launch();
 
+// Kernel-variant selection (megb200_set_option).  Defaults come from the MEGB200_* environment variables of the same
+// meaning, read once; tests flip them in-process so that every variant is reachable on small shapes.
+struct Options {
+  long long tapgemm_pair_min_items;   // work items from which the CTA-pair tap-GEMM is used; -1 = 2 x SM count
+  int tapgemm_force_1cta;             // 1: always the single-CTA tap-GEMM
+  int tapgemm_pair_halo;              // 0: plain pair kernel for k > 1 instead of the halo-staged one
+  int tapgemm_halo;                   // 1: single-CTA halo form for k > 1 (opt-in experiment)
+  int tapgemm_ragged_n;               // 1: 256-wide N tiles + narrower tail
+  int tapgemm_direct_epi;             // 1: per-thread global stores instead of the TMA-store epilogue
+  int clip_dz_large;                  // 1: always the large-K dZ kernel (default: small-K form when By <= 512)
+  int rowloop_direct;                 // 1: direct-load streaming kernels instead of the bulk-copy staged ones
+  int wgrad_splits;                   // > 0: force the split count of the weight-gradient GEMM
+  // written by the launchers (read back with megb200_get_option; the tests assert which form actually ran)
+  int last_tapgemm_kernel;            // 0 = single CTA, 1 = CTA pair, 2 = CTA pair + halo, 3 = single CTA + halo
+  int last_clip_dz_kernel;            // 0 = small-K (stream-bound) form, 1 = large-K form
+  int last_wgrad_splits;
+};
+Options& options();
+
 // ------------------------------------------------------------------------------------------ dtype helpers
 template <typename T> struct Vec8;              // 8 consecutive channels
 template <> struct Vec8<float> {

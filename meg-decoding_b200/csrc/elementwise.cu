@@ -683,10 +683,7 @@ struct GluBwdOp {
   }
 };
 
-static bool rowloop_direct_env() {
-  static const bool v = getenv("MEGB200_ROWLOOP_DIRECT") != nullptr;
-  return v;
-}
+static bool rowloop_direct_env() { return options().rowloop_direct != 0; }
 
 template <class Op>
 static int launch_rowloop(Op op, long long rows, int C, int Cs, const int32_t* group, int Tn, float* out0,

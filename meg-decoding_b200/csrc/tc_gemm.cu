@@ -36,7 +36,7 @@ __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
 
 // ================================================================================================ tap GEMM
 struct TapGemmParams {
-  int T, N, Cos, Crs, Co2s, taps, dil, Kp, kchunks, tiles_per_sample, ntiles, NT, n_last, stages, epi, debug_skip_io, tma_epi;
+  int T, N, Cos, Crs, Co2s, taps, dil, Kp, kchunks, tiles_per_sample, ntiles, NT, n_last, stages, epi, tma_epi;
   uint32_t stg_bytes;   // CTA-pair kernel: dedicated staging area of the TMA-store epilogue
   float* stats;         // optional BatchNorm statistics sums[2][N] (sum, sum of squares) fused into the f32 epilogue
   long long* dbg;       // MEGB200_DEBUG_TIMING: per-CTA clock64 stamps {start, first data, accumulator ready, end}
@@ -55,7 +55,6 @@ __device__ __forceinline__ void tap_epilogue(const TapGemmParams& p, uint32_t tr
   const bool glu = p.epi == MEGB200_EPI_GLU;
   const int half = p.NT / 2;
   const int Ch = p.N / 2;
-  if (p.debug_skip_io) valid = false;     // profiling experiment: TMEM drain only, no global traffic
   if (glu) {
     __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.Out) + row * p.Cos;
     __nv_bfloat16* vrow = p.Out2 + row * p.Co2s;
@@ -1576,10 +1575,7 @@ tc_clip_dz_small_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_co
 }
 
 // ================================================================================================ host launchers
-static bool halo_mode_env_off() {
-  static const char* e = getenv("MEGB200_TAPGEMM_HALO");
-  return e == nullptr || atoi(e) == 0;
-}
+static bool halo_mode_env_off() { return options().tapgemm_halo == 0; }
 
 static int pick_stages(uint32_t stage_bytes, uint32_t budget, int max_stages) {
   int s = (int)(budget / stage_bytes);
@@ -1626,17 +1622,21 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
   MEGB_CHECK_ARG(Kp % 64 == 0 && Np % 16 == 0 && Np >= N, "tc_tapgemm: Kp %% 64 and Np %% 16 required (Kp=%d Np=%d)", Kp, Np);
   const bool glu = epi == MEGB200_EPI_GLU;
   TapGemmParams p;
-  static const bool skip_io = getenv("MEGB200_DEBUG_EPI_SKIP_IO") != nullptr;
-  p.debug_skip_io = skip_io ? 1 : 0;
+  // Per-phase clock64 accounting is a developer build only (-DMEGB200_DEBUG, then MEGB200_DEBUG_TIMING=1): the
+  // production library carries no debug mode that could change results or leak memory.
+#ifdef MEGB200_DEBUG
   static const bool dbg_timing = getenv("MEGB200_DEBUG_TIMING") != nullptr;
   static long long* dbg_buf = nullptr;
   if (dbg_timing && dbg_buf == nullptr) cudaMalloc(&dbg_buf, sizeof(long long) * 16 * 65536);
+#else
+  constexpr bool dbg_timing = false;
+  long long* const dbg_buf = nullptr;
+#endif
   p.dbg = nullptr;
   p.T = T; p.N = N; p.Cos = Cos; p.Crs = Crs; p.Co2s = Co2s; p.taps = taps; p.dil = dil; p.Kp = Kp; p.epi = epi;
   p.kchunks = (Ca + kBlockK - 1) / kBlockK;
   p.tiles_per_sample = (T + kTileM - 1) / kTileM;
-  static const bool direct_epi = getenv("MEGB200_TAPGEMM_DIRECT_EPI") != nullptr;
-  p.tma_epi = direct_epi ? 0 : 1;
+  p.tma_epi = options().tapgemm_direct_epi ? 0 : 1;
   p.stg_bytes = 0;
   if (glu) {
     const int Ch = N / 2;
@@ -1664,7 +1664,7 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
     const int ncover = Cos > Np ? Cos : Np;
     // MEGB200_TAPGEMM_RAGGED_N=1: 256-wide tiles plus one narrower tail (320 = 256 + 64).  Measured slower than uniform
     // 160-wide tiles at config 2 (576 vs 647 TFLOP/s: the 48 KB stages leave a 2-deep ring), so it is off by default.
-    static const bool uniform_tiles = getenv("MEGB200_TAPGEMM_RAGGED_N") == nullptr;
+    const bool uniform_tiles = options().tapgemm_ragged_n == 0;
     const int cover32 = (ncover + 31) / 32 * 32;
     if (!uniform_tiles && cover32 > 256 && halo_mode_env_off()) {
       p.NT = 256;
@@ -1705,9 +1705,9 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
   // warps, 128-wide k stages) reaches 647 TFLOP/s, the single-CTA kernel with two co-resident CTAs per SM 608; the pair
   // kernel is used for large ungrouped problems.  MEGB200_TAPGEMM_1CTA=1 forces the single-CTA kernel,
   // MEGB200_TAPGEMM_2CTA_MIN_ITEMS=<n> lowers the pair kernel's work threshold (the tests exercise it on small shapes).
-  static const char* min_items_env = getenv("MEGB200_TAPGEMM_2CTA_MIN_ITEMS");
-  static const bool force_1cta = getenv("MEGB200_TAPGEMM_1CTA") != nullptr;
-  const long long min_items = min_items_env ? atoll(min_items_env) : 2ll * num_sms();
+  const Options& opt = options();
+  const bool force_1cta = opt.tapgemm_force_1cta != 0;
+  const long long min_items = opt.tapgemm_pair_min_items >= 0 ? opt.tapgemm_pair_min_items : 2ll * num_sms();
   const long long m_tiles_total = (long long)B * p.tiles_per_sample;
   if (group == nullptr && G == 1 && !force_1cta && p.tma_epi && p.NT % 32 == 0 && m_tiles_total * p.ntiles >= min_items) {
     // ---- CTA-pair persistent kernel
@@ -1794,8 +1794,7 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
     };
     // halo form of the pair kernel, default for k > 1 (653 vs 599 TFLOP/s on the same box, r1_tapgemm_variants.md);
     // MEGB200_TAPGEMM_PAIR_HALO=0 selects the plain pair kernel
-    static const char* ph_env = getenv("MEGB200_TAPGEMM_PAIR_HALO");
-    static const bool no_halo = ph_env != nullptr && atoi(ph_env) == 0;
+    const bool no_halo = opt.tapgemm_pair_halo == 0;
     const int a_rows2 = ((kTileM + (taps - 1) * dil) + 7) / 8 * 8;
     if (dbg_timing) {
       p.dbg = dbg_buf;
@@ -1823,6 +1822,7 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
                                       a_rows2, stagesA));
       MEGB_LAUNCH_OK();
       *stats_fused = fuse_stats ? 1 : 0;
+      options().last_tapgemm_kernel = 2;
       if (p.dbg != nullptr) report_pair_timing("pair+halo");
       return 0;
     }
@@ -1835,6 +1835,7 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
     MEGB_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_tapgemm2_kernel, tmA2, tmW2, maps, p, (int)m_tiles_total, num_items));
     MEGB_LAUNCH_OK();
     *stats_fused = fuse_stats ? 1 : 0;
+    options().last_tapgemm_kernel = 1;
     if (p.dbg != nullptr) report_pair_timing("pair");
     return 0;
   }
@@ -1842,8 +1843,7 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
   // ---- single-CTA halo form for k > 1 convolutions, opt-in (MEGB200_TAPGEMM_HALO=1).  The row-shifted descriptor uses
   // base_offset = 0: the swizzle is a function of the absolute shared-memory address (setting the field gave wrong
   // results, profiles/r1_tapgemm_variants.md)
-  static const char* halo_env = getenv("MEGB200_TAPGEMM_HALO");
-  const int halo_mode = halo_env ? atoi(halo_env) : 0;
+  const int halo_mode = opt.tapgemm_halo;
   const int a_rows = ((kTileM + (taps - 1) * dil) + 7) / 8 * 8;
   if (halo_mode > 0 && taps > 1 && group == nullptr && G == 1 && a_rows <= 256) {
     p.stats = nullptr;
@@ -1878,6 +1878,7 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
     MEGB_CHECK_ARG(blocks > 0 && blocks < 2147483647ll, "tc_tapgemm: grid too large");
     tc_tapgemm_halo_kernel<<<(unsigned)blocks, kThreads, smemh, st>>>(tmAh, tmWh, maps, p, a_rows, stagesA);
     MEGB_LAUNCH_OK();
+    options().last_tapgemm_kernel = 3;
     return 0;
   }
 
@@ -1911,6 +1912,7 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
   if (dbg_timing && blocks <= 65536) p.dbg = dbg_buf;
   tc_tapgemm_kernel<<<(unsigned)blocks, kThreads, smem, st>>>(tmA, tmW, maps, p);
   MEGB_LAUNCH_OK();
+  options().last_tapgemm_kernel = 0;
   *stats_fused = p.stats != nullptr ? 1 : 0;
   if (p.dbg != nullptr) {
     // debug only: phase durations per CTA in SM clocks (synchronises!)
@@ -1968,6 +1970,7 @@ int tc_wgrad(const void* dU, int M, int Ms, const void* Xin, int C, int Cs, int 
     // ONE wave: floor, not ceil.  (ceil gave 15 x 10 = 150 CTAs for the 320->640 layers and 16 x 10 = 160 for the 640->1024
     // head on 148 SMs at one CTA per SM: a second wave of 2 / 12 CTAs doubled those launches -- seen in the ncu grid sizes.)
     splits = (int)(num_sms() / base);
+    if (options().wgrad_splits > 0) splits = options().wgrad_splits;
     if (splits < 1) splits = 1;
     if (splits > B) splits = B;
     const long long max_slots = (long long)(ws_bytes / sizeof(float)) / slot_elems;
@@ -2006,6 +2009,7 @@ int tc_wgrad(const void* dU, int M, int Ms, const void* Xin, int C, int Cs, int 
   dim3 grid(p.m_tiles * p.c_tiles, taps, splits);
   tc_wgrad_kernel<<<grid, kThreads, smem, st>>>(tmU, tmX, p);
   MEGB_LAUNCH_OK();
+  options().last_wgrad_splits = splits;
   if (p.mode == 0) {
     long long blocks = ((long long)M * C + 127) / 128;
     if (blocks > num_sms() * 16) blocks = num_sms() * 16;
@@ -2067,7 +2071,7 @@ int tc_clip_dz(const void* coef, int ldc, const void* Yp, const void* Z, const f
   MEGB_CHECK_ARG(D % 16 == 0 && ldc % 8 == 0, "tc_clip_dz: D %% 16 and ldc %% 8 required (D=%lld ldc=%d)", D, ldc);
   DzParams p;
   p.By = By; p.Bz = Bz; p.D = D;
-  static const bool no_small = getenv("MEGB200_CLIP_DZ_LARGE") != nullptr;
+  const bool no_small = options().clip_dz_large != 0;
   if (By <= 512 && D >= 128 && D % 64 == 0 && (D + 127) / 128 <= 65535 && !no_small) {
     // stream-bound regime: TMA-staged Z / dZ tiles, 128 x 128 tiles, two CTAs per SM
     p.NT = 128;
@@ -2107,6 +2111,7 @@ int tc_clip_dz(const void* coef, int ldc, const void* Yp, const void* Z, const f
     dim3 grid((Bz + kTileM - 1) / kTileM, (unsigned)((D + 127) / 128));
     tc_clip_dz_small_kernel<<<grid, kThreads, smem, st>>>(tmC, tmY, tmZ, tmDZ, p);
     MEGB_LAUNCH_OK();
+    options().last_clip_dz_kernel = 0;
     return 0;
   }
   p.NT = D >= 256 ? 256 : (int)((D + 63) / 64 * 64);
@@ -2141,6 +2146,7 @@ int tc_clip_dz(const void* coef, int ldc, const void* Yp, const void* Z, const f
   if (p.swap_grid) grid = dim3((Bz + kTileM - 1) / kTileM, (unsigned)dt);
   tc_clip_dz_kernel<<<grid, kThreads, smem, st>>>(tmC, tmY, p);
   MEGB_LAUNCH_OK();
+  options().last_clip_dz_kernel = 1;
   return 0;
 }
 

@@ -20,7 +20,7 @@ import torch
 import torch.nn as nn
 
 import megb200
-from megb200.engine import EncoderEngine
+from megb200.engine import EncoderEngine, validate_subject_idxs
 from meg_decoding.utils.layout import ch_locations_2d
 
 
@@ -62,6 +62,20 @@ class SpatialAttention(nn.Module):
         self.register_buffer("sin", torch.sin(phi).contiguous(), persistent=False)
         self.spatial_dropout = SpatialDropout(loc, args.d_drop)
         self.register_buffer("drop_masks", self.spatial_dropout.all_masks().contiguous(), persistent=False)
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                              error_msgs):
+        """A checkpoint the reference wrote while running on CUDA has no ``z`` key: there ``nn.Parameter(...).to(device)``
+        turns z into a plain tensor that is neither trained nor saved (models.py:186-188).  Such a checkpoint loads
+        here (strict or not) with z left at its current value and a warning, instead of a missing-key error."""
+        if prefix + "z" not in state_dict:
+            import warnings
+            warnings.warn("megb200: checkpoint has no '{}z' (written by the reference on CUDA, where z is not a "
+                          "registered parameter); keeping the current z".format(prefix))
+            state_dict = dict(state_dict)
+            state_dict[prefix + "z"] = self.z.detach()
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                                      error_msgs)
 
 
 class SubjectBlock(nn.Module):
@@ -221,11 +235,12 @@ class BrainEncoder(nn.Module):
         S = self.num_subjects
         present = None
         subject_idxs = torch.as_tensor(subject_idxs)
-        if not subject_idxs.is_cuda:
-            if subject_idxs.numel() and (int(subject_idxs.max()) >= S or int(subject_idxs.min()) < -S):
-                raise IndexError("index {} is out of range".format(int(subject_idxs.max())))  # ModuleList semantics
-            subject_idxs = torch.where(subject_idxs < 0, subject_idxs + S, subject_idxs)
-            present = set(int(s) for s in subject_idxs.tolist())
+        # ModuleList semantics (models.py:270-272): IndexError outside [-S, S), negative indices wrap.  The reference
+        # keeps subject_idxs on the CPU (train.py:199 moves X and Y only); a device-resident index tensor is validated
+        # too -- one small device->host read -- because the grouped kernels index weights and shared memory with it.
+        # (megb200.graph.GraphedTrainStep validates in load(), outside the captured region.)
+        subject_idxs = validate_subject_idxs(subject_idxs, S)
+        present = set(int(s) for s in (torch.unique(subject_idxs) if subject_idxs.is_cuda else subject_idxs).tolist())
         subj = subject_idxs.to(device=dev, dtype=torch.int32, non_blocking=True).contiguous()
         X = X.to(device=dev, dtype=torch.float32).contiguous()
         mask = None

@@ -28,6 +28,19 @@ def _zeros(dev, *shape):
     return torch.zeros(*shape, dtype=torch.float32, device=dev)
 
 
+def validate_subject_idxs(idx: torch.Tensor, S: int) -> torch.Tensor:
+    """Range-check (IndexError like ``nn.ModuleList.__getitem__``) and wrap negative subject indices; CPU or CUDA."""
+    if idx.numel() == 0:
+        return idx
+    if idx.dtype not in (torch.int32, torch.int64, torch.int16, torch.int8, torch.uint8):
+        raise TypeError("subject_idxs must be an integer tensor, got {}".format(idx.dtype))
+    lo, hi = torch.aminmax(idx)
+    lo, hi = int(lo), int(hi)                      # a device tensor: one synchronising read of two scalars
+    if hi >= S or lo < -S:
+        raise IndexError("index {} is out of range".format(hi if hi >= S else lo))
+    return torch.where(idx < 0, idx + S, idx) if lo < 0 else idx
+
+
 class _ZeroPool:
     """One memset per pass instead of ~60 tiny ones: f32 accumulators / gradient buffers are carved out of a single
     zero-filled allocation (256-byte aligned views).  Falls back to torch.zeros when exhausted."""

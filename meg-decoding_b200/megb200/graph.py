@@ -175,11 +175,8 @@ class GraphedTrainStep:
         """Refill the static inputs (async on the current stream; pinned host tensors do not block)."""
         self.X.copy_(X, non_blocking=True)
         self.Y.copy_(Y, non_blocking=True)
-        s = torch.as_tensor(subject_idxs)
-        if not s.is_cuda:
-            if s.numel() and (int(s.max()) >= self.S or int(s.min()) < -self.S):
-                raise IndexError("index {} is out of range".format(int(s.max())))      # ModuleList semantics
-            s = torch.where(s < 0, s + self.S, s)
+        from .engine import validate_subject_idxs
+        s = validate_subject_idxs(torch.as_tensor(subject_idxs), self.S)     # IndexError like ModuleList; CPU or CUDA
         self.subj.copy_(s.to(torch.int32), non_blocking=True)
         if self.enc.training:
             c = drop_center if drop_center is not None else self._user_center

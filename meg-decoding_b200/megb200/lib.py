@@ -53,6 +53,7 @@ SIGNATURES = {
     "megb200_robust_scale": [_p, _p, _ll, _i, _i, _f, _i, _p],
     "megb200_adam_multi": [_p, _i, _f, _f, _f, _f, _f, _p],
     "megb200_cast": [_p, _p, _ll, _i, _i, _p],
+    "megb200_set_option": [_p, _ll],
 }
 
 _lib = None
@@ -74,6 +75,8 @@ def load():
     lib.megb200_last_error.argtypes = []
     lib.megb200_launch_count.restype = C.c_longlong
     lib.megb200_launch_count.argtypes = []
+    lib.megb200_get_option.restype = C.c_longlong
+    lib.megb200_get_option.argtypes = [C.c_char_p]
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
@@ -91,6 +94,35 @@ def check(rc: int, what: str):
 
 def launch_count() -> int:
     return int(load().megb200_launch_count())
+
+
+def set_option(name: str, value: int) -> int:
+    """Force a kernel variant (see include/megb200.h); returns the previous value."""
+    lib = load()
+    old = int(lib.megb200_get_option(name.encode()))
+    check(lib.megb200_set_option(name.encode(), int(value)), "megb200_set_option")
+    return old
+
+
+def get_option(name: str) -> int:
+    return int(load().megb200_get_option(name.encode()))
+
+
+class options:
+    """Context manager: ``with lib.options(tapgemm_pair_min_items=1): ...`` restores the previous values on exit."""
+
+    def __init__(self, **kw):
+        self.kw, self.old = kw, {}
+
+    def __enter__(self):
+        for k, v in self.kw.items():
+            self.old[k] = set_option(k, v)
+        return self
+
+    def __exit__(self, *exc):
+        for k, v in self.old.items():
+            set_option(k, v)
+        return False
 
 
 def call(name: str, *args):

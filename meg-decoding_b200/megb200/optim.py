@@ -28,25 +28,69 @@ class Adam(torch.optim.Optimizer):
         self._static = {}      # group index -> per-parameter constants (pointers of p / exp_avg / exp_avg_sq / counter)
         self._tables = {}      # (group index, gradient pointers) -> device table
 
+    # The kernel works from a table of raw device pointers into ``self.state``; anything that replaces the state tensors
+    # (load_state_dict, add_param_group, unpickling) must drop the cached pointers, and ``step`` re-validates them.
+    def _invalidate(self):
+        self._static = {}
+        self._tables = {}
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._invalidate()
+
+    def add_param_group(self, param_group):
+        super().add_param_group(param_group)
+        if hasattr(self, "_static"):
+            self._invalidate()
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._invalidate()
+
+    @staticmethod
+    def _usable(t, p):
+        return (torch.is_tensor(t) and t.shape == p.shape and t.dtype == p.dtype and t.device == p.device
+                and t.is_contiguous())
+
     def _prepare(self, gi, group):
-        """Per-parameter state, created once: moments like the parameter, one int64 step counter each (device)."""
+        """Per-parameter state: moments like the parameter, one int64 step counter each (device).  Existing state (a
+        resumed run: ``load_state_dict`` of this class's or ``torch.optim.Adam``'s checkpoint) is adopted, not zeroed."""
         ps = group["params"]
         for p in ps:
             if not p.is_cuda or _real(p).dtype != torch.float32 or not p.is_contiguous():
                 raise RuntimeError("megb200.optim.Adam: parameters must be contiguous f32 (or complex64) CUDA tensors")
         dev = ps[0].device
-        steps = torch.zeros(len(ps), dtype=torch.int64, device=dev)
+        counts = []
+        for p in ps:
+            st = self.state[p]
+            if self._usable(st.get("exp_avg"), p) and self._usable(st.get("exp_avg_sq"), p):
+                counts.append(int(float(st.get("step", 0))))       # torch.optim.Adam stores a float tensor
+            else:
+                st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                counts.append(0)
+        steps = torch.tensor(counts, dtype=torch.int64).to(dev)
         info = []
         for i, p in enumerate(ps):
             st = self.state[p]
-            st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-            st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
             st["step"] = steps[i]                       # 0-dim view: torch.optim.Adam's state key, device-resident
             pr = _real(p)
             info.append((pr.data_ptr(), _real(st["exp_avg"]).data_ptr(), _real(st["exp_avg_sq"]).data_ptr(), pr.numel(),
                          steps.data_ptr() + 8 * i))
         self._static[gi] = (dev, steps, info)
         return self._static[gi]
+
+    def _still_valid(self, gi, group):
+        """The cached pointers still name the live parameter / moment tensors (someone may have replaced state[p] or
+        p.data behind our back; a stale table would make the kernel write freed memory)."""
+        ent = self._static.get(gi)
+        if ent is None or len(ent[2]) != len(group["params"]):
+            return False
+        for p, (pp, m, v, _, _) in zip(group["params"], ent[2]):
+            st = self.state.get(p)
+            if st is None or p.data_ptr() != pp or st["exp_avg"].data_ptr() != m or st["exp_avg_sq"].data_ptr() != v:
+                return False
+        return True
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -58,7 +102,10 @@ class Adam(torch.optim.Optimizer):
             ps = group["params"]
             if not ps:
                 continue
-            dev, _, info = self._static.get(gi) or self._prepare(gi, group)
+            if not self._still_valid(gi, group):
+                self._tables = {k: v for k, v in self._tables.items() if k[0] != gi}
+                self._prepare(gi, group)
+            dev, _, info = self._static[gi]
             gptrs = []
             for p in ps:
                 g = p.grad

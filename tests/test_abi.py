@@ -42,7 +42,7 @@ def test_ctypes_signatures_match_header(built_lib):
     for name, argtypes in L.SIGNATURES.items():
         assert name in decls, name
         assert [a for a in argtypes] == decls[name], f"{name}: binding {argtypes} != header {decls[name]}"
-    missing = set(decls) - set(L.SIGNATURES) - {"megb200_version", "megb200_last_error", "megb200_launch_count"}
+    missing = set(decls) - set(L.SIGNATURES) - {"megb200_version", "megb200_last_error", "megb200_launch_count", "megb200_get_option"}
     assert not missing, f"header functions without a binding: {missing}"
 
 
@@ -56,3 +56,12 @@ def test_argument_errors_do_not_need_a_gpu(built_lib):
     rc = built_lib.megb200_gelu(None, None, 8, L.BF16, None)
     assert rc == -1
     assert b"gelu" in built_lib.megb200_last_error()
+
+
+def test_set_option_roundtrip_and_unknown_name(built_lib):
+    assert L.get_option("tapgemm_pair_min_items") == -1
+    with L.options(tapgemm_pair_min_items=1, clip_dz_large=1):
+        assert L.get_option("tapgemm_pair_min_items") == 1 and L.get_option("clip_dz_large") == 1
+    assert L.get_option("tapgemm_pair_min_items") == -1 and L.get_option("clip_dz_large") == 0
+    assert built_lib.megb200_set_option(b"no_such_option", 1) == -1
+    assert b"no_such_option" in built_lib.megb200_last_error()

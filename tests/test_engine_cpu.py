@@ -55,6 +55,32 @@ def test_state_dict_layout_matches_reference(torch_ops):
     assert list(lossf.state_dict().keys()) == ["temp"]
 
 
+def test_checkpoint_written_by_the_reference_on_cuda_loads(torch_ops):
+    """On CUDA the reference's z is not a registered parameter (models.py:186-188), so its checkpoints lack the key:
+    they must load (strict) with a warning and leave z untouched."""
+    cfg = synth.get_config("tiny")
+    enc, _ = H.make_modules(cfg, seed=1)
+    sd = H.make_modules(cfg, seed=0)[0].state_dict()
+    del sd["subject_block.spatial_attention.z"]
+    z_before = enc.subject_block.spatial_attention.z.detach().clone()
+    with pytest.warns(UserWarning, match="no 'subject_block.spatial_attention.z'"):
+        res = enc.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert torch.equal(enc.subject_block.spatial_attention.z.detach(), z_before)
+    assert torch.equal(enc.conv_final2.weight, sd["conv_final2.weight"])
+
+
+def test_subject_index_validation():
+    from megb200.engine import validate_subject_idxs
+    s = torch.tensor([0, 3, -1, -4], dtype=torch.int32)
+    assert validate_subject_idxs(s, 4).tolist() == [0, 3, 3, 0]           # ModuleList wraps negatives
+    for bad in ([0, 4], [-5, 1]):
+        with pytest.raises(IndexError):
+            validate_subject_idxs(torch.tensor(bad), 4)
+    with pytest.raises(TypeError):
+        validate_subject_idxs(torch.tensor([0.0, 1.0]), 4)
+
+
 def test_reference_error_conventions(torch_ops):
     cfg = synth.get_config("tiny")
     enc, lossf = H.make_modules(cfg)

@@ -4,6 +4,7 @@ run on both engines (SIMT fp32 CUDA cores and tcgen05 tensor cores)."""
 import pytest
 import torch
 
+from megb200 import lib as L
 from megb200.ops import pad8, pad16, pad64
 from oracle.ops_restatement import TorchOps
 
@@ -77,7 +78,15 @@ TAPGEMM_CASES = [
     (1, 360, 640, 1024, 1, 1, 1, True, False),    # head conv, N tile 256
     (3, 130, 208, 270, 1, 1, 5, True, False),     # subject GEMM at real widths (N = 272 -> 2 x 144)
     (2, 129, 320, 320, 3, 1, 1, False, True),     # dgrad-like: no bias, residual, T = 128 + 1
+    # --- shapes that cross the persistent CTA-pair kernels' work threshold NATIVELY (>= 2 x 148 tile items), i.e. the
+    # kernels config 2 runs (tc_tapgemm2h_kernel / tc_tapgemm2_kernel), with no option forced
+    (64, 360, 320, 320, 3, 1, 1, False, True),    # conv data gradient: STORE + residual, pair + halo (384 items)
+    (51, 360, 320, 320, 3, 2, 1, True, False),    # dilation 2 halo, odd number of M tiles (153: last pair half empty)
+    (50, 360, 640, 320, 1, 1, 1, False, False),   # head data gradient 640 -> 320: plain pair kernel (taps = 1)
 ]
+
+# which tensor-core kernel each natively-large case must have launched (megb200_get_option("last_tapgemm_kernel"))
+PAIR_EXPECT = {(64, 360, 320, 320, 3): 2, (51, 360, 320, 320, 3): 2, (50, 360, 640, 320, 1): 1}
 
 
 @pytest.mark.parametrize("dtype,backend", CONTRACTION_MODES)
@@ -100,6 +109,8 @@ def test_tapgemm(dtype, backend, case):
     ref.tapgemm(A, Ca, W, N, taps, dil, bias, Res, group, Outr)
     torch.cuda.synchronize()
     _close(Out, Outr, dtype, f"tapgemm {case} {backend}")
+    if backend == "tc" and case[:5] in PAIR_EXPECT:
+        assert L.get_option("last_tapgemm_kernel") == PAIR_EXPECT[case[:5]], "the product (CTA-pair) kernel did not run"
 
 
 EPI_CASES = [
@@ -112,7 +123,15 @@ EPI_CASES = [
     (3, 130, 32, 64, 1, "gelu"),
     (2, 360, 320, 640, 1, "gelu"),
     (1, 360, 640, 1024, 1, "gelu"),
+    # --- natively above the CTA-pair threshold: the product forms of every fused epilogue (config 2's kernels)
+    (64, 360, 320, 320, 3, "store_f32"),     # conv1: f32 store + residual + BatchNorm statistics, pair + halo
+    (64, 360, 270, 320, 3, "store_f32_nores"),  # block-0 conv0: K = 270 (OOB channels in the last k chunk), no residual
+    (50, 360, 320, 640, 3, "glu"),           # conv2 + GLU, pair + halo (750 items)
+    (64, 360, 320, 640, 1, "gelu"),          # head conv 1, pair
+    (32, 360, 640, 1024, 1, "gelu"),         # head conv 2: 1024 wide, N tile 256, pair
 ]
+EPI_PAIR_EXPECT = {(64, 360, 320, 320, 3): 2, (64, 360, 270, 320, 3): 2, (50, 360, 320, 640, 3): 2,
+                   (64, 360, 320, 640, 1): 1, (32, 360, 640, 1024, 1): 1}
 
 
 @pytest.mark.parametrize("dtype,backend", CONTRACTION_MODES)
@@ -127,7 +146,11 @@ def test_tapgemm_fused_epilogues(dtype, backend, case):
     W = W.view(1, pad16(N), taps * pad64(Ca)).to(dtype)
     bias = _rand(gen, 1, N)
     Res, Resd = (None, None)
-    if epi == "store_f32":
+    if epi == "store_f32_nores":
+        epi = "store_f32"
+        Out, Outr = torch.empty(B, T, pad8(N), device=DEV), torch.empty(B, T, pad8(N))
+        Out2 = Out2r = None
+    elif epi == "store_f32":
         Res, Resd = _act(gen, dtype, B, T, N)
         Out, Outr = torch.empty(B, T, pad8(N), device=DEV), torch.empty(B, T, pad8(N))
         Out2 = Out2r = None
@@ -148,6 +171,35 @@ def test_tapgemm_fused_epilogues(dtype, backend, case):
            atol_scale=5 if epi == "store_f32" else 1)
     if Out2 is not None:
         _close(Out2, Out2r, dtype, f"tapgemm {epi} Out2 {backend}")
+    if backend == "tc" and case[:5] in EPI_PAIR_EXPECT:
+        assert L.get_option("last_tapgemm_kernel") == EPI_PAIR_EXPECT[case[:5]], "the product (CTA-pair) kernel did not run"
+
+
+# Every hand-written form of the tap GEMM on every shape above that it accepts, forced in-process through
+# megb200_set_option (the size thresholds would otherwise keep small shapes on the single-CTA kernel).
+TAPGEMM_VARIANTS = {
+    "pair_halo": dict(tapgemm_pair_min_items=1),                              # tc_tapgemm2h_kernel for k > 1
+    "pair_plain": dict(tapgemm_pair_min_items=1, tapgemm_pair_halo=0),        # tc_tapgemm2_kernel for every k
+    "single": dict(tapgemm_force_1cta=1),                                     # tc_tapgemm_kernel even above the threshold
+    "single_halo": dict(tapgemm_force_1cta=1, tapgemm_halo=1),                # tc_tapgemm_halo_kernel
+    "single_direct_epi": dict(tapgemm_force_1cta=1, tapgemm_direct_epi=1),    # per-thread global stores
+}
+
+
+@pytest.mark.parametrize("variant", list(TAPGEMM_VARIANTS))
+@pytest.mark.parametrize("case", [c for c in TAPGEMM_CASES if c[6] == 1 and c[0] <= 8])
+def test_tapgemm_forced_variants(variant, case):
+    with L.options(**TAPGEMM_VARIANTS[variant]):
+        test_tapgemm(torch.bfloat16, "tc", case)
+        if variant.startswith("pair") and case[3] % 32 == 0:
+            assert L.get_option("last_tapgemm_kernel") in (1, 2)
+
+
+@pytest.mark.parametrize("variant", list(TAPGEMM_VARIANTS))
+@pytest.mark.parametrize("case", [c for c in EPI_CASES if c[0] <= 8])
+def test_tapgemm_fused_epilogues_forced_variants(variant, case):
+    with L.options(**TAPGEMM_VARIANTS[variant]):
+        test_tapgemm_fused_epilogues(torch.bfloat16, "tc", case)
 
 
 WGRAD_CASES = [
@@ -160,6 +212,11 @@ WGRAD_CASES = [
     (2, 360, 1024, 640, 1, 1, 1),    # head: two c tiles
     (5, 130, 270, 208, 1, 1, 3),     # grouped at real widths
     (20, 72, 320, 270, 3, 1, 1),     # more samples than one CTA range; c = 270 (OOB channels)
+    # --- config 2's split plans (B = 256): one wave of CTAs, several samples per CTA
+    (256, 360, 320, 320, 3, 1, 1),   # 9 tiles x 16 splits
+    (256, 360, 640, 320, 3, 1, 1),   # 15 tiles x 9 splits (floor: one wave)
+    (256, 360, 1024, 640, 1, 1, 1),  # head: 16 tiles x 9 splits
+    (256, 360, 270, 208, 1, 1, 27),  # grouped subject wgrad at the Gwilliams shape
 ]
 
 
@@ -186,6 +243,15 @@ def test_wgrad(dtype, backend, case):
     got, want = dW.cpu(), dWr
     err = float((got - want).abs().max()) / (float(want.abs().max()) + 1e-30)
     assert torch.isfinite(got).all() and err < 2e-4, f"wgrad {case} {backend}: {err:.3e}"
+    if backend == "tc" and B == 256 and G == 1:
+        assert L.get_option("last_wgrad_splits") > 1, "config 2's split plan was not exercised"
+
+
+@pytest.mark.parametrize("splits", [1, 2, 5])
+def test_wgrad_forced_splits(splits):
+    with L.options(wgrad_splits=splits):
+        test_wgrad(torch.bfloat16, "tc", (20, 72, 320, 270, 3, 1, 1))
+        assert L.get_option("last_wgrad_splits") == splits
 
 
 @pytest.mark.parametrize("dtype", EW_DTYPES)
@@ -365,7 +431,11 @@ CLIP_CASES = [
     (24, 8, 8, 64, 24),        # one-sided data-parallel shard: rank 1 of 3
     (16, 16, 0, 1024, 360),    # the real contraction length D = 368 640
     (300, 150, 150, 512, 1),   # GOD-like: several tiles in both directions
+    (256, 256, 0, 1024, 72),   # config 2's batch (single rank): small-K dZ form at By = 256
+    (2048, 256, 512, 1024, 36),  # 8-rank shape, rank 2: By > 512 -> tc_clip_dz_kernel (large-K form), 16 i-tiles
+    (2048, 2048, 0, 512, 1),   # GOD-like global batch on one rank
 ]
+CLIP_DZ_EXPECT = {(256, 256): 0, (2048, 256): 1, (2048, 2048): 1}
 
 
 @pytest.mark.parametrize("dtype,backend", CONTRACTION_MODES)
@@ -423,3 +493,13 @@ def test_clip_pipeline(dtype, backend, case):
     ref.clip_dz(coef.cpu(), Yp.cpu(), Z, cvec.cpu(), gs, dZr)
     torch.cuda.synchronize()
     _close(dZ, dZr, dtype, f"clip_dz {backend}")
+    if backend == "tc" and (By, Bz) in CLIP_DZ_EXPECT and not L.get_option("clip_dz_large"):
+        assert L.get_option("last_clip_dz_kernel") == CLIP_DZ_EXPECT[(By, Bz)]
+
+
+@pytest.mark.parametrize("case", [c for c in CLIP_CASES if c[0] <= 512])
+def test_clip_pipeline_large_k_dz_forced(case):
+    """tc_clip_dz_kernel (the form every >= 4-GPU job runs) on the shapes the small-K form normally takes."""
+    with L.options(clip_dz_large=1):
+        test_clip_pipeline(torch.bfloat16, "tc", case)
+        assert L.get_option("last_clip_dz_kernel") == 1

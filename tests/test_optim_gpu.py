@@ -41,6 +41,65 @@ def test_adam_matches_torch_adam(wd):
     assert worst <= 2e-6
 
 
+def _rand_grads(params, twins, gen):
+    for p, q in zip(params, twins):
+        g = torch.randn(p.shape, device=DEV, generator=gen, dtype=torch.float32)
+        if p.is_complex():
+            g = torch.complex(g, torch.randn(p.shape, device=DEV, generator=gen))
+        p.grad, q.grad = g.clone(), g.clone()
+
+
+def _worst(params, twins):
+    worst = 0.0
+    for p, q in zip(params, twins):
+        a, b = (torch.view_as_real(t) if t.is_complex() else t for t in (p.detach(), q.detach()))
+        worst = max(worst, float((a - b).abs().max()) / (float(b.abs().max()) + 1e-12))
+    return worst
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("source", ["megb200", "torch"])
+def test_adam_resume_from_checkpoint(source):
+    """save -> load_state_dict -> step, against torch.optim.Adam doing the same (the reference's optimizer resumes):
+    the loaded moments and step counts must be USED (not zeroed) and the kernel must write the NEW state tensors.
+    `source` = whose checkpoint is loaded: this class's own, or one written by torch.optim.Adam."""
+    cfg = synth.get_config("tiny")
+    enc, lossf = H.make_modules(cfg, DEV)
+    params = list(enc.parameters()) + list(lossf.parameters())
+    twins = [torch.nn.Parameter(p.detach().clone()) for p in params]
+    kw = dict(lr=3e-3, betas=(0.9, 0.99), eps=1e-8)
+    ours, ref = Adam(params, **kw), torch.optim.Adam(twins, **kw)
+    gen = torch.Generator(device=DEV).manual_seed(2)
+    for _ in range(3):
+        _rand_grads(params, twins, gen)
+        ours.step()
+        ref.step()
+    ckpt = (ours if source == "megb200" else ref).state_dict()
+    ckpt_ref = ref.state_dict()
+    # resume into FRESH optimizers (load before the first step) ...
+    ours2, ref2 = Adam(params, **kw), torch.optim.Adam(twins, **kw)
+    ours2.load_state_dict(ckpt)
+    ref2.load_state_dict(ckpt_ref)
+    for _ in range(2):
+        _rand_grads(params, twins, gen)
+        ours2.step()
+        ref2.step()
+    assert _worst(params, twins) <= 2e-6
+    assert int(ours2.state[params[0]]["step"]) == 5
+    # ... and into a LIVE optimizer (load after steps: the cached pointer table must be dropped)
+    old_m = ours2.state[params[1]]["exp_avg"]
+    ours2.load_state_dict(ckpt)
+    ref2.load_state_dict(ckpt_ref)
+    keep = old_m.clone()
+    for _ in range(2):
+        _rand_grads(params, twins, gen)
+        ours2.step()
+        ref2.step()
+    assert _worst(params, twins) <= 2e-6
+    assert torch.equal(old_m, keep), "the kernel kept writing the moment buffer of the replaced state"
+    assert int(ours2.state[params[0]]["step"]) == 5
+
+
 def test_adam_rejects_cpu_parameters():          # CPU tier: the product path has no CPU fallback
     p = torch.nn.Parameter(torch.zeros(4))
     p.grad = torch.ones(4)

@@ -117,6 +117,14 @@ def test_subject_routing_bit_exact_and_permutation_equivariant(mode):
         Zb = enc(X2, torch.tensor([3, 4] + [0] * 10, dtype=torch.int32))
     assert torch.equal(Za[0], Za[1])
     assert not torch.equal(Zb[0], Zb[1])
+    # device-resident indices are range-checked too (the grouped kernels index weights with them): ModuleList's IndexError
+    S = cfg.num_subjects
+    for bad in (S, -S - 1):
+        with pytest.raises(IndexError):
+            enc(X, torch.full((12,), bad, dtype=torch.int32, device=DEV))
+    with torch.no_grad():
+        Zneg = enc(X, (subj - S).to(DEV))                # negative indices wrap like ModuleList[-k]
+    assert torch.equal(Zneg, Z)
 
 
 def test_full_size_tensor_core_path_agrees_with_check_mode():
@@ -139,6 +147,88 @@ def test_full_size_tensor_core_path_agrees_with_check_mode():
         e = H.rel_fro(res["bf16"][2][k].float(), res["fp32"][2][k].float())
         print(f"[parity]   grad {k}: {e:.2e}")
         assert e <= 0.2, k
+
+
+# ------------------------------------------------------------------------------------------------ config 2, full size
+_ORACLE_CACHE = {}
+
+
+def _oracle_full(name, B, seed):
+    """CPU oracle (fp32, all host threads) of one training step at the full BASELINE.json shape, with the per-layer
+    activations; cached so that the bf16 and the fp32 runs of one seed share it."""
+    from oracle import restatement as R
+    key = (name, B, seed)
+    if key not in _ORACLE_CACHE:
+        cfg = synth.get_config(name, B=B)
+        P = R.state_to_torch(synth.make_state(cfg, seed), requires_grad=True)
+        temp = torch.tensor([float(cfg.init_temperature)], requires_grad=True)
+        X, Y, subj = synth.make_batch(cfg, seed)
+        X, Y, subj = torch.from_numpy(X), torch.from_numpy(Y), torch.from_numpy(subj)
+        Z, inter = R.encoder_forward(P, X, subj, synth.sensor_locations(cfg.C), K=cfg.K, d_drop=cfg.d_drop,
+                                     seq2seq=cfg.seq2seq, training=True, drop_center=synth.drop_center(cfg),
+                                     return_intermediates=True)
+        loss = R.clip_loss(Y, Z, temp)
+        names = ["conv_final2.weight", "conv_blocks.conv2.conv1.weight", "conv_blocks.conv0.conv0.weight",
+                 "subject_block.conv.weight"]
+        grads = torch.autograd.grad(loss, [P[n] for n in names] + [temp])
+        _ORACLE_CACHE.clear()            # one seed resident at a time (~1.5 GB of host memory each)
+        _ORACLE_CACHE[key] = dict(
+            Z=Z.detach(), loss=float(loss.detach()), inter={k: v.detach() for k, v in inter.items() if k != "sa"},
+            grads={n: g for n, g in zip(names + ["temp"], grads)})
+    return _ORACLE_CACHE[key]
+
+
+def _layer_errors(enc, X, subj, center, ref):
+    """Per-layer rel-Frobenius errors of one more forward through the engine (position-major activations -> NCW)."""
+    sa = enc.subject_block.spatial_attention
+    eng = enc._engine()
+    with torch.no_grad():
+        params = enc._param_list()
+        _, ctx = eng.forward(enc._param_dict(params), X, subj.to(X.device).to(torch.int32), sa.drop_masks[center], True)
+    out = {"subject": H.rel_fro(ctx["H2"][:, :, :enc.D1].float().permute(0, 2, 1).cpu(), ref["subject"])}
+    for k in range(5):
+        t = ctx["blocks"][k + 1]["x"] if k < 4 else ctx["x5"]
+        out[f"block{k}"] = H.rel_fro(t[:, :, :enc.D2].float().permute(0, 2, 1).cpu(), ref[f"block{k}"])
+    return out
+
+
+@pytest.mark.parametrize("prec,seed", [("bf16", 0), ("fp32", 0), ("bf16", 1), ("bf16", 2)])
+def test_config2_full_batch_against_cpu_oracle(prec, seed):
+    """BASELINE.json configs[1] at its real size (B=256, C=208, T=360, 27 subjects): the kernels that run here are
+    the product kernels (persistent CTA-pair tap-GEMMs, one-wave weight-gradient splits, B=256 CLIP forms).  Loss,
+    embeddings, per-layer activations and a few gradients against the CPU oracle on the same seeded inputs; three
+    seeds in bf16 because the 2e-2 bar leaves little margin (the margin is printed)."""
+    tz, tl, _ = MODES[prec]
+    ref = _oracle_full("gwilliams", 256, seed)
+    old = megb200.get_precision()
+    megb200.set_precision(prec)
+    try:
+        cfg = synth.get_config("gwilliams", B=256)
+        enc, lossf = H.make_modules(cfg, DEV, seed=seed)
+        X, Y, subj = H.make_inputs(cfg, DEV, seed=seed)
+        center = synth.drop_center(cfg)
+        Z, loss, grads = H.train_step(enc, lossf, X, Y, subj, center)
+        torch.cuda.synchronize()
+        ez = H.rel_fro(Z.float().cpu(), ref["Z"])
+        el = abs(float(loss) - ref["loss"]) / abs(ref["loss"])
+        layers = _layer_errors(enc, X, subj, center, ref["inter"])
+        gerr = {k: H.rel_fro((torch.view_as_real(grads[k]) if grads[k].is_complex() else grads[k]).float().cpu(), g)
+                for k, g in ref["grads"].items()}
+    finally:
+        megb200.set_precision(old)
+    print(f"[parity] gwilliams B=256 {prec} seed {seed}: Z={ez:.3e} (bar {tz:.0e}, margin {100 * (1 - ez / tz):.0f} %) "
+          f"loss={el:.2e} | " + " ".join(f"{k}={v:.2e}" for k, v in layers.items()) + " | grads " +
+          " ".join(f"{k.split('.')[-2] if '.' in k else k}={v:.2e}" for k, v in gerr.items()))
+    assert el <= tl, f"loss rel error {el:.3e} > {tl}"
+    for k, v in layers.items():          # a failure bisects to the first layer that leaves the budget
+        assert v <= tz, f"layer {k}: rel-Fro {v:.3e} > {tz}"
+    assert ez <= tz, f"Z rel-Fro {ez:.3e} > {tz}"
+    gt = 5e-3 if prec == "fp32" else 0.2
+    for k, v in gerr.items():
+        assert v <= (gt if k != "temp" else (5e-3 if prec == "fp32" else 5e-2)), f"grad {k}: {v:.3e}"
+    if prec == "bf16":
+        from megb200 import lib
+        assert lib.get_option("last_wgrad_splits") >= 1 and lib.get_option("last_clip_dz_kernel") == 0
 
 
 def test_bf16_is_the_default_precision_and_output_is_bf16():
