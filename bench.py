@@ -502,6 +502,8 @@ def run_megb200(args):
         "step_frac_of_peak": flops_step / (ms * 1e-3) / 1e12 / peaks["bf16_sustained"],
         "launch_path": "cuda_graph" if graph_ms is not None else "eager", "ms_per_step_eager": eager_ms,
         "ms_per_step_graph": graph_ms, "graph_note": graph_note,
+        "dp_target_gather": (parallel.context().gather_mode if parallel.context() is not None else None),
+        "dp_target_gather_note": (parallel.context().gather_note if parallel.context() is not None else None),
         "adam_ms": adam_ms, "adam_ms_torch_optim": adam_torch_ms, "host_enqueue_ms_per_step": host_ms, "loss": loss_value, "precision": args.precision,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -532,6 +534,7 @@ def run_megb200(args):
         barrier()
         gstep = None          # noqa: F841  (drops the recording)
         prefetcher = None     # noqa: F841
+        parallel.shutdown()   # unmaps the peer slabs
         gc.enable()
         gc.collect()
         torch.cuda.synchronize()

@@ -187,6 +187,11 @@ int megb200_clip_logits(const void* Yp, const void* Zp, float* raw, int By, int 
  * (max, sum exp) over the local brains; per brain column j the complete log-sum-exp over all speech rows. */
 int megb200_clip_ce_partial(const float* raw, const float* ysq, const float* zsq, const float* temp, float* L,
                             float* row_max, float* row_sumexp, float* col_lse, int By, int Bz, void* stream);
+/* row_lse[i] = log sum_w parts[w][1][i] * exp(parts[w][0][i])  (max-shifted): completes the per-speech-row log-sum-exp
+ * over ALL brains from the W ranks' partial (max, sum exp) pairs; parts is [W][2][By] f32, the layout an all-gather of
+ * the ranks' [2][By] blocks (row_max then row_sumexp of megb200_clip_ce_partial, allocated back to back) produces.
+ * W = 1: the single-process loss.  One all-gather + this kernel replace a MAX and a SUM all-reduce. */
+int megb200_clip_lse_merge(const float* parts, int W, int By, float* row_lse, void* stream);
 /* Given the complete row LSEs: out[0] += loss contribution of this shard, out[1] += d loss / d temp;
  * coef[j][i] = dL[i][j] * exp(temp)/(|y_i||z_j|)  (`dtype`), cvec[j] = sum_i dL[i][j]*L[i][j] / zsq[j].
  * dL = (exp(L-row_lse[i]) + exp(L-col_lse[j]) - 2*[i == off + j]) * wscale, wscale = 1/(2*Bglob) for
@@ -231,6 +236,21 @@ int megb200_robust_scale(const float* X, float* Out, long long rows, int T, int 
  * the L2 form (added to the gradient), amsgrad is not supported -- the reference uses neither. */
 int megb200_adam_multi(const long long* table, int n, float lr, float beta1, float beta2, float eps, float weight_decay,
                        void* stream);
+/* ---------------------------------------------------------------------------------------------- peer memory (data parallel)
+ * The all-gather of the packed speech targets (189 MB per rank, 1.3 GB received per rank at 8 GPUs) runs on
+ * the COPY ENGINES over NVLink peer memory, so that no SM is taken from the persistent one-CTA-per-SM contraction
+ * kernels that execute meanwhile: every rank exports its slab once (CUDA IPC), maps the peers' slabs, and each step
+ * pulls the peers' slots with plain asynchronous copies on a side stream.
+ *   export: handle (64 bytes, HOST memory) of the cudaMalloc allocation that contains dev_ptr, and dev_ptr's byte offset
+ *           inside it (the caching allocator sub-allocates);
+ *   import: maps a peer process's allocation into this process (peer access enabled lazily) -> *base_out; the caller
+ *           adds the offset.  One import per (process, peer allocation); release unmaps it.
+ *   copy:   cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault) on `stream` -- device/peer/pinned-host pointers (UVA). */
+int megb200_ipc_export(const void* dev_ptr, unsigned char* handle64, long long* offset_bytes);
+int megb200_ipc_import(const unsigned char* handle64, void** base_out);
+int megb200_ipc_release(void* base);
+int megb200_copy_async(void* dst, const void* src, size_t bytes, void* stream);
+
 /* d[i] = s[i] cast between f32 and the activation dtype (n elements) */
 int megb200_cast(const void* src, void* dst, long long n, int src_dtype, int dst_dtype, void* stream);
 #ifdef __cplusplus

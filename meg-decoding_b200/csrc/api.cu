@@ -224,6 +224,61 @@ long long megb200_get_option(const char* name) {
                       : (long long)*reinterpret_cast<const int*>(base + e->off);
 }
 
+// ---------------------------------------------------------------------------------------------- peer memory
+typedef CUresult (*GetAddressRangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+
+int megb200_ipc_export(const void* dev_ptr, unsigned char* handle64, long long* offset_bytes) {
+  MEGB_CHECK_ARG(dev_ptr && handle64 && offset_bytes, "ipc_export: bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  static GetAddressRangeFn get_range = nullptr;
+  if (get_range == nullptr) {
+    void* fp = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaFree(nullptr);
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fp, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess || fp == nullptr) {
+      set_last_error("ipc_export: cuMemGetAddressRange is not available from the driver");
+      return MEGB200_ERR_DRIVER;
+    }
+    get_range = reinterpret_cast<GetAddressRangeFn>(fp);
+  }
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  CUresult r = get_range(&base, &size, (CUdeviceptr)(uintptr_t)dev_ptr);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("ipc_export: cuMemGetAddressRange failed with CUresult %d", (int)r);
+    return MEGB200_ERR_DRIVER;
+  }
+  cudaIpcMemHandle_t h;
+  MEGB_CUDA_OK(cudaIpcGetMemHandle(&h, reinterpret_cast<void*>((uintptr_t)base)));
+  memcpy(handle64, &h, 64);
+  *offset_bytes = (long long)((uintptr_t)dev_ptr - (uintptr_t)base);
+  return 0;
+}
+
+int megb200_ipc_import(const unsigned char* handle64, void** base_out) {
+  MEGB_CHECK_ARG(handle64 && base_out, "ipc_import: bad arguments");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  MEGB_CUDA_OK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *base_out = p;
+  return 0;
+}
+
+int megb200_ipc_release(void* base) {
+  MEGB_CHECK_ARG(base != nullptr, "ipc_release: null pointer");
+  MEGB_CUDA_OK(cudaIpcCloseMemHandle(base));
+  return 0;
+}
+
+int megb200_copy_async(void* dst, const void* src, size_t bytes, void* stream) {
+  MEGB_CHECK_ARG(dst && src, "copy_async: null pointer");
+  if (bytes == 0) return 0;
+  MEGB_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+  return 0;
+}
+
 int megb200_group_order(const int32_t* group, int B, int G, int32_t* order, void* stream) {
   MEGB_CHECK_ARG(group && order && B > 0 && G > 0 && G < 8192, "group_order: bad arguments");
   group_order_kernel<<<1, 256, (G + 1) * sizeof(int), (cudaStream_t)stream>>>(group, B, G, order);

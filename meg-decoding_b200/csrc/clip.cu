@@ -64,6 +64,22 @@ __global__ void clip_cols_kernel(const float* __restrict__ L, float* __restrict_
   }
 }
 
+// Complete the per-speech-row log-sum-exp over ALL brains from the ranks' partial (max, sum exp) pairs (SURVEY appendix
+// A6: in data parallel a rank only sees its own brain columns).  parts: [W][2][By] -- rank-major, row 0 = max, row 1 =
+// sum of exp(L - max) -- as an all-gather of the ranks' [2][By] blocks lays them out; W = 1 is the single-process case.
+__global__ void clip_lse_merge_kernel(const float* __restrict__ parts, int W, int By, float* __restrict__ row_lse) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= By) return;
+  float M = -INFINITY;
+  for (int w = 0; w < W; ++w) M = fmaxf(M, parts[((long long)w * 2) * By + i]);
+  float S = 0.f;
+  for (int w = 0; w < W; ++w) {
+    const float m = parts[((long long)w * 2) * By + i];
+    if (m > -INFINITY) S += parts[((long long)w * 2 + 1) * By + i] * expf(m - M);
+  }
+  row_lse[i] = M + logf(S);
+}
+
 // 32x32 tiles: dL, loss/dtemp partials, per-column sum dL*L, transposed coefficient tile for the dZ contraction
 template <typename T>
 __global__ void clip_finish_kernel(const float* __restrict__ L, const float* __restrict__ row_lse,
@@ -156,6 +172,13 @@ int megb200_clip_ce_partial(const float* raw, const float* ysq, const float* zsq
   clip_rows_kernel<<<(By * 32 + 255) / 256, 256, 0, st>>>(raw, ysq, zsq, temp, L, row_max, row_sumexp, By, Bz);
   MEGB_LAUNCH_OK();
   clip_cols_kernel<<<(Bz + 31) / 32, dim3(32, 8), 0, st>>>(L, col_lse, By, Bz);
+  MEGB_LAUNCH_OK();
+  return 0;
+}
+
+int megb200_clip_lse_merge(const float* parts, int W, int By, float* row_lse, void* stream) {
+  MEGB_CHECK_ARG(parts && row_lse && W > 0 && By > 0, "clip_lse_merge: bad arguments");
+  clip_lse_merge_kernel<<<(By + 255) / 256, 256, 0, (cudaStream_t)stream>>>(parts, W, By, row_lse);
   MEGB_LAUNCH_OK();
   return 0;
 }

@@ -49,6 +49,7 @@ class _ZeroPool:
         self.dev = dev
         self.buf = torch.zeros(int(nfloats), dtype=torch.float32, device=dev)
         self.off = 0
+        self.spilled = False       # a take() did not fit: that tensor is NOT part of the flat buffer
 
     def take(self, *shape):
         n = 1
@@ -56,6 +57,7 @@ class _ZeroPool:
             n *= int(d)
         n_al = (n + 63) // 64 * 64
         if self.off + n_al > self.buf.numel():
+            self.spilled = True
             return torch.zeros(*shape, dtype=torch.float32, device=self.dev)
         v = self.buf[self.off:self.off + n].view(*shape)
         self.off += n_al
@@ -200,9 +202,17 @@ class EncoderEngine:
         return h, st
 
     # ------------------------------------------------------------------------------------------ backward
-    def backward(self, P: Dict, ctx: Dict, dZ: torch.Tensor):
+    def backward(self, P: Dict, ctx: Dict, dZ: torch.Tensor, sync=None):
         """dZ: gradient w.r.t. the returned embedding, PC layout ([B,T,Fs] or [B,1,Fs]).  Returns a dict of f32
-        gradients keyed like P."""
+        gradients keyed like P.
+
+        Every parameter gradient is a view of ONE flat zero-initialised f32 buffer, laid out in the order the backward
+        pass completes them: [head | block 4 .. block 1 | block 0 | subject block, spatial attention | 2 spare floats];
+        ``G["_flat"]`` is that range, so data parallel all-reduces it in place (no gather / scatter copies; the caller may
+        put the loss and the temperature gradient into ``G["_extra"]`` first).  ``sync`` (optional): ``sync.early(t)`` is
+        called with the [head .. block 1] sub-range as soon as those gradients are final -- the caller starts their
+        all-reduce on a side stream while block 0 and the subject block are still running -- and ``G["_flat_late"]`` is
+        the rest."""
         ops, dev = self.ops, dZ.device
         B, T = ctx["B"], ctx["T"]
         D1, D2, Fo, S, C = self.D1, self.D2, self.F, self.S, self.C
@@ -210,7 +220,8 @@ class EncoderEngine:
         G: Dict = {"blocks": [dict() for _ in range(5)]}
         self._wd = self._pack_all(P, 1, dev)
         nparam = sum(int(w.numel()) + N for _, w, N, _, _ in self._conv_list(P))
-        self._zp = _ZeroPool(dev, nparam + S * D1 * C + S * D1 + 20 * 2 * pad64(D2) + 64 * 80)
+        ntail = S * D1 * D1 + D1 * D1 + D1 + 2 * int(P["z_re"].numel())
+        self._zp = zp = _ZeroPool(dev, nparam + ntail + S * D1 * C + S * D1 + 20 * 2 * pad64(D2) + 64 * 96)
 
         if not self.seq2seq:
             full = ops.empty(B, T, pad8(Fo), device=dev)
@@ -228,6 +239,7 @@ class EncoderEngine:
         dx = self._dgrad(dp1, 2 * D2, "wf1", D2, 1, None, taps=1)
 
         # ---- conv blocks, last to first
+        early_end = 0
         for k in range(4, -1, -1):
             pk, bc, d, g = P["blocks"][k], ctx["blocks"][k], self.dil[k], G["blocks"][k]
             dv = ops.empty(*bc["v"].shape, device=dev)
@@ -245,35 +257,42 @@ class EncoderEngine:
             du0, g["g0"], g["be0"], g["b0"] = self._bn_gelu_bwd(dh0, bc["u0"], bc["bn0"], pk["g0"], n)
             g["w0"] = self._wgrad(du0, D2, bc["x"], bc["cin"], 3, d[0])
             dx = self._dgrad(du0, D2, f"b{k}.w0", bc["cin"], d[0], du0 if k > 0 else None)
+            if k == 1:
+                early_end = zp.off
+                if sync is not None and not zp.spilled:
+                    sync.early(zp.buf[:early_end])
         dH2 = dx
 
         # ---- subject block + spatial attention, fp32 small algebra
         subj = ctx["subj"]
         order = torch.empty_like(subj)
         ops.group_order(subj, S, order)
+        dWs, dWc, dbc = zp.take(S, D1, D1), zp.take(D1, D1), zp.take(D1, 1)
+        dzr, dzi = zp.take(*P["z_re"].shape), zp.take(*P["z_im"].shape)
+        G["_extra"] = zp.take(2)              # spare floats inside the flat range (loss, temperature gradient)
+        grad_end = zp.off
         dWeff = self._zp.take(S, D1, C, 1)
         ops.wgrad(dH2, D1, ctx["Xp"], C, 1, 1, subj, order, dWeff)
         dWeff = dWeff.view(S, D1, C)
         dbeff = self._zp.take(S, D1)
         ops.colsum(dH2, D1, subj, dbeff)
-        dWs = _f32(dev, S, D1, D1)
         ops.matmul(dWeff, ctx["M1"], dWs, transB=True)
         ops.matmul(dbeff.view(S, D1, 1), P["bc"].view(1, D1), dWs, beta=1.0)
         Ws2d = P["Ws"].view(S * D1, D1)
         dM1 = _f32(dev, D1, C)
         ops.matmul(Ws2d, dWeff.view(S * D1, C), dM1, transA=True)
-        dbc = _f32(dev, D1, 1)
         ops.matmul(Ws2d, dbeff.view(S * D1, 1), dbc, transA=True)
-        dWc = _f32(dev, D1, D1)
         ops.matmul(dM1, ctx["Wm"], dWc, transB=True)
         dWm = _f32(dev, D1, C)
         ops.matmul(P["Wc"], dM1, dWm, transA=True)
         da = _f32(dev, D1, C)
         ops.sa_softmax_bwd(ctx["Wt"], dWm, ctx["mask"], da)
-        dzr, dzi = _f32(dev, *P["z_re"].shape), _f32(dev, *P["z_im"].shape)
         ops.matmul(da, P["cos"], dzr, transB=True)
         ops.matmul(da, P["sin"], dzi, transB=True)
         G.update(Ws=dWs, Wc=dWc, bc=dbc.view(D1), z_re=dzr, z_im=dzi)
+        if not zp.spilled:
+            G["_flat"] = zp.buf[:grad_end]
+            G["_flat_late"] = zp.buf[early_end:grad_end] if (sync is not None and early_end) else G["_flat"]
         return G
 
     def _wgrad(self, dU, M, Xin, C, taps, dil):
@@ -319,10 +338,27 @@ class ClipEngine:
     def prepare_targets(self, Y, dist_ctx=None):
         """Pack the (constant) targets: f32 [B,F,T] | [B,F] -> position-major rows in the activation dtype plus their
         squared norms, all-gathered over the ranks in data parallel.  Independent of the encoder, so callers may run
-        it on a side stream while the encoder forward executes (CLIPLoss.prefetch_targets)."""
+        it on a side stream while the encoder forward executes (CLIPLoss.prefetch_targets).
+
+        Data parallel on CUDA: the pack kernel writes this rank's slot of a peer-mapped slab and the other ranks' slots
+        are pulled by the copy engines over NVLink (parallel.PeerGather) -- no SM is used, so the gather overlaps the
+        encoder forward without slowing its persistent kernels.  The returned tensors are views of that slab: they stay
+        valid until the next prepare_targets call with the same shape."""
         ops, dev = self.ops, Y.device
         B = Y.shape[0]
         D = Y.numel() // B
+        if dist_ctx is not None and dist_ctx.world > 1:
+            pair = dist_ctx.target_gather(B, D, ops.act_dtype, dev)
+            if pair is not None:
+                gy, gs = pair
+                Yp, ysq = gy.slot().view(B, D), gs.slot()
+                ysq.zero_()
+                ops.clip_prep_y(Y, Yp, ysq)
+                gy.fence()
+                gy.pull()
+                gs.pull()
+                gy.fence()
+                return gy.buf.view(dist_ctx.world * B, D), gs.buf.view(dist_ctx.world * B)
         Yp = ops.empty(B, D, device=dev)
         ysq = _zeros(dev, B)
         ops.clip_prep_y(Y, Yp, ysq)
@@ -330,8 +366,11 @@ class ClipEngine:
             Yp, ysq = dist_ctx.all_gather_rows(Yp), dist_ctx.all_gather_rows(ysq)
         return Yp, ysq
 
-    def forward(self, Y, Zi, temp, reduction="mean", dist_ctx=None, want_logits=False, prepared=None):
-        """Y: f32 targets [B,F,T] | [B,F]; Zi: embeddings in PC layout, contiguous [B, T, F] | [B, 1, F]."""
+    def forward(self, Y, Zi, temp, reduction="mean", dist_ctx=None, want_logits=False, prepared=None,
+                reduce_loss=True):
+        """Y: f32 targets [B,F,T] | [B,F]; Zi: embeddings in PC layout, contiguous [B, T, F] | [B, 1, F].
+        reduce_loss=False (data parallel): return this rank's loss CONTRIBUTION; the caller sums it over the ranks
+        (GraphedTrainStep lets it ride in the gradient all-reduce)."""
         ops, dev = self.ops, Zi.device
         B = Zi.shape[0]
         D = Zi.numel() // B
@@ -345,13 +384,12 @@ class ClipEngine:
         raw = _zeros(dev, Bg, B)
         ops.clip_logits(Yp, Zf, raw)
         Lg = _f32(dev, Bg, B)
-        row_max, row_se, col_lse = _f32(dev, Bg), _f32(dev, Bg), _f32(dev, B)
-        ops.clip_ce_partial(raw, ysq, zsq, temp, Lg, row_max, row_se, col_lse)
+        parts, col_lse = _f32(dev, 1, 2, Bg), _f32(dev, B)         # per speech row: (max, sum exp) over the LOCAL brains
+        ops.clip_ce_partial(raw, ysq, zsq, temp, Lg, parts[0, 0], parts[0, 1], col_lse)
         if world > 1:
-            m = dist_ctx.all_reduce_max(row_max.clone())
-            row_se = dist_ctx.all_reduce_sum(row_se * torch.exp(row_max - m))
-            row_max = m
-        row_lse = row_max + torch.log(row_se)
+            parts = dist_ctx.all_gather_rows(parts)                 # [world, 2, Bg]: one collective, merged on the device
+        row_lse = _f32(dev, Bg)
+        ops.clip_lse_merge(parts, row_lse)
         if reduction == "mean":
             wscale = 0.5 / Bg
         elif reduction == "sum":
@@ -363,7 +401,7 @@ class ClipEngine:
         cvec = _zeros(dev, B)
         ops.clip_ce_finish(Lg, row_lse, col_lse, ysq, zsq, temp, off, wscale, out2, coef, cvec)
         loss = out2[0:1].clone()
-        if world > 1:
+        if world > 1 and reduce_loss:
             loss = dist_ctx.all_reduce_sum(loss)
         ctx = dict(coef=coef, Yp=Yp, Zf=Zf, cvec=cvec, dtemp=out2[1:2], shape=Zi.shape)
         return loss.view(()), (Lg if want_logits else None), ctx

@@ -34,6 +34,32 @@ from . import lib, parallel
 __all__ = ["GraphedTrainStep"]
 
 
+class _GradSync:
+    """Starts the all-reduce of the gradients that are final early (head + conv blocks 4..1, ~70 % of the bytes) on a
+    side stream while the backward pass of block 0 and the subject block still runs (EncoderEngine.backward calls
+    ``early``); ``join`` makes the main stream wait for it.  MEGB200_DP_EARLY_BUCKET=0 disables the split."""
+
+    def __init__(self, dev):
+        self.dev = dev
+        self.side = torch.cuda.Stream(device=dev)
+        self.enabled = os.environ.get("MEGB200_DP_EARLY_BUCKET", "1") != "0"
+        self.pending = False
+
+    def early(self, flat):
+        self.pending = False
+        if not self.enabled:
+            return
+        cur = torch.cuda.current_stream(self.dev)
+        self.side.wait_stream(cur)
+        with torch.cuda.stream(self.side):
+            parallel.allreduce_flat(flat)
+        self.pending = True
+
+    def join(self):
+        if self.pending:
+            torch.cuda.current_stream(self.dev).wait_stream(self.side)
+
+
 class GraphedTrainStep:
     def __init__(self, encoder, loss_fn, X, Y, subject_idxs, drop_center: Optional[int] = None, warmup: int = 3):
         self.dist = parallel.context()
@@ -52,6 +78,7 @@ class GraphedTrainStep:
         self.params = [p for p in list(encoder.parameters()) + list(loss_fn.parameters()) if p.requires_grad]
         self._user_center = encoder.drop_center
         self._side = torch.cuda.Stream(device=dev) if self.dist is not None else None
+        self._sync = _GradSync(dev) if self.dist is not None else None
         self.load(X, Y, subject_idxs, drop_center)
 
         # warm-up on a side stream (torch's capture recipe); module buffers (BatchNorm running statistics, counters) are
@@ -159,15 +186,24 @@ class GraphedTrainStep:
             if self.dist is not None:
                 torch.cuda.current_stream(self.dev).wait_stream(self._side)
             loss, _, csaved = ceng.forward(self.Y, Zl, lossf.temp.detach(), lossf.reduction, self.dist, False,
-                                           prepared=prepared)
+                                           prepared=prepared, reduce_loss=False)
             dZ, dtemp = ceng.backward(csaved, self._one)
             if Fs != Fo:
                 dZ = torch.nn.functional.pad(dZ, (0, Fs - Fo))
-            G = eng.backward(P, saved, dZ.contiguous())
+            G = eng.backward(P, saved, dZ.contiguous(), sync=self._sync)
+            if self.dist is not None and "_flat" in G:
+                # the gradients are views of one flat f32 buffer: SUM all-reduce it in place; the loss contribution and
+                # the temperature gradient ride in its two spare floats (one collective for everything)
+                G["_extra"][0:1].copy_(loss.reshape(1))
+                G["_extra"][1:2].copy_(dtemp.reshape(1))
+                parallel.allreduce_flat(G["_flat_late"] if self._sync.pending else G["_flat"])
+                self._sync.join()
+                loss, dtemp = G["_extra"][0], G["_extra"][1:2]
             for p, g in zip(params, enc._grad_list(G, None)):
                 p.grad = g if g.shape == p.shape else g.reshape(p.shape)
             lossf.temp.grad = dtemp.reshape(lossf.temp.shape)
-            if self.dist is not None:
+            if self.dist is not None and "_flat" not in G:
+                loss = self.dist.all_reduce_sum(loss.reshape(1)).reshape(())
                 parallel.allreduce_grads(self.params)           # part of the recording: replay returns summed gradients
         return loss.detach()
 

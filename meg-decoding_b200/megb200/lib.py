@@ -54,6 +54,11 @@ SIGNATURES = {
     "megb200_adam_multi": [_p, _i, _f, _f, _f, _f, _f, _p],
     "megb200_cast": [_p, _p, _ll, _i, _i, _p],
     "megb200_set_option": [_p, _ll],
+    "megb200_clip_lse_merge": [_p, _i, _i, _p, _p],
+    "megb200_ipc_export": [_p, _p, _p],
+    "megb200_ipc_import": [_p, _p],
+    "megb200_ipc_release": [_p],
+    "megb200_copy_async": [_p, _p, _sz, _p],
 }
 
 _lib = None

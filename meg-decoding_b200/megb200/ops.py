@@ -338,6 +338,13 @@ class CudaOps:
         L.call("megb200_clip_ce_partial", raw.data_ptr(), ysq.data_ptr(), zsq.data_ptr(), temp.data_ptr(),
                Lg.data_ptr(), row_max.data_ptr(), row_sumexp.data_ptr(), col_lse.data_ptr(), By, Bz, self._stream())
 
+    def clip_lse_merge(self, parts, row_lse):
+        """parts f32 [W, 2, By] ((max, sum exp) pairs of the W ranks) -> row_lse [By]."""
+        self._chk_f32(parts, row_lse)
+        W, two, By = parts.shape
+        assert two == 2 and row_lse.numel() == By
+        L.call("megb200_clip_lse_merge", parts.data_ptr(), W, By, row_lse.data_ptr(), self._stream())
+
     def clip_ce_finish(self, Lg, row_lse, col_lse, ysq, zsq, temp, off, wscale, out2, coef, cvec):
         self._chk_f32(Lg, row_lse, col_lse, ysq, zsq, temp, out2, cvec)
         self._chk_act(coef)

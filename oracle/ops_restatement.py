@@ -244,6 +244,9 @@ class TorchOps:
         row_sumexp.copy_(torch.exp(Lv - m[:, None]).sum(1))
         col_lse.copy_(torch.logsumexp(Lv, dim=0))
 
+    def clip_lse_merge(self, parts, row_lse):
+        row_lse.copy_(torch.logsumexp(parts[:, 0, :] + torch.log(parts[:, 1, :]), dim=0))
+
     def clip_ce_finish(self, Lg, row_lse, col_lse, ysq, zsq, temp, off, wscale, out2, coef, cvec):
         By, Bz = Lg.shape
         E = torch.zeros(By, Bz)

@@ -476,7 +476,9 @@ def test_clip_pipeline(dtype, backend, case):
     _close(st["rm"] + torch.log(st["rs"]), str_["rm"] + torch.log(str_["rs"]), torch.float32, "row lse", atol_scale=5)
     _close(st["cl"], str_["cl"], torch.float32, "col lse", atol_scale=5)
     # complete the row LSE as a single rank would see it (other ranks' brains contribute nothing here)
-    row_lse = (st["rm"] + torch.log(st["rs"])).contiguous()
+    row_lse = torch.empty(By, device=DEV)
+    ops.clip_lse_merge(torch.stack([st["rm"], st["rs"]]).view(1, 2, By).contiguous(), row_lse)
+    _close(row_lse, st["rm"] + torch.log(st["rs"]), torch.float32, "clip_lse_merge (single rank)", atol_scale=5)
     wscale = 0.5 / By
     out2, out2r = torch.zeros(2, device=DEV), torch.zeros(2)
     coef, coefr = ops.empty(Bz, pad8(By), device=DEV), ref.empty(Bz, pad8(By), device="cpu")
@@ -495,6 +497,23 @@ def test_clip_pipeline(dtype, backend, case):
     _close(dZ, dZr, dtype, f"clip_dz {backend}")
     if backend == "tc" and (By, Bz) in CLIP_DZ_EXPECT and not L.get_option("clip_dz_large"):
         assert L.get_option("last_clip_dz_kernel") == CLIP_DZ_EXPECT[(By, Bz)]
+
+
+@pytest.mark.parametrize("W,By", [(1, 37), (2, 512), (8, 2048)])
+def test_clip_lse_merge(W, By):
+    """The ranks' partial (max, sum exp) pairs -> complete per-row log-sum-exp (one all-gather + this kernel replace a MAX
+    and a SUM all-reduce); a rank whose whole shard is far below the maximum must not produce inf/nan."""
+    gen = torch.Generator().manual_seed(12)
+    ops, ref = _ops(torch.float32, "simt"), TorchOps()
+    parts = torch.empty(W, 2, By)
+    parts[:, 0] = _rand(gen, W, By, scale=40.0)
+    parts[:, 1] = torch.rand(W, By, generator=gen) * 255 + 1.0
+    if W > 1:
+        parts[0, 0, :5] = -150.0                     # exp underflows against the other ranks' maxima
+    out, outr = torch.empty(By, device=DEV), torch.empty(By)
+    ops.clip_lse_merge(parts.to(DEV), out)
+    ref.clip_lse_merge(parts, outr)
+    _close(out, outr, torch.float32, "clip_lse_merge", atol_scale=5)
 
 
 @pytest.mark.parametrize("case", [c for c in CLIP_CASES if c[0] <= 512])

@@ -74,12 +74,15 @@ def test_adam_resume_from_checkpoint(source):
         _rand_grads(params, twins, gen)
         ours.step()
         ref.step()
-    ckpt = (ours if source == "megb200" else ref).state_dict()
-    ckpt_ref = ref.state_dict()
+    # deep copies, as torch.save / torch.load would give: Optimizer.load_state_dict ALIASES the tensors it is handed, so
+    # a live state_dict() would keep changing under the optimizer that loaded it
+    import copy
+    ckpt = copy.deepcopy((ours if source == "megb200" else ref).state_dict())
+    ckpt_ref = copy.deepcopy(ref.state_dict())
     # resume into FRESH optimizers (load before the first step) ...
     ours2, ref2 = Adam(params, **kw), torch.optim.Adam(twins, **kw)
-    ours2.load_state_dict(ckpt)
-    ref2.load_state_dict(ckpt_ref)
+    ours2.load_state_dict(copy.deepcopy(ckpt))
+    ref2.load_state_dict(copy.deepcopy(ckpt_ref))
     for _ in range(2):
         _rand_grads(params, twins, gen)
         ours2.step()
@@ -88,8 +91,8 @@ def test_adam_resume_from_checkpoint(source):
     assert int(ours2.state[params[0]]["step"]) == 5
     # ... and into a LIVE optimizer (load after steps: the cached pointer table must be dropped)
     old_m = ours2.state[params[1]]["exp_avg"]
-    ours2.load_state_dict(ckpt)
-    ref2.load_state_dict(ckpt_ref)
+    ours2.load_state_dict(copy.deepcopy(ckpt))
+    ref2.load_state_dict(copy.deepcopy(ckpt_ref))
     keep = old_m.clone()
     for _ in range(2):
         _rand_grads(params, twins, gen)
