@@ -202,6 +202,16 @@ def run_megb200(args):
     Xh, Yh, subj_h = synth.make_batch(cfg, seed=rank)
     Xh, Yh, subj_h = torch.from_numpy(Xh).pin_memory(), torch.from_numpy(Yh).pin_memory(), torch.from_numpy(subj_h)
     Xd, Yd = Xh.to(dev), Yh.to(dev)
+    # The speech targets are PRECOMPUTED wav2vec2 features (north_star): the data pipeline stores them once in the form
+    # the loss contracts -- position-major bf16 rows + f32 norms (megb200.data.PackedTargets; same rounding point as the
+    # dense f32 path, so the same loss).  The CUDA-graph step and the end-to-end leg take them in that form: no per-step
+    # transpose/cast pass and half the host->device bytes.  The eager timed region (per-launch roofline events) and the
+    # parity step keep the reference collator's dense f32 tensor.
+    from megb200.data import PackedTargets
+    packed_ok = args.precision.startswith("bf16") and args.targets == "packed"
+    if packed_ok:
+        Yph = PackedTargets.from_dense(Yh, dtype=torch.bfloat16).pin_memory()
+        Ypd = Yph.to(dev)
 
     def step(X, Y, subj):
         for p in params:
@@ -352,7 +362,7 @@ def run_megb200(args):
         gstep, ok = None, 1
         try:
             from megb200.graph import GraphedTrainStep
-            gstep = GraphedTrainStep(enc, lossf, Xd, Yd, subj_h, drop_center=enc.drop_center)
+            gstep = GraphedTrainStep(enc, lossf, Xd, Ypd if packed_ok else Yd, subj_h, drop_center=enc.drop_center)
         except Exception as e:          # capture is an optimisation of the launch path, never a different compute path
             graph_note, ok = f"capture failed: {type(e).__name__}: {e}"[:200], 0
             if os.environ.get("MEGB200_GRAPH_DEBUG"):
@@ -421,9 +431,15 @@ def run_megb200(args):
 
     def host_batches(n):
         for _ in range(n):
-            yield (Xh, Yh, subj_h)
+            yield (Xh, Yph.rows, Yph.sumsq, subj_h) if packed_ok else (Xh, Yh, subj_h)
 
-    prefetcher = DevicePrefetcher(host_batches(0), dev, keep_on_host=(2,))
+    def unpack(batch):
+        if packed_ok:
+            X, rows, sumsq, subj = batch
+            return X, PackedTargets(rows, sumsq, Yph.feature_shape), subj
+        return batch
+
+    prefetcher = DevicePrefetcher(host_batches(0), dev, keep_on_host=(3,) if packed_ok else (2,))
     PRIME = 2
     fill = {}
 
@@ -440,7 +456,8 @@ def run_megb200(args):
         got, t0, t1 = [], 0.0, 0.0
         barrier()
         ta = time.perf_counter()
-        for i, (X, Y, subj) in enumerate(prefetcher.reset(host_batches(n))):
+        for i, batch in enumerate(prefetcher.reset(host_batches(n))):
+            X, Y, subj = unpack(batch)
             if i == PRIME:
                 g0.record()
                 t0 = time.perf_counter()
@@ -479,17 +496,26 @@ def run_megb200(args):
     c0.record()
     for _ in range(3):
         Xd.copy_(Xh, non_blocking=True)
-        Yd.copy_(Yh, non_blocking=True)
+        if packed_ok:
+            Ypd.rows.copy_(Yph.rows, non_blocking=True)
+            Ypd.sumsq.copy_(Yph.sumsq, non_blocking=True)
+        else:
+            Yd.copy_(Yh, non_blocking=True)
     c1.record()
     barrier()
     h2d_alone_ms = c0.elapsed_time(c1) / 3
-    h2d = Xh.numel() * 4 + Yh.numel() * 4 + subj_h.numel() * 4
+    y_bytes = (Yph.rows.numel() * 2 + Yph.sumsq.numel() * 4) if packed_ok else Yh.numel() * 4
+    h2d = Xh.numel() * 4 + y_bytes + subj_h.numel() * 4
     e2e = {"value": B * world / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
            "ms_per_step": e2e_ms, "loss_read": "every step, pipelined one step behind (AsyncScalarReader)",
            "window": "K steps in the steady state of one continuous run (2 priming steps before, 2 after)",
            "ms_per_step_sync_read": e2e_sync_ms, "launch_path": e2e_path, "ms_per_step_eager": e2e_eager_ms,
            "runs_ms_graph": graph_runs, "runs_ms": pipe_runs, "runs_ms_sync_read": sync_runs,
-           "ms_per_step_whole_run_incl_fill": fill.get(1), "h2d_alone_ms": h2d_alone_ms, "h2d_alone_GBps": h2d / (h2d_alone_ms * 1e-3) / 1e9}
+           "ms_per_step_whole_run_incl_fill": fill.get(1), "h2d_alone_ms": h2d_alone_ms, "h2d_alone_GBps": h2d / (h2d_alone_ms * 1e-3) / 1e9,
+           "inputs": ("X f32 (B,C,T) + targets as megb200.data.PackedTargets (bf16 position-major rows + f32 norms, the "
+                      "stored form of the precomputed features) + int32 subject indices" if packed_ok else
+                      "X f32 (B,C,T) + Y f32 (B,F,T) + int32 subject indices (the reference collator's tensors)"),
+           "h2d_bytes_per_step_f32_dense_targets": Xh.numel() * 4 + Yh.numel() * 4 + subj_h.numel() * 4}
 
     flops_step = B * synth.encoder_flops_per_sample(cfg) + synth.clip_flops(cfg, B, B * world)
     line = {
@@ -501,6 +527,7 @@ def run_megb200(args):
         "step_tflops": flops_step / (ms * 1e-3) / 1e12,
         "step_frac_of_peak": flops_step / (ms * 1e-3) / 1e12 / peaks["bf16_sustained"],
         "launch_path": "cuda_graph" if graph_ms is not None else "eager", "ms_per_step_eager": eager_ms,
+        "targets": "packed bf16 (megb200.data.PackedTargets)" if (packed_ok and graph_ms is not None) else "dense f32",
         "ms_per_step_graph": graph_ms, "graph_note": graph_note,
         "dp_target_gather": (parallel.context().gather_mode if parallel.context() is not None else None),
         "dp_target_gather_note": (parallel.context().gather_note if parallel.context() is not None else None),
@@ -549,7 +576,10 @@ def run_megb200(args):
 
 
 def main():
+    # a hung collective must never burn the GPU budget: dump every thread's stack and exit after --max-seconds
+    import faulthandler
     ap = argparse.ArgumentParser()
+    ap.add_argument("--max-seconds", type=float, default=1500.0, help="watchdog: dump stacks and exit after this long")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
@@ -560,8 +590,12 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="samples per CPU-baseline step (0 = the full batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time only the eager launch path")
+    ap.add_argument("--targets", default="packed", choices=["packed", "dense"],
+                    help="target format of the CUDA-graph step and the end-to-end leg: PackedTargets (bf16) or dense f32")
     ap.add_argument("--ncu-step", action="store_true", help="run one step inside cudaProfilerStart/Stop and exit")
     args = ap.parse_args()
+    if args.max_seconds > 0:
+        faulthandler.dump_traceback_later(args.max_seconds, exit=True)
     if args.impl == "reference":
         return run_reference(args)
     return run_megb200(args)

@@ -51,7 +51,8 @@ long long megb200_launch_count(void);
  * several hand-written forms of one contraction by problem size (e.g. the persistent CTA-pair tap-GEMM from 2 x #SM work
  * items up); these switches let a caller -- the test-suite -- force each form on any shape.  Names:
  *   "tapgemm_pair_min_items" (-1 = default), "tapgemm_force_1cta", "tapgemm_pair_halo", "tapgemm_halo",
- *   "tapgemm_ragged_n", "tapgemm_direct_epi", "clip_dz_large", "rowloop_direct", "wgrad_splits" (0 = automatic).
+ *   "tapgemm_ragged_n", "tapgemm_direct_epi", "clip_dz_large", "rowloop_direct", "wgrad_splits" (0 = automatic),
+ *   "clip_fused" (policy of the host-side loss: -1 auto, 0 never, 1 whenever supported).
  * Read-only (written by the launchers, for tests): "last_tapgemm_kernel" (0 single CTA, 1 CTA pair, 2 CTA pair + halo,
  * 3 single CTA + halo), "last_clip_dz_kernel" (0 small-K, 1 large-K), "last_wgrad_splits".
  * Initial values come from the MEGB200_* environment variables.  Results never depend on the variant beyond f32
@@ -175,9 +176,11 @@ int megb200_time_mean(const void* Z, void* Zm, int B, int T, int F, int Fs, int 
 int megb200_time_mean_bwd(const void* dZm, void* dZ, int B, int T, int F, int Fs, int dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------- CLIP loss */
-/* Y f32 [B][F][T] (NCW) -> Yp [B][T][F] of `dtype` and ysq[b] += sum Y^2 (f32, from the unrounded values).
+/* Y [B][F][T] (NCW; `y_dtype` = MEGB200_F32 as the reference's collator delivers it, or MEGB200_BF16 when the data
+ * pipeline stores the precomputed wav2vec2 targets in bf16 -- the loss rounds them to bf16 anyway, and the host->device
+ * copy halves) -> Yp [B][T][F] of `dtype` and ysq[b] += sum Y^2 (f32, from the values as delivered).
  * T == 1 handles the static [B][F] targets.  loss.py:88-93 (reshape + norm). */
-int megb200_clip_prep_y(const float* Y, void* Yp, float* ysq, int B, int F, int T, int dtype, void* stream);
+int megb200_clip_prep_y(const void* Y, int y_dtype, void* Yp, float* ysq, int B, int F, int T, int dtype, void* stream);
 /* sq[b] += sum_d Z[b][d]^2   (loss.py:93) */
 int megb200_rowsumsq(const void* Z, float* sq, int B, long long D, int dtype, void* stream);
 /* raw[i][j] += sum_d Yp[i][d] * Zp[j][d]   f32 [By][Bz]  (loss.py:96, split-K over D with f32 atomics) */
@@ -203,6 +206,30 @@ int megb200_clip_ce_finish(const float* L, const float* row_lse, const float* co
  * coef is [Bz][ldc] with ldc >= By a multiple of 8 (ragged batches keep TMA's 16-byte stride rule). */
 int megb200_clip_dz(const void* coef, int ldc, const void* Yp, const void* Z, const float* cvec, const float* gscale,
                     void* dZ, int By, int Bz, long long D, int dtype, int backend, void* stream);
+
+/* ---- CLIPLoss at large batch with short embeddings (static targets: D = F, e.g. 512-d image features; BASELINE config
+ * "GOD ... B x B logits sweep to 16k"): the B x B logits matrix is NEVER materialised (north_star: "logits matmul fused
+ * with a warp-shuffle online-softmax CE").  bf16 / tensor-core engine only; the fp32 check mode uses the calls above.
+ *
+ * stats: one tcgen05 tile GEMM per 128 x 128 logits tile over the whole K = D, epilogue from TMEM: per-row online
+ *        (max, sum exp) over the tile's columns -> row_part [ceil(Bz/128)][2][By], per-column (max, sum exp) over its rows
+ *        (warp shuffles) -> col_part [ceil(By/128)][2][Bz], positives -> diag[j] = L[off+j][j].  megb200_clip_lse_merge
+ *        completes both tables (W = number of tiles; in data parallel the ranks' row tables are all-gathered first).
+ * loss:  out2[0] += wscale * sum_j (row_lse[off+j] + col_lse[j] - 2 diag[j])                           (loss.py:107)
+ * coef:  backward with recompute, for brain columns [j_begin, j_begin + j_count): the tiles are contracted again,
+ *        dL = (exp(L-row_lse[i]) + exp(L-col_lse[j]) - 2[i == off+j]) * wscale, and what leaves is
+ *        coef[j - j_begin][i] = dL * exp(temp)/(|y_i||z_j|) (bf16, [j_count][ldc]), cvec[j] += sum_i dL*L / zsq[j],
+ *        out2[1] += sum dL*L (d loss / d temp).  megb200_clip_dz then runs on that chunk (Z, dZ, cvec offset by j_begin):
+ *        peak extra memory is one chunk of coefficients instead of three B x B matrices. */
+int megb200_clip_fused_stats(const void* Yp, const void* Zp, const float* ysq, const float* zsq, const float* temp,
+                             int By, int Bz, long long D, int off, float* row_part, float* col_part, float* diag,
+                             int dtype, int backend, void* stream);
+int megb200_clip_fused_loss(const float* row_lse, const float* col_lse, const float* diag, int off, int Bz, float wscale,
+                            float* out2, void* stream);
+int megb200_clip_fused_coef(const void* Yp, const void* Zp, const float* ysq, const float* zsq, const float* temp,
+                            const float* row_lse, const float* col_lse, int By, int Bz, long long D, int off, float wscale,
+                            int j_begin, int j_count, void* coef, int ldc, float* cvec, float* out2, int dtype,
+                            int backend, void* stream);
 
 /* Top-k retrieval metric (the reference's Classifier, models.py:403-460; "next" row N1): given the f32 dot-product
  * matrix raw[By][Bz] (rows speech, columns brain) and the squared brain norms, rank[r] = number of brain embeddings

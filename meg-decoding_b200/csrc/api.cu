@@ -36,6 +36,7 @@ Options& options() {
       getenv("MEGB200_CLIP_DZ_LARGE") != nullptr ? 1 : 0,
       getenv("MEGB200_ROWLOOP_DIRECT") != nullptr ? 1 : 0,
       (int)env_ll("MEGB200_WGRAD_SPLITS", 0),
+      (int)env_ll("MEGB200_CLIP_FUSED", -1),
       -1, -1, -1,
   };
   return o;
@@ -52,6 +53,7 @@ static const OptionEntry kOptionTable[] = {
     {"clip_dz_large", 1, offsetof(Options, clip_dz_large)},
     {"rowloop_direct", 1, offsetof(Options, rowloop_direct)},
     {"wgrad_splits", 1, offsetof(Options, wgrad_splits)},
+    {"clip_fused", 1, offsetof(Options, clip_fused)},
     {"last_tapgemm_kernel", 1, offsetof(Options, last_tapgemm_kernel)},
     {"last_clip_dz_kernel", 1, offsetof(Options, last_clip_dz_kernel)},
     {"last_wgrad_splits", 1, offsetof(Options, last_wgrad_splits)},
@@ -160,6 +162,12 @@ int tc_wgrad(const void* dU, int M, int Ms, const void* Xin, int C, int Cs, int 
 int tc_clip_logits(const void* Yp, const void* Zp, float* raw, int By, int Bz, long long D, cudaStream_t st);
 int tc_clip_dz(const void* coef, int ldc, const void* Yp, const void* Z, const float* cvec, const float* gscale,
                void* dZ, int By, int Bz, long long D, cudaStream_t st);
+int tc_clip_fused(const void* Yp, const void* Zp, const float* ysq, const float* zsq, const float* temp, int By, int Bz,
+                  long long D, int off, int mode, float* row_part, float* col_part, float* diag, const float* row_lse,
+                  const float* col_lse, float wscale, int j_begin, int j_count, void* coef, int ldc, float* cvec,
+                  float* out2, cudaStream_t st);
+int tc_clip_fused_loss(const float* row_lse, const float* col_lse, const float* diag, int off, int Bz, float wscale,
+                       float* out2, cudaStream_t st);
 }  // namespace tc
 
 template <typename T>
@@ -379,6 +387,41 @@ int megb200_clip_dz(const void* coef, int ldc, const void* Yp, const void* Z, co
   if (dtype == MEGB200_F32) return simt_clip_dz<float>(coef, ldc, Yp, Z, cvec, gscale, dZ, By, Bz, D, st);
   if (dtype == MEGB200_BF16) return simt_clip_dz<__nv_bfloat16>(coef, ldc, Yp, Z, cvec, gscale, dZ, By, Bz, D, st);
   MEGB_CHECK_ARG(false, "clip_dz: unknown dtype %d", dtype);
+}
+
+// ---------------------------------------------------------------------------------------------- fused large-batch CLIP
+int megb200_clip_fused_stats(const void* Yp, const void* Zp, const float* ysq, const float* zsq, const float* temp,
+                             int By, int Bz, long long D, int off, float* row_part, float* col_part, float* diag,
+                             int dtype, int backend, void* stream) {
+  MEGB_CHECK_ARG(Yp && Zp && ysq && zsq && temp && row_part && col_part && diag && By > 0 && Bz > 0 && D > 0,
+                 "clip_fused_stats: bad arguments");
+  if (backend != MEGB200_TC || dtype != MEGB200_BF16) {
+    set_last_error("clip_fused_stats: tensor-core engine / bf16 only (the fp32 check mode materialises the logits)");
+    return MEGB200_ERR_UNSUPPORTED;
+  }
+  return tc::tc_clip_fused(Yp, Zp, ysq, zsq, temp, By, Bz, D, off, 0, row_part, col_part, diag, nullptr, nullptr, 0.f, 0,
+                           Bz, nullptr, 0, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int megb200_clip_fused_loss(const float* row_lse, const float* col_lse, const float* diag, int off, int Bz, float wscale,
+                            float* out2, void* stream) {
+  MEGB_CHECK_ARG(row_lse && col_lse && diag && out2 && Bz > 0 && off >= 0, "clip_fused_loss: bad arguments");
+  return tc::tc_clip_fused_loss(row_lse, col_lse, diag, off, Bz, wscale, out2, (cudaStream_t)stream);
+}
+
+int megb200_clip_fused_coef(const void* Yp, const void* Zp, const float* ysq, const float* zsq, const float* temp,
+                            const float* row_lse, const float* col_lse, int By, int Bz, long long D, int off, float wscale,
+                            int j_begin, int j_count, void* coef, int ldc, float* cvec, float* out2, int dtype,
+                            int backend, void* stream) {
+  MEGB_CHECK_ARG(Yp && Zp && ysq && zsq && temp && row_lse && col_lse && coef && cvec && out2 && By > 0 && Bz > 0 && D > 0,
+                 "clip_fused_coef: bad arguments");
+  MEGB_CHECK_ARG(ldc >= By && ldc % 8 == 0, "clip_fused_coef: ldc must be >= By and a multiple of 8");
+  if (backend != MEGB200_TC || dtype != MEGB200_BF16) {
+    set_last_error("clip_fused_coef: tensor-core engine / bf16 only");
+    return MEGB200_ERR_UNSUPPORTED;
+  }
+  return tc::tc_clip_fused(Yp, Zp, ysq, zsq, temp, By, Bz, D, off, 1, nullptr, nullptr, nullptr, row_lse, col_lse, wscale,
+                           j_begin, j_count, coef, ldc, cvec, out2, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -23,29 +23,36 @@ static inline int ew_grid(long long work_items, int threads) {
 // (The first form used 32 x 32 tiles and 2-byte stores: half-line writes, 3.4 TB/s on the 566 MB target pack.)
 constexpr int kTpTile = 64;
 
-template <typename T>
-__global__ void __launch_bounds__(256) transpose_pack_kernel(const float* __restrict__ in, T* __restrict__ out,
+template <typename Tin, typename T>
+__global__ void __launch_bounds__(256) transpose_pack_kernel(const Tin* __restrict__ in, T* __restrict__ out,
                                                              float* __restrict__ sq, int B, int C, int Tn, int Cs) {
   __shared__ float tile[kTpTile][kTpTile + 1];
   __shared__ float red[8];
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * kTpTile, c0 = blockIdx.y * kTpTile;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool t_vec = (Tn & 1) == 0 && (reinterpret_cast<uintptr_t>(in) & 7) == 0;   // 8-byte loads: even rows, aligned base
+  // two-element loads: even rows, base aligned to two elements
+  const bool t_vec = (Tn & 1) == 0 && (reinterpret_cast<uintptr_t>(in) & (2 * sizeof(Tin) - 1)) == 0;
   float ss = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int cl = warp + 8 * i, c = c0 + cl, t = t0 + 2 * lane;
     float v0 = 0.f, v1 = 0.f;
     if (c < C) {
-      const float* src = in + ((long long)b * C + c) * Tn + t;
+      const Tin* src = in + ((long long)b * C + c) * Tn + t;
       if (t_vec && t + 1 < Tn) {
-        const float2 v = *reinterpret_cast<const float2*>(src);
-        v0 = v.x;
-        v1 = v.y;
+        if constexpr (sizeof(Tin) == 2) {
+          const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(src));
+          v0 = v.x;
+          v1 = v.y;
+        } else {
+          const float2 v = *reinterpret_cast<const float2*>(src);
+          v0 = v.x;
+          v1 = v.y;
+        }
       } else {
-        if (t < Tn) v0 = src[0];
-        if (t + 1 < Tn) v1 = src[1];
+        if (t < Tn) v0 = to_f(src[0]);
+        if (t + 1 < Tn) v1 = to_f(src[1]);
       }
     }
     tile[cl][2 * lane] = v0;
@@ -79,11 +86,11 @@ __global__ void __launch_bounds__(256) transpose_pack_kernel(const float* __rest
   }
 }
 
-template <typename T>
-static int launch_transpose_pack(const float* in, void* out, float* sq, int B, int C, int Tn, int Cs,
+template <typename T, typename Tin = float>
+static int launch_transpose_pack(const Tin* in, void* out, float* sq, int B, int C, int Tn, int Cs,
                                  cudaStream_t st) {
   dim3 grid((Tn + kTpTile - 1) / kTpTile, (Cs + kTpTile - 1) / kTpTile, B);
-  transpose_pack_kernel<T><<<grid, 256, 0, st>>>(in, (T*)out, sq, B, C, Tn, Cs);
+  transpose_pack_kernel<Tin, T><<<grid, 256, 0, st>>>(in, (T*)out, sq, B, C, Tn, Cs);
   MEGB_LAUNCH_OK();
   return 0;
 }
@@ -1001,10 +1008,15 @@ int megb200_pack_x(const float* X, void* Xp, int B, int C, int T, int Cs, int dt
   DISPATCH_DTYPE(dtype, return launch_transpose_pack<DT>(X, Xp, nullptr, B, C, T, Cs, (cudaStream_t)stream);)
 }
 
-int megb200_clip_prep_y(const float* Y, void* Yp, float* ysq, int B, int F, int T, int dtype, void* stream) {
+int megb200_clip_prep_y(const void* Y, int y_dtype, void* Yp, float* ysq, int B, int F, int T, int dtype, void* stream) {
   MEGB_CHECK_ARG(Y && Yp && ysq && B > 0 && F > 0 && T > 0 && F % 8 == 0, "clip_prep_y: bad arguments (F %% 8)");
   MEGB_CHECK_ARG(B <= 65535, "clip_prep_y: B too large");
-  DISPATCH_DTYPE(dtype, return launch_transpose_pack<DT>(Y, Yp, ysq, B, F, T, F, (cudaStream_t)stream);)
+  if (y_dtype == MEGB200_BF16) {
+    DISPATCH_DTYPE(dtype, return (launch_transpose_pack<DT, __nv_bfloat16>((const __nv_bfloat16*)Y, Yp, ysq, B, F, T, F,
+                                                                          (cudaStream_t)stream));)
+  }
+  MEGB_CHECK_ARG(y_dtype == MEGB200_F32, "clip_prep_y: unknown target dtype %d", y_dtype);
+  DISPATCH_DTYPE(dtype, return launch_transpose_pack<DT>((const float*)Y, Yp, ysq, B, F, T, F, (cudaStream_t)stream);)
 }
 
 int megb200_pack_weight(const float* w, void* out, int G, int O, int I, int Kt, int Np, int Kp, int mode, int dtype,

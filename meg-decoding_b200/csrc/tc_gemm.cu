@@ -1574,6 +1574,223 @@ tc_clip_dz_small_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_co
   }
 }
 
+
+// ================================================================================================ CLIP, fused large-batch form
+// Static embeddings (D = F <= a few thousand: the GOD / seq2static configs) at large batch: the B x B logits matrix is
+// never written.  One CTA contracts a 128 x 128 tile over the WHOLE (short) K = D and its epilogue works on the tile in
+// TMEM / registers:
+//   mode 0 (forward):  L = s * y_i.z_j / (|y_i||z_j|); per-row online (max, sum exp) over the tile's columns, per-column
+//                      (max, sum exp) over its rows (warp shuffles, then the four row quarters meet in shared memory),
+//                      the positives L[off+j][j].  Partials go to [j_tiles][2][By] / [i_tiles][2][Bz] tables that
+//                      clip_lse_merge_kernel completes (the same kernel that merges the ranks' partials in data parallel).
+//   mode 1 (backward): the tile is RECOMPUTED, dL = (exp(L - row_lse) + exp(L - col_lse) - 2 [positive]) * wscale is formed
+//                      in registers, and what leaves is the bf16 coefficient tile of the dZ contraction (transposed,
+//                      for a chunk of brain columns at a time), sum_i dL*L per column and d loss / d temp.
+// loss.py:92-107 with SURVEY appendix A5/A6 (one-sided data-parallel form: rows = all speech targets, columns = local brains).
+struct ClipFusedParams {
+  int By, Bz, kchunks, stages, i_tiles, mode, off, ldc, j_begin, j_end;
+  float wscale;
+  uint32_t idesc;
+  const float* ysq;
+  const float* zsq;
+  const float* temp;
+  float* row_part;
+  float* col_part;
+  float* diag;
+  const float* row_lse;
+  const float* col_lse;
+  __nv_bfloat16* coef;
+  float* cvec;
+  float* out2;
+};
+
+constexpr int kFusedNT = 128;
+
+__global__ void __launch_bounds__(kThreads)
+tc_clip_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmZ,
+                     const ClipFusedParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  Header* hdr = reinterpret_cast<Header*>(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t a_bytes = kTileM * 128, b_bytes = kFusedNT * 128;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  uint8_t* ring = smem + kHeaderBytes;
+  float* srz = reinterpret_cast<float*>(ring + (size_t)p.stages * stage_bytes);   // [NT] 1/|z_j|
+  float* scl = srz + kFusedNT;                                                    // [NT] col_lse (mode 1)
+  float* scm = scl + kFusedNT;                                                    // [4][NT] per-warp column max / dL*L sums
+  float* scs = scm + 4 * kFusedNT;                                                // [4][NT] per-warp column sum exp
+  const int i_tile = blockIdx.x % p.i_tiles, j_tile = blockIdx.x / p.i_tiles;
+  const int i0 = i_tile * kTileM;
+  const int j0 = p.j_begin + j_tile * kFusedNT;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmY);
+    tma_prefetch_desc(&tmZ);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&hdr->full[s]), 1);
+      mbar_init(smem_u32(&hdr->empty[s]), 1);
+    }
+    mbar_init(smem_u32(&hdr->tmem_full), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&hdr->tmem_slot), kFusedNT);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = hdr->tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < p.kchunks; ++it) {
+        const int s = it % p.stages;
+        mbar_wait(smem_u32(&hdr->empty[s]), ((it / p.stages) & 1) ^ 1);
+        const uint32_t full = smem_u32(&hdr->full[s]);
+        mbar_arrive_expect_tx(full, stage_bytes);
+        const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
+        tma_load_2d(sa, &tmY, it * kBlockK, i0, full);
+        tma_load_2d(sa + a_bytes, &tmZ, it * kBlockK, j0, full);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int it = 0; it < p.kchunks; ++it) {
+        const int s = it % p.stages;
+        mbar_wait(smem_u32(&hdr->full[s]), (it / p.stages) & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
+        const uint64_t da = make_smem_desc(sa, 16, 1024);
+        const uint64_t db = make_smem_desc(sa + a_bytes, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < kBlockK / kUmmaK; ++k)
+          umma_bf16(tmem_base, desc_advance(da, k * 32), desc_advance(db, k * 32), p.idesc, (it | k) != 0);
+        umma_commit(smem_u32(&hdr->empty[s]));
+      }
+      umma_commit(smem_u32(&hdr->tmem_full));
+    }
+  } else {
+    const int et = threadIdx.x - 64;                // 0..127
+    const int q = warp & 3;
+    const int i = i0 + q * 32 + lane;               // this thread's speech row (TMEM lane)
+    const bool iv = i < p.By;
+    {
+      const int j = j0 + et;
+      const bool jv = j < p.j_end;
+      srz[et] = jv ? rsqrtf(p.zsq[j]) : 0.f;
+      scl[et] = (jv && p.mode == 1) ? p.col_lse[j] : 0.f;
+      if (p.mode == 1) {
+#pragma unroll
+        for (int w = 0; w < 4; ++w) scm[w * kFusedNT + et] = 0.f;
+      }
+    }
+    const float s = expf(p.temp[0]);
+    const float ri = iv ? s * rsqrtf(p.ysq[i]) : 0.f;
+    const float rl = (iv && p.mode == 1) ? p.row_lse[i] : 0.f;
+    named_bar_sync(1, 128);
+    mbar_wait(smem_u32(&hdr->tmem_full), 0);
+    tc_fence_after();
+    float rm = -INFINITY, rs = 0.f, dtemp = 0.f;
+    for (int g = 0; g < kFusedNT / 32; ++g) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(32 * g), v);
+      if (j0 + 32 * g >= p.j_end) continue;         // whole group outside the column range (uniform across the CTA)
+      if (p.mode == 0) {
+        float gm = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const bool ok = iv && (j0 + 32 * g + e) < p.j_end;
+          v[e] = ok ? v[e] * ri * srz[32 * g + e] : -INFINITY;
+          gm = fmaxf(gm, v[e]);
+        }
+        if (gm > -INFINITY) {                        // row-wise online log-sum-exp over this group
+          const float nm = fmaxf(rm, gm);
+          float acc = rs * __expf(rm - nm);          // rm = -inf: rs = 0 and exp(-inf) = 0
+#pragma unroll
+          for (int e = 0; e < 32; ++e) acc += __expf(v[e] - nm);      // masked entries: exp(-inf) = 0
+          rm = nm;
+          rs = acc;
+        }
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {               // column-wise over this warp's 32 rows
+          const float cm = warp_max(v[e]);
+          const float cs = warp_sum(v[e] > -INFINITY ? __expf(v[e] - cm) : 0.f);
+          if (lane == 0) {
+            scm[q * kFusedNT + 32 * g + e] = cm;
+            scs[q * kFusedNT + 32 * g + e] = cs;
+          }
+          if (iv && i == p.off + j0 + 32 * g + e && v[e] > -INFINITY) p.diag[j0 + 32 * g + e] = v[e];
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int j = j0 + 32 * g + e;
+          const bool ok = iv && j < p.j_end;
+          float t = 0.f;
+          if (ok) {
+            const float l = v[e] * ri * srz[32 * g + e];
+            const float dl = (__expf(l - rl) + __expf(l - scl[32 * g + e]) - (i == p.off + j ? 2.f : 0.f)) * p.wscale;
+            t = dl * l;
+            p.coef[(long long)(j - p.j_begin) * p.ldc + i] = __float2bfloat16_rn(dl * ri * srz[32 * g + e]);
+          }
+          dtemp += t;
+          const float cs = warp_sum(t);
+          if (lane == 0) scm[q * kFusedNT + 32 * g + e] = cs;
+        }
+      }
+    }
+    tc_fence_before();
+    if (p.mode == 0) {
+      if (iv) {
+        p.row_part[((long long)j_tile * 2) * p.By + i] = rm;
+        p.row_part[((long long)j_tile * 2 + 1) * p.By + i] = rs;
+      }
+      named_bar_sync(1, 128);
+      const int j = j0 + et;
+      if (j < p.j_end) {
+        float M = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) M = fmaxf(M, scm[w * kFusedNT + et]);
+        float S = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const float m = scm[w * kFusedNT + et];
+          if (m > -INFINITY) S += scs[w * kFusedNT + et] * __expf(m - M);
+        }
+        p.col_part[((long long)i_tile * 2) * p.Bz + j] = M;
+        p.col_part[((long long)i_tile * 2 + 1) * p.Bz + j] = S;
+      }
+    } else {
+      named_bar_sync(1, 128);
+      const int j = j0 + et;
+      if (j < p.j_end) {
+        const float c = scm[et] + scm[kFusedNT + et] + scm[2 * kFusedNT + et] + scm[3 * kFusedNT + et];
+        atomicAdd(&p.cvec[j], c * srz[et] * srz[et]);
+      }
+      dtemp = warp_sum(dtemp);
+      if (lane == 0 && dtemp != 0.f) atomicAdd(&p.out2[1], dtemp);
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kFusedNT);
+  }
+}
+
+// loss = wscale * sum_j (row_lse[off + j] + col_lse[j] - 2 L[off + j][j])  (loss.py:107 on the completed log-sum-exps)
+__global__ void clip_fused_loss_kernel(const float* __restrict__ row_lse, const float* __restrict__ col_lse,
+                                       const float* __restrict__ diag, int off, int Bz, float wscale,
+                                       float* __restrict__ out2) {
+  float a = 0.f;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < Bz; j += gridDim.x * blockDim.x)
+    a += (row_lse[off + j] + col_lse[j] - 2.f * diag[j]) * wscale;
+  a = warp_sum(a);
+  if ((threadIdx.x & 31) == 0 && a != 0.f) atomicAdd(&out2[0], a);
+}
+
 // ================================================================================================ host launchers
 static bool halo_mode_env_off() { return options().tapgemm_halo == 0; }
 
@@ -2147,6 +2364,58 @@ int tc_clip_dz(const void* coef, int ldc, const void* Yp, const void* Z, const f
   tc_clip_dz_kernel<<<grid, kThreads, smem, st>>>(tmC, tmY, p);
   MEGB_LAUNCH_OK();
   options().last_clip_dz_kernel = 1;
+  return 0;
+}
+
+
+int tc_clip_fused(const void* Yp, const void* Zp, const float* ysq, const float* zsq, const float* temp, int By, int Bz,
+                  long long D, int off, int mode, float* row_part, float* col_part, float* diag, const float* row_lse,
+                  const float* col_lse, float wscale, int j_begin, int j_count, void* coef, int ldc, float* cvec,
+                  float* out2, cudaStream_t st) {
+  MEGB_CHECK_ARG(D % 8 == 0 && D <= 65536, "tc_clip_fused: D must be a multiple of 8 (and short: %lld)", D);
+  MEGB_CHECK_ARG(j_begin >= 0 && j_count > 0 && j_begin + j_count <= Bz, "tc_clip_fused: column range outside [0, Bz)");
+  MEGB_CHECK_ARG(off >= 0 && off + Bz <= By, "tc_clip_fused: positives [off, off+Bz) outside the %d speech rows", By);
+  ClipFusedParams p;
+  p.By = By; p.Bz = Bz; p.mode = mode; p.off = off; p.ldc = ldc; p.j_begin = j_begin; p.j_end = j_begin + j_count;
+  p.wscale = wscale;
+  p.kchunks = (int)((D + kBlockK - 1) / kBlockK);
+  p.i_tiles = (By + kTileM - 1) / kTileM;
+  const int j_tiles = (j_count + kFusedNT - 1) / kFusedNT;
+  p.stages = p.kchunks < 3 ? (p.kchunks < 2 ? 2 : p.kchunks) : 3;       // 96 KB: two CTAs per SM
+  p.idesc = make_idesc(kFusedNT, 0, 0);
+  p.ysq = ysq; p.zsq = zsq; p.temp = temp; p.row_part = row_part; p.col_part = col_part; p.diag = diag;
+  p.row_lse = row_lse; p.col_lse = col_lse; p.coef = (__nv_bfloat16*)coef; p.cvec = cvec; p.out2 = out2;
+  CUtensorMap tmY, tmZ;
+  {
+    const uint64_t dims[2] = {(uint64_t)D, (uint64_t)By};
+    const uint64_t strides[1] = {(uint64_t)D * 2};
+    const uint32_t box[2] = {kBlockK, kTileM};
+    int rc = encode_tmap_bf16(&tmY, Yp, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)D, (uint64_t)Bz};
+    const uint64_t strides[1] = {(uint64_t)D * 2};
+    const uint32_t box[2] = {kBlockK, (uint32_t)kFusedNT};
+    int rc = encode_tmap_bf16(&tmZ, Zp, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  const size_t smem = 1024 + kHeaderBytes + (size_t)p.stages * (kTileM * 128 + kFusedNT * 128) + 10 * kFusedNT * sizeof(float);
+  int rc = set_smem(tc_clip_fused_kernel, smem);
+  if (rc) return rc;
+  const long long blocks = (long long)p.i_tiles * j_tiles;
+  MEGB_CHECK_ARG(blocks < 2147483647ll, "tc_clip_fused: grid too large");
+  tc_clip_fused_kernel<<<(unsigned)blocks, kThreads, smem, st>>>(tmY, tmZ, p);
+  MEGB_LAUNCH_OK();
+  return 0;
+}
+
+int tc_clip_fused_loss(const float* row_lse, const float* col_lse, const float* diag, int off, int Bz, float wscale,
+                       float* out2, cudaStream_t st) {
+  int blocks = (Bz + 255) / 256;
+  if (blocks > 64) blocks = 64;
+  clip_fused_loss_kernel<<<blocks, 256, 0, st>>>(row_lse, col_lse, diag, off, Bz, wscale, out2);
+  MEGB_LAUNCH_OK();
   return 0;
 }
 

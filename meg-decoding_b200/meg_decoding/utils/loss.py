@@ -75,7 +75,7 @@ class CLIPLoss(nn.Module):
         if dtype is None:
             dtype = torch.float32 if megb200.get_precision() == "fp32" else torch.bfloat16
         eng = self._engine(dtype)
-        Y = x.detach().to(device=dev, dtype=torch.float32).contiguous()
+        Y = self._as_targets(x, dev)
         if self._side_stream is None:
             self._side_stream = torch.cuda.Stream(device=dev)
         cur = torch.cuda.current_stream(dev)
@@ -84,12 +84,29 @@ class CLIPLoss(nn.Module):
             prepared = eng.prepare_targets(Y, parallel.context())
             done = torch.cuda.Event()
             done.record(self._side_stream)
-        Y.record_stream(self._side_stream)
-        self._prefetched = (Y.data_ptr(), tuple(Y.shape), eng, prepared, done)
+        for t in ((Y.rows, Y.sumsq) if hasattr(Y, "rows") else (Y,)):
+            t.record_stream(self._side_stream)
+        self._prefetched = (self._key(Y), tuple(Y.shape), eng, prepared, done)
+
+    @staticmethod
+    def _key(Y):
+        return Y.rows.data_ptr() if hasattr(Y, "rows") else Y.data_ptr()
+
+    @staticmethod
+    def _as_targets(x, dev):
+        """The targets as the kernels take them: dense f32 or bf16 (B, F, T) | (B, F) on the device (bf16 is kept -- the
+        loss contracts bf16 operands anyway, and a pipeline that stores the precomputed features in bf16 halves the
+        host->device copy), or ``megb200.data.PackedTargets`` (already position-major + norms: no per-step pass at all)."""
+        if hasattr(x, "rows"):
+            return x if x.device == dev else x.to(dev)
+        x = x.detach()
+        if x.dtype != torch.bfloat16:
+            x = x.to(torch.float32)
+        return x.to(device=dev).contiguous()
 
     def _take_prefetched(self, Y, eng):
         pf, self._prefetched = self._prefetched, None
-        if pf is None or pf[0] != Y.data_ptr() or pf[1] != tuple(Y.shape) or pf[2] is not eng:
+        if pf is None or pf[0] != self._key(Y) or pf[1] != tuple(Y.shape) or pf[2] is not eng:
             return None
         torch.cuda.current_stream(Y.device).wait_event(pf[4])
         for t in pf[3]:
@@ -114,7 +131,7 @@ class CLIPLoss(nn.Module):
             Zi = y.contiguous().unsqueeze(1)
         else:
             raise ValueError("CLIPLoss expects (B, F, T) or (B, F) embeddings")
-        Y = x.detach().to(device=dev, dtype=torch.float32).contiguous()
+        Y = self._as_targets(x, dev)
         out = _ClipFn.apply(self, Y, Zi.to(dev), self.temp, bool(return_logits))
         if return_logits:
             loss, logits = out

@@ -347,21 +347,31 @@ class ClipEngine:
         ops, dev = self.ops, Y.device
         B = Y.shape[0]
         D = Y.numel() // B
+        packed = hasattr(Y, "rows")            # megb200.data.PackedTargets: already position-major in the activation dtype
+        if packed and (Y.rows.dtype != ops.act_dtype or not Y.rows.is_contiguous() or Y.sumsq.dtype != torch.float32):
+            raise RuntimeError(f"PackedTargets must hold contiguous {ops.act_dtype} rows and f32 norms for this precision")
         if dist_ctx is not None and dist_ctx.world > 1:
             pair = dist_ctx.target_gather(B, D, ops.act_dtype, dev)
             if pair is not None:
                 gy, gs = pair
                 Yp, ysq = gy.slot().view(B, D), gs.slot()
-                ysq.zero_()
-                ops.clip_prep_y(Y, Yp, ysq)
+                if packed:
+                    Yp.copy_(Y.rows)
+                    ysq.copy_(Y.sumsq)
+                else:
+                    ysq.zero_()
+                    ops.clip_prep_y(Y, Yp, ysq)
                 gy.fence()
                 gy.pull()
                 gs.pull()
                 gy.fence()
                 return gy.buf.view(dist_ctx.world * B, D), gs.buf.view(dist_ctx.world * B)
-        Yp = ops.empty(B, D, device=dev)
-        ysq = _zeros(dev, B)
-        ops.clip_prep_y(Y, Yp, ysq)
+        if packed:
+            Yp, ysq = Y.rows, Y.sumsq
+        else:
+            Yp = ops.empty(B, D, device=dev)
+            ysq = _zeros(dev, B)
+            ops.clip_prep_y(Y, Yp, ysq)
         if dist_ctx is not None and dist_ctx.world > 1:
             Yp, ysq = dist_ctx.all_gather_rows(Yp), dist_ctx.all_gather_rows(ysq)
         return Yp, ysq
@@ -381,6 +391,14 @@ class ClipEngine:
         ops.rowsumsq(Zf, zsq)
         world, rank = (dist_ctx.world, dist_ctx.rank) if dist_ctx is not None else (1, 0)
         Bg, off = B * world, rank * B
+        if reduction == "mean":
+            wscale = 0.5 / Bg
+        elif reduction == "sum":
+            wscale = 0.5
+        else:
+            raise ValueError(f"unsupported reduction {reduction!r}")
+        if not want_logits and self._use_fused(Bg, B, D):
+            return self._forward_fused(Yp, ysq, Zf, zsq, temp, wscale, world, off, dist_ctx, reduce_loss, Zi.shape)
         raw = _zeros(dev, Bg, B)
         ops.clip_logits(Yp, Zf, raw)
         Lg = _f32(dev, Bg, B)
@@ -390,12 +408,6 @@ class ClipEngine:
             parts = dist_ctx.all_gather_rows(parts)                 # [world, 2, Bg]: one collective, merged on the device
         row_lse = _f32(dev, Bg)
         ops.clip_lse_merge(parts, row_lse)
-        if reduction == "mean":
-            wscale = 0.5 / Bg
-        elif reduction == "sum":
-            wscale = 0.5
-        else:
-            raise ValueError(f"unsupported reduction {reduction!r}")
         out2 = _zeros(dev, 2)
         coef = ops.empty(B, pad8(Bg), device=dev)
         cvec = _zeros(dev, B)
@@ -405,6 +417,59 @@ class ClipEngine:
             loss = dist_ctx.all_reduce_sum(loss)
         ctx = dict(coef=coef, Yp=Yp, Zf=Zf, cvec=cvec, dtemp=out2[1:2], shape=Zi.shape)
         return loss.view(()), (Lg if want_logits else None), ctx
+
+    # ------------------------------------------------------------------ large batch, short embeddings
+    FUSED_MAX_D = 4096                 # the whole contraction runs inside one CTA's k loop
+    FUSED_MIN_LOGITS = 1 << 22         # auto: from 2048 x 2048 logits up (below that three small matrices are cheaper)
+
+    def _use_fused(self, Bg, B, D):
+        """The never-materialised form (loss.py:86-107 at the GOD sweep's batch sizes)?  Policy option
+        "clip_fused": -1 auto, 0 never, 1 whenever the engine supports it."""
+        from . import lib
+        if not getattr(self.ops, "has_fused_clip", False) or D > self.FUSED_MAX_D or D % 8 != 0:
+            return False
+        mode = lib.get_option("clip_fused")
+        return mode == 1 or (mode != 0 and Bg * B >= self.FUSED_MIN_LOGITS)
+
+    def _forward_fused(self, Yp, ysq, Zf, zsq, temp, wscale, world, off, dist_ctx, reduce_loss, shape):
+        """Logits tiles live in TMEM only: per-tile online (max, sum exp) partials for rows and columns + the positives;
+        two merges give the log-sum-exps; the backward pass recomputes the tiles (FlashAttention-style)."""
+        ops, dev = self.ops, Zf.device
+        B, Bg = Zf.shape[0], Yp.shape[0]
+        row_part = _f32(dev, (B + 127) // 128, 2, Bg)
+        col_part = _f32(dev, (Bg + 127) // 128, 2, B)
+        diag = _zeros(dev, B)
+        ops.clip_fused_stats(Yp, Zf, ysq, zsq, temp, off, row_part, col_part, diag)
+        if world > 1:
+            row_part = dist_ctx.all_gather_rows(row_part)           # the other ranks' brain columns
+        row_lse, col_lse = _f32(dev, Bg), _f32(dev, B)
+        ops.clip_lse_merge(row_part, row_lse)
+        ops.clip_lse_merge(col_part, col_lse)
+        out2 = _zeros(dev, 2)
+        ops.clip_fused_loss(row_lse, col_lse, diag, off, wscale, out2)
+        loss = out2[0:1].clone()
+        if world > 1 and reduce_loss:
+            loss = dist_ctx.all_reduce_sum(loss)
+        ctx = dict(fused=True, Yp=Yp, Zf=Zf, ysq=ysq, zsq=zsq, temp=temp, row_lse=row_lse, col_lse=col_lse, off=off,
+                   wscale=wscale, out2=out2, shape=shape)
+        return loss.view(()), None, ctx
+
+    def _backward_fused(self, ctx, gscale):
+        ops = self.ops
+        Yp, Zf = ctx["Yp"], ctx["Zf"]
+        B, Bg, dev = Zf.shape[0], Yp.shape[0], Zf.device
+        ldc = pad8(Bg)
+        # brain columns in chunks of <= 64 M coefficients (128 MB of bf16): what exists of dL at any time
+        chunk = max(128, min((B + 127) // 128 * 128, ((64 << 20) // ldc) // 128 * 128))
+        coef = ops.empty(min(chunk, B), ldc, device=dev)
+        cvec = _zeros(dev, B)
+        dZ = ops.empty(*Zf.shape, device=dev)
+        for j0 in range(0, B, chunk):
+            n = min(chunk, B - j0)
+            ops.clip_fused_coef(Yp, Zf, ctx["ysq"], ctx["zsq"], ctx["temp"], ctx["row_lse"], ctx["col_lse"], ctx["off"],
+                                ctx["wscale"], j0, coef[:n], cvec, ctx["out2"])
+            ops.clip_dz(coef[:n], Yp, Zf[j0:j0 + n], cvec[j0:j0 + n], gscale, dZ[j0:j0 + n])
+        return dZ.view(ctx["shape"]), ctx["out2"][1:2] * gscale
 
     def retrieval_ranks(self, Y, Zi):
         """Rank of the matching brain embedding among all brains of the batch for every speech segment (cosine
@@ -424,6 +489,8 @@ class ClipEngine:
 
     def backward(self, ctx, gscale):
         """gscale: f32 [1] upstream gradient of the (scalar) loss.  Returns (dZ in PC layout, dtemp f32 [1])."""
+        if ctx.get("fused"):
+            return self._backward_fused(ctx, gscale)
         ops = self.ops
         dZ = ops.empty(*ctx["Zf"].shape, device=gscale.device)
         ops.clip_dz(ctx["coef"], ctx["Yp"], ctx["Zf"], ctx["cvec"], gscale, dZ)

@@ -42,7 +42,7 @@ SIGNATURES = {
     "megb200_gelu_bwd": [_p, _p, _p, _p, _ll, _i, _i, _i, _p],
     "megb200_time_mean": [_p, _p, _i, _i, _i, _i, _i, _p],
     "megb200_time_mean_bwd": [_p, _p, _i, _i, _i, _i, _i, _p],
-    "megb200_clip_prep_y": [_p, _p, _p, _i, _i, _i, _i, _p],
+    "megb200_clip_prep_y": [_p, _i, _p, _p, _i, _i, _i, _i, _p],
     "megb200_rowsumsq": [_p, _p, _i, _ll, _i, _p],
     "megb200_clip_logits": [_p, _p, _p, _i, _i, _ll, _i, _i, _p],
     "megb200_clip_ce_partial": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p],
@@ -55,6 +55,9 @@ SIGNATURES = {
     "megb200_cast": [_p, _p, _ll, _i, _i, _p],
     "megb200_set_option": [_p, _ll],
     "megb200_clip_lse_merge": [_p, _i, _i, _p, _p],
+    "megb200_clip_fused_stats": [_p, _p, _p, _p, _p, _i, _i, _ll, _i, _p, _p, _p, _i, _i, _p],
+    "megb200_clip_fused_loss": [_p, _p, _p, _i, _i, _f, _p, _p],
+    "megb200_clip_fused_coef": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _ll, _i, _f, _i, _i, _p, _i, _p, _p, _i, _i, _p],
     "megb200_ipc_export": [_p, _p, _p],
     "megb200_ipc_import": [_p, _p],
     "megb200_ipc_release": [_p],

@@ -311,13 +311,15 @@ class CudaOps:
 
     # ------------------------------------------------------------------ CLIP
     def clip_prep_y(self, Y, Yp, ysq):
-        """Y f32 [B,F,T] or [B,F] -> Yp [B, T*F] (position-major) and ysq[b] += |Y_b|^2."""
-        self._chk_f32(Y, ysq)
+        """Y f32 | bf16 [B,F,T] or [B,F] -> Yp [B, T*F] (position-major) and ysq[b] += |Y_b|^2."""
+        assert Y.is_cuda and Y.is_contiguous() and Y.dtype in (torch.float32, torch.bfloat16), (Y.dtype, Y.shape)
+        self._chk_f32(ysq)
         self._chk_act(Yp)
         B, F = Y.shape[0], Y.shape[1]
         T = Y.shape[2] if Y.dim() == 3 else 1
         assert Yp.numel() == B * F * T
-        L.call("megb200_clip_prep_y", Y.data_ptr(), Yp.data_ptr(), ysq.data_ptr(), B, F, T, self.dt, self._stream())
+        L.call("megb200_clip_prep_y", Y.data_ptr(), L.F32 if Y.dtype == torch.float32 else L.BF16, Yp.data_ptr(),
+               ysq.data_ptr(), B, F, T, self.dt, self._stream())
 
     def rowsumsq(self, Z, sq):
         self._chk_act(Z)
@@ -344,6 +346,36 @@ class CudaOps:
         W, two, By = parts.shape
         assert two == 2 and row_lse.numel() == By
         L.call("megb200_clip_lse_merge", parts.data_ptr(), W, By, row_lse.data_ptr(), self._stream())
+
+    # ---- fused large-batch form (short embeddings): the B x B logits are never written (bf16 / tensor cores only)
+    @property
+    def has_fused_clip(self):
+        return self.be == L.TC
+
+    def clip_fused_stats(self, Yp, Zp, ysq, zsq, temp, off, row_part, col_part, diag):
+        """row_part f32 [ceil(Bz/128), 2, By], col_part f32 [ceil(By/128), 2, Bz], diag f32 [Bz]."""
+        self._chk_act(Yp, Zp)
+        self._chk_f32(ysq, zsq, temp, row_part, col_part, diag)
+        By, Bz = Yp.shape[0], Zp.shape[0]
+        assert row_part.shape == ((Bz + 127) // 128, 2, By) and col_part.shape == ((By + 127) // 128, 2, Bz)
+        L.call("megb200_clip_fused_stats", Yp.data_ptr(), Zp.data_ptr(), ysq.data_ptr(), zsq.data_ptr(), temp.data_ptr(),
+               By, Bz, Yp.numel() // By, int(off), row_part.data_ptr(), col_part.data_ptr(), diag.data_ptr(), self.dt,
+               self.be, self._stream())
+
+    def clip_fused_loss(self, row_lse, col_lse, diag, off, wscale, out2):
+        self._chk_f32(row_lse, col_lse, diag, out2)
+        L.call("megb200_clip_fused_loss", row_lse.data_ptr(), col_lse.data_ptr(), diag.data_ptr(), int(off),
+               col_lse.numel(), float(wscale), out2.data_ptr(), self._stream())
+
+    def clip_fused_coef(self, Yp, Zp, ysq, zsq, temp, row_lse, col_lse, off, wscale, j_begin, coef, cvec, out2):
+        """coef [j_count, ldc] (activation dtype) for brain columns [j_begin, j_begin + j_count); cvec / out2[1] accumulated."""
+        self._chk_act(Yp, Zp, coef)
+        self._chk_f32(ysq, zsq, temp, row_lse, col_lse, cvec, out2)
+        By, Bz = Yp.shape[0], Zp.shape[0]
+        L.call("megb200_clip_fused_coef", Yp.data_ptr(), Zp.data_ptr(), ysq.data_ptr(), zsq.data_ptr(), temp.data_ptr(),
+               row_lse.data_ptr(), col_lse.data_ptr(), By, Bz, Yp.numel() // By, int(off), float(wscale), int(j_begin),
+               coef.shape[0], coef.data_ptr(), coef.shape[1], cvec.data_ptr(), out2.data_ptr(), self.dt, self.be,
+               self._stream())
 
     def clip_ce_finish(self, Lg, row_lse, col_lse, ysq, zsq, temp, off, wscale, out2, coef, cvec):
         self._chk_f32(Lg, row_lse, col_lse, ysq, zsq, temp, out2, cvec)

@@ -226,9 +226,9 @@ class TorchOps:
     # ------------------------------------------------------------------ CLIP
     def clip_prep_y(self, Y, Yp, ysq):
         B = Y.shape[0]
-        y = Y if Y.dim() == 3 else Y[:, :, None]
+        y = (Y if Y.dim() == 3 else Y[:, :, None]).float()
         Yp.copy_(self._r(y.permute(0, 2, 1).reshape(B, -1)).view(Yp.shape))
-        ysq += (Y.reshape(B, -1) ** 2).sum(-1)
+        ysq += (Y.float().reshape(B, -1) ** 2).sum(-1)
 
     def rowsumsq(self, Z, sq):
         sq += (Z.float().reshape(Z.shape[0], -1) ** 2).sum(-1)

@@ -161,3 +161,31 @@ def test_async_scalar_reader_returns_every_value_in_order():
                 got.append(v)
         got += r.drain()
         assert got == [i + 0.5 for i in range(7)]
+
+
+def test_packed_and_bf16_targets_equal_dense_f32(torch_ops):
+    """CLIPLoss accepts the targets dense in f32 (the reference's collator), dense in bf16, or pre-packed
+    (megb200.data.PackedTargets: position-major rows + norms).  Packed must reproduce dense f32 exactly (same rounding
+    point, same norms); on this f32 op restatement that means bit for bit."""
+    from megb200.data import PackedTargets
+    cfg = synth.get_config("tiny")
+    enc, lossf = H.make_modules(cfg)
+    X, Y, subj = H.make_inputs(cfg)
+    enc.eval()
+    with torch.no_grad():
+        Z = enc(X, subj)
+        dense = lossf(Y, Z)
+        packed = lossf(PackedTargets.from_dense(Y, dtype=torch.float32), Z)
+        half = lossf(Y.to(torch.bfloat16), Z)
+    assert torch.equal(dense, packed)
+    assert abs(float(half) - float(dense)) / abs(float(dense)) < 5e-3
+    pt = PackedTargets.from_dense(Y, dtype=torch.float32)
+    assert pt.size(0) == cfg.B and pt.shape == tuple(Y.shape) and pt[[1, 0]].rows.shape == (2, pt.rows.shape[1])
+    # static (B, F) targets
+    cfg2 = synth.get_config("tiny_static")
+    enc2, lossf2 = H.make_modules(cfg2)
+    X2, Y2, subj2 = H.make_inputs(cfg2)
+    enc2.eval()
+    with torch.no_grad():
+        Z2 = enc2(X2, subj2)
+        assert torch.equal(lossf2(Y2, Z2), lossf2(PackedTargets.from_dense(Y2, dtype=torch.float32), Z2))

@@ -499,6 +499,72 @@ def test_clip_pipeline(dtype, backend, case):
         assert L.get_option("last_clip_dz_kernel") == CLIP_DZ_EXPECT[(By, Bz)]
 
 
+FUSED_CLIP_CASES = [
+    # By (speech rows, all ranks), Bz (local brains), off, D
+    (6, 6, 0, 48),              # one ragged tile, one (partial) k chunk
+    (300, 150, 150, 512),       # several tiles both ways, data-parallel shard
+    (2048, 256, 512, 512),      # 8-rank GOD shard
+    (2048, 2048, 0, 512),       # GOD global batch on one rank
+    (1000, 1000, 0, 1024),      # ragged last tiles, 16 k chunks
+]
+
+
+@pytest.mark.parametrize("case", FUSED_CLIP_CASES)
+def test_clip_fused_never_materialised(case):
+    """The large-batch form of the loss (logits tiles live in TMEM only; backward recomputes them) against the op
+    restatement of the materialised pipeline on the same stored operands: log-sum-exps, loss, d/dtemp, the coefficient
+    matrix (in two column chunks), cvec and dZ."""
+    By, Bz, off, D = case
+    dtype = torch.bfloat16
+    gen = torch.Generator().manual_seed(13)
+    ops, ref = _ops(dtype, "tc"), TorchOps(dtype)
+    Yp = _rand(gen, By, D).to(dtype)
+    Z = (_rand(gen, Bz, D) * 0.3).to(dtype)
+    Z[: min(Bz, By - off)] += 0.05 * Yp[off:off + Bz].float().to(dtype)[: min(Bz, By - off)]      # positives stand out a little
+    temp = torch.tensor([3.0])
+    ysq, zsq = (Yp.float() ** 2).sum(1), (Z.float() ** 2).sum(1)
+    # ---- reference: the materialised pipeline
+    raw = torch.zeros(By, Bz)
+    ref.clip_logits(Yp, Z, raw)
+    Lg, rm, rs, cl = torch.empty(By, Bz), torch.empty(By), torch.empty(By), torch.empty(Bz)
+    ref.clip_ce_partial(raw, ysq, zsq, temp, Lg, rm, rs, cl)
+    row_lse_r = rm + torch.log(rs)
+    wscale = 0.5 / By
+    out2r, coefr, cvecr = torch.zeros(2), ref.empty(Bz, pad8(By), device="cpu"), torch.zeros(Bz)
+    ref.clip_ce_finish(Lg, row_lse_r, cl, ysq, zsq, temp, off, wscale, out2r, coefr, cvecr)
+    # ---- fused
+    Ypd, Zd, ysqd, zsqd, td = Yp.to(DEV), Z.to(DEV), ysq.to(DEV), zsq.to(DEV), temp.to(DEV)
+    row_part = torch.full(((Bz + 127) // 128, 2, By), float("nan"), device=DEV)
+    col_part = torch.full(((By + 127) // 128, 2, Bz), float("nan"), device=DEV)
+    diag = torch.zeros(Bz, device=DEV)
+    ops.clip_fused_stats(Ypd, Zd, ysqd, zsqd, td, off, row_part, col_part, diag)
+    row_lse, col_lse = torch.empty(By, device=DEV), torch.empty(Bz, device=DEV)
+    ops.clip_lse_merge(row_part, row_lse)
+    ops.clip_lse_merge(col_part, col_lse)
+    _close(row_lse, row_lse_r, torch.float32, "fused row lse", atol_scale=20)
+    _close(col_lse, cl, torch.float32, "fused col lse", atol_scale=20)
+    j = torch.arange(Bz)
+    _close(diag, Lg[off + j, j], torch.float32, "fused positives", atol_scale=20)
+    out2 = torch.zeros(2, device=DEV)
+    ops.clip_fused_loss(row_lse, col_lse, diag, off, wscale, out2)
+    cvec = torch.zeros(Bz, device=DEV)
+    half = max(1, (Bz // 2 + 127) // 128 * 128)
+    coef = ops.empty(Bz, pad8(By), device=DEV)
+    for j0 in range(0, Bz, half):
+        n = min(half, Bz - j0)
+        ops.clip_fused_coef(Ypd, Zd, ysqd, zsqd, td, row_lse, col_lse, off, wscale, j0, coef[j0:j0 + n], cvec, out2)
+    torch.cuda.synchronize()
+    _close(out2, out2r, torch.float32, "fused loss / dtemp", atol_scale=100)
+    _close(coef[:, :By], coefr[:, :By], dtype, "fused coef")
+    _close(cvec, cvecr, torch.float32, "fused cvec", atol_scale=100)
+    gs = torch.tensor([0.7])
+    dZ, dZr = ops.empty(Bz, D, device=DEV), ref.empty(Bz, D, device="cpu")
+    ops.clip_dz(coef, Ypd, Zd, cvec, gs.to(DEV), dZ)
+    ref.clip_dz(coefr, Yp, Z, cvecr, gs, dZr)
+    torch.cuda.synchronize()
+    _close(dZ, dZr, dtype, "fused dZ")
+
+
 @pytest.mark.parametrize("W,By", [(1, 37), (2, 512), (8, 2048)])
 def test_clip_lse_merge(W, By):
     """The ranks' partial (max, sum exp) pairs -> complete per-row log-sum-exp (one all-gather + this kernel replace a MAX

@@ -57,6 +57,22 @@ def test_train_step_matches_reference_golden(mode, name):
     print(f"[parity] {name} {mode}: " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()))
 
 
+@pytest.mark.parametrize("name", ["tiny_static", "narrow_static"])
+def test_fused_clip_train_step_matches_reference_golden(name):
+    """The never-materialised CLIP form (the GOD sweep's large-batch path) forced on the static golden configs: the
+    whole train step against the reference's stored outputs, bf16 tolerances."""
+    from megb200 import lib
+    tz, tl, tg = MODES["bf16"]
+    cfg = synth.get_config(name)
+    enc, lossf = H.make_modules(cfg, DEV)
+    X, Y, subj = H.make_inputs(cfg, DEV)
+    with lib.options(clip_fused=1):
+        Z, loss, grads = H.train_step(enc, lossf, X, Y, subj, synth.drop_center(cfg))
+        torch.cuda.synchronize()
+    errs = H.compare_with_golden(name, Z, loss, grads, tz, tl, tg)
+    print(f"[parity] {name} bf16 fused CLIP: " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()))
+
+
 def test_eval_mode_matches_reference_golden(mode):
     tz, tl, _ = MODES[mode]
     cfg = synth.get_config("narrow")
@@ -229,6 +245,33 @@ def test_config2_full_batch_against_cpu_oracle(prec, seed):
     if prec == "bf16":
         from megb200 import lib
         assert lib.get_option("last_wgrad_splits") >= 1 and lib.get_option("last_clip_dz_kernel") == 0
+
+
+@pytest.mark.parametrize("name", ["narrow", "narrow_static"])
+def test_packed_and_bf16_targets_match_dense_f32(name):
+    """Data formats on the target side of the path: dense f32 (reference collator), dense bf16, PackedTargets.  The
+    packed form must give the dense-f32 result (same rounding point; norms differ only in f32 summation order)."""
+    from megb200.data import PackedTargets
+    from megb200.graph import GraphedTrainStep
+    cfg = synth.get_config(name)
+    enc, lossf = H.make_modules(cfg, DEV)
+    X, Y, subj = H.make_inputs(cfg, DEV)
+    center = synth.drop_center(cfg)
+    res = {}
+    for kind, tgt in (("dense", Y), ("packed", PackedTargets.from_dense(Y.cpu()).to(DEV)), ("bf16", Y.to(torch.bfloat16))):
+        enc2, lossf2 = H.make_modules(cfg, DEV)
+        Z, loss, grads = H.train_step(enc2, lossf2, X, tgt, subj, center)
+        res[kind] = (float(loss), grads["conv_final2.weight"].float(), float(grads["temp"]))
+    l0, g0, t0 = res["dense"]
+    for kind, tl, tg in (("packed", 1e-5, 1e-3), ("bf16", 5e-3, 5e-2)):
+        l, g, t = res[kind]
+        print(f"[parity] targets {kind} vs dense f32 ({name}): loss {abs(l - l0) / abs(l0):.2e} dWf2 {H.rel_fro(g, g0):.2e} "
+              f"dtemp {abs(t - t0) / abs(t0):.2e}")
+        assert abs(l - l0) / abs(l0) <= tl and H.rel_fro(g, g0) <= tg and abs(t - t0) / abs(t0) <= tg
+    # the CUDA-graph step on packed targets
+    gstep = GraphedTrainStep(enc, lossf, X, PackedTargets.from_dense(Y.cpu()).to(DEV), subj, drop_center=center)
+    gl = float(gstep())
+    assert abs(gl - l0) / abs(l0) <= 1e-2
 
 
 def test_bf16_is_the_default_precision_and_output_is_bf16():
