@@ -98,8 +98,8 @@ def cpu_reference_step_time(cfg, B_sample, steps, warmup, threads=None, seed=0, 
         torch.set_num_threads(threads)
     P = R.state_to_torch(synth.make_state(cfg), requires_grad=True)
     temp = torch.tensor([float(cfg.init_temperature)], requires_grad=True)
-    X, Y, subj = synth.make_batch(cfg, seed, B=B_sample)
-    X, Y, subj = torch.from_numpy(X), torch.from_numpy(Y), torch.from_numpy(subj)
+    X, Y, subj = synth.make_batch(cfg, seed)           # the workload's batch; the sample is its first B_sample samples
+    X, Y, subj = (torch.from_numpy(a[:B_sample].copy()) for a in (X, Y, subj))
     loc = synth.sensor_locations(cfg.C)
     center = synth.drop_center(cfg)
     times, first = [], None

@@ -175,6 +175,14 @@ int megb200_gelu_bwd(const void* dQ, const void* P, void* dP, float* dbias, long
 int megb200_time_mean(const void* Z, void* Zm, int B, int T, int F, int Fs, int dtype, void* stream);
 int megb200_time_mean_bwd(const void* dZm, void* dZ, int B, int T, int F, int Fs, int dtype, void* stream);
 
+/* nn.AvgPool1d(k, stride) over time, no padding (BrainEncoderSeq2Static puts AvgPool1d(3, 2) between its conv blocks,
+ * models.py:483-485; "next" row N4): Out [B][To][Cs], To = (T - k) / stride + 1; backward spreads dOut / k over each window
+ * (positions past the last window get zero).  nn.AdaptiveAvgPool1d(1) after the last block (models.py:487) is
+ * megb200_time_mean. */
+int megb200_avgpool1d(const void* X, void* Out, int B, int T, int C, int Cs, int k, int stride, int dtype, void* stream);
+int megb200_avgpool1d_bwd(const void* dOut, void* dX, int B, int T, int C, int Cs, int k, int stride, int dtype,
+                          void* stream);
+
 /* ---------------------------------------------------------------------------------------------- CLIP loss */
 /* Y [B][F][T] (NCW; `y_dtype` = MEGB200_F32 as the reference's collator delivers it, or MEGB200_BF16 when the data
  * pipeline stores the precomputed wav2vec2 targets in bf16 -- the loss rounds them to bf16 anyway, and the host->device

@@ -847,6 +847,59 @@ __global__ void time_mean_kernel(const T* __restrict__ Z, T* __restrict__ Zm, in
   }
 }
 
+// AvgPool1d(k, stride) over time on the PC layout (BrainEncoderSeq2Static, models.py:483-485: kernel 3, stride 2, no
+// padding): Out[b][to][c] = mean_{j<k} X[b][to*stride + j][c].  Thread = 8 channels of one output position.
+template <typename T>
+__global__ void avgpool_kernel(const T* __restrict__ X, T* __restrict__ Out, int B, int Tn, int To, int Cs, int k,
+                               int stride) {
+  const int cg = Cs >> 3;
+  const long long nvec = (long long)B * To * cg;
+  const float inv = 1.f / (float)k;
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvec;
+       v += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(v % cg) * 8;
+    const long long bt = v / cg;
+    const int to = (int)(bt % To), b = (int)(bt / To);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int j = 0; j < k; ++j) {
+      float x[8];
+      load8(X + ((long long)b * Tn + to * stride + j) * Cs + c0, x);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += x[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] *= inv;
+    store8(Out + v * 8, acc);
+  }
+}
+
+// dX[b][t][c] = (1/k) * sum over the windows that contain t of dOut[b][to][c]; positions past the last window get 0
+template <typename T>
+__global__ void avgpool_bwd_kernel(const T* __restrict__ dOut, T* __restrict__ dX, int B, int Tn, int To, int Cs, int k,
+                                   int stride) {
+  const int cg = Cs >> 3;
+  const long long nvec = (long long)B * Tn * cg;
+  const float inv = 1.f / (float)k;
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvec;
+       v += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(v % cg) * 8;
+    const long long bt = v / cg;
+    const int t = (int)(bt % Tn), b = (int)(bt / Tn);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int lo = t - k + 1;
+    lo = lo <= 0 ? 0 : (lo + stride - 1) / stride;           // first window with to*stride + k - 1 >= t
+    for (int to = lo; to < To && to * stride <= t; ++to) {
+      float x[8];
+      load8(dOut + ((long long)b * To + to) * Cs + c0, x);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += x[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] *= inv;
+    store8(dX + v * 8, acc);
+  }
+}
+
 template <typename T>
 __global__ void time_mean_bwd_kernel(const T* __restrict__ dZm, T* __restrict__ dZ, int B, int Tn, int Fs) {
   const int fg = Fs >> 3;
@@ -1164,6 +1217,23 @@ int megb200_time_mean_bwd(const void* dZm, void* dZ, int B, int T, int F, int Fs
   DISPATCH_DTYPE(dtype,
                  time_mean_bwd_kernel<DT><<<ew_grid((long long)B * T * Fs / 8, 256), 256, 0, (cudaStream_t)stream>>>(
                      (const DT*)dZm, (DT*)dZ, B, T, Fs);
+                 MEGB_LAUNCH_OK(); return 0;)
+}
+
+int megb200_avgpool1d(const void* X, void* Out, int B, int T, int C, int Cs, int k, int stride, int dtype, void* stream) {
+  MEGB_CHECK_ARG(X && Out && B > 0 && k > 0 && stride > 0 && T >= k && Cs % 8 == 0 && Cs >= C, "avgpool1d: bad arguments");
+  const int To = (T - k) / stride + 1;
+  DISPATCH_DTYPE(dtype, avgpool_kernel<DT><<<ew_grid((long long)B * To * Cs / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+                            (const DT*)X, (DT*)Out, B, T, To, Cs, k, stride);
+                 MEGB_LAUNCH_OK(); return 0;)
+}
+
+int megb200_avgpool1d_bwd(const void* dOut, void* dX, int B, int T, int C, int Cs, int k, int stride, int dtype,
+                          void* stream) {
+  MEGB_CHECK_ARG(dOut && dX && B > 0 && k > 0 && stride > 0 && T >= k && Cs % 8 == 0 && Cs >= C, "avgpool1d_bwd: bad arguments");
+  const int To = (T - k) / stride + 1;
+  DISPATCH_DTYPE(dtype, avgpool_bwd_kernel<DT><<<ew_grid((long long)B * T * Cs / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+                            (const DT*)dOut, (DT*)dX, B, T, To, Cs, k, stride);
                  MEGB_LAUNCH_OK(); return 0;)
 }
 

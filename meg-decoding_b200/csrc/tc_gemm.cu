@@ -2017,7 +2017,12 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
       p.dbg = dbg_buf;
       cudaMemsetAsync(dbg_buf, 0, sizeof(long long) * 16 * 2 * clusters, st);
     }
-    if (taps > 1 && a_rows2 <= 256 && !no_halo && p.n_last == p.NT) {
+    // the halo form needs two stages of (activation rows with halo + ALL taps' weight half-tiles): wide kernels (k = 11 of
+    // BrainEncoderSeq2Static) and large dilations take the plain pair kernel, one activation box per tap
+    const uint32_t halo_stage = (((uint32_t)a_rows2 * 128u + 1023u) & ~1023u) + (uint32_t)taps * (uint32_t)half * 128u;
+    const bool halo_fits = a_rows2 <= 256 &&
+                           pick_stages(halo_stage, kSmemMax - 2048 - (2 * p.NT * 4 + 2 * Cos * 4) - p.stg_bytes, 4) >= 2;
+    if (taps > 1 && halo_fits && !no_halo && p.n_last == p.NT) {
       // halo form: activation ring (with halo rows) + weight ring
       const uint32_t a_slot = ((uint32_t)a_rows2 * 128u + 1023u) & ~1023u;
       const uint32_t b_half = (uint32_t)half * 128;

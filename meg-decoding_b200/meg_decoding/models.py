@@ -28,6 +28,8 @@ def get_model(args):
     """models.py:18-30; only the BrainEncoder branch is on the accelerated path."""
     if args.model == "brain_encoder":
         return BrainEncoder(args)
+    if args.model == "brain_endcoder_seq2static":            # the reference's spelling (models.py:21)
+        return BrainEncoderSeq2Static(args)
     raise ValueError("no model named {} is prepared by megb200 (only 'brain_encoder' is on the hot path)".format(args.model))
 
 
@@ -100,6 +102,7 @@ class ConvBlock(nn.Module):
         self.k = k
         self.D2 = D2
         self.in_channels = D1 if k == 0 else D2
+        self.ks = ks
         self.conv0 = nn.Conv1d(self.in_channels, D2, kernel_size=ks, padding="same")
         self.batchnorm0 = nn.BatchNorm1d(num_features=D2)
         self.conv1 = nn.Conv1d(D2, D2, kernel_size=ks, padding="same")
@@ -136,8 +139,24 @@ class _EncoderFn(torch.autograd.Function):
         return (None, None, None, None, None) + tuple(grads)
 
 
+def _arg(args, name, default=None):
+    try:
+        return args.get(name, default) if hasattr(args, "get") else getattr(args, name, default)
+    except Exception:
+        return default
+
+
 class BrainEncoder(nn.Module):
-    """models.py:341-383."""
+    """models.py:341-383.
+
+    ``args.conv_dilations`` (optional megb200 extension; 5 x 3 integers or ``"paper"``) enables the dilated block of the
+    paper, which the reference keeps as an alternative formulation (tests/test_modules/models.py:267-312) while its
+    ``ConvBlock`` runs with dilation 1 (models.py:289,297,305 commented out) -- the default here too."""
+
+    pooled = False                       # BrainEncoderSeq2Static: pooling between the blocks
+
+    def _kernel_sizes(self, args):
+        return [3] * 5
 
     def __init__(self, args):
         super().__init__()
@@ -153,8 +172,20 @@ class BrainEncoder(nn.Module):
 
         self.subject_block = SubjectBlock(args)
         self.conv_blocks = nn.Sequential()
+        self.ks = self._kernel_sizes(args)
         for k in range(5):
-            self.conv_blocks.add_module(f"conv{k}", ConvBlock(k, self.D1, self.D2))
+            self.conv_blocks.add_module(f"conv{k}", ConvBlock(k, self.D1, self.D2, ks=self.ks[k]))
+            if self.pooled:                                                      # models.py:483-487 (no parameters)
+                if k < 4:
+                    self.conv_blocks.add_module(f"avgpool{k}", nn.AvgPool1d(3, stride=2))
+                else:
+                    self.conv_blocks.add_module(f"globalavgpool{k}", nn.AdaptiveAvgPool1d(output_size=1))
+        dil = _arg(args, "conv_dilations")
+        if isinstance(dil, str):
+            if dil != "paper":
+                raise ValueError(f"unknown conv_dilations {dil!r}")
+            dil = [(2 ** (2 * k % 5), 2 ** (2 * k + 1 % 5), 2) for k in range(1, 6)]   # tests/test_modules/models.py:275-297
+        self.dilations = [tuple(int(x) for x in row) for row in dil] if dil is not None else None
         self.conv_final1 = nn.Conv1d(self.D2, 2 * self.D2, kernel_size=1)
         self.conv_final2 = nn.Conv1d(2 * self.D2, self.F, kernel_size=1)
 
@@ -162,6 +193,12 @@ class BrainEncoder(nn.Module):
             self.precision = args.get("precision") if hasattr(args, "get") else getattr(args, "precision", None)
         except Exception:
             self.precision = None
+        # dtype of the returned embeddings: None = the precision mode's storage type (bf16 by default).  The reference's
+        # evaluation / inference scripts call ``Z.detach().cpu().numpy()`` (evaluate.py:340, examples/inference.py:105),
+        # which numpy cannot do for bf16: set ``args.output_dtype = "float32"`` (or ``enc.output_dtype = torch.float32``)
+        # there -- one extra cast pass (megb200_cast) over Z, outside autograd (eval / no_grad only).
+        od = _arg(args, "output_dtype")
+        self.output_dtype = getattr(torch, od) if isinstance(od, str) else od
         self.drop_center = None          # set to an int to pin the spatial-dropout centre (tests, data parallel)
         self._eng = None
 
@@ -171,7 +208,7 @@ class BrainEncoder(nn.Module):
         if self._eng is None or self._eng.ops is not ops:
             C = self.subject_block.spatial_attention.cos.shape[1]
             self._eng = EncoderEngine(ops, C=C, D1=self.D1, D2=self.D2, F=self.F, S=self.num_subjects,
-                                      seq2seq=self.seq2seq)
+                                      seq2seq=self.seq2seq, dilations=self.dilations, ks=self.ks, pooled=self.pooled)
         return self._eng
 
     def _param_list(self):
@@ -261,10 +298,32 @@ class BrainEncoder(nn.Module):
             Zi = _EncoderFn.apply(self, X, subj, mask, present, *params)
         else:
             Zi, _ = self._engine().forward(self._param_dict(params), X, subj, mask, self.training)
+            if self.output_dtype is not None and self.output_dtype != Zi.dtype:
+                Zo = torch.empty(Zi.shape, dtype=self.output_dtype, device=Zi.device)
+                self._engine().ops.cast(Zi, Zo)
+                Zi = Zo
         # PC layout [B,T,F] -> the reference's (B, F, T) (a view) or (B, F)
         if self.seq2seq:
             return Zi.permute(0, 2, 1)
         return Zi[:, 0, : self.F]
+
+
+class BrainEncoderSeq2Static(BrainEncoder):
+    """models.py:465-512 (``args.model == "brain_endcoder_seq2static"``, the GOD image-decoding configs): the same
+    SubjectBlock / ConvBlock / 1x1 head, but block k convolves with kernel size ``args.ConvBlocks.ks[k]`` (3, 5 or 11 in
+    the reference's configs), ``AvgPool1d(3, stride=2)`` follows blocks 0..3 and ``AdaptiveAvgPool1d(1)`` block 4, so the
+    head runs on one time step.  Returns (B, F) for ``seq2seq=False`` (the mean over the single step, :510) and
+    (B, F, 1) otherwise.  Same state_dict keys as the reference (the pooling layers have no parameters)."""
+
+    pooled = True
+
+    def _kernel_sizes(self, args):
+        cb = _arg(args, "ConvBlocks")
+        ks = cb["ks"] if isinstance(cb, dict) else cb.ks
+        ks = [int(k) for k in ks]
+        if len(ks) != 5:
+            raise ValueError("args.ConvBlocks.ks must list five kernel sizes")
+        return ks
 
 
 class Classifier(nn.Module):

@@ -2,7 +2,9 @@
 
 The reference reads the layout from raw recordings through mne / mne_bids (not installed here, data absent).  The hot
 path only needs the (C, 2) coordinates, min-max normalised and scaled into [0.1, 0.9]; they can be supplied directly
-through ``args.sensor_locations`` (array-like (C, 2), raw coordinates).  Otherwise mne is tried, as the reference does.
+through ``args.sensor_locations`` (array-like (C, 2), raw coordinates).  Otherwise the reference's branches run: the GOD
+branch (layout.py:36-38) reads ``args.montage_path`` / ``args.ch_region_path`` / ``args.region`` like
+``matlab_utils/load_meg.py:105-143``; the Brennan / Gwilliams branches need mne (+ the raw data), as in the reference.
 """
 import numpy as np
 import torch
@@ -16,6 +18,37 @@ def normalise_locations(loc) -> torch.Tensor:
     return torch.from_numpy(loc.astype(np.float32))
 
 
+def _get(args, name, default=None):
+    try:
+        return args.get(name, default) if hasattr(args, "get") else getattr(args, name, default)
+    except Exception:
+        return default
+
+
+def roi_channels(args):
+    """matlab_utils/load_meg.py:105-121 — 0-based channel indices of the requested "region/subregion" entries of the
+    channel-region table (the JSON lists MATLAB's 1-based channel numbers)."""
+    import json
+    with open(args.ch_region_path, "r") as f:
+        info = json.load(f)
+    out = []
+    for reg in args.region:
+        parts = reg.split("/")
+        assert len(parts) == 2, "got {}".format(parts)
+        out += info[parts[0]][parts[1]]
+    return [r - 1 for r in out]
+
+
+def read_montage(args) -> np.ndarray:
+    """matlab_utils/load_meg.py:133-143 — sensor positions (x, y, z) of the ROI channels from the montage CSV."""
+    import csv
+    rows = []
+    with open(args.montage_path) as f:
+        for row in csv.reader(f):
+            rows.append([float(r) for r in row])
+    return np.array(rows)[roi_channels(args), :]
+
+
 def ch_locations_2d(args):
     given = None
     try:
@@ -25,6 +58,8 @@ def ch_locations_2d(args):
     if given is not None:
         return normalise_locations(np.asarray(given)[:, :2])
     dataset_name = args.dataset
+    if dataset_name == "GOD":                                    # layout.py:36-38: montage file, no mne involved
+        return normalise_locations(read_montage(args)[:, :2])
     try:
         import mne  # noqa: F401
     except ImportError as e:

@@ -68,10 +68,18 @@ class EncoderEngine:
     """BrainEncoder.forward / backward (models.py:367-383 and the modules it owns)."""
 
     def __init__(self, ops, *, C: int, D1: int, D2: int, F: int, S: int, seq2seq: bool, dilations=None,
-                 eps: float = 1e-5, momentum: float = 0.1):
+                 eps: float = 1e-5, momentum: float = 0.1, ks=None, pooled: bool = False):
+        """``ks`` (five odd kernel sizes) and ``pooled`` select BrainEncoderSeq2Static (models.py:465-512): block k convolves
+        with kernel size ks[k], AvgPool1d(3, 2) follows blocks 0..3 and a global average over time block 4, so the 1x1 head
+        runs on one position per sample.  ``dilations`` (5 x 3) is the paper's dilated block
+        (tests/test_modules/models.py:275-297); the reference code as it runs has 1 everywhere."""
         self.ops, self.C, self.D1, self.D2, self.F, self.S = ops, C, D1, D2, F, S
         self.seq2seq = seq2seq
-        self.dil = dilations if dilations is not None else [(1, 1, 1)] * 5
+        self.dil = [tuple(d) for d in dilations] if dilations is not None else [(1, 1, 1)] * 5
+        self.ks = [int(k) for k in ks] if ks is not None else [3] * 5
+        if any(k < 1 or k % 2 == 0 for k in self.ks):
+            raise ValueError("megb200: Conv1d kernel sizes must be odd (padding='same' is symmetric only then)")
+        self.pooled = bool(pooled)
         self.eps, self.momentum = eps, momentum
         self._packed = {}        # persistent packed-weight buffers, keyed by (name, mode, device)
         self._zp = None          # zero pool of the pass in flight
@@ -83,9 +91,9 @@ class EncoderEngine:
         out = []
         for k in range(5):
             pk = P["blocks"][k]
-            out.append((f"b{k}.w0", pk["w0"], D2, D1 if k == 0 else D2, 3))
-            out.append((f"b{k}.w1", pk["w1"], D2, D2, 3))
-            out.append((f"b{k}.w2", pk["w2"], 2 * D2, D2, 3))
+            out.append((f"b{k}.w0", pk["w0"], D2, D1 if k == 0 else D2, self.ks[k]))
+            out.append((f"b{k}.w1", pk["w1"], D2, D2, self.ks[k]))
+            out.append((f"b{k}.w2", pk["w2"], 2 * D2, D2, self.ks[k]))
         out.append(("wf1", P["wf1"], 2 * D2, D2, 1))
         out.append(("wf2", P["wf2"], Fo, 2 * D2, 1))
         return out
@@ -138,27 +146,43 @@ class EncoderEngine:
         x, cin = H2, D1
         blocks = []
         for k in range(5):
-            pk, d = P["blocks"][k], self.dil[k]
+            pk, d, kt = P["blocks"][k], self.dil[k], self.ks[k]
             bc = {"x": x, "cin": cin}
             # pre-BatchNorm tensors stay in f32: the normalisation sees the unrounded convolution (+ residual)
             # (the train-mode batch statistics ride on the conv epilogue: sums[2][D2])
             s0 = self._zp.take(2, D2) if training else None
-            u0 = self._conv(x, cin, f"b{k}.w0", pk["b0"], D2, d[0], x if k > 0 else None, epi="store_f32", stats=s0)
+            u0 = self._conv(x, cin, f"b{k}.w0", pk["b0"], D2, d[0], x if k > 0 else None, taps=kt, epi="store_f32", stats=s0)
             h0, bc["bn0"] = self._bn_gelu(u0, pk, "0", training, s0)
             s1 = self._zp.take(2, D2) if training else None
-            u1 = self._conv(h0, D2, f"b{k}.w1", pk["b1"], D2, d[1], h0, epi="store_f32", stats=s1)
+            u1 = self._conv(h0, D2, f"b{k}.w1", pk["b1"], D2, d[1], h0, taps=kt, epi="store_f32", stats=s1)
             h1, bc["bn1"] = self._bn_gelu(u1, pk, "1", training, s1)
-            out, v = self._conv(h1, D2, f"b{k}.w2", pk["b2"], 2 * D2, d[2], None, epi="glu")
+            out, v = self._conv(h1, D2, f"b{k}.w2", pk["b2"], 2 * D2, d[2], None, taps=kt, epi="glu")
             bc.update(u0=u0, h0=h0, u1=u1, h1=h1, v=v)
             blocks.append(bc)
+            if self.pooled:                                                             # models.py:483-487
+                Tk = out.shape[1]
+                if k < 4:
+                    assert Tk >= 3, "sequence too short for AvgPool1d(3, 2)"
+                    pooled = ops.empty(B, (Tk - 3) // 2 + 1, out.shape[2], device=dev)
+                    ops.avgpool(out, pooled, D2, 3, 2)
+                else:
+                    pooled = ops.empty(B, 1, out.shape[2], device=dev)
+                    ops.time_mean(out, pooled, D2)
+                out = pooled
             x, cin = out, D2
         ctx["blocks"] = blocks
         ctx["x5"] = x
 
-        # ---- 1x1 head (models.py:373-374): GELU after both convs
+        # ---- 1x1 head (models.py:373-374): GELU after both convs.  After the global average there is one position per
+        # sample: a 1x1 conv is position-wise, so the batch is laid out as the positions of ONE sample (full tiles)
+        if self.pooled:
+            x = x.view(1, B, x.shape[2])
+            ctx["x5"] = x
         q1, p1 = self._conv(x, D2, "wf1", P["bf1"], 2 * D2, 1, None, taps=1, epi="gelu")
         Z, p2 = self._conv(q1, 2 * D2, "wf2", P["bf2"], Fo, 1, None, taps=1, epi="gelu")
         ctx.update(p1=p1, q1=q1, p2=p2)
+        if self.pooled:
+            return Z.view(B, 1, Z.shape[2]), ctx        # mean over the single time step (models.py:510) is the identity
         if not self.seq2seq:                                                            # models.py:382
             Zm = ops.empty(B, 1, pad8(Fo), device=dev)
             ops.time_mean(Z, Zm, Fo)
@@ -223,7 +247,9 @@ class EncoderEngine:
         ntail = S * D1 * D1 + D1 * D1 + D1 + 2 * int(P["z_re"].numel())
         self._zp = zp = _ZeroPool(dev, nparam + ntail + S * D1 * C + S * D1 + 20 * 2 * pad64(D2) + 64 * 96)
 
-        if not self.seq2seq:
+        if self.pooled:
+            dZ = dZ.reshape(1, B, dZ.shape[-1])          # the head ran with the batch as positions (see forward)
+        elif not self.seq2seq:
             full = ops.empty(B, T, pad8(Fo), device=dev)
             ops.time_mean_bwd(dZ, full, Fo)
             dZ = full
@@ -241,7 +267,15 @@ class EncoderEngine:
         # ---- conv blocks, last to first
         early_end = 0
         for k in range(4, -1, -1):
-            pk, bc, d, g = P["blocks"][k], ctx["blocks"][k], self.dil[k], G["blocks"][k]
+            pk, bc, d, g, kt = P["blocks"][k], ctx["blocks"][k], self.dil[k], G["blocks"][k], self.ks[k]
+            n = B * bc["v"].shape[1]                     # positions this block's BatchNorms averaged over
+            if self.pooled:                              # undo the pooling that followed this block (models.py:483-487)
+                full = ops.empty(B, bc["v"].shape[1], dx.shape[-1], device=dev)
+                if k == 4:
+                    ops.time_mean_bwd(dx.reshape(B, 1, dx.shape[-1]), full, D2)
+                else:
+                    ops.avgpool_bwd(dx, full, D2, 3, 2)
+                dx = full
             dv = ops.empty(*bc["v"].shape, device=dev)
             g["b2"] = self._zp.take(2 * D2)
             if D2 % 8 == 0 and bc["v"].shape[2] == 2 * D2:
@@ -249,14 +283,14 @@ class EncoderEngine:
             else:
                 ops.glu_bwd(dx, bc["v"], dv, D2)
                 ops.colsum(dv, 2 * D2, None, g["b2"])
-            g["w2"] = self._wgrad(dv, 2 * D2, bc["h1"], D2, 3, d[2])
-            dh1 = self._dgrad(dv, 2 * D2, f"b{k}.w2", D2, d[2], None)
+            g["w2"] = self._wgrad(dv, 2 * D2, bc["h1"], D2, kt, d[2])
+            dh1 = self._dgrad(dv, 2 * D2, f"b{k}.w2", D2, d[2], None, taps=kt)
             du1, g["g1"], g["be1"], g["b1"] = self._bn_gelu_bwd(dh1, bc["u1"], bc["bn1"], pk["g1"], n)
-            g["w1"] = self._wgrad(du1, D2, bc["h0"], D2, 3, d[1])
-            dh0 = self._dgrad(du1, D2, f"b{k}.w1", D2, d[1], du1)
+            g["w1"] = self._wgrad(du1, D2, bc["h0"], D2, kt, d[1])
+            dh0 = self._dgrad(du1, D2, f"b{k}.w1", D2, d[1], du1, taps=kt)
             du0, g["g0"], g["be0"], g["b0"] = self._bn_gelu_bwd(dh0, bc["u0"], bc["bn0"], pk["g0"], n)
-            g["w0"] = self._wgrad(du0, D2, bc["x"], bc["cin"], 3, d[0])
-            dx = self._dgrad(du0, D2, f"b{k}.w0", bc["cin"], d[0], du0 if k > 0 else None)
+            g["w0"] = self._wgrad(du0, D2, bc["x"], bc["cin"], kt, d[0])
+            dx = self._dgrad(du0, D2, f"b{k}.w0", bc["cin"], d[0], du0 if k > 0 else None, taps=kt)
             if k == 1:
                 early_end = zp.off
                 if sync is not None and not zp.spilled:

@@ -42,6 +42,8 @@ SIGNATURES = {
     "megb200_gelu_bwd": [_p, _p, _p, _p, _ll, _i, _i, _i, _p],
     "megb200_time_mean": [_p, _p, _i, _i, _i, _i, _i, _p],
     "megb200_time_mean_bwd": [_p, _p, _i, _i, _i, _i, _i, _p],
+    "megb200_avgpool1d": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
+    "megb200_avgpool1d_bwd": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p],
     "megb200_clip_prep_y": [_p, _i, _p, _p, _i, _i, _i, _i, _p],
     "megb200_rowsumsq": [_p, _p, _i, _ll, _i, _p],
     "megb200_clip_logits": [_p, _p, _p, _i, _i, _ll, _i, _i, _p],

@@ -309,6 +309,19 @@ class CudaOps:
         B, T, Fs = dZ.shape
         L.call("megb200_time_mean_bwd", dZm.data_ptr(), dZ.data_ptr(), B, T, F, Fs, self.dt, self._stream())
 
+    def avgpool(self, X, Out, C, k=3, stride=2):
+        """nn.AvgPool1d(k, stride) over time: X [B,T,Cs] -> Out [B,(T-k)//stride+1,Cs]."""
+        self._chk_act(X, Out)
+        B, T, Cs = X.shape
+        assert Out.shape == (B, (T - k) // stride + 1, Cs)
+        L.call("megb200_avgpool1d", X.data_ptr(), Out.data_ptr(), B, T, C, Cs, k, stride, self.dt, self._stream())
+
+    def avgpool_bwd(self, dOut, dX, C, k=3, stride=2):
+        self._chk_act(dOut, dX)
+        B, T, Cs = dX.shape
+        assert dOut.shape == (B, (T - k) // stride + 1, Cs)
+        L.call("megb200_avgpool1d_bwd", dOut.data_ptr(), dX.data_ptr(), B, T, C, Cs, k, stride, self.dt, self._stream())
+
     # ------------------------------------------------------------------ CLIP
     def clip_prep_y(self, Y, Yp, ysq):
         """Y f32 | bf16 [B,F,T] or [B,F] -> Yp [B, T*F] (position-major) and ysq[b] += |Y_b|^2."""

@@ -45,6 +45,17 @@ CONFIGS: Dict[str, dict] = {
     "narrow": dict(_BASE, B=4, C=60, T=360, num_subjects=5, dataset="Brennan2018"),
     "narrow_static": dict(_BASE, B=6, C=160, T=200, num_subjects=3, F=512, seq2seq=False, dataset="GOD",
                           preprocs={"last4layers": False}),
+    # encoder variants ("next" row N4): BrainEncoderSeq2Static (models.py:465-512: per-block kernel sizes, AvgPool1d(3,2)
+    # between blocks, global average after block 4) and the dilated paper block (tests/test_modules/models.py:267-312)
+    "tiny_pooled": dict(_BASE, B=5, C=12, T=100, num_subjects=3, D1=30, D2=32, F=48, K=8, seq2seq=False,
+                        preprocs={"last4layers": False}, model="brain_endcoder_seq2static",
+                        ConvBlocks={"ks": [11, 5, 5, 3, 3]}),
+    "narrow_pooled": dict(_BASE, B=6, C=160, T=200, num_subjects=3, F=512, seq2seq=False, dataset="GOD",
+                          preprocs={"last4layers": False}, model="brain_endcoder_seq2static",
+                          ConvBlocks={"ks": [11, 11, 5, 3, 3]}),
+    "tiny_dilated": dict(_BASE, B=6, C=20, T=40, num_subjects=4, D1=30, D2=32, F=64, K=8,
+                         preprocs={"last4layers": False}, conv_dilations="paper"),
+    "narrow_dilated": dict(_BASE, B=4, C=60, T=360, num_subjects=5, dataset="Brennan2018", conv_dilations="paper"),
     # BASELINE.json configs
     "brennan": dict(_BASE, B=64, C=60, T=360, num_subjects=33, dataset="Brennan2018"),          # configs[0]
     "gwilliams": dict(_BASE, B=256, C=208, T=360, num_subjects=27),                             # configs[1]
@@ -64,6 +75,31 @@ def get_config(name: str, **overrides) -> Args:
 def out_features(cfg) -> int:
     """models.py:348 — F is forced to 1024 when wav2vec2 last-4-layer targets are used."""
     return 1024 if cfg.preprocs["last4layers"] else cfg.F
+
+
+def conv_kernel_sizes(cfg):
+    """Per-block Conv1d kernel sizes: 3 (models.py:277), or ``args.ConvBlocks.ks`` for BrainEncoderSeq2Static (models.py:481)."""
+    cb = cfg.get("ConvBlocks") if hasattr(cfg, "get") else getattr(cfg, "ConvBlocks", None)
+    if cb is None or cfg.get("model") != "brain_endcoder_seq2static":
+        return [3] * 5
+    return [int(k) for k in (cb["ks"] if isinstance(cb, dict) else cb.ks)]
+
+
+def paper_dilations():
+    """Dilations of the paper's block as the reference's alternative formulation writes them
+    (tests/test_modules/models.py:275-297, k = 1..5; ``2 * k + 1 % 5`` parses as ``2 * k + 1``)."""
+    return [(2 ** (2 * k % 5), 2 ** (2 * k + 1 % 5), 2) for k in range(1, 6)]
+
+
+def conv_dilations(cfg):
+    d = cfg.get("conv_dilations") if hasattr(cfg, "get") else getattr(cfg, "conv_dilations", None)
+    if d is None:
+        return [(1, 1, 1)] * 5                                   # the reference code as it runs (models.py:289,297,305)
+    if isinstance(d, str):
+        if d != "paper":
+            raise ValueError(f"unknown conv_dilations {d!r}")
+        return paper_dilations()
+    return [tuple(int(x) for x in row) for row in d]
 
 
 def sensor_locations_raw(C: int, seed: int = 0) -> np.ndarray:
@@ -98,12 +134,13 @@ def make_state(cfg, seed: int = 0) -> Dict[str, np.ndarray]:
     st["subject_block.conv.bias"] = _uniform(rng, (D1,), b)
     for s in range(S):
         st[f"subject_block.subject_layer.{s}.weight"] = _uniform(rng, (D1, D1, 1), b)
+    ks = conv_kernel_sizes(cfg)
     for k in range(5):
         cin = D1 if k == 0 else D2
         pre = f"conv_blocks.conv{k}."
         for name, ci, co in (("conv0", cin, D2), ("conv1", D2, D2), ("conv2", D2, 2 * D2)):
-            bb = 1.0 / math.sqrt(ci * 3)
-            st[pre + name + ".weight"] = _uniform(rng, (co, ci, 3), bb)
+            bb = 1.0 / math.sqrt(ci * ks[k])
+            st[pre + name + ".weight"] = _uniform(rng, (co, ci, ks[k]), bb)
             st[pre + name + ".bias"] = _uniform(rng, (co,), bb)
         for bn in ("batchnorm0", "batchnorm1"):
             st[pre + bn + ".weight"] = (0.5 + rng.random(D2)).astype(np.float32)

@@ -224,6 +224,16 @@ class TorchOps:
         dZ.copy_(self._r((dZm.float() / dZ.shape[1]).expand_as(dZ)))
 
     # ------------------------------------------------------------------ CLIP
+    def avgpool(self, X, Out, C, k=3, stride=2):
+        Out.copy_(self._r(F.avg_pool1d(X.float().permute(0, 2, 1), k, stride=stride).permute(0, 2, 1)))
+
+    def avgpool_bwd(self, dOut, dX, C, k=3, stride=2):
+        with torch.enable_grad():
+            x = torch.zeros(dX.shape, dtype=torch.float32).permute(0, 2, 1).contiguous().requires_grad_(True)
+            y = F.avg_pool1d(x, k, stride=stride)
+            g, = torch.autograd.grad(y, x, dOut.float().permute(0, 2, 1))
+        dX.copy_(self._r(g.permute(0, 2, 1)))
+
     def clip_prep_y(self, Y, Yp, ysq):
         B = Y.shape[0]
         y = (Y if Y.dim() == 3 else Y[:, :, None]).float()

@@ -46,7 +46,7 @@ def spatial_attention_weights(z_re, z_im, cos, sin):
 def encoder_forward(P: Dict[str, torch.Tensor], X: torch.Tensor, subject_idxs, loc, *, K: int, d_drop: float,
                     seq2seq: bool, training: bool, drop_center: Optional[int] = None,
                     bn_buffers: Optional[Dict[str, torch.Tensor]] = None, dilations=None,
-                    return_intermediates: bool = False):
+                    return_intermediates: bool = False, ks=None, pooled: bool = False):
     """BrainEncoder.forward restated functionally.  models.py:200-220, 232-241, 267-273, 308-322, 367-383.
 
     P maps reference state_dict keys to tensors; ``subject_block.spatial_attention.z`` may be complex or
@@ -54,6 +54,9 @@ def encoder_forward(P: Dict[str, torch.Tensor], X: torch.Tensor, subject_idxs, l
     normalisation, running stats updated in ``bn_buffers`` with momentum 0.1 and the unbiased variance),
     running statistics otherwise.  ``dilations`` (optional, 5x3) enables the paper variant
     (tests/test_modules/models.py:275-297); the reference itself uses 1 everywhere (models.py:289,297,305).
+    ``ks`` (optional, 5 odd kernel sizes) and ``pooled`` restate ``BrainEncoderSeq2Static`` (models.py:465-512):
+    block k uses kernel size ks[k] (``args.ConvBlocks.ks``), ``AvgPool1d(3, stride=2)`` follows blocks 0..3 and
+    ``AdaptiveAvgPool1d(1)`` block 4 (models.py:483-487), so the 1x1 head runs on one time step.
     """
     dt = X.dtype
     inter = {}
@@ -97,9 +100,11 @@ def encoder_forward(P: Dict[str, torch.Tensor], X: torch.Tensor, subject_idxs, l
     for k in range(5):
         pre = f"conv_blocks.conv{k}."
         dil = dilations[k] if dilations is not None else (1, 1, 1)
+        kk = ks[k] if ks is not None else 3
 
         def conv(x, name, d):
-            return F.conv1d(x, P[pre + name + ".weight"], P[pre + name + ".bias"], padding=d, dilation=d)
+            # padding="same" for an odd kernel: d * (k - 1) / 2 on both sides
+            return F.conv1d(x, P[pre + name + ".weight"], P[pre + name + ".bias"], padding=d * (kk - 1) // 2, dilation=d)
 
         u0 = conv(h, "conv0", dil[0])
         if k > 0:
@@ -109,6 +114,8 @@ def encoder_forward(P: Dict[str, torch.Tensor], X: torch.Tensor, subject_idxs, l
         h1 = F.gelu(bn(u1, pre + "batchnorm1"))
         v = conv(h1, "conv2", dil[2])
         h = F.glu(v, dim=-2)
+        if pooled:                                                       # models.py:483-487
+            h = F.avg_pool1d(h, 3, stride=2) if k < 4 else h.mean(dim=2, keepdim=True)
         inter[f"block{k}"] = h
     h = F.gelu(F.conv1d(h, P["conv_final1.weight"], P["conv_final1.bias"]))
     h = F.gelu(F.conv1d(h, P["conv_final2.weight"], P["conv_final2.bias"]))
@@ -192,11 +199,18 @@ def state_to_torch(state: Dict[str, np.ndarray], dtype=torch.float32, requires_g
     return P
 
 
+def paper_dilations():
+    """The dilated ConvBlock of the paper as the reference's alternative formulation has it
+    (tests/test_modules/models.py:275-297, blocks numbered k = 1..5): conv1 ``2 ** (2 * k % 5)``, conv2
+    ``2 ** (2 * k + 1 % 5)`` -- operator precedence makes that ``2 ** (2 * k + 1)``, up to 2048 -- and conv3 2."""
+    return [(2 ** (2 * k % 5), 2 ** (2 * k + 1 % 5), 2) for k in range(1, 6)]
+
+
 def train_step(P, temp, X, Y, subject_idxs, loc, *, K, d_drop, seq2seq, drop_center, bn_buffers=None,
-               reduction="mean"):
+               reduction="mean", dilations=None, ks=None, pooled=False):
     """One training step's math: Z = encoder(X), loss = CLIP(Y, Z), grads by autograd (train.py:201-215)."""
     Z = encoder_forward(P, X, subject_idxs, loc, K=K, d_drop=d_drop, seq2seq=seq2seq, training=True,
-                        drop_center=drop_center, bn_buffers=bn_buffers)
+                        drop_center=drop_center, bn_buffers=bn_buffers, dilations=dilations, ks=ks, pooled=pooled)
     loss = clip_loss(Y, Z, temp, reduction)
     leaves = {k: v for k, v in P.items() if v.requires_grad}
     grads = torch.autograd.grad(loss, list(leaves.values()) + [temp], allow_unused=True)

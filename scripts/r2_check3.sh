@@ -4,6 +4,7 @@ set -u
 mkdir -p gpurun_out
 S=gpurun_out/r2_c3_summary.txt
 : > $S
+bash meg-decoding_b200/csrc/build.sh > gpurun_out/r2_build.log 2>&1 || { echo "BUILD FAILED" | tee -a $S; tail -5 gpurun_out/r2_build.log | tee -a $S; }
 timeout 900 python -m pytest tests/test_ops_gpu.py tests/test_optim_gpu.py tests/test_parity_gpu.py -m gpu -q -p no:cacheprovider -s \
    -k "fused or lse_merge or clip or optim or targets or golden" > gpurun_out/r2_c3_tests.log 2>&1
 echo "tests rc=$?" | tee -a $S

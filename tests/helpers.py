@@ -33,11 +33,11 @@ def load_golden(name):
 
 def make_modules(cfg, device="cpu", seed=0):
     """(BrainEncoder, CLIPLoss) with the deterministic synthetic weights loaded, on `device`."""
-    from meg_decoding.models import BrainEncoder
+    from meg_decoding.models import get_model
     from meg_decoding.utils.loss import CLIPLoss
     cfg = synth.Args(cfg)
     cfg["sensor_locations"] = synth.sensor_locations_raw(cfg.C)
-    enc = BrainEncoder(cfg)
+    enc = get_model(cfg)             # BrainEncoder, or BrainEncoderSeq2Static for model == "brain_endcoder_seq2static"
     sd = {k: torch.from_numpy(np.asarray(v)) for k, v in synth.make_state(cfg, seed).items()}
     enc.load_state_dict(sd, strict=True)
     lossf = CLIPLoss(cfg)

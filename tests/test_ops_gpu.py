@@ -423,6 +423,44 @@ def test_glu_gelu_timemean(dtype, C):
     _close(dZ, dZr, dtype, "time_mean_bwd")
 
 
+@pytest.mark.parametrize("dtype", EW_DTYPES)
+@pytest.mark.parametrize("shape", [(3, 100, 30), (2, 49, 320), (5, 3, 32), (4, 200, 320)])
+def test_avgpool_fwd_bwd(dtype, shape):
+    """AvgPool1d(3, 2) over time (BrainEncoderSeq2Static, models.py:483-485) and its backward; even and odd lengths (the
+    last position of an even-length sequence belongs to no window and gets zero gradient)."""
+    B, T, C = shape
+    gen = torch.Generator().manual_seed(14)
+    ops, ref = _ops(dtype, "simt"), TorchOps(dtype)
+    X, Xd = _act(gen, dtype, B, T, C)
+    To = (T - 3) // 2 + 1
+    out, outr = ops.empty(B, To, pad8(C), device=DEV), ref.empty(B, To, pad8(C), device="cpu")
+    ops.avgpool(Xd, out, C)
+    ref.avgpool(X, outr, C)
+    _close(out, outr, dtype, "avgpool")
+    g, gd = _act(gen, dtype, B, To, C)
+    dX, dXr = ops.empty(B, T, pad8(C), device=DEV), ref.empty(B, T, pad8(C), device="cpu")
+    ops.avgpool_bwd(gd, dX, C)
+    ref.avgpool_bwd(g, dXr, C)
+    _close(dX, dXr, dtype, "avgpool_bwd")
+
+
+WIDE_TAP_CASES = [
+    # B, T, Ca, N, taps, dil: kernel sizes 5 / 11 (BrainEncoderSeq2Static) and the paper's dilations (some beyond T)
+    (2, 200, 320, 320, 11, 1), (3, 100, 32, 64, 5, 1), (2, 360, 320, 320, 3, 32), (2, 360, 320, 320, 3, 2048),
+    (64, 200, 320, 320, 11, 1),          # above the CTA-pair threshold: k = 11 does not fit the halo form -> plain pair
+    (64, 360, 320, 320, 3, 128),         # halo rows would exceed one box -> plain pair
+]
+
+
+@pytest.mark.parametrize("dtype,backend", CONTRACTION_MODES)
+@pytest.mark.parametrize("case", WIDE_TAP_CASES)
+def test_tapgemm_and_wgrad_wide_kernels_and_dilations(dtype, backend, case):
+    B, T, Ca, N, taps, dil = case
+    test_tapgemm(dtype, backend, (B, T, Ca, N, taps, dil, 1, True, True if Ca == N else False))
+    if B <= 8:
+        test_wgrad(dtype, backend, (B, T, N, Ca, taps, dil, 1))
+
+
 # ------------------------------------------------------------------------------------------------ CLIP
 CLIP_CASES = [
     # By (speech rows, all ranks), Bz (local brains), off, F, T

@@ -73,6 +73,41 @@ def test_fused_clip_train_step_matches_reference_golden(name):
     print(f"[parity] {name} bf16 fused CLIP: " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()))
 
 
+@pytest.mark.parametrize("name", ["tiny_pooled", "narrow_pooled", "tiny_dilated", "narrow_dilated"])
+def test_encoder_variants_match_reference_golden(mode, name):
+    """"Next" row N4: BrainEncoderSeq2Static (kernel sizes 11/5/3, AvgPool1d(3,2) between blocks, global average; models.py:
+    465-512) and the dilated paper block (dilations up to 2048 > T; tests/test_modules/models.py:267-312) against the
+    UNMODIFIED reference's stored outputs (oracle/make_golden_variants.py)."""
+    tz, tl, tg = MODES[mode]
+    cfg = synth.get_config(name)
+    enc, lossf = H.make_modules(cfg, DEV)
+    X, Y, subj = H.make_inputs(cfg, DEV)
+    Z, loss, grads = H.train_step(enc, lossf, X, Y, subj, synth.drop_center(cfg))
+    torch.cuda.synchronize()
+    errs = H.compare_with_golden(name, Z, loss, grads, tz, tl, tg)
+    print(f"[parity] {name} {mode}: " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()))
+
+
+def test_classifier_matches_reference_golden(mode):
+    """"Next" row N1: the drop-in Classifier (tcgen05 logits + rank kernel) against the reference Classifier's stored
+    (top1, top10, top5) on the seeded cases of tests/golden/classifier.npz.  bf16 may flip one near-tie per case."""
+    from meg_decoding.models import Classifier
+    clf = Classifier(synth.Args(normalize_image_features=False))
+    dt = torch.float32 if mode == "fp32" else torch.bfloat16
+    for seed, B, Fo, T, top1, top10, top5 in H.load_golden("classifier")["cases"]:
+        B = int(B)
+        g = torch.Generator().manual_seed(100 + int(seed))
+        shape = (B, int(Fo), int(T)) if T > 1 else (B, int(Fo))
+        Y = torch.randn(*shape, generator=g)
+        Z = 0.25 * Y + torch.randn(*shape, generator=g)
+        if shape[1] % 8 != 0:
+            continue                                     # the kernels need F % 8 == 0 (as BrainEncoder does)
+        r1, r10, r5 = clf(Z.to(DEV).to(dt), Y.to(DEV), top_k=5)
+        slack = 1e-6 if mode == "fp32" else 1.0 / B + 1e-6
+        print(f"[parity] classifier {mode} seed {int(seed)}: top1 {r1:.4f}/{top1:.4f} top10 {r10:.4f}/{top10:.4f} top5 {r5:.4f}/{top5:.4f}")
+        assert abs(r1 - top1) <= slack and abs(r10 - top10) <= slack and abs(r5 - top5) <= slack
+
+
 def test_eval_mode_matches_reference_golden(mode):
     tz, tl, _ = MODES[mode]
     cfg = synth.get_config("narrow")
@@ -249,29 +284,38 @@ def test_config2_full_batch_against_cpu_oracle(prec, seed):
 
 @pytest.mark.parametrize("name", ["narrow", "narrow_static"])
 def test_packed_and_bf16_targets_match_dense_f32(name):
-    """Data formats on the target side of the path: dense f32 (reference collator), dense bf16, PackedTargets.  The
-    packed form must give the dense-f32 result (same rounding point; norms differ only in f32 summation order)."""
+    """Data formats on the target side of the path: dense f32 (reference collator), dense bf16, PackedTargets.  On the
+    SAME embeddings the packed form must give the dense-f32 loss and gradients (same rounding point; the norms differ only
+    in f32 summation order); bf16 targets differ by their own rounding of the norm."""
     from megb200.data import PackedTargets
     from megb200.graph import GraphedTrainStep
     cfg = synth.get_config(name)
     enc, lossf = H.make_modules(cfg, DEV)
     X, Y, subj = H.make_inputs(cfg, DEV)
     center = synth.drop_center(cfg)
+    enc.eval()
+    with torch.no_grad():
+        Z0 = enc(X, subj)
     res = {}
     for kind, tgt in (("dense", Y), ("packed", PackedTargets.from_dense(Y.cpu()).to(DEV)), ("bf16", Y.to(torch.bfloat16))):
-        enc2, lossf2 = H.make_modules(cfg, DEV)
-        Z, loss, grads = H.train_step(enc2, lossf2, X, tgt, subj, center)
-        res[kind] = (float(loss), grads["conv_final2.weight"].float(), float(grads["temp"]))
+        Z = Z0.clone().requires_grad_(True)
+        lossf.temp.grad = None
+        loss = lossf(tgt, Z)
+        loss.backward()
+        res[kind] = (float(loss), Z.grad.float().clone(), float(lossf.temp.grad))
     l0, g0, t0 = res["dense"]
     for kind, tl, tg in (("packed", 1e-5, 1e-3), ("bf16", 5e-3, 5e-2)):
         l, g, t = res[kind]
-        print(f"[parity] targets {kind} vs dense f32 ({name}): loss {abs(l - l0) / abs(l0):.2e} dWf2 {H.rel_fro(g, g0):.2e} "
+        print(f"[parity] targets {kind} vs dense f32 ({name}): loss {abs(l - l0) / abs(l0):.2e} dZ {H.rel_fro(g, g0):.2e} "
               f"dtemp {abs(t - t0) / abs(t0):.2e}")
-        assert abs(l - l0) / abs(l0) <= tl and H.rel_fro(g, g0) <= tg and abs(t - t0) / abs(t0) <= tg
-    # the CUDA-graph step on packed targets
+        assert abs(l - l0) / abs(l0) <= tl and H.rel_fro(g, g0) <= tg and abs(t - t0) / abs(t0) <= max(tg, 1e-3)
+    # the whole step through the public modules and through the CUDA-graph step on packed targets
+    _, lp, _ = H.train_step(enc, lossf, X, PackedTargets.from_dense(Y.cpu()).to(DEV), subj, center)
+    _, ld, _ = H.train_step(enc, lossf, X, Y, subj, center)
+    assert abs(float(lp) - float(ld)) / abs(float(ld)) <= 1e-2           # run-to-run bf16 / atomic-order noise only
     gstep = GraphedTrainStep(enc, lossf, X, PackedTargets.from_dense(Y.cpu()).to(DEV), subj, drop_center=center)
     gl = float(gstep())
-    assert abs(gl - l0) / abs(l0) <= 1e-2
+    assert abs(gl - float(ld)) / abs(float(ld)) <= 1e-2
 
 
 def test_bf16_is_the_default_precision_and_output_is_bf16():
@@ -283,6 +327,22 @@ def test_bf16_is_the_default_precision_and_output_is_bf16():
     with torch.no_grad():
         Z = enc(X, subj)
     assert Z.dtype == torch.bfloat16 and Z.shape == (cfg.B, cfg.F, cfg.T)
+
+
+def test_output_dtype_float32_for_numpy_callers():
+    """evaluate.py:340 / examples/inference.py:105 do ``Z.detach().cpu().numpy()``: ``args.output_dtype = "float32"`` makes
+    the no-grad forward return f32 (one cast pass), same values as the bf16 output."""
+    cfg = synth.get_config("tiny", output_dtype="float32")
+    enc, _ = H.make_modules(cfg, DEV)
+    X, _, subj = H.make_inputs(cfg, DEV)
+    enc.eval()
+    with torch.no_grad():
+        Z32 = enc(X, subj)
+        enc.output_dtype = None
+        Z16 = enc(X, subj)
+    assert Z32.dtype == torch.float32 and Z16.dtype == torch.bfloat16
+    assert torch.equal(Z32, Z16.float())
+    assert Z32.detach().cpu().numpy().shape == (cfg.B, cfg.F, cfg.T)
 
 
 def test_classifier_topk_matches_oracle(mode):
