@@ -36,6 +36,7 @@ Options& options() {
       getenv("MEGB200_CLIP_DZ_LARGE") != nullptr ? 1 : 0,
       getenv("MEGB200_ROWLOOP_DIRECT") != nullptr ? 1 : 0,
       (int)env_ll("MEGB200_WGRAD_SPLITS", 0),
+      (int)env_ll("MEGB200_CLIP_DZ_JT", 0),
       (int)env_ll("MEGB200_CLIP_FUSED", -1),
       -1, -1, -1,
   };
@@ -53,6 +54,7 @@ static const OptionEntry kOptionTable[] = {
     {"clip_dz_large", 1, offsetof(Options, clip_dz_large)},
     {"rowloop_direct", 1, offsetof(Options, rowloop_direct)},
     {"wgrad_splits", 1, offsetof(Options, wgrad_splits)},
+    {"clip_dz_jt", 1, offsetof(Options, clip_dz_jt)},
     {"clip_fused", 1, offsetof(Options, clip_fused)},
     {"last_tapgemm_kernel", 1, offsetof(Options, last_tapgemm_kernel)},
     {"last_clip_dz_kernel", 1, offsetof(Options, last_clip_dz_kernel)},

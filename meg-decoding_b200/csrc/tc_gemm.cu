@@ -1333,7 +1333,7 @@ tc_clip_logits_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_cons
 
 // ================================================================================================ CLIP dZ
 struct DzParams {
-  int By, Bz, NT /*d columns per CTA, multiple of 64*/, stages, kchunks, swap_grid;
+  int By, Bz, NT /*d columns per CTA, multiple of 64*/, stages, kchunks, swap_grid, jt /*j tiles of 128 rows per CTA*/;
   long long D;
   uint32_t tmem_cols, idesc;
   const __nv_bfloat16* Z;
@@ -1342,6 +1342,11 @@ struct DzParams {
   __nv_bfloat16* dZ;
 };
 
+// Large-K form (By > 512: every >= 4-GPU job, and the GOD shards).  A CTA owns NT d-columns for `jt` tiles of 128 brain
+// rows: the Y tile of a k step (the big operand: By x D is read once per j tile) is staged ONCE and contracted against
+// every j tile's coefficient block into its own TMEM accumulator (jt * NT <= 512 columns).  With jt = 2 at the 8-GPU
+// speech shape (256 local brains) Y is fetched once instead of twice: the kernel sits close to both floors there
+// (1.9 GB of DRAM traffic ~ 290 us, 386 GFLOP ~ 290 us), so operand re-reads show directly in its time.
 __global__ void __launch_bounds__(kThreads)
 tc_clip_dz_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmY,
                   const DzParams p) {
@@ -1352,11 +1357,11 @@ tc_clip_dz_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constant
   const uint32_t atom_bytes = kBlockK * 128;
   const uint32_t a_bytes = kTileM * 128;
   const uint32_t b_bytes = (uint32_t)(p.NT / 64) * atom_bytes;
-  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const uint32_t stage_bytes = (uint32_t)p.jt * a_bytes + b_bytes;
   uint8_t* ring = smem + kHeaderBytes;
-  // blockIdx.x = j tile (fastest) when the launcher could swap: CTAs sharing a Y tile run together (L2 hit on the re-read)
+  // blockIdx.x = j group (fastest) when the launcher could swap: CTAs sharing a Y tile run together (L2 hit on the re-read)
   const long long d0 = (long long)(p.swap_grid ? blockIdx.y : blockIdx.x) * p.NT;
-  const int j0 = (p.swap_grid ? blockIdx.x : blockIdx.y) * kTileM;
+  const int j0 = (p.swap_grid ? blockIdx.x : blockIdx.y) * kTileM * p.jt;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmC);
@@ -1385,9 +1390,10 @@ tc_clip_dz_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constant
         const uint32_t full = smem_u32(&hdr->full[s]);
         mbar_arrive_expect_tx(full, stage_bytes);
         const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
-        tma_load_2d(sa, &tmC, it * kBlockK, j0, full);                                    // coef[j][i]: K-major
+        for (int t = 0; t < p.jt; ++t)                                                    // coef[j][i]: K-major
+          tma_load_2d(sa + (uint32_t)t * a_bytes, &tmC, it * kBlockK, j0 + t * kTileM, full);   // rows >= Bz: zero filled
         for (int a = 0; a < p.NT / 64; ++a)                                               // Y[i][d]: MN-major
-          tma_load_2d(sa + a_bytes + a * atom_bytes, &tmY, (int)(d0 + a * 64), it * kBlockK, full);
+          tma_load_2d(sa + (uint32_t)p.jt * a_bytes + a * atom_bytes, &tmY, (int)(d0 + a * 64), it * kBlockK, full);
       }
     }
   } else if (warp == 1) {
@@ -1397,11 +1403,14 @@ tc_clip_dz_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constant
         mbar_wait(smem_u32(&hdr->full[s]), (it / p.stages) & 1);
         tc_fence_after();
         const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
-        const uint64_t da = make_smem_desc(sa, 16, 1024);
-        const uint64_t db = make_smem_desc(sa + a_bytes, atom_bytes, 1024);
+        const uint64_t db = make_smem_desc(sa + (uint32_t)p.jt * a_bytes, atom_bytes, 1024);
+        for (int t = 0; t < p.jt; ++t) {
+          const uint64_t da = make_smem_desc(sa + (uint32_t)t * a_bytes, 16, 1024);
 #pragma unroll
-        for (int k = 0; k < kBlockK / kUmmaK; ++k)
-          umma_bf16(tmem_base, desc_advance(da, k * 32), desc_advance(db, k * kUmmaK * 128), p.idesc, (it | k) != 0);
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)
+            umma_bf16(tmem_base + (uint32_t)(t * p.NT), desc_advance(da, k * 32), desc_advance(db, k * kUmmaK * 128),
+                      p.idesc, (it | k) != 0);
+        }
         umma_commit(smem_u32(&hdr->empty[s]));
       }
       umma_commit(smem_u32(&hdr->tmem_full));
@@ -1410,23 +1419,25 @@ tc_clip_dz_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constant
     mbar_wait(smem_u32(&hdr->tmem_full), 0);
     tc_fence_after();
     const int q = warp & 3;
-    const int j = j0 + q * 32 + lane;
-    const bool valid = j < p.Bz;
-    const float cj = valid ? p.cvec[j] : 0.f;
     const float gs = p.gscale[0];
-    for (int ch = 0; ch < p.NT / 16; ++ch) {
-      float v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 16), v);
-      if (!valid) continue;
-      const long long d = d0 + ch * 16;
-      if (d >= p.D) continue;   // D is a multiple of 16 on this path
-      float z[16];
-      load8(p.Z + (long long)j * p.D + d, reinterpret_cast<float(&)[8]>(z[0]));
-      load8(p.Z + (long long)j * p.D + d + 8, reinterpret_cast<float(&)[8]>(z[8]));
+    for (int t = 0; t < p.jt; ++t) {
+      const int j = j0 + t * kTileM + q * 32 + lane;
+      const bool valid = j < p.Bz;
+      const float cj = valid ? p.cvec[j] : 0.f;
+      for (int ch = 0; ch < p.NT / 16; ++ch) {
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * p.NT + ch * 16), v);
+        if (!valid) continue;
+        const long long d = d0 + ch * 16;
+        if (d >= p.D) continue;   // D is a multiple of 16 on this path
+        float z[16];
+        load8(p.Z + (long long)j * p.D + d, reinterpret_cast<float(&)[8]>(z[0]));
+        load8(p.Z + (long long)j * p.D + d + 8, reinterpret_cast<float(&)[8]>(z[8]));
 #pragma unroll
-      for (int e = 0; e < 16; ++e) z[e] = gs * (v[e] - z[e] * cj);
-      store8(p.dZ + (long long)j * p.D + d, reinterpret_cast<float(&)[8]>(z[0]));
-      store8(p.dZ + (long long)j * p.D + d + 8, reinterpret_cast<float(&)[8]>(z[8]));
+        for (int e = 0; e < 16; ++e) z[e] = gs * (v[e] - z[e] * cj);
+        store8(p.dZ + (long long)j * p.D + d, reinterpret_cast<float(&)[8]>(z[0]));
+        store8(p.dZ + (long long)j * p.D + d + 8, reinterpret_cast<float(&)[8]>(z[8]));
+      }
     }
     tc_fence_before();
   }
@@ -2338,9 +2349,18 @@ int tc_clip_dz(const void* coef, int ldc, const void* Yp, const void* Z, const f
   }
   p.NT = D >= 256 ? 256 : (int)((D + 63) / 64 * 64);
   p.kchunks = (By + kBlockK - 1) / kBlockK;
-  const uint32_t stage_bytes = kTileM * 128 + (p.NT / 64) * kBlockK * 128;
-  p.stages = pick_stages(stage_bytes, 100 * 1024, 4);
-  p.tmem_cols = tmem_cols_for(p.NT);
+  const long long dt = (D + p.NT - 1) / p.NT;
+  const int j_tiles = (Bz + kTileM - 1) / kTileM;
+  // j tiles per CTA: two share one staged Y tile when that still leaves at least two waves of CTAs (speech shapes: D / 256
+  // = 1440 d tiles); short embeddings (GOD, D = 512) keep one j tile per CTA for parallelism
+  p.jt = 1;
+  if (options().clip_dz_jt > 0) p.jt = options().clip_dz_jt;
+  else if (j_tiles >= 2 && 2 * p.NT <= 512 && dt * ((j_tiles + 1) / 2) >= 2ll * num_sms()) p.jt = 2;
+  MEGB_CHECK_ARG(p.jt >= 1 && p.jt * p.NT <= 512, "tc_clip_dz: %d j tiles of %d columns do not fit TMEM", p.jt, p.NT);
+  const uint32_t stage_bytes = p.jt * kTileM * 128 + (p.NT / 64) * kBlockK * 128;
+  p.stages = pick_stages(stage_bytes, p.jt > 1 ? 200 * 1024 : 100 * 1024, 4);
+  MEGB_CHECK_ARG(p.stages >= 2, "tc_clip_dz: tile too large");
+  p.tmem_cols = tmem_cols_for(p.jt * p.NT);
   p.idesc = make_idesc(p.NT, 0, 1);
   p.Z = (const __nv_bfloat16*)Z; p.cvec = cvec; p.gscale = gscale; p.dZ = (__nv_bfloat16*)dZ;
   CUtensorMap tmC, tmY;
@@ -2361,17 +2381,16 @@ int tc_clip_dz(const void* coef, int ldc, const void* Yp, const void* Z, const f
   const size_t smem = 1024 + kHeaderBytes + (size_t)p.stages * stage_bytes;
   int rc = set_smem(tc_clip_dz_kernel, smem);
   if (rc) return rc;
-  const long long dt = (D + p.NT - 1) / p.NT;
   MEGB_CHECK_ARG(dt < 2147483647ll, "tc_clip_dz: grid too large");
+  const int j_groups = (j_tiles + p.jt - 1) / p.jt;
   p.swap_grid = dt <= 65535 ? 1 : 0;
-  dim3 grid((unsigned)dt, (Bz + kTileM - 1) / kTileM);
-  if (p.swap_grid) grid = dim3((Bz + kTileM - 1) / kTileM, (unsigned)dt);
+  dim3 grid((unsigned)dt, j_groups);
+  if (p.swap_grid) grid = dim3(j_groups, (unsigned)dt);
   tc_clip_dz_kernel<<<grid, kThreads, smem, st>>>(tmC, tmY, p);
   MEGB_LAUNCH_OK();
   options().last_clip_dz_kernel = 1;
   return 0;
 }
-
 
 int tc_clip_fused(const void* Yp, const void* Zp, const float* ysq, const float* zsq, const float* temp, int By, int Bz,
                   long long D, int off, int mode, float* row_part, float* col_part, float* diag, const float* row_lse,

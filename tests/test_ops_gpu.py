@@ -620,6 +620,15 @@ def test_clip_lse_merge(W, By):
     _close(out, outr, torch.float32, "clip_lse_merge", atol_scale=5)
 
 
+@pytest.mark.parametrize("case", [c for c in CLIP_CASES if c[1] > 128 or c[0] > 512])
+def test_clip_pipeline_dz_two_row_tiles_per_cta(case):
+    """Large-K dZ kernel with two 128-row brain tiles per CTA sharing one staged target tile (what the 8-GPU speech shape
+    runs: 256 local brains x 1440 column tiles), forced on the smaller shapes."""
+    with L.options(clip_dz_large=1, clip_dz_jt=2):
+        test_clip_pipeline(torch.bfloat16, "tc", case)
+        assert L.get_option("last_clip_dz_kernel") == 1
+
+
 @pytest.mark.parametrize("case", [c for c in CLIP_CASES if c[0] <= 512])
 def test_clip_pipeline_large_k_dz_forced(case):
     """tc_clip_dz_kernel (the form every >= 4-GPU job runs) on the shapes the small-K form normally takes."""
