@@ -201,6 +201,12 @@ class BrainEncoder(nn.Module):
         self.output_dtype = getattr(torch, od) if isinstance(od, str) else od
         self.drop_center = None          # set to an int to pin the spatial-dropout centre (tests, data parallel)
         self._eng = None
+        # CUDA-graph replay of the unchanged training loop (megb200.graph.ModuleGraphs): opt-in
+        self._runner = None
+        import os
+        if _arg(args, "cuda_graphs") or os.environ.get("MEGB200_MODULE_GRAPHS", "0") == "1":
+            from megb200.graph import accelerate
+            accelerate(self)
 
     # ------------------------------------------------------------------ plumbing
     def _engine(self) -> EncoderEngine:
@@ -269,6 +275,10 @@ class BrainEncoder(nn.Module):
         dev = sa.cos.device
         C = sa.cos.shape[1]
         assert X.shape[1] == C                                                  # models.py:233
+        if self._runner is not None and self.training and torch.is_grad_enabled() and dev.type == "cuda":
+            Z = self._runner.encoder_forward(X.to(dev) if torch.is_tensor(X) else X, subject_idxs)
+            if Z is not None:
+                return Z
         S = self.num_subjects
         present = None
         subject_idxs = torch.as_tensor(subject_idxs)

@@ -120,6 +120,14 @@ class CLIPLoss(nn.Module):
             raise NotImplementedError("megb200: only the fast path of CLIPLoss (loss.py:86-99) is implemented; the slow "
                                       "CosineSimilarity path is never called by the reference scripts")
         dev = self.temp.device
+        tag = getattr(y, "_megb200_runner", None)
+        if tag is not None and torch.is_grad_enabled():
+            # graph mode (megb200.graph.ModuleGraphs): y is the Z the encoder's recording just produced; loss forward +
+            # the whole backward are one graph replay
+            if return_logits:
+                raise NotImplementedError("megb200 graph mode: return_logits needs the eager path "
+                                          "(megb200.graph.accelerate(encoder, False))")
+            return tag[0].loss_forward(self, x, tag[1])
         if y.dtype not in (torch.bfloat16, torch.float32):
             y = y.float()
         # brain embeddings -> position-major PC layout [B, T, F] (a free view for BrainEncoder's output)

@@ -31,7 +31,7 @@ import torch
 
 from . import lib, parallel
 
-__all__ = ["GraphedTrainStep"]
+__all__ = ["GraphedTrainStep", "ModuleGraphs", "accelerate"]
 
 
 class _GradSync:
@@ -243,3 +243,223 @@ class GraphedTrainStep:
             if p.grad is not g:
                 p.grad = g
         return self.loss
+
+
+
+# ================================================================================================ the unchanged loop, graphed
+class _SpecLoss(torch.autograd.Function):
+    """The loss tensor ``CLIPLoss.forward`` returns in graph mode.  Its value and the gradients of every parameter were
+    already produced by the replayed recording (the reference loop always calls ``loss.backward()`` next: the backward
+    pass is run speculatively, with upstream gradient 1); ``backward`` hands those gradients to autograd scaled by the
+    actual upstream gradient.  Fresh tensors every time, so gradient accumulation over several backward calls works."""
+
+    @staticmethod
+    def forward(ctx, runner, *params):
+        ctx.runner, ctx.token = runner, runner.token
+        return runner.loss_out.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        r = ctx.runner
+        if ctx.token != r.token:
+            raise RuntimeError("megb200 graph mode: backward() of a loss whose step has been overwritten by a newer forward "
+                               "(the recorded buffers hold one step); call loss.backward() before the next batch")
+        scaled = torch._foreach_mul(r.static_grads, g.reshape(()).to(torch.float32))
+        return (None,) + tuple(scaled)
+
+
+class ModuleGraphs:
+    """The reference's UNCHANGED training loop (train.py:185-215: ``Z = brain_encoder(X, subject_idxs)``, ``loss =
+    loss_func(Y, Z)``, ``classifier(Z, Y)``, ``loss.item()``, ``optimizer.zero_grad(); loss.backward(); optimizer.step()``)
+    at CUDA-graph speed: the ~145 kernel launches of a step cost 6-10 ms of host time when enqueued one by one from
+    Python, against ~7 ms of device time.  Installed on an encoder (``megb200.graph.accelerate(enc)``, or
+    ``MEGB200_MODULE_GRAPHS=1`` / ``args.cuda_graphs`` at construction), it lets the first steps of a new input shape
+    run eagerly (real training steps; they also create tensor maps and kernel attributes), then records
+
+      G1  BrainEncoder.forward                                   replayed by ``brain_encoder(X, subject_idxs)``
+      G2  CLIPLoss forward + backward, BrainEncoder backward     replayed by ``loss_func(Y, Z)``
+
+    -- the same C-ABI launches, captured -- and ``loss.backward()`` only hands the recorded gradients to autograd
+    (_SpecLoss).  Assumptions, all checked: training mode with gradients enabled, ``loss_func`` receives the Z just
+    returned, ``fast=True`` / no ``return_logits``, one backward per forward.  Anything else (eval, no_grad, other
+    shapes, other uses of Z) takes the eager path; Z carries no autograd history in graph mode, so using it in any
+    differentiable way other than ``loss_func(Y, Z)`` raises.  Subjects absent from a batch receive zero gradients
+    (eager mode: None, as the reference).  Data parallel works (collectives are part of G2) but the target gather is then
+    not overlapped with the forward; GraphedTrainStep is the data-parallel fast path."""
+
+    WARMUP = 3
+
+    def __init__(self, encoder):
+        self.enc = encoder
+        self.key, self.eager_left = None, self.WARMUP
+        self.g1 = self.g2 = None
+        self.token = 0
+        self.enabled = True
+        self.stats = {"eager_steps": 0, "graph_steps": 0, "captures": 0}
+
+    # ------------------------------------------------------------------ plumbing
+    def _reset(self, key):
+        self.key, self.eager_left = key, self.WARMUP
+        self.g1 = self.g2 = None
+        self.lossf = None
+        self.static_grads = self.loss_out = None
+
+    def _capture(self, fn):
+        dev = self.dev
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        mode = {} if parallel.context() is None else {"capture_error_mode": "thread_local"}
+        kw = dict(pool=self.pool) if self.pool is not None else {}
+        with torch.cuda.graph(g, **kw, **mode):
+            out = fn()
+        if self.pool is None:
+            self.pool = g.pool()
+        self.stats["captures"] += 1
+        return g, out
+
+    # ------------------------------------------------------------------ G1: encoder forward
+    def encoder_forward(self, X, subject_idxs):
+        """Returns Z (the reference's (B, F, T) view or (B, F)), or None when this call has to run eagerly."""
+        enc = self.enc
+        if not self.enabled or not torch.is_tensor(X) or not X.is_cuda:
+            return None
+        key = (tuple(X.shape), str(X.device), megb200_precision(), id(enc._engine()))
+        if key != self.key:
+            self._reset(key)
+        if self.eager_left > 0:
+            self.eager_left -= 1
+            self.stats["eager_steps"] += 1
+            return None
+        from .engine import validate_subject_idxs
+        dev = X.device
+        if self.g1 is None:
+            self.dev, self.pool = dev, None
+            self.X = torch.empty(tuple(X.shape), dtype=torch.float32, device=dev)
+            self.subj = torch.zeros(int(X.shape[0]), dtype=torch.int32, device=dev)
+            self.center = torch.zeros(1, dtype=torch.int64, device=dev)
+            self._one = torch.ones(1, dtype=torch.float32, device=dev)
+        self.X.copy_(X, non_blocking=True)
+        s = validate_subject_idxs(torch.as_tensor(subject_idxs), enc.num_subjects)
+        self.subj.copy_(s.to(torch.int32), non_blocking=True)
+        c = enc.drop_center
+        if torch.is_tensor(c):
+            self.center.copy_(c.reshape(1))
+        else:
+            self.center.fill_(int(c) if c is not None else int(np.random.randint(int(X.shape[1]))))   # models.py:236
+        if self.g1 is None:
+            self.g1, _ = self._capture(self._record_forward)
+            self.g2 = None
+        self.g1.replay()
+        self.token += 1
+        self.stats["graph_steps"] += 1
+        Zi = self.Zi
+        Z = Zi.permute(0, 2, 1) if enc.seq2seq else Zi[:, 0, : enc.F]
+        Z = _GraphZ.apply(Z, self.enc.conv_final2.bias)       # a leash: any differentiable use other than the loss raises
+        Z._megb200_runner = (self, self.token)
+        return Z
+
+    def _record_forward(self):
+        enc = self.enc
+        with torch.no_grad():
+            sa = enc.subject_block.spatial_attention
+            mask = sa.drop_masks.index_select(0, self.center).reshape(-1)
+            nbt = []
+            for k in range(5):
+                cb = getattr(enc.conv_blocks, f"conv{k}")
+                nbt += [cb.batchnorm0.num_batches_tracked, cb.batchnorm1.num_batches_tracked]
+            torch._foreach_add_(nbt, 1)
+            self.params_enc = enc._param_list()
+            self.P = enc._param_dict(self.params_enc)
+            self.eng = enc._engine()
+            self.Zi, self.saved = self.eng.forward(self.P, self.X, self.subj, mask, True)
+
+    # ------------------------------------------------------------------ G2: loss forward + whole backward
+    def loss_forward(self, lossf, x, token):
+        if token != self.token:
+            raise RuntimeError("megb200 graph mode: loss_func(Y, Z) received the Z of an earlier step")
+        if self.g2 is None or self.lossf is not lossf or self._ykey != self._target_key(x):
+            self.lossf, self._ykey = lossf, self._target_key(x)
+            Y = lossf._as_targets(x, self.dev)
+            if hasattr(Y, "rows"):
+                from .data import PackedTargets
+                self.Y = PackedTargets(torch.empty_like(Y.rows), torch.empty_like(Y.sumsq), Y.feature_shape)
+            else:
+                self.Y = torch.empty_like(Y)
+            self._load_targets(Y)
+            self.g2, _ = self._capture(self._record_backward)
+        else:
+            self._load_targets(lossf._as_targets(x, self.dev))
+        self.g2.replay()
+        params = [p for p in self.params_enc] + [lossf.temp]
+        return _SpecLoss.apply(self, *params)
+
+    @staticmethod
+    def _target_key(x):
+        if hasattr(x, "rows"):
+            return ("packed", tuple(x.rows.shape), x.rows.dtype)
+        return ("dense", tuple(x.shape), torch.bfloat16 if x.dtype == torch.bfloat16 else torch.float32)
+
+    def _load_targets(self, Y):
+        if hasattr(self.Y, "rows"):
+            self.Y.rows.copy_(Y.rows, non_blocking=True)
+            self.Y.sumsq.copy_(Y.sumsq, non_blocking=True)
+        else:
+            self.Y.copy_(Y, non_blocking=True)
+
+    def _record_backward(self):
+        enc, lossf, dist_ctx = self.enc, self.lossf, parallel.context()
+        with torch.no_grad():
+            ceng = lossf._engine(self.eng.ops.act_dtype)
+            Zi = self.Zi
+            Fs, Fo = Zi.shape[2], enc.F
+            Zl = Zi if Fs == Fo else Zi[:, :, :Fo].contiguous()
+            loss, _, csaved = ceng.forward(self.Y, Zl, lossf.temp.detach(), lossf.reduction, dist_ctx, False,
+                                           reduce_loss=False)
+            dZ, dtemp = ceng.backward(csaved, self._one)
+            if Fs != Fo:
+                dZ = torch.nn.functional.pad(dZ, (0, Fs - Fo))
+            G = self.eng.backward(self.P, self.saved, dZ.contiguous())
+            if dist_ctx is not None:
+                if "_flat" in G:
+                    G["_extra"][0:1].copy_(loss.reshape(1))
+                    G["_extra"][1:2].copy_(dtemp.reshape(1))
+                    parallel.allreduce_flat(G["_flat"])
+                    loss, dtemp = G["_extra"][0], G["_extra"][1:2]
+                else:
+                    raise RuntimeError("megb200 graph mode: gradient pool spilled in data parallel")
+            grads = []
+            for p, g in zip(self.params_enc, enc._grad_list(G, None)):
+                grads.append(g if g.shape == p.shape else g.reshape(p.shape))
+            grads.append(dtemp.reshape(lossf.temp.shape))
+            self.static_grads = grads
+            self.loss_out = loss.reshape(())
+
+
+class _GraphZ(torch.autograd.Function):
+    """Identity on the recorded embeddings that ties them to autograd: differentiating through Z in graph mode (anything
+    but ``loss_func(Y, Z)``, which never backpropagates through this node) is an error, not silently-zero gradients."""
+
+    @staticmethod
+    def forward(ctx, Z, anchor):
+        return Z.view_as(Z)
+
+    @staticmethod
+    def backward(ctx, g):
+        raise RuntimeError("megb200 graph mode (ModuleGraphs): the embeddings Z are only differentiable through "
+                           "loss_func(Y, Z); disable it with megb200.graph.accelerate(enc, False) for other uses")
+
+
+def megb200_precision():
+    import megb200
+    return megb200.get_precision()
+
+
+def accelerate(encoder, on: bool = True):
+    """Install (or remove) CUDA-graph replay of the unchanged training loop on a drop-in BrainEncoder.  Returns the
+    ModuleGraphs runner (``runner.stats`` counts eager / graph steps and captures)."""
+    if not on:
+        encoder._runner = None
+        return None
+    if getattr(encoder, "_runner", None) is None:
+        encoder._runner = ModuleGraphs(encoder)
+    return encoder._runner

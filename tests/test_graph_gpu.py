@@ -77,3 +77,73 @@ def test_graph_replay_equals_eager_step(name, precision):
                     assert H.rel_fro(a, b) <= tg, (it, k, H.rel_fro(a, b))
         for k, v in enc.named_buffers():
             assert H.rel_fro(bufs_g[k].float(), v.float()) <= tb, (it, k)      # late-layer batch means inherit the bf16 spread
+
+
+def _reference_loop(enc, lossf, classifier, optimizer, batches, centers):
+    """The statements of the reference's hot loop (train.py:185-215), verbatim in order."""
+    losses, accs = [], []
+    enc.train()
+    for (X, Y, subject_idxs), c in zip(batches, centers):
+        enc.drop_center = c
+        X, Y = X.to(DEV), Y.to(DEV)
+        Z = enc(X, subject_idxs)
+        loss = lossf(Y, Z)
+        with torch.no_grad():
+            top1, top10 = classifier(Z, Y)
+        losses.append(loss.item())
+        accs.append((top1, top10))
+        optimizer.zero_grad()
+        loss.backward()
+        optimizer.step()
+    return losses, accs
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["narrow", "tiny_static"])
+def test_unchanged_training_loop_replayed_from_module_graphs(precision, name):
+    """megb200.graph.ModuleGraphs: the reference loop, unchanged (enc(X, s) / lossf(Y, Z) / classifier / loss.item() /
+    zero_grad / backward / Adam step), with the launches replayed from two CUDA graphs, against the same loop with eager
+    launches from the same initial state: same loss trajectory over 7 optimizer steps (3 eager warm-up + 4 replayed)."""
+    from meg_decoding.models import Classifier
+    from megb200.graph import accelerate
+    megb200.set_precision(precision)
+    cfg = synth.get_config(name)
+    batches = [H.make_inputs(cfg, "cpu", seed=i) for i in range(7)]
+    centers = [(3 * i + 1) % cfg.C for i in range(7)]
+    out = {}
+    for mode in ("eager", "graph"):
+        enc, lossf = H.make_modules(cfg, DEV)
+        runner = accelerate(enc, mode == "graph")
+        opt = torch.optim.Adam(list(enc.parameters()) + list(lossf.parameters()), lr=1e-3)
+        losses, accs = _reference_loop(enc, lossf, Classifier(cfg | {"normalize_image_features": False}), opt, batches, centers)
+        out[mode] = (losses, accs, {k: v.detach().float().clone() for k, v in enc.state_dict().items() if v.is_floating_point()})
+        if mode == "graph":
+            assert runner.stats["eager_steps"] == 3 and runner.stats["graph_steps"] == 4 and runner.stats["captures"] == 2
+    le, lg = out["eager"][0], out["graph"][0]
+    tol = 2e-3 if precision == "fp32" else 5e-2
+    print(f"[parity] module graphs {name} {precision}: eager {['%.4f' % v for v in le]} graph {['%.4f' % v for v in lg]}")
+    for a, b in zip(le, lg):
+        assert abs(a - b) / abs(a) <= tol
+    assert le[-1] < le[0]                                    # it trains
+    w = "conv_final2.weight"
+    assert H.rel_fro(out["graph"][2][w], out["eager"][2][w]) <= (1e-3 if precision == "fp32" else 5e-2)
+    # guard rails: Z of graph mode is differentiable only through the loss; a stale loss cannot be back-propagated
+    enc, lossf = H.make_modules(cfg, DEV)
+    runner = accelerate(enc)
+    enc.train()
+    X, Y, subj = (t for t in batches[0])
+    for _ in range(4):
+        Z = enc(X.to(DEV), subj)
+    with pytest.raises(RuntimeError):
+        Z.float().sum().backward()
+    Z = enc(X.to(DEV), subj)
+    old = lossf(Y.to(DEV), Z)
+    Z2 = enc(X.to(DEV), subj)
+    with pytest.raises(RuntimeError):
+        old.backward()
+    with pytest.raises(RuntimeError):
+        lossf(Y.to(DEV), Z)                                   # the Z of an earlier step
+    enc.eval()
+    with torch.no_grad():
+        Ze = enc(X.to(DEV), subj)                             # eval / no_grad: plain eager path
+    assert not hasattr(Ze, "_megb200_runner")
