@@ -409,6 +409,42 @@ def run_megb200(args):
     if graph_ms is not None:
         ms = graph_ms
 
+    # ---- the UNCHANGED reference loop API (enc(X, s); lossf(Y, Z); loss.backward()) with its launches replayed from two
+    # CUDA graphs (megb200.graph.ModuleGraphs, opt-in): what `train.py` gets with MEGB200_MODULE_GRAPHS=1
+    module_graph_ms, module_graph_note = None, None
+    if world == 1 and not args.no_graph:
+        try:
+            from megb200.graph import accelerate
+            runner = accelerate(enc)
+            Yt = Ypd if packed_ok else Yd
+
+            def loop_step():
+                for p in params:
+                    p.grad = None
+                Z = enc(Xd, subj_h)
+                loss = lossf(Yt, Z)
+                loss.backward()
+                return loss
+            for _ in range(runner.WARMUP + 3):
+                lm = loop_step()
+            barrier()
+            m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            m0.record()
+            for _ in range(args.steps):
+                lm = loop_step()
+            m1.record()
+            barrier()
+            module_graph_ms = m0.elapsed_time(m1) / args.steps
+            lmv = float(lm.detach())
+            if not math.isfinite(lmv) or abs(lmv - loss_value) > 0.05 * abs(loss_value):
+                module_graph_note, module_graph_ms = f"module-graph loss {lmv} disagrees with eager {loss_value}", None
+            elif runner.stats["graph_steps"] < args.steps:
+                module_graph_note = f"only {runner.stats['graph_steps']} steps were replayed"
+        except Exception as e:
+            module_graph_note = f"{type(e).__name__}: {e}"[:200]
+        finally:
+            accelerate(enc, False)
+
     # ---- optimizer step, reported separately; taken AFTER the timed regions so they see the initial weights
     barrier()
     for _ in range(2):                       # Adam's lazy state init must not land in its own timed region
@@ -535,6 +571,7 @@ def run_megb200(args):
         "launch_path": "cuda_graph" if graph_ms is not None else "eager", "ms_per_step_eager": eager_ms,
         "targets": "packed bf16 (megb200.data.PackedTargets)" if (packed_ok and graph_ms is not None) else "dense f32",
         "ms_per_step_graph": graph_ms, "graph_note": graph_note,
+        "ms_per_step_unchanged_loop_module_graphs": module_graph_ms, "module_graphs_note": module_graph_note,
         "dp_target_gather": (parallel.context().gather_mode if parallel.context() is not None else None),
         "dp_target_gather_note": (parallel.context().gather_note if parallel.context() is not None else None),
         "adam_ms": adam_ms, "adam_ms_torch_optim": adam_torch_ms, "host_enqueue_ms_per_step": host_ms, "loss": loss_value, "precision": args.precision,
