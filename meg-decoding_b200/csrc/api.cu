@@ -36,9 +36,10 @@ Options& options() {
       getenv("MEGB200_CLIP_DZ_LARGE") != nullptr ? 1 : 0,
       getenv("MEGB200_ROWLOOP_DIRECT") != nullptr ? 1 : 0,
       (int)env_ll("MEGB200_WGRAD_SPLITS", 0),
+      (int)env_ll("MEGB200_WGRAD_PAIR", 1),
       (int)env_ll("MEGB200_CLIP_DZ_JT", 0),
       (int)env_ll("MEGB200_CLIP_FUSED", -1),
-      -1, -1, -1,
+      -1, -1, -1, -1,
   };
   return o;
 }
@@ -54,11 +55,13 @@ static const OptionEntry kOptionTable[] = {
     {"clip_dz_large", 1, offsetof(Options, clip_dz_large)},
     {"rowloop_direct", 1, offsetof(Options, rowloop_direct)},
     {"wgrad_splits", 1, offsetof(Options, wgrad_splits)},
+    {"wgrad_pair", 1, offsetof(Options, wgrad_pair)},
     {"clip_dz_jt", 1, offsetof(Options, clip_dz_jt)},
     {"clip_fused", 1, offsetof(Options, clip_fused)},
     {"last_tapgemm_kernel", 1, offsetof(Options, last_tapgemm_kernel)},
     {"last_clip_dz_kernel", 1, offsetof(Options, last_clip_dz_kernel)},
     {"last_wgrad_splits", 1, offsetof(Options, last_wgrad_splits)},
+    {"last_wgrad_kernel", 1, offsetof(Options, last_wgrad_kernel)},
 };
 
 static const OptionEntry* find_option(const char* name) {

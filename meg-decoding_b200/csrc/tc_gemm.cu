@@ -1212,6 +1212,166 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__
   }
 }
 
+
+// ================================================================================================ weight gradient, CTA pair
+// tc_wgrad_kernel contracts a 128 x 320 output tile per CTA: 56 KB of operands per 64 positions for 2.6 M MACs, i.e. the
+// kernel pulls ~10 TB/s from L2 (ncu: 0.8 - 1.4 GB per launch against 0.12 - 0.32 GB from DRAM) and stalls on it.  Here a
+// cluster of two CTAs computes a 256-row tile with tcgen05.mma.cta_group::2 and each CTA stages only HALF of the N
+// operand: 36-40 KB per CTA for the same MACs.  Roles are swapped with respect to the single-CTA kernel so that the
+// 256-row M dimension is filled without padding: M = (tap, input channel) -- taps * ceil(C/64) atoms of 64 channels, four
+// atoms per cluster, each with its own tap shift on the TMA coordinate -- and N = output channels in UMMA tiles of 256 /
+// 128 (320 = 256 + 128 with the last 64 zero-filled; 640 = [256 + 128] + [256]; 1024 = 2 x [256 + 256]).
+// D[(tap, c)][m] = sum_pos X[pos + off(tap)][c] * dU[pos][m]; both operands MN-major straight from the PC layout.
+struct Wgrad2Params {
+  int T, M, C, taps, dil, B, kchunks, catoms, atoms_total, pair_tiles, n_groups, group_cols, samples_per_cta, stages;
+  uint32_t tmem_cols;
+  float* out;   // partial[slot][tap][M][C]
+};
+
+struct HeaderW2 {
+  uint64_t full[8];
+  uint64_t empty[8];
+  uint64_t tmem_full;
+  uint32_t tmem_slot;
+  uint32_t pad;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmX,
+                 const Wgrad2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  HeaderW2* hdr = reinterpret_cast<HeaderW2*>(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const uint32_t atom_bytes = kBlockK * 128;                // 64 positions x 64 channels of bf16
+  const int cluster = blockIdx.x >> 1;
+  const int pt = cluster % p.pair_tiles;
+  const int ng = (cluster / p.pair_tiles) % p.n_groups;
+  const int split = cluster / (p.pair_tiles * p.n_groups);
+  const int s0 = split * p.samples_per_cta;
+  const int s1 = min(s0 + p.samples_per_cta, p.B);
+  // output-channel tiles of this group: 256-wide while at least 256 columns remain, then one 128-wide tile
+  const int n0 = ng * p.group_cols;
+  int ncols = p.M - n0;
+  ncols = ncols > p.group_cols ? p.group_cols : (ncols + 127) / 128 * 128;
+  const int n_tiles = (ncols + 255) / 256;
+  const int b_atoms = ncols / 128;                          // per CTA: two atoms per 256-wide tile, one per 128-wide tile
+  const uint32_t a_bytes = 2 * atom_bytes;
+  const uint32_t stage_bytes = a_bytes + (uint32_t)b_atoms * atom_bytes;
+  uint8_t* ring = smem + kHeaderBytes;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmU);
+    tma_prefetch_desc(&tmX);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&hdr->full[s]), 1);      // the leader's producer arrives once and expects both CTAs' bytes
+      mbar_init(smem_u32(&hdr->empty[s]), 1);     // one multicast tcgen05.commit per use
+    }
+    mbar_init(smem_u32(&hdr->tmem_full), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2sm(smem_u32(&hdr->tmem_slot), p.tmem_cols);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = hdr->tmem_slot;
+  const int total_it = (s1 - s0) * p.kchunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // this CTA's two M atoms: (tap, 64 input channels) each; atoms past the end read a sample index out of range (zero fill)
+      int a_tap[2], a_c0[2];
+      bool a_ok[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int a = 4 * pt + 2 * (int)rank + u;
+        a_ok[u] = a < p.atoms_total;
+        a_tap[u] = a_ok[u] ? a / p.catoms : 0;
+        a_c0[u] = a_ok[u] ? (a % p.catoms) * 64 : 0;
+      }
+      int it = 0;
+      for (int b = s0; b < s1; ++b) {
+        for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
+          const int s = it % p.stages;
+          mbar_wait(smem_u32(&hdr->empty[s]), ((it / p.stages) & 1) ^ 1);
+          const uint32_t full = smem_u32(&hdr->full[s]);
+          if (leader) mbar_arrive_expect_tx(full, 2 * stage_bytes);
+          const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+            tma_load_3d_2sm(sa + (uint32_t)u * atom_bytes, &tmX, a_c0[u],
+                            kc * kBlockK + (a_tap[u] - p.taps / 2) * p.dil, a_ok[u] ? b : 0x3fffffff, full);
+          // N operand: tile t of width w: this CTA holds channels n0 + 256 t + rank * (w / 2) + [0, w / 2)
+          int atom = 0;
+          for (int t = 0; t < n_tiles; ++t) {
+            const int w = (ncols - 256 * t) >= 256 ? 256 : 128;
+            const int ch0 = n0 + 256 * t + (int)rank * (w / 2);
+            for (int u = 0; u < w / 128; ++u, ++atom)
+              tma_load_3d_2sm(sa + a_bytes + (uint32_t)atom * atom_bytes, &tmU, ch0 + 64 * u, kc * kBlockK, b, full);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      for (int it = 0; it < total_it; ++it) {
+        const int s = it % p.stages;
+        mbar_wait(smem_u32(&hdr->full[s]), (it / p.stages) & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes);
+        // MN-major: LBO = distance between 64-channel atoms, SBO = distance between 8-position groups
+        const uint64_t da = make_smem_desc(sa, atom_bytes, 1024);
+#pragma unroll
+        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+          int atom = 0;
+          for (int t = 0; t < n_tiles; ++t) {
+            const int w = (ncols - 256 * t) >= 256 ? 256 : 128;
+            const uint64_t db = make_smem_desc(sa + a_bytes + (uint32_t)atom * atom_bytes, atom_bytes, 1024);
+            umma_bf16_2sm(tmem_base + (uint32_t)(256 * t), desc_advance(da, k * kUmmaK * 128),
+                          desc_advance(db, k * kUmmaK * 128), make_idesc_m(256, w, 1, 1), (it | k) != 0);
+            atom += w / 128;
+          }
+        }
+        umma_commit_2sm(smem_u32(&hdr->empty[s]), 3);
+      }
+      umma_commit_2sm(smem_u32(&hdr->tmem_full), 3);
+    }
+  } else {
+    // ---------------- epilogue (both CTAs): thread = one accumulator row = (tap, input channel); columns = output channels
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int a = 4 * pt + 2 * (int)rank + (r >> 6);
+    const bool ok = a < p.atoms_total;
+    const int tap = ok ? a / p.catoms : 0;
+    const int c = ok ? (a % p.catoms) * 64 + (r & 63) : 0;
+    const bool valid = ok && c < p.C && total_it > 0;
+    mbar_wait(smem_u32(&hdr->tmem_full), 0);
+    tc_fence_after();
+    float* dst = p.out + (((long long)split * p.taps + tap) * p.M) * p.C + c;
+    for (int ch = 0; ch < ncols / 16; ++ch) {
+      float v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 16), v);
+      if (!valid) continue;
+      const int nb = n0 + ch * 16;
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (nb + i < p.M) dst[(long long)(nb + i) * p.C] = v[i];        // lanes = consecutive input channels: coalesced
+    }
+    tc_fence_before();
+  }
+  tc_fence_before();
+  cluster_sync_all();                              // nobody leaves while the peer may still touch its smem / TMEM
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, p.tmem_cols);
+  }
+}
+
 // partial[slot][tap][M][C] -> dW[m][c][tap] += sum_slot.  Thread = one (m, c): coalesced slot reads (all independent,
 // unrolled for memory-level parallelism) and one contiguous run of `taps` floats written per thread.
 __global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dW, int slots, int taps, int M,
@@ -2178,6 +2338,76 @@ int tc_wgrad(const void* dU, int M, int Ms, const void* Xin, int C, int Cs, int 
              const int32_t* group, const int32_t* order, int G, float* dW, float* workspace, size_t ws_bytes,
              cudaStream_t st) {
   MEGB_CHECK_ARG(Ms % 8 == 0 && Cs % 8 == 0, "tc_wgrad: strides must be multiples of 8");
+  if (group == nullptr && options().wgrad_pair != 0) {
+    // ---- CTA-pair form (default for the ungrouped convolutions)
+    Wgrad2Params q;
+    q.T = T; q.M = M; q.C = C; q.taps = taps; q.dil = dil; q.B = B;
+    q.kchunks = (T + kBlockK - 1) / kBlockK;
+    q.catoms = (C + 63) / 64;
+    q.atoms_total = taps * q.catoms;
+    q.pair_tiles = (q.atoms_total + 3) / 4;
+    const int m128 = (M + 127) / 128 * 128;
+    // output channels per cluster pass: <= 512 TMEM columns, balanced over the groups (640 -> 384 + 256, 1024 -> 512 + 512)
+    q.n_groups = (m128 + 511) / 512;
+    q.group_cols = ((m128 / 128 + q.n_groups - 1) / q.n_groups) * 128;
+    q.tmem_cols = tmem_cols_for(q.group_cols);
+    const uint32_t stage_w2 = (2 + q.group_cols / 128) * kBlockK * 128;
+    q.stages = pick_stages(stage_w2, 232448 - 2048, 8);
+    MEGB_CHECK_ARG(q.stages >= 2, "tc_wgrad(pair): tile too large");
+    const long long base2 = (long long)q.pair_tiles * q.n_groups;
+    const long long slot_elems2 = (long long)taps * M * C;
+    int splits2 = (int)((num_sms() / 2) / base2);              // ONE wave of clusters
+    if (options().wgrad_splits > 0) splits2 = options().wgrad_splits;
+    if (splits2 < 1) splits2 = 1;
+    if (splits2 > B) splits2 = B;
+    const long long max_slots2 = (long long)(ws_bytes / sizeof(float)) / slot_elems2;
+    if (splits2 > max_slots2) splits2 = (int)max_slots2;
+    MEGB_CHECK_ARG(splits2 >= 1, "tc_wgrad: workspace too small (%zu bytes, need >= %lld)", ws_bytes, slot_elems2 * 4);
+    q.samples_per_cta = (B + splits2 - 1) / splits2;
+    splits2 = (B + q.samples_per_cta - 1) / q.samples_per_cta;
+    q.out = workspace;
+    CUtensorMap tmU2, tmX2;
+    {
+      const uint64_t dims[3] = {(uint64_t)M, (uint64_t)T, (uint64_t)B};
+      const uint64_t strides[2] = {(uint64_t)Ms * 2, (uint64_t)T * Ms * 2};
+      const uint32_t box[3] = {64, kBlockK, 1};
+      int rc = encode_tmap_bf16(&tmU2, dU, 3, dims, strides, box);
+      if (rc) return rc;
+    }
+    {
+      const uint64_t dims[3] = {(uint64_t)C, (uint64_t)T, (uint64_t)B};
+      const uint64_t strides[2] = {(uint64_t)Cs * 2, (uint64_t)T * Cs * 2};
+      const uint32_t box[3] = {64, kBlockK, 1};
+      int rc = encode_tmap_bf16(&tmX2, Xin, 3, dims, strides, box);
+      if (rc) return rc;
+    }
+    const size_t smem2 = 1024 + kHeaderBytes + (size_t)q.stages * stage_w2;
+    int rc = set_smem(tc_wgrad2_kernel, smem2);
+    if (rc) return rc;
+    // the partial slots of padded (tap, channel) rows / channels are never written: the reduce only reads [taps][M][C]
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * base2 * splits2));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem2;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MEGB_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_wgrad2_kernel, tmU2, tmX2, q));
+    MEGB_LAUNCH_OK();
+    options().last_wgrad_splits = splits2;
+    options().last_wgrad_kernel = 1;
+    long long blocks = ((long long)M * C + 127) / 128;
+    if (blocks > num_sms() * 16) blocks = num_sms() * 16;
+    wgrad_reduce_kernel<<<(int)blocks, 128, 0, st>>>(workspace, dW, splits2, taps, M, C);
+    MEGB_LAUNCH_OK();
+    return 0;
+  }
+  options().last_wgrad_kernel = 0;
   WgradParams p;
   p.T = T; p.M = M; p.C = C; p.taps = taps; p.dil = dil; p.B = B;
   p.kchunks = (T + kBlockK - 1) / kBlockK;

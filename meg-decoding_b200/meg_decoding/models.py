@@ -136,6 +136,8 @@ class _EncoderFn(torch.autograd.Function):
         G = eng.backward(ctx.P, ctx.saved, dZ)
         grads = module._grad_list(G, ctx.present)
         ctx.saved = None
+        if module._runner is not None:
+            module._runner.note_eager_backward()
         return (None, None, None, None, None) + tuple(grads)
 
 

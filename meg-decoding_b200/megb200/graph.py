@@ -265,6 +265,8 @@ class _SpecLoss(torch.autograd.Function):
             raise RuntimeError("megb200 graph mode: backward() of a loss whose step has been overwritten by a newer forward "
                                "(the recorded buffers hold one step); call loss.backward() before the next batch")
         scaled = torch._foreach_mul(r.static_grads, g.reshape(()).to(torch.float32))
+        if r.absent:                       # subjects without a sample in this batch: grad None, as the reference / eager path
+            scaled = [None if i in r.absent else t for i, t in enumerate(scaled)]
         return (None,) + tuple(scaled)
 
 
@@ -283,23 +285,29 @@ class ModuleGraphs:
     (_SpecLoss).  Assumptions, all checked: training mode with gradients enabled, ``loss_func`` receives the Z just
     returned, ``fast=True`` / no ``return_logits``, one backward per forward.  Anything else (eval, no_grad, other
     shapes, other uses of Z) takes the eager path; Z carries no autograd history in graph mode, so using it in any
-    differentiable way other than ``loss_func(Y, Z)`` raises.  Subjects absent from a batch receive zero gradients
-    (eager mode: None, as the reference).  Data parallel works (collectives are part of G2) but the target gather is then
+    differentiable way other than ``loss_func(Y, Z)`` raises.  Subjects absent from a batch receive ``grad = None`` as in
+    the reference (the recording computes zeros for them; they are dropped when the gradients are handed out).  Data parallel works (collectives are part of G2) but the target gather is then
     not overlapped with the forward; GraphedTrainStep is the data-parallel fast path."""
 
     WARMUP = 3
 
     def __init__(self, encoder):
         self.enc = encoder
-        self.key, self.eager_left = None, self.WARMUP
+        self.key, self.eager_done = None, 0
         self.g1 = self.g2 = None
         self.token = 0
+        self.absent = set()
         self.enabled = True
         self.stats = {"eager_steps": 0, "graph_steps": 0, "captures": 0}
 
     # ------------------------------------------------------------------ plumbing
+    def note_eager_backward(self):
+        """Called by the eager autograd node after a complete eager step (forward + loss + backward): only such steps count
+        as warm-up, because they are what creates the tensor maps / descriptor tables the recordings must not create."""
+        self.eager_done += 1
+
     def _reset(self, key):
-        self.key, self.eager_left = key, self.WARMUP
+        self.key, self.eager_done = key, 0
         self.g1 = self.g2 = None
         self.lossf = None
         self.static_grads = self.loss_out = None
@@ -326,8 +334,7 @@ class ModuleGraphs:
         key = (tuple(X.shape), str(X.device), megb200_precision(), id(enc._engine()))
         if key != self.key:
             self._reset(key)
-        if self.eager_left > 0:
-            self.eager_left -= 1
+        if self.eager_done < self.WARMUP:
             self.stats["eager_steps"] += 1
             return None
         from .engine import validate_subject_idxs
@@ -341,6 +348,9 @@ class ModuleGraphs:
         self.X.copy_(X, non_blocking=True)
         s = validate_subject_idxs(torch.as_tensor(subject_idxs), enc.num_subjects)
         self.subj.copy_(s.to(torch.int32), non_blocking=True)
+        present = set(int(v) for v in (torch.unique(s) if s.is_cuda else s).tolist())
+        # positions (in _SpecLoss's parameter list) of the subject layers that see no sample in this batch
+        self.absent = {3 + k for k in range(enc.num_subjects) if k not in present}
         c = enc.drop_center
         if torch.is_tensor(c):
             self.center.copy_(c.reshape(1))

@@ -124,7 +124,10 @@ class CudaOps:
                 rows.append([w.data_ptr(), o.data_ptr(), G, O, I, Kt, Np, Kp, m, G * Np * Kt * Kp])
             if len(cached) > 64:
                 cached.clear()
-            tab = cached[key] = torch.tensor(rows, dtype=torch.int64).to(items[0][0].device)
+            # pinned source: legal (and replay-safe: the cache keeps it alive) even if the first use is under graph capture
+            host = torch.tensor(rows, dtype=torch.int64).pin_memory()
+            tab = cached[key] = host.to(items[0][0].device, non_blocking=True)
+            cached[("host",) + key] = host
         L.call("megb200_pack_weight_multi", tab.data_ptr(), len(items), self.dt, self._stream())
 
     # ------------------------------------------------------------------ contractions

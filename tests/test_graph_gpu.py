@@ -118,6 +118,7 @@ def test_unchanged_training_loop_replayed_from_module_graphs(precision, name):
         losses, accs = _reference_loop(enc, lossf, Classifier(cfg | {"normalize_image_features": False}), opt, batches, centers)
         out[mode] = (losses, accs, {k: v.detach().float().clone() for k, v in enc.state_dict().items() if v.is_floating_point()})
         if mode == "graph":
+            out["graph_modules"] = (enc, lossf)
             assert runner.stats["eager_steps"] == 3 and runner.stats["graph_steps"] == 4 and runner.stats["captures"] == 2
     le, lg = out["eager"][0], out["graph"][0]
     tol = 2e-3 if precision == "fp32" else 5e-2
@@ -127,13 +128,13 @@ def test_unchanged_training_loop_replayed_from_module_graphs(precision, name):
     assert le[-1] < le[0]                                    # it trains
     w = "conv_final2.weight"
     assert H.rel_fro(out["graph"][2][w], out["eager"][2][w]) <= (1e-3 if precision == "fp32" else 5e-2)
-    # guard rails: Z of graph mode is differentiable only through the loss; a stale loss cannot be back-propagated
-    enc, lossf = H.make_modules(cfg, DEV)
-    runner = accelerate(enc)
+    # guard rails (the modules of the graph run are in replay mode now): Z is differentiable only through the loss; a stale
+    # loss cannot be back-propagated; eval / no_grad take the plain eager path
+    enc, lossf = out["graph_modules"]
     enc.train()
     X, Y, subj = (t for t in batches[0])
-    for _ in range(4):
-        Z = enc(X.to(DEV), subj)
+    Z = enc(X.to(DEV), subj)
+    assert hasattr(Z, "_megb200_runner")
     with pytest.raises(RuntimeError):
         Z.float().sum().backward()
     Z = enc(X.to(DEV), subj)
@@ -145,5 +146,13 @@ def test_unchanged_training_loop_replayed_from_module_graphs(precision, name):
         lossf(Y.to(DEV), Z)                                   # the Z of an earlier step
     enc.eval()
     with torch.no_grad():
-        Ze = enc(X.to(DEV), subj)                             # eval / no_grad: plain eager path
+        Ze = enc(X.to(DEV), subj)
     assert not hasattr(Ze, "_megb200_runner")
+    # absent subjects keep grad None (reference semantics) also when the step is replayed
+    enc.train()
+    for p in enc.parameters():
+        p.grad = None
+    s0 = torch.zeros_like(subj)
+    lossf(Y.to(DEV), enc(X.to(DEV), s0)).backward()
+    assert enc.subject_block.subject_layer[0].weight.grad is not None
+    assert enc.subject_block.subject_layer[1].weight.grad is None

@@ -86,7 +86,8 @@ TAPGEMM_CASES = [
 ]
 
 # which tensor-core kernel each natively-large case must have launched (megb200_get_option("last_tapgemm_kernel"))
-PAIR_EXPECT = {(64, 360, 320, 320, 3): 2, (51, 360, 320, 320, 3): 2, (50, 360, 640, 320, 1): 1}
+PAIR_EXPECT = {(64, 360, 320, 320, 3, 1): 2, (51, 360, 320, 320, 3, 2): 2, (50, 360, 640, 320, 1, 1): 1,
+               (64, 200, 320, 320, 11, 1): 1, (64, 360, 320, 320, 3, 128): 1}      # wide kernel / long halo: plain pair
 
 
 @pytest.mark.parametrize("dtype,backend", CONTRACTION_MODES)
@@ -109,8 +110,9 @@ def test_tapgemm(dtype, backend, case):
     ref.tapgemm(A, Ca, W, N, taps, dil, bias, Res, group, Outr)
     torch.cuda.synchronize()
     _close(Out, Outr, dtype, f"tapgemm {case} {backend}")
-    if backend == "tc" and case[:5] in PAIR_EXPECT:
-        assert L.get_option("last_tapgemm_kernel") == PAIR_EXPECT[case[:5]], "the product (CTA-pair) kernel did not run"
+    if backend == "tc" and case[:6] in PAIR_EXPECT and L.get_option("tapgemm_pair_min_items") < 0 \
+            and not L.get_option("tapgemm_force_1cta"):
+        assert L.get_option("last_tapgemm_kernel") == PAIR_EXPECT[case[:6]], "the product (CTA-pair) kernel did not run"
 
 
 EPI_CASES = [
@@ -245,6 +247,17 @@ def test_wgrad(dtype, backend, case):
     assert torch.isfinite(got).all() and err < 2e-4, f"wgrad {case} {backend}: {err:.3e}"
     if backend == "tc" and B == 256 and G == 1:
         assert L.get_option("last_wgrad_splits") > 1, "config 2's split plan was not exercised"
+    if backend == "tc" and G == 1:
+        assert L.get_option("last_wgrad_kernel") == L.get_option("wgrad_pair"), "unexpected weight-gradient kernel"
+
+
+@pytest.mark.parametrize("case", [c for c in WGRAD_CASES if c[6] == 1 and c[0] <= 20] + [(256, 360, 320, 320, 3, 1, 1)])
+def test_wgrad_single_cta_kernel_forced(case):
+    """The single-CTA weight-gradient kernel (still used for the grouped subject GEMM) on the ungrouped shapes the
+    CTA-pair kernel takes by default."""
+    with L.options(wgrad_pair=0):
+        test_wgrad(torch.bfloat16, "tc", case)
+        assert L.get_option("last_wgrad_kernel") == 0
 
 
 @pytest.mark.parametrize("splits", [1, 2, 5])
