@@ -1225,7 +1225,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__
 struct Wgrad2Params {
   int T, M, C, taps, dil, B, kchunks, catoms, atoms_total, pair_tiles, n_groups, group_cols, samples_per_cta, stages;
   uint32_t tmem_cols;
-  float* out;   // partial[slot][tap][M][C]
+  float* out;   // partial[slot][tap][C][M]
 };
 
 struct HeaderW2 {
@@ -1352,15 +1352,25 @@ tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
     const bool valid = ok && c < p.C && total_it > 0;
     mbar_wait(smem_u32(&hdr->tmem_full), 0);
     tc_fence_after();
-    float* dst = p.out + (((long long)split * p.taps + tap) * p.M) * p.C + c;
+    // partial layout of this kernel: [slot][tap][C][M] -- the thread's accumulator row (one input channel) is contiguous
+    // in the output channels it holds, so it leaves as 16-byte stores (a [..][M][C] layout would need one 4-byte store
+    // per element: 49 k store instructions per CTA, as long as the main loop)
+    float* dst = p.out + (((long long)split * p.taps + tap) * p.C + c) * p.M;
+    const bool vec = (p.M & 3) == 0;
     for (int ch = 0; ch < ncols / 16; ++ch) {
       float v[16];
       tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 16), v);
       if (!valid) continue;
       const int nb = n0 + ch * 16;
+      if (vec && nb + 16 <= p.M) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i)
-        if (nb + i < p.M) dst[(long long)(nb + i) * p.C] = v[i];        // lanes = consecutive input channels: coalesced
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<float4*>(dst + nb + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (nb + i < p.M) dst[nb + i] = v[i];
+      }
     }
     tc_fence_before();
   }
@@ -1375,11 +1385,14 @@ tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
 // partial[slot][tap][M][C] -> dW[m][c][tap] += sum_slot.  Thread = one (m, c): coalesced slot reads (all independent,
 // unrolled for memory-level parallelism) and one contiguous run of `taps` floats written per thread.
 __global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dW, int slots, int taps, int M,
-                                    int C) {
+                                    int C, int cmajor) {
   const long long mc = (long long)M * C;
   const long long n = (long long)taps * mc;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < mc;
        idx += (long long)gridDim.x * blockDim.x) {
+    // cmajor = 0: partial[slot][tap][M][C] (single-CTA kernel), idx = m * C + c
+    // cmajor = 1: partial[slot][tap][C][M] (CTA-pair kernel),   idx = c * M + m: coalesced reads either way
+    const long long o = cmajor ? ((idx % M) * C + idx / M) : idx;      // m * C + c
     for (int tap = 0; tap < taps; ++tap) {
       const float* src = part + (long long)tap * mc + idx;
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -1391,7 +1404,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __res
         s3 += src[(long long)(k + 3) * n];
       }
       for (; k < slots; ++k) s0 += src[(long long)k * n];
-      dW[idx * taps + tap] += (s0 + s1) + (s2 + s3);
+      dW[o * taps + tap] += (s0 + s1) + (s2 + s3);
     }
   }
 }
@@ -2403,7 +2416,7 @@ int tc_wgrad(const void* dU, int M, int Ms, const void* Xin, int C, int Cs, int 
     options().last_wgrad_kernel = 1;
     long long blocks = ((long long)M * C + 127) / 128;
     if (blocks > num_sms() * 16) blocks = num_sms() * 16;
-    wgrad_reduce_kernel<<<(int)blocks, 128, 0, st>>>(workspace, dW, splits2, taps, M, C);
+    wgrad_reduce_kernel<<<(int)blocks, 128, 0, st>>>(workspace, dW, splits2, taps, M, C, 1);
     MEGB_LAUNCH_OK();
     return 0;
   }
@@ -2476,7 +2489,7 @@ int tc_wgrad(const void* dU, int M, int Ms, const void* Xin, int C, int Cs, int 
   if (p.mode == 0) {
     long long blocks = ((long long)M * C + 127) / 128;
     if (blocks > num_sms() * 16) blocks = num_sms() * 16;
-    wgrad_reduce_kernel<<<(int)blocks, 128, 0, st>>>(workspace, dW, splits, taps, M, C);
+    wgrad_reduce_kernel<<<(int)blocks, 128, 0, st>>>(workspace, dW, splits, taps, M, C, 0);
     MEGB_LAUNCH_OK();
   }
   return 0;

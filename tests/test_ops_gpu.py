@@ -87,7 +87,7 @@ TAPGEMM_CASES = [
 
 # which tensor-core kernel each natively-large case must have launched (megb200_get_option("last_tapgemm_kernel"))
 PAIR_EXPECT = {(64, 360, 320, 320, 3, 1): 2, (51, 360, 320, 320, 3, 2): 2, (50, 360, 640, 320, 1, 1): 1,
-               (64, 200, 320, 320, 11, 1): 1, (64, 360, 320, 320, 3, 128): 1}      # wide kernel / long halo: plain pair
+               (80, 200, 320, 320, 11, 1): 1, (64, 360, 320, 320, 3, 128): 1}      # wide kernel / long halo: plain pair
 
 
 @pytest.mark.parametrize("dtype,backend", CONTRACTION_MODES)
@@ -460,7 +460,7 @@ def test_avgpool_fwd_bwd(dtype, shape):
 WIDE_TAP_CASES = [
     # B, T, Ca, N, taps, dil: kernel sizes 5 / 11 (BrainEncoderSeq2Static) and the paper's dilations (some beyond T)
     (2, 200, 320, 320, 11, 1), (3, 100, 32, 64, 5, 1), (2, 360, 320, 320, 3, 32), (2, 360, 320, 320, 3, 2048),
-    (64, 200, 320, 320, 11, 1),          # above the CTA-pair threshold: k = 11 does not fit the halo form -> plain pair
+    (80, 200, 320, 320, 11, 1),          # above the CTA-pair threshold: k = 11 does not fit the halo form -> plain pair
     (64, 360, 320, 320, 3, 128),         # halo rows would exceed one box -> plain pair
 ]
 
