@@ -49,6 +49,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Long waits (epilogue warps waiting for a whole main loop): back off with nanosleep instead of spinning.  ncu's sampling
+// of the weight-gradient kernel had 64 % of all warp samples in the spin branch of the four epilogue warps -- they share
+// warp schedulers (and the barrier unit) with the TMA producer and the MMA-issuing warp, whose time is the critical path.
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, uint32_t ns = 256) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if (++spins > (1u << 24)) {
+      printf("megb200: mbarrier wait timed out (block %d,%d thread %d bar 0x%x parity %u)\n", blockIdx.x, blockIdx.y,
+             threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

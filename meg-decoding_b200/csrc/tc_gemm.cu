@@ -461,7 +461,7 @@ tc_tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       sbias[i] = (p.bias != nullptr && ok) ? p.bias[(long long)g * p.N + n] : 0.f;
     }
     named_bar_sync(1, 128);
-    mbar_wait(smem_u32(&hdr->tmem_full), 0);
+    mbar_wait_sleep(smem_u32(&hdr->tmem_full), 0);
     if (p.dbg != nullptr && et == 0) p.dbg[16 * blockIdx.x + 2] = clock64();
     tc_fence_after();
     const int q = warp & 3;
@@ -626,7 +626,7 @@ tc_tapgemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       sbias[i] = (p.bias != nullptr && ok) ? p.bias[n] : 0.f;
     }
     named_bar_sync(1, 128);
-    mbar_wait(smem_u32(&hdr->tmem_full), 0);
+    mbar_wait_sleep(smem_u32(&hdr->tmem_full), 0);
     tc_fence_after();
     const int q = warp & 3;
     const int t = t0 + q * 32 + lane;
@@ -817,7 +817,7 @@ tc_tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
       named_bar_sync(1, 256);
       const long long w3 = p.dbg ? clock64() : 0;
-      mbar_wait(smem_u32(&hdr->tmem_full[acc]), (tile >> 1) & 1);
+      mbar_wait_sleep(smem_u32(&hdr->tmem_full[acc]), (tile >> 1) & 1, 64);
       const long long w4 = p.dbg ? clock64() : 0;
       dbg_epi_wait += w4 - w3;
       tc_fence_after();
@@ -1010,7 +1010,7 @@ tc_tapgemm2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       named_bar_sync(1, 256);
       const long long w3 = p.dbg ? clock64() : 0;
-      mbar_wait(smem_u32(&hdr->tmem_full[acc]), (tile >> 1) & 1);
+      mbar_wait_sleep(smem_u32(&hdr->tmem_full[acc]), (tile >> 1) & 1, 64);
       const long long w4 = p.dbg ? clock64() : 0;
       dbg_epi_wait += w4 - w3;
       tc_fence_after();
@@ -1173,7 +1173,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__
       } else {
         se = s1;
       }
-      mbar_wait(smem_u32(&hdr->tmem_full), flushes & 1);
+      mbar_wait_sleep(smem_u32(&hdr->tmem_full), flushes & 1);
       tc_fence_after();
       const int ncols = p.n0_cols + p.n1_cols;
       for (int ch = 0; ch < ncols / 16; ++ch) {
@@ -1350,7 +1350,7 @@ tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
     const int tap = ok ? a / p.catoms : 0;
     const int c = ok ? (a % p.catoms) * 64 + (r & 63) : 0;
     const bool valid = ok && c < p.C && total_it > 0;
-    mbar_wait(smem_u32(&hdr->tmem_full), 0);
+    mbar_wait_sleep(smem_u32(&hdr->tmem_full), 0);
     tc_fence_after();
     // partial layout of this kernel: [slot][tap][C][M] -- the thread's accumulator row (one input channel) is contiguous
     // in the output channels it holds, so it leaves as 16-byte stores (a [..][M][C] layout would need one 4-byte store
@@ -1481,7 +1481,7 @@ tc_clip_logits_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_cons
         umma_commit(smem_u32(&hdr->tmem_full));
       }
     } else {
-      mbar_wait(smem_u32(&hdr->tmem_full), 0);
+      mbar_wait_sleep(smem_u32(&hdr->tmem_full), 0);
       tc_fence_after();
       const int q = warp & 3;
       const int i = i0 + q * 32 + lane;
@@ -1589,7 +1589,7 @@ tc_clip_dz_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constant
       umma_commit(smem_u32(&hdr->tmem_full));
     }
   } else {
-    mbar_wait(smem_u32(&hdr->tmem_full), 0);
+    mbar_wait_sleep(smem_u32(&hdr->tmem_full), 0);
     tc_fence_after();
     const int q = warp & 3;
     const float gs = p.gscale[0];
@@ -1717,8 +1717,8 @@ tc_clip_dz_small_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_co
     const int j = j0 + rloc;
     const float cj = j < p.Bz ? p.cvec[j] : 0.f;
     const float gs = p.gscale[0];
-    mbar_wait(smem_u32(&hdr->zfull), 0);
-    mbar_wait(smem_u32(&hdr->tmem_full), 0);
+    mbar_wait_sleep(smem_u32(&hdr->zfull), 0);
+    mbar_wait_sleep(smem_u32(&hdr->tmem_full), 0);
     tc_fence_after();
     const uint32_t sw = (uint32_t)rloc & 7u;
 #pragma unroll
@@ -1874,7 +1874,7 @@ tc_clip_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
     const float ri = iv ? s * rsqrtf(p.ysq[i]) : 0.f;
     const float rl = (iv && p.mode == 1) ? p.row_lse[i] : 0.f;
     named_bar_sync(1, 128);
-    mbar_wait(smem_u32(&hdr->tmem_full), 0);
+    mbar_wait_sleep(smem_u32(&hdr->tmem_full), 0);
     tc_fence_after();
     float rm = -INFINITY, rs = 0.f, dtemp = 0.f;
     for (int g = 0; g < kFusedNT / 32; ++g) {
