@@ -52,7 +52,7 @@ long long megb200_launch_count(void);
  * items up); these switches let a caller -- the test-suite -- force each form on any shape.  Names:
  *   "tapgemm_pair_min_items" (-1 = default), "tapgemm_force_1cta", "tapgemm_pair_halo", "tapgemm_halo",
  *   "tapgemm_ragged_n", "tapgemm_direct_epi", "clip_dz_large", "rowloop_direct", "wgrad_splits" (0 = automatic),
- *   "wgrad_pair" (1 = CTA-pair weight-gradient kernel for ungrouped problems, 0 = single-CTA kernel),
+ *   "wgrad_pair" (1 = CTA-pair weight-gradient kernel for ungrouped problems; default 0 = single-CTA kernel),
  *   "clip_dz_jt" (0 = automatic: brain-row tiles per CTA of the large-K dZ kernel),
  *   "clip_fused" (policy of the host-side loss: -1 auto, 0 never, 1 whenever supported).
  * Read-only (written by the launchers, for tests): "last_tapgemm_kernel" (0 single CTA, 1 CTA pair, 2 CTA pair + halo,

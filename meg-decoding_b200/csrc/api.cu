@@ -36,7 +36,7 @@ Options& options() {
       getenv("MEGB200_CLIP_DZ_LARGE") != nullptr ? 1 : 0,
       getenv("MEGB200_ROWLOOP_DIRECT") != nullptr ? 1 : 0,
       (int)env_ll("MEGB200_WGRAD_SPLITS", 0),
-      (int)env_ll("MEGB200_WGRAD_PAIR", 1),
+      (int)env_ll("MEGB200_WGRAD_PAIR", 0),
       (int)env_ll("MEGB200_CLIP_DZ_JT", 0),
       (int)env_ll("MEGB200_CLIP_FUSED", -1),
       -1, -1, -1, -1,

@@ -56,7 +56,7 @@ struct Options {
   int clip_dz_large;                  // 1: always the large-K dZ kernel (default: small-K form when By <= 512)
   int rowloop_direct;                 // 1: direct-load streaming kernels instead of the bulk-copy staged ones
   int wgrad_splits;                   // > 0: force the split count of the weight-gradient GEMM
-  int wgrad_pair;                     // 0: single-CTA weight-gradient kernel for ungrouped problems too (default 1: CTA pair)
+  int wgrad_pair;                     // 1: CTA-pair weight-gradient kernel for ungrouped problems (default 0: measured slower)
   int clip_dz_jt;                     // > 0: j tiles (128 brain rows) per CTA of the large-K dZ kernel (default: automatic)
   int clip_fused;                     // host-side policy read by the Python engine: -1 auto (large batch, short
                                       // embeddings), 0 never, 1 whenever supported -- the never-materialised CLIP form

@@ -2352,7 +2352,10 @@ int tc_wgrad(const void* dU, int M, int Ms, const void* Xin, int C, int Cs, int 
              cudaStream_t st) {
   MEGB_CHECK_ARG(Ms % 8 == 0 && Cs % 8 == 0, "tc_wgrad: strides must be multiples of 8");
   if (group == nullptr && options().wgrad_pair != 0) {
-    // ---- CTA-pair form (default for the ungrouped convolutions)
+    // ---- CTA-pair form: opt-in (option "wgrad_pair").  Measured on B200 at config 2 it is SLOWER than the single-CTA
+    // kernel (320->320 k=3: 92 vs 73 us; profiles/r2_wgrad_ncu.md) although it moves 37 % fewer bytes from L2: ncu shows the
+    // tensor pipe busy ~90 % of the time in BOTH kernels at half the K-major MMA rate -- the weight gradient contracts over
+    // positions, so both operands are MN-major in the position-major layout, and that operand form is what bounds it.
     Wgrad2Params q;
     q.T = T; q.M = M; q.C = C; q.taps = taps; q.dil = dil; q.B = B;
     q.kchunks = (T + kBlockK - 1) / kBlockK;

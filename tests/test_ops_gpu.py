@@ -251,13 +251,14 @@ def test_wgrad(dtype, backend, case):
         assert L.get_option("last_wgrad_kernel") == L.get_option("wgrad_pair"), "unexpected weight-gradient kernel"
 
 
-@pytest.mark.parametrize("case", [c for c in WGRAD_CASES if c[6] == 1 and c[0] <= 20] + [(256, 360, 320, 320, 3, 1, 1)])
-def test_wgrad_single_cta_kernel_forced(case):
-    """The single-CTA weight-gradient kernel (still used for the grouped subject GEMM) on the ungrouped shapes the
-    CTA-pair kernel takes by default."""
-    with L.options(wgrad_pair=0):
+@pytest.mark.parametrize("case", [c for c in WGRAD_CASES if c[6] == 1 and c[0] <= 20] +
+                         [(256, 360, 320, 320, 3, 1, 1), (256, 360, 640, 320, 3, 1, 1), (64, 360, 1024, 640, 1, 1, 1)])
+def test_wgrad_cta_pair_kernel_forced(case):
+    """The CTA-pair weight-gradient kernel (cta_group::2, M = (tap, input channel) atoms; opt-in: measured slower than the
+    single-CTA kernel, see profiles/r2_wgrad_ncu.md) on the ungrouped shapes."""
+    with L.options(wgrad_pair=1):
         test_wgrad(torch.bfloat16, "tc", case)
-        assert L.get_option("last_wgrad_kernel") == 0
+        assert L.get_option("last_wgrad_kernel") == 1
 
 
 @pytest.mark.parametrize("splits", [1, 2, 5])
