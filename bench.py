@@ -445,6 +445,37 @@ def run_megb200(args):
         finally:
             accelerate(enc, False)
 
+    # ---- optional per-kernel timeline of ONE replayed step on rank 0 (torch.profiler / CUPTI; never part of a timed region)
+    if args.timeline and use_graph and gstep is not None and graph_ms is not None:
+        # every rank replays (the recording holds collectives); rank 0 does it under the profiler
+        if rank != 0:
+            gstep()
+            torch.cuda.synchronize()
+        else:
+            try:
+                from torch.profiler import ProfilerActivity, profile
+                torch.cuda.synchronize()
+                with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+                    gstep()
+                    torch.cuda.synchronize()
+                evs = [e for e in prof.events() if e.device_type is not None and "cuda" in str(e.device_type).lower()]
+                evs.sort(key=lambda e: e.time_range.start)
+                t0 = evs[0].time_range.start if evs else 0
+                rows = [{"t_us": round(e.time_range.start - t0, 1), "dur_us": round(e.time_range.end - e.time_range.start, 1),
+                         "name": e.name[:90]} for e in evs]
+                agg = {}
+                for r in rows:
+                    a = agg.setdefault(r["name"], [0, 0.0])
+                    a[0] += 1
+                    a[1] += r["dur_us"]
+                span = (max(r["t_us"] + r["dur_us"] for r in rows) if rows else 0)
+                json.dump({"n_gpus": world, "config": cfg.name, "span_us": span,
+                           "by_kernel": sorted(([k, v[0], round(v[1], 1)] for k, v in agg.items()), key=lambda x: -x[2]),
+                           "events": rows}, open(args.timeline, "w"))
+            except Exception as e:
+                print(f"timeline failed: {type(e).__name__}: {e}", file=sys.stderr)
+        barrier()
+
     # ---- optimizer step, reported separately; taken AFTER the timed regions so they see the initial weights
     barrier()
     for _ in range(2):                       # Adam's lazy state init must not land in its own timed region
@@ -633,6 +664,7 @@ def main():
     ap.add_argument("--targets", default="packed", choices=["packed", "dense"],
                     help="target format of the CUDA-graph step and the end-to-end leg: PackedTargets (bf16) or dense f32")
     ap.add_argument("--ncu-step", action="store_true", help="run one step inside cudaProfilerStart/Stop and exit")
+    ap.add_argument("--timeline", default="", help="rank 0 writes a per-kernel timeline of one replayed step to this JSON file")
     args = ap.parse_args()
     if args.max_seconds > 0:
         faulthandler.dump_traceback_later(args.max_seconds, exit=True)
