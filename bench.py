@@ -256,13 +256,19 @@ def run_megb200(args):
     # priming (setup, not warm-up): ~1 s of steps so that clocks, the caching allocator and NCCL channels are in steady
     # state; then EXACTLY max(W, 3) warm-up steps, then the K timed steps.  No optimizer step is taken before the timed
     # regions: the timed weights are the initial weights, so `loss` in the line is comparable with the oracle's.
-    n_prime = 0
+    # The NUMBER of priming steps must be the same on every rank (each step issues collectives): it is derived from the
+    # slowest rank's measured step time, not from each rank's own clock -- a per-rank "run for one second" loop lets
+    # ranks disagree by a step and deadlocks the job in its next collective (seen at 8 GPUs).
     torch.cuda.synchronize()
     t_warm = time.perf_counter()
-    while (time.perf_counter() - t_warm < 1.0 and n_prime < 400) or n_prime < 2:
+    for _ in range(4):
         loss = step(Xd, Yd, subj_h)
-        n_prime += 1
-        if n_prime % 4 == 0:
+    torch.cuda.synchronize()
+    t_step = max_over_ranks((time.perf_counter() - t_warm) / 4)
+    n_prime = 4 + int(min(400, max(2, 1.0 / max(t_step, 1e-4))))
+    for i in range(n_prime - 4):
+        loss = step(Xd, Yd, subj_h)
+        if i % 4 == 3:
             torch.cuda.synchronize()
     barrier()
     n_warm = max(args.warmup, 3)
@@ -548,8 +554,9 @@ def run_megb200(args):
 
     e2e_time(1)
     # three repetitions of the K-step loop each (PCIe traffic makes single runs noisy); the median is reported
-    sync_runs = [e2e_time(0) for _ in range(3)]
-    pipe_runs = [e2e_time(1) for _ in range(3)]
+    reps = 1 if args.no_e2e else 3           # --no-e2e: one repetition of each (profiling runs that only need the field)
+    sync_runs = [e2e_time(0) for _ in range(reps)]
+    pipe_runs = [e2e_time(1) for _ in range(reps)]
     e2e_sync_ms, e2e_ms = statistics.median(sync_runs), statistics.median(pipe_runs)
     e2e_eager_ms, e2e_path, graph_runs = e2e_ms, "eager", None
     if gstep_ok:
@@ -557,8 +564,8 @@ def run_megb200(args):
         # static inputs (device -> device, inside the timed window), then one cudaGraphLaunch
         try:
             e2e_time(1, gstep)
-            graph_runs = [e2e_time(1, gstep) for _ in range(3)]
-            gsync = statistics.median([e2e_time(0, gstep) for _ in range(3)])
+            graph_runs = [e2e_time(1, gstep) for _ in range(reps)]
+            gsync = statistics.median([e2e_time(0, gstep) for _ in range(reps)])
             if statistics.median(graph_runs) < e2e_ms:
                 e2e_ms, e2e_sync_ms, e2e_path = statistics.median(graph_runs), min(gsync, e2e_sync_ms), "cuda_graph"
         except Exception as e:
@@ -661,6 +668,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="samples per CPU-baseline step (0 = the full batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time only the eager launch path")
+    ap.add_argument("--no-e2e", action="store_true", help="one repetition of the end-to-end (host buffers) loops instead of three")
     ap.add_argument("--targets", default="packed", choices=["packed", "dense"],
                     help="target format of the CUDA-graph step and the end-to-end leg: PackedTargets (bf16) or dense f32")
     ap.add_argument("--ncu-step", action="store_true", help="run one step inside cudaProfilerStart/Stop and exit")

@@ -7,8 +7,8 @@ S=gpurun_out/r2_c8_summary_n$N.txt
 : > $S
 bash meg-decoding_b200/csrc/build.sh > gpurun_out/r2_build.log 2>&1 || { echo "BUILD FAILED" | tee -a $S; }
 nvidia-smi topo -m > gpurun_out/r2_c8_topo.txt 2>&1
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 \
-    bench.py --gpus $N --steps 10 --warmup 3 --max-seconds 500 --timeline gpurun_out/r2_timeline_n$N.json \
+timeout ${MAXT:-400} python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 \
+    bench.py --gpus $N --steps 10 --warmup 3 --max-seconds ${MAXS:-300} --no-e2e --timeline gpurun_out/r2_timeline_n$N.json \
     > gpurun_out/r2_c8_bench_n$N.json 2> gpurun_out/r2_c8_bench_n$N.err
 echo "bench n$N rc=$?" | tee -a $S
 python - <<PY | tee -a $S
