@@ -193,7 +193,12 @@ __global__ void group_order_kernel(const int32_t* __restrict__ group, int B, int
   extern __shared__ int cnt[];  // [G + 1]
   for (int i = threadIdx.x; i <= G; i += blockDim.x) cnt[i] = 0;
   __syncthreads();
-  for (int i = threadIdx.x; i < B; i += blockDim.x) atomicAdd(&cnt[group[i] + 1], 1);
+  // indices outside [0, G) are ignored here (the Python boundary raises IndexError for them before any launch, like the
+  // reference's ModuleList; a raw C-ABI caller must not be able to scribble over shared memory)
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    const int g = group[i];
+    if ((unsigned)g < (unsigned)G) atomicAdd(&cnt[g + 1], 1);
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int g = 0; g < G; ++g) cnt[g + 1] += cnt[g];  // cnt[g] = first slot of group g
