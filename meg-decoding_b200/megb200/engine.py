@@ -206,7 +206,13 @@ class EncoderEngine:
         out = ops.empty(B, T, pad8(N), device=dev)
         if epi == "gelu":
             pre = ops.empty(B, T, pad8(N), device=dev)
-            ops.tapgemm(x, cin, Wpk, N, taps, dil, b, res, None, out, epi=epi, Out2=pre)
+            if taps == 1 and res is None:
+                # a 1x1 conv is position-wise: B*T positions as ONE sample fill every 128-row tile (T = 360 alone leaves
+                # the third tile of each sample 81 % full)
+                ops.tapgemm(x.view(1, B * T, x.shape[2]), cin, Wpk, N, 1, 1, b, None, None, out.view(1, B * T, out.shape[2]),
+                            epi=epi, Out2=pre.view(1, B * T, pre.shape[2]))
+            else:
+                ops.tapgemm(x, cin, Wpk, N, taps, dil, b, res, None, out, epi=epi, Out2=pre)
             return out, pre
         ops.tapgemm(x, cin, Wpk, N, taps, dil, b, res, None, out)
         return out
@@ -339,8 +345,12 @@ class EncoderEngine:
         """dX = conv_transpose(dU): same tap-GEMM with the transposed, tap-flipped weight pack `wname`."""
         ops = self.ops
         Wd = self._wd[wname]
-        out = ops.empty(dU.shape[0], dU.shape[1], pad8(cin), device=dU.device)
-        ops.tapgemm(dU, M, Wd, cin, taps, dil, None, res, None, out)
+        B, T = dU.shape[0], dU.shape[1]
+        out = ops.empty(B, T, pad8(cin), device=dU.device)
+        if taps == 1 and res is None:          # position-wise: flatten (see _conv)
+            ops.tapgemm(dU.view(1, B * T, dU.shape[2]), M, Wd, cin, 1, 1, None, None, None, out.view(1, B * T, out.shape[2]))
+        else:
+            ops.tapgemm(dU, M, Wd, cin, taps, dil, None, res, None, out)
         return out
 
     def _bn_gelu_bwd(self, dh, u, st, gamma, n):
