@@ -13,6 +13,7 @@ Math follows SURVEY appendix A (verified against the reference): reference op si
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import torch
@@ -64,6 +65,41 @@ class _ZeroPool:
         return v
 
 
+class _SideStream:
+    """Fork / join of a second CUDA stream for the small fp32 launches that do not depend on each other (the per-step
+    algebra of the pre-multiplied subject block is ~25 latency-bound launches, 0.43 ms when issued back to back).  All
+    tensors are allocated by the caller on the main stream BEFORE the side block; the side block only launches kernels
+    and the main stream joins before anything is freed or consumed, so the caching allocator needs no extra care.  Under
+    CUDA-graph capture the fork/join becomes two parallel branches of the graph.  No-op on CPU (op restatement)."""
+
+    _streams = {}
+
+    def __init__(self, dev):
+        self.on = dev.type == "cuda" and os.environ.get("MEGB200_SIDE_STREAM", "1") != "0"
+        self.dev = dev
+        if self.on:
+            key = (dev.index if dev.index is not None else torch.cuda.current_device())
+            if key not in _SideStream._streams:
+                _SideStream._streams[key] = torch.cuda.Stream(device=dev)
+            self.side = _SideStream._streams[key]
+
+    def __enter__(self):
+        if self.on:
+            self.side.wait_stream(torch.cuda.current_stream(self.dev))
+            self._ctx = torch.cuda.stream(self.side)
+            self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            self._ctx.__exit__(*exc)
+        return False
+
+    def join(self):
+        if self.on:
+            torch.cuda.current_stream(self.dev).wait_stream(self.side)
+
+
 class EncoderEngine:
     """BrainEncoder.forward / backward (models.py:367-383 and the modules it owns)."""
 
@@ -98,6 +134,15 @@ class EncoderEngine:
         out.append(("wf2", P["wf2"], Fo, 2 * D2, 1))
         return out
 
+    def _prepare_packs(self, P, mode, dev):
+        """Allocate (once) the persistent packed-weight buffers of `mode` on the calling stream."""
+        for name, w, N, cin, taps in self._conv_list(P):
+            key = (name, mode, str(dev))
+            buf = self._packed.get(key)
+            shape = (1, pad16(N), taps * pad64(cin)) if mode == 0 else (1, pad16(cin), taps * pad64(N))
+            if buf is None or tuple(buf.shape) != shape or buf.dtype != self.ops.act_dtype:
+                self._packed[key] = self.ops.empty(*shape, device=dev)
+
     def _pack_all(self, P, mode, dev):
         """Pack every conv weight for the forward (mode 0) or the data-gradient (mode 1) tap-GEMMs in one launch."""
         items, bufs = [], {}
@@ -119,25 +164,28 @@ class EncoderEngine:
         D1, D2, Fo, S = self.D1, self.D2, self.F, self.S
         assert C == self.C, f"expected {self.C} sensors, got {C}"                       # models.py:233
         ctx = {"B": B, "T": T, "subj": subj, "mask": mask}
-        self._wf = self._pack_all(P, 0, dev)
         self._zp = _ZeroPool(dev, 10 * 2 * pad64(D2) + 1024)
 
-        # ---- spatial attention weights + subject chain, fp32 (models.py:204-213, 252, 269-272)
-        a = _f32(dev, D1, C)
+        # ---- spatial attention weights + subject chain, fp32 (models.py:204-213, 252, 269-272).  The chain
+        # a -> softmax -> W_c. -> W_s[s]. -> pack is sequential; the launches that do not depend on it (operand packs of
+        # all conv weights and of X, the effective bias) run beside it on a second stream.
+        a, Wt, Wm = _f32(dev, D1, C), _f32(dev, D1, C), _f32(dev, D1, C)
+        M1, Weff, beff = _f32(dev, D1, C), _f32(dev, S, D1, C), _f32(dev, S, D1, 1)
+        Wp = ops.empty(S, pad16(D1), pad64(C), device=dev)
+        Xp = ops.empty(B, T, pad8(C), device=dev)
+        self._prepare_packs(P, 0, dev)
+        side = _SideStream(dev)
+        with side:
+            self._wf = self._pack_all(P, 0, dev)
+            ops.pack_x(X, Xp)
+            ops.matmul(P["Ws"], P["bc"].view(D1, 1), beff)
         ops.matmul(P["z_re"], P["cos"], a)
         ops.matmul(P["z_im"], P["sin"], a, beta=1.0)
-        Wt, Wm = _f32(dev, D1, C), _f32(dev, D1, C)
         ops.sa_softmax(a, mask, Wt, Wm)
-        M1 = _f32(dev, D1, C)
         ops.matmul(P["Wc"], Wm, M1)
-        Weff = _f32(dev, S, D1, C)
         ops.matmul(P["Ws"], M1, Weff)
-        beff = _f32(dev, S, D1, 1)
-        ops.matmul(P["Ws"], P["bc"].view(D1, 1), beff)
-        Wp = ops.empty(S, pad16(D1), pad64(C), device=dev)
         ops.pack_weight(Weff.view(S, D1, C, 1), Wp, 0)
-        Xp = ops.empty(B, T, pad8(C), device=dev)
-        ops.pack_x(X, Xp)
+        side.join()
         H2 = ops.empty(B, T, pad8(D1), device=dev)
         ops.tapgemm(Xp, C, Wp, D1, 1, 1, beff.view(S, D1), None, subj, H2)
         ctx.update(Wt=Wt, Wm=Wm, M1=M1, Xp=Xp, H2=H2)
@@ -316,19 +364,22 @@ class EncoderEngine:
         dWeff = dWeff.view(S, D1, C)
         dbeff = self._zp.take(S, D1)
         ops.colsum(dH2, D1, subj, dbeff)
-        ops.matmul(dWeff, ctx["M1"], dWs, transB=True)
-        ops.matmul(dbeff.view(S, D1, 1), P["bc"].view(1, D1), dWs, beta=1.0)
+        # two independent strands of small fp32 GEMMs: the subject-weight / bias gradients on a second stream, the chain
+        # dM1 -> dWm -> softmax Jacobian -> dz on the main one
         Ws2d = P["Ws"].view(S * D1, D1)
-        dM1 = _f32(dev, D1, C)
+        dM1, dWm, da = _f32(dev, D1, C), _f32(dev, D1, C), _f32(dev, D1, C)
+        side = _SideStream(dev)
+        with side:
+            ops.matmul(dWeff, ctx["M1"], dWs, transB=True)
+            ops.matmul(dbeff.view(S, D1, 1), P["bc"].view(1, D1), dWs, beta=1.0)
+            ops.matmul(Ws2d, dbeff.view(S * D1, 1), dbc, transA=True)
         ops.matmul(Ws2d, dWeff.view(S * D1, C), dM1, transA=True)
-        ops.matmul(Ws2d, dbeff.view(S * D1, 1), dbc, transA=True)
-        ops.matmul(dM1, ctx["Wm"], dWc, transB=True)
-        dWm = _f32(dev, D1, C)
         ops.matmul(P["Wc"], dM1, dWm, transA=True)
-        da = _f32(dev, D1, C)
         ops.sa_softmax_bwd(ctx["Wt"], dWm, ctx["mask"], da)
         ops.matmul(da, P["cos"], dzr, transB=True)
         ops.matmul(da, P["sin"], dzi, transB=True)
+        ops.matmul(dM1, ctx["Wm"], dWc, transB=True)
+        side.join()
         G.update(Ws=dWs, Wc=dWc, bc=dbc.view(D1), z_re=dzr, z_im=dzi)
         if not zp.spilled:
             G["_flat"] = zp.buf[:grad_end]
