@@ -70,12 +70,16 @@ class _SideStream:
     algebra of the pre-multiplied subject block is ~25 latency-bound launches, 0.43 ms when issued back to back).  All
     tensors are allocated by the caller on the main stream BEFORE the side block; the side block only launches kernels
     and the main stream joins before anything is freed or consumed, so the caching allocator needs no extra care.  Under
-    CUDA-graph capture the fork/join becomes two parallel branches of the graph.  No-op on CPU (op restatement)."""
+    CUDA-graph capture the fork/join becomes two parallel branches of the graph.  No-op on CPU (op restatement).
+
+    Opt-in (MEGB200_SIDE_STREAM=1).  Measured at config 2: 7.242 vs 7.257 ms per replayed step -- the sequential chain, not
+    the launches beside it, is the critical path -- while eager launches get SLOWER (8.9 vs 7.9 ms: the stream switches
+    cost host time in a host-bound loop), so the default is one stream."""
 
     _streams = {}
 
     def __init__(self, dev):
-        self.on = dev.type == "cuda" and os.environ.get("MEGB200_SIDE_STREAM", "1") != "0"
+        self.on = dev.type == "cuda" and os.environ.get("MEGB200_SIDE_STREAM", "0") == "1"
         self.dev = dev
         if self.on:
             key = (dev.index if dev.index is not None else torch.cuda.current_device())
