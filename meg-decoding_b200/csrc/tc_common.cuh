@@ -258,6 +258,23 @@ __host__ __device__ inline uint32_t make_idesc_m(int m, int n, int a_mn_major, i
   return d;
 }
 
+// Single-thread roles (TMA producer, MMA issuer).  `if (lane == 0)` makes nvcc treat every value inside the role's loop as
+// per-thread: each UTMALDG / UTCHMMA (which take their operands from UNIFORM registers) is then wrapped in a
+// "for every active thread: ELECT, 4-5 x R2UR.BROADCAST, issue, BRA.U.ANY" loop -- ~160 cycles per issued MMA, which is
+// exactly what the MMA loops of round 1 measured (9 600 cycles per 60-MMA tile), twice the cost of the MMA itself.
+// With a provably warp-uniform warp index (a shuffle result) and `elect.sync` choosing the lane, the compiler knows one
+// thread is active and keeps descriptors / coordinates in uniform registers.
+__device__ __forceinline__ int warp_idx_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

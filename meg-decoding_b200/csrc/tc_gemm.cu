@@ -199,7 +199,7 @@ __device__ __forceinline__ void tap_epilogue_tma(const TapGemmParams& p, const T
   for (int jj0 = 0; jj0 < iters; jj0 += cap_iters) {
     if (jj0 > 0 || kPersistent) {
       // the staging area is reused: the previous stores must have finished reading it
-      if ((etid & 31) == 0) tma_store_wait_read();
+      if (elect_one()) tma_store_wait_read();
       dbg_phase(0);
       named_bar_sync(2, kEpiThreads);
       dbg_phase(1);
@@ -282,7 +282,7 @@ __device__ __forceinline__ void tap_epilogue_tma(const TapGemmParams& p, const T
     if (!kPersistent && p.dbg != nullptr && etid == 0 && jj0 == 0) p.dbg[16 * blockIdx.x + 5] = clock64();
     // the stores are issued BEFORE the statistics pass: both only read the staging area, so the TMA engine drains it
     // while the warps reduce it
-    if ((etid & 31) == 0 && tile_valid) {
+    if (tile_valid && elect_one()) {
       // one elected lane per warp issues the stores of "its" slices (a single issuing thread spent ~380 cycles per
       // store, 1900 per tile); the bulk group is per thread, so the same lanes wait for it before the area is reused
       const int nslots = (jj1 - jj0) * kHalves;
@@ -352,7 +352,7 @@ __device__ __forceinline__ void tap_epilogue_tma(const TapGemmParams& p, const T
     dbg_phase(5);
     if (!kPersistent && p.dbg != nullptr && etid == 0 && jj0 == 0) p.dbg[16 * blockIdx.x + 6] = clock64();
   }
-  if (!kPersistent && (etid & 31) == 0) tma_store_wait_read();   // shared memory must stay alive until the stores have read it
+  if (!kPersistent && elect_one()) tma_store_wait_read();   // shared memory must stay alive until the stores have read it
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -362,7 +362,7 @@ tc_tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint8_t* smem = align1024(smem_raw);
   Header* hdr = reinterpret_cast<Header*>(smem);
   float* sbias = reinterpret_cast<float*>(smem + 512);  // NT <= 128 floats fit in the header; larger go below
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
   const uint32_t a_bytes = kTileM * 128, b_bytes = (uint32_t)p.NT * 128;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   uint8_t* ring = smem + kHeaderBytes;
@@ -406,7 +406,7 @@ tc_tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t tmem_base = hdr->tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       for (int it = 0; it < num_k; ++it) {
         const int s = it % p.stages;
         mbar_wait(smem_u32(&hdr->empty[s]), ((it / p.stages) & 1) ^ 1);
@@ -426,7 +426,7 @@ tc_tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       for (int it = 0; it < num_k; ++it) {
         const int s = it % p.stages;
         mbar_wait(smem_u32(&hdr->full[s]), (it / p.stages) & 1);
@@ -521,7 +521,7 @@ tc_tapgemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   uint8_t* smem = align1024(smem_raw);
   HeaderH* hdr = reinterpret_cast<HeaderH*>(smem);
   float* sbias = reinterpret_cast<float*>(smem + 512);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
   const uint32_t a_slot = ((uint32_t)a_rows * 128u + 1023u) & ~1023u;
   const uint32_t b_bytes = (uint32_t)p.NT * 128;
   uint8_t* ringA = smem + kHeaderBytes;
@@ -563,7 +563,7 @@ tc_tapgemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const uint32_t tmem_base = hdr->tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int itb = 0;
       for (int kc = 0; kc < p.kchunks; ++kc) {
         const int sa = kc % stagesA;
@@ -588,7 +588,7 @@ tc_tapgemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       int itb = 0;
       for (int kc = 0; kc < p.kchunks; ++kc) {
         const int sa = kc % stagesA;
@@ -669,7 +669,7 @@ tc_tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   Header2* hdr = reinterpret_cast<Header2*>(smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int half = p.NT / 2;                                  // weight rows staged by each CTA
@@ -709,7 +709,7 @@ tc_tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const uint32_t tmem_base = hdr->tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int it = 0;
       long long dbg_prod_wait = 0;
       for (int item = cluster_id; item < num_items; item += num_clusters) {
@@ -743,7 +743,7 @@ tc_tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       if (p.dbg) p.dbg[16 * blockIdx.x + 0] = dbg_prod_wait;
     }
   } else if (warp == 1) {
-    if (leader && lane == 0) {
+    if (leader && elect_one()) {
       int it = 0, tile = 0;
       long long dbg_full_wait = 0, dbg_acc_wait = 0;
       const long long dbg_t0 = p.dbg ? clock64() : 0;
@@ -844,7 +844,7 @@ tc_tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       p.dbg[16 * blockIdx.x + 5] = dbg_epi_work;
     }
   }
-  if (p.tma_epi && warp >= 2 && lane == 0) tma_store_wait_read();
+  if (p.tma_epi && warp >= 2 && elect_one()) tma_store_wait_read();
   tc_fence_before();
   cluster_sync_all();                              // nobody leaves while the peer may still touch its smem / TMEM
   if (warp == 1) {
@@ -874,7 +874,7 @@ tc_tapgemm2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   Header2H* hdr = reinterpret_cast<Header2H*>(smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int half = p.NT / 2;                                  // weight rows staged by each CTA
@@ -915,7 +915,7 @@ tc_tapgemm2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t tmem_base = hdr->tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int ita = 0;
       long long dbg_prod_wait = 0;
       for (int item = cluster_id; item < num_items; item += num_clusters) {
@@ -940,7 +940,7 @@ tc_tapgemm2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (p.dbg) p.dbg[16 * blockIdx.x + 0] = dbg_prod_wait;
     }
   } else if (warp == 1) {
-    if (leader && lane == 0) {
+    if (leader && elect_one()) {
       int ita = 0, tile = 0;
       long long dbg_full_wait = 0, dbg_acc_wait = 0;
       const long long dbg_t0 = p.dbg ? clock64() : 0;
@@ -1035,7 +1035,7 @@ tc_tapgemm2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   }
-  if (p.tma_epi && warp >= 2 && lane == 0) tma_store_wait_read();
+  if (p.tma_epi && warp >= 2 && elect_one()) tma_store_wait_read();
   tc_fence_before();
   cluster_sync_all();                              // nobody leaves while the peer may still touch its smem / TMEM
   if (warp == 1) {
@@ -1061,7 +1061,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   Header* hdr = reinterpret_cast<Header*>(smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
   const uint32_t atom_bytes = kBlockK * 128;                // 64 k-rows x 128 B
   const uint32_t a_bytes = 2 * atom_bytes;                  // 128 m channels = 2 atoms
   const uint32_t b_bytes = (uint32_t)(p.ctile / 64) * atom_bytes;
@@ -1097,7 +1097,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__
   const uint32_t tmem_base = hdr->tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int it = 0;
       for (int si = s0; si < s1; ++si) {
         const int b = p.order ? p.order[si] : si;
@@ -1115,7 +1115,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       int it = 0, flushes = 0;
       int cur = (p.group && s0 < s1) ? p.group[p.order ? p.order[s0] : s0] : 0;
       bool fresh = true;
@@ -1242,7 +1242,7 @@ tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   HeaderW2* hdr = reinterpret_cast<HeaderW2*>(smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const uint32_t atom_bytes = kBlockK * 128;                // 64 positions x 64 channels of bf16
@@ -1283,7 +1283,7 @@ tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
   const int total_it = (s1 - s0) * p.kchunks;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       // this CTA's two M atoms: (tap, 64 input channels) each; atoms past the end read a sample index out of range (zero fill)
       int a_tap[2], a_c0[2];
       bool a_ok[2];
@@ -1318,7 +1318,7 @@ tc_wgrad2_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (leader && lane == 0) {
+    if (leader && elect_one()) {
       for (int it = 0; it < total_it; ++it) {
         const int s = it % p.stages;
         mbar_wait(smem_u32(&hdr->full[s]), (it / p.stages) & 1);
@@ -1422,7 +1422,7 @@ tc_clip_logits_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   Header* hdr = reinterpret_cast<Header*>(smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
   const uint32_t a_bytes = kTileM * 128, b_bytes = (uint32_t)p.NT * 128;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   uint8_t* ring = smem + kHeaderBytes;
@@ -1453,7 +1453,7 @@ tc_clip_logits_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_cons
 
   if (num_k > 0) {
     if (warp == 0) {
-      if (lane == 0) {
+      if (elect_one()) {
         for (int it = 0; it < num_k; ++it) {
           const int s = it % p.stages;
           mbar_wait(smem_u32(&hdr->empty[s]), ((it / p.stages) & 1) ^ 1);
@@ -1465,7 +1465,7 @@ tc_clip_logits_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_cons
         }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
+      if (elect_one()) {
         for (int it = 0; it < num_k; ++it) {
           const int s = it % p.stages;
           mbar_wait(smem_u32(&hdr->full[s]), (it / p.stages) & 1);
@@ -1526,7 +1526,7 @@ tc_clip_dz_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   Header* hdr = reinterpret_cast<Header*>(smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
   const uint32_t atom_bytes = kBlockK * 128;
   const uint32_t a_bytes = kTileM * 128;
   const uint32_t b_bytes = (uint32_t)(p.NT / 64) * atom_bytes;
@@ -1556,7 +1556,7 @@ tc_clip_dz_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constant
   const uint32_t tmem_base = hdr->tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       for (int it = 0; it < p.kchunks; ++it) {
         const int s = it % p.stages;
         mbar_wait(smem_u32(&hdr->empty[s]), ((it / p.stages) & 1) ^ 1);
@@ -1570,7 +1570,7 @@ tc_clip_dz_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       for (int it = 0; it < p.kchunks; ++it) {
         const int s = it % p.stages;
         mbar_wait(smem_u32(&hdr->full[s]), (it / p.stages) & 1);
@@ -1643,7 +1643,7 @@ tc_clip_dz_small_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_co
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   DzSmallHeader* hdr = reinterpret_cast<DzSmallHeader*>(smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
   constexpr int kNT = 128;
   const uint32_t atom_bytes = kBlockK * 128;                // 64 k-rows x 128 B (= 64 d columns)
   const uint32_t a_bytes = kTileM * 128;                    // coef tile: 128 j rows x 64 k
@@ -1679,7 +1679,7 @@ tc_clip_dz_small_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_co
   const uint32_t tmem_base = hdr->tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t zf = smem_u32(&hdr->zfull);
       mbar_arrive_expect_tx(zf, 2 * zslice);
       tma_load_2d(smem_u32(zt), &tmZ, (int)d0, j0, zf);
@@ -1696,7 +1696,7 @@ tc_clip_dz_small_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_co
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       for (int it = 0; it < p.kchunks; ++it) {
         const int s = it % p.stages;
         mbar_wait(smem_u32(&hdr->full[s]), (it / p.stages) & 1);
@@ -1744,7 +1744,7 @@ tc_clip_dz_small_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_co
     tc_fence_before();
     fence_proxy_async();
     named_bar_sync(1, 128);
-    if (threadIdx.x == 64) {
+    if (warp == 2 && elect_one()) {
       tma_store_2d(&tmDZ, smem_u32(zt), (int)d0, j0);
       tma_store_2d(&tmDZ, smem_u32(zt) + zslice, (int)d0 + 64, j0);
       tma_store_commit();
@@ -1796,7 +1796,7 @@ tc_clip_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   Header* hdr = reinterpret_cast<Header*>(smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
   const uint32_t a_bytes = kTileM * 128, b_bytes = kFusedNT * 128;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   uint8_t* ring = smem + kHeaderBytes;
@@ -1828,7 +1828,7 @@ tc_clip_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
   const uint32_t tmem_base = hdr->tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       for (int it = 0; it < p.kchunks; ++it) {
         const int s = it % p.stages;
         mbar_wait(smem_u32(&hdr->empty[s]), ((it / p.stages) & 1) ^ 1);
@@ -1840,7 +1840,7 @@ tc_clip_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       for (int it = 0; it < p.kchunks; ++it) {
         const int s = it % p.stages;
         mbar_wait(smem_u32(&hdr->full[s]), (it / p.stages) & 1);
@@ -1901,7 +1901,7 @@ tc_clip_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
         for (int e = 0; e < 32; ++e) {               // column-wise over this warp's 32 rows
           const float cm = warp_max(v[e]);
           const float cs = warp_sum(v[e] > -INFINITY ? __expf(v[e] - cm) : 0.f);
-          if (lane == 0) {
+          if (elect_one()) {
             scm[q * kFusedNT + 32 * g + e] = cm;
             scs[q * kFusedNT + 32 * g + e] = cs;
           }
