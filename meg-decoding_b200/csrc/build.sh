@@ -7,7 +7,12 @@ obj="${here}/../../build/obj"
 mkdir -p "${obj}"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall
-       --expt-relaxed-constexpr -Xptxas -v)
+       --expt-relaxed-constexpr -Xptxas -v ${MEGB200_EXTRA_NVCC_FLAGS:-})
+# developer builds (e.g. MEGB200_EXTRA_NVCC_FLAGS=-DMEGB200_DEBUG for the per-phase clock64 accounting) go to their own
+# object directory / library so that they can never be mistaken for the product library
+if [[ -n "${MEGB200_EXTRA_NVCC_FLAGS:-}" ]]; then
+  obj="${obj}_dev"; out="${MEGB200_DEV_OUT:-/tmp/libmegb200_dev.so}"; mkdir -p "${obj}"
+fi
 pids=()
 for f in api elementwise simt clip tc_gemm; do
   src="${here}/${f}.cu"

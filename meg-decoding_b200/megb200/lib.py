@@ -10,6 +10,9 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmegb200.so")
+# developer builds only (csrc/build.sh with MEGB200_EXTRA_NVCC_FLAGS writes /tmp/libmegb200_dev.so): never set in production
+if os.environ.get("MEGB200_DEV_LIB"):
+    LIB_PATH = os.environ["MEGB200_DEV_LIB"]
 
 F32, BF16 = 0, 1
 EPI_STORE, EPI_STORE_F32, EPI_GELU, EPI_GLU = 0, 1, 2, 3
