@@ -36,7 +36,7 @@ __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
 
 // ================================================================================================ tap GEMM
 struct TapGemmParams {
-  int T, N, Cos, Crs, Co2s, taps, dil, Kp, kchunks, tiles_per_sample, ntiles, NT, n_last, stages, epi, tma_epi;
+  int T, N, Cos, Crs, Co2s, taps, dil, Kp, kchunks, tiles_per_sample, ntiles, NT, n_last, stages, epi, tma_epi, prefetch;
   uint32_t stg_bytes;   // CTA-pair kernel: dedicated staging area of the TMA-store epilogue
   float* stats;         // optional BatchNorm statistics sums[2][N] (sum, sum of squares) fused into the f32 epilogue
   long long* dbg;       // MEGB200_DEBUG_TIMING: per-CTA clock64 stamps {start, first data, accumulator ready, end}
@@ -722,6 +722,16 @@ tc_tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // [half a-channels | their half gate channels], i.e. the leader stages the a rows and the peer the gates
         const int wN = (n_tile == p.ntiles - 1) ? p.n_last : p.NT;
         const int wrow = glu ? (n_tile * half + (rank ? Ch : 0)) : (n_tile * p.NT + (int)rank * (wN / 2));
+        if (p.prefetch) {
+          const int nitem = item + num_clusters;
+          const int nm = (nitem / p.ntiles) * 2 + (int)rank;
+          if (nitem < num_items && nm < total_m_tiles && nm != m_tile) {
+            const int nb = nm / p.tiles_per_sample, nt0 = (nm % p.tiles_per_sample) * kTileM;
+            for (int tap = 0; tap < p.taps; ++tap)
+              for (int kc = 0; kc < p.kchunks; ++kc)
+                tma_prefetch_3d(&tmA, kc * kBlockK, nt0 + (tap - p.taps / 2) * p.dil, nb);
+          }
+        }
         // a stage holds kSub consecutive 64-wide k chunks: one barrier round trip and one commit per 8 MMAs (the single
         // MMA-issuing thread of the pair is issue-latency bound, measured ~630 cycles per 4-MMA stage)
         for (int kit = 0; kit < num_k; kit += kSub, ++it) {
@@ -924,6 +934,15 @@ tc_tapgemm2h_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int b = m_tile < total_m_tiles ? m_tile / p.tiles_per_sample : 0x3fffffff;
         const int t0 = (m_tile % p.tiles_per_sample) * kTileM;
         const int wrow = glu ? (n_tile * half + (rank ? Ch : 0)) : (n_tile * p.NT + (int)rank * half);
+        if (p.prefetch) {
+          // activation boxes of this cluster's next tile -> L2 (its weights are shared by all tiles and stay there)
+          const int nitem = item + num_clusters;
+          const int nm = (nitem / p.ntiles) * 2 + (int)rank;
+          if (nitem < num_items && nm < total_m_tiles && nm != m_tile) {
+            const int nb = nm / p.tiles_per_sample, nt0 = (nm % p.tiles_per_sample) * kTileM;
+            for (int kc = 0; kc < p.kchunks; ++kc) tma_prefetch_3d(&tmA, kc * kBlockK, nt0 - (p.taps / 2) * p.dil, nb);
+          }
+        }
         for (int kc = 0; kc < p.kchunks; ++kc, ++ita) {
           const int sa = ita % stagesA;
           const long long w0 = p.dbg ? clock64() : 0;
@@ -2038,6 +2057,7 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
   p.kchunks = (Ca + kBlockK - 1) / kBlockK;
   p.tiles_per_sample = (T + kTileM - 1) / kTileM;
   p.tma_epi = options().tapgemm_direct_epi ? 0 : 1;
+  p.prefetch = options().tapgemm_l2_prefetch;
   p.stg_bytes = 0;
   if (glu) {
     const int Ch = N / 2;
