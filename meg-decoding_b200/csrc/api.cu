@@ -33,7 +33,7 @@ Options& options() {
       (int)env_ll("MEGB200_TAPGEMM_HALO", 0),
       getenv("MEGB200_TAPGEMM_RAGGED_N") != nullptr ? 1 : 0,
       getenv("MEGB200_TAPGEMM_DIRECT_EPI") != nullptr ? 1 : 0,
-      (int)env_ll("MEGB200_TAPGEMM_L2_PREFETCH", 1),
+      (int)env_ll("MEGB200_TAPGEMM_L2_PREFETCH", 0),
       getenv("MEGB200_CLIP_DZ_LARGE") != nullptr ? 1 : 0,
       getenv("MEGB200_ROWLOOP_DIRECT") != nullptr ? 1 : 0,
       (int)env_ll("MEGB200_WGRAD_SPLITS", 0),

@@ -81,10 +81,10 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, 
       : "memory");
 }
 
-// L2 prefetch of a tensor-map box (a hint: no shared memory, no barrier).  The persistent tap-GEMM producers issue it for
-// the activation boxes of their NEXT tile, so that the real loads a few thousand cycles later are L2 hits instead of
-// DRAM round trips (the per-phase accounting showed the MMA thread waiting for data 27-57 % of its loop with a ring of
-// only 2-4 stages -- shared memory, not issue rate, limits the ring depth).
+// L2 prefetch of a tensor-map box (a hint: no shared memory, no barrier).  Opt-in experiment ("tapgemm_l2_prefetch"): the
+// persistent tap-GEMM producers issue it for the activation boxes of their NEXT tile.  The per-phase accounting shows the
+// MMA thread waiting for data 27-57 % of its loop with a ring of 2-4 stages; measured, the prefetch does not help
+// (6.77 vs 6.74 ms per step, tap-GEMM 881 vs 910 TFLOP/s): the wait is L2->SM bandwidth, not DRAM latency.
 __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* m, int x, int y, int z) {
   asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(x), "r"(y), "r"(z)
