@@ -34,6 +34,7 @@ Options& options() {
       getenv("MEGB200_TAPGEMM_RAGGED_N") != nullptr ? 1 : 0,
       getenv("MEGB200_TAPGEMM_DIRECT_EPI") != nullptr ? 1 : 0,
       (int)env_ll("MEGB200_TAPGEMM_L2_PREFETCH", 0),
+      (int)env_ll("MEGB200_TAPGEMM_KSUB", 0),
       getenv("MEGB200_CLIP_DZ_LARGE") != nullptr ? 1 : 0,
       getenv("MEGB200_ROWLOOP_DIRECT") != nullptr ? 1 : 0,
       (int)env_ll("MEGB200_WGRAD_SPLITS", 0),
@@ -54,6 +55,7 @@ static const OptionEntry kOptionTable[] = {
     {"tapgemm_ragged_n", 1, offsetof(Options, tapgemm_ragged_n)},
     {"tapgemm_direct_epi", 1, offsetof(Options, tapgemm_direct_epi)},
     {"tapgemm_l2_prefetch", 1, offsetof(Options, tapgemm_l2_prefetch)},
+    {"tapgemm_ksub", 1, offsetof(Options, tapgemm_ksub)},
     {"clip_dz_large", 1, offsetof(Options, clip_dz_large)},
     {"rowloop_direct", 1, offsetof(Options, rowloop_direct)},
     {"wgrad_splits", 1, offsetof(Options, wgrad_splits)},

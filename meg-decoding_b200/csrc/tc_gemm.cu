@@ -36,7 +36,7 @@ __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
 
 // ================================================================================================ tap GEMM
 struct TapGemmParams {
-  int T, N, Cos, Crs, Co2s, taps, dil, Kp, kchunks, tiles_per_sample, ntiles, NT, n_last, stages, epi, tma_epi, prefetch;
+  int T, N, Cos, Crs, Co2s, taps, dil, Kp, kchunks, tiles_per_sample, ntiles, NT, n_last, stages, epi, tma_epi, prefetch, ksub;
   uint32_t stg_bytes;   // CTA-pair kernel: dedicated staging area of the TMA-store epilogue
   float* stats;         // optional BatchNorm statistics sums[2][N] (sum, sum of squares) fused into the f32 epilogue
   long long* dbg;       // MEGB200_DEBUG_TIMING: per-CTA clock64 stamps {start, first data, accumulator ready, end}
@@ -673,7 +673,7 @@ tc_tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int half = p.NT / 2;                                  // weight rows staged by each CTA
-  constexpr int kSub = 2;                                     // 64-wide k chunks per pipeline stage
+  const int kSub = p.ksub;                                    // 64-wide k chunks per pipeline stage (2, or 1 for a deeper ring)
   const uint32_t a_bytes = kTileM * 128, b_bytes = (uint32_t)half * 128;
   const uint32_t sub_bytes = a_bytes + b_bytes;
   const uint32_t stage_bytes = kSub * sub_bytes;
@@ -2058,6 +2058,7 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
   p.tiles_per_sample = (T + kTileM - 1) / kTileM;
   p.tma_epi = options().tapgemm_direct_epi ? 0 : 1;
   p.prefetch = options().tapgemm_l2_prefetch;
+  p.ksub = 2;
   p.stg_bytes = 0;
   if (glu) {
     const int Ch = N / 2;
@@ -2252,9 +2253,17 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
       if (p.dbg != nullptr) report_pair_timing("pair+halo");
       return 0;
     }
-    p.stages = grow_staging(2 * stage2, 2 * p.NT * 4 + 2 * Cos * 4, 8);   // two k chunks per stage
+    // two k chunks per stage (one barrier round trip per 8 MMAs) while the ring is still at least four deep; otherwise one
+    // chunk per stage: the per-phase accounting showed the MMA thread of the 1x1 head convs waiting for data 32-57 % of its
+    // loop behind a two-stage ring, and single-thread issue is cheap since the roles are elected
+    p.ksub = 2;
+    p.stages = grow_staging(2 * stage2, 2 * p.NT * 4 + 2 * Cos * 4, 8);
+    if (p.stages < 4 && options().tapgemm_ksub != 2) {
+      p.ksub = 1;
+      p.stages = grow_staging(stage2, 2 * p.NT * 4 + 2 * Cos * 4, 8);
+    }
     MEGB_CHECK_ARG(p.stages >= 2, "tc_tapgemm(pair): tile too large");
-    const size_t smem2 = 1024 + kHeaderBytes + (size_t)p.stages * 2 * stage2 + p.stg_bytes + 2 * p.NT * 4 + 2 * Cos * 4;
+    const size_t smem2 = 1024 + kHeaderBytes + (size_t)p.stages * p.ksub * stage2 + p.stg_bytes + 2 * p.NT * 4 + 2 * Cos * 4;
     int rc = set_smem(tc_tapgemm2_kernel, smem2);
     if (rc) return rc;
     cfg.dynamicSmemBytes = smem2;
