@@ -51,7 +51,7 @@ long long megb200_launch_count(void);
  * several hand-written forms of one contraction by problem size (e.g. the persistent CTA-pair tap-GEMM from 2 x #SM work
  * items up); these switches let a caller -- the test-suite -- force each form on any shape.  Names:
  *   "tapgemm_pair_min_items" (-1 = default), "tapgemm_force_1cta", "tapgemm_pair_halo", "tapgemm_halo",
- *   "tapgemm_l2_prefetch" (1 = next tile's activation boxes are prefetched into L2; default 0: measured no gain), "tapgemm_ksub" (2 = two k chunks per stage always; 0 = automatic), "tapgemm_ragged_n", "tapgemm_direct_epi", "clip_dz_large", "rowloop_direct", "wgrad_splits" (0 = automatic),
+ *   "tapgemm_l2_prefetch" (1 = next tile's activation boxes are prefetched into L2; default 0: measured no gain), "tapgemm_ksub" (1 = one k chunk per pipeline stage in the plain pair kernel; default two), "tapgemm_ragged_n", "tapgemm_direct_epi", "clip_dz_large", "rowloop_direct", "wgrad_splits" (0 = automatic),
  *   "wgrad_pair" (1 = CTA-pair weight-gradient kernel for ungrouped problems; default 0 = single-CTA kernel),
  *   "clip_dz_jt" (0 = automatic: brain-row tiles per CTA of the large-K dZ kernel),
  *   "clip_fused" (policy of the host-side loss: -1 auto, 0 never, 1 whenever supported).

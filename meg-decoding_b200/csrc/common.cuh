@@ -54,7 +54,7 @@ struct Options {
   int tapgemm_ragged_n;               // 1: 256-wide N tiles + narrower tail
   int tapgemm_direct_epi;             // 1: per-thread global stores instead of the TMA-store epilogue
   int tapgemm_l2_prefetch;            // 1: the pair tap-GEMM producers prefetch their next tile's activations into L2 (default 0)
-  int tapgemm_ksub;                   // 2: always two k chunks per stage in the plain pair kernel (default 0: automatic)
+  int tapgemm_ksub;                   // 1: one k chunk per stage in the plain pair kernel (deeper ring; default: two)
   int clip_dz_large;                  // 1: always the large-K dZ kernel (default: small-K form when By <= 512)
   int rowloop_direct;                 // 1: direct-load streaming kernels instead of the bulk-copy staged ones
   int wgrad_splits;                   // > 0: force the split count of the weight-gradient GEMM

@@ -2253,12 +2253,12 @@ int tc_tapgemm(const void* A, int B, int T, int Ca, int Cas, const void* W, int 
       if (p.dbg != nullptr) report_pair_timing("pair+halo");
       return 0;
     }
-    // two k chunks per stage (one barrier round trip per 8 MMAs) while the ring is still at least four deep; otherwise one
-    // chunk per stage: the per-phase accounting showed the MMA thread of the 1x1 head convs waiting for data 32-57 % of its
-    // loop behind a two-stage ring, and single-thread issue is cheap since the roles are elected
+    // two k chunks per stage (one barrier round trip per 8 MMAs).  One chunk per stage doubles the ring depth (the MMA
+    // thread of the 1x1 head convs waits for data 32-57 % of its loop behind a two-stage ring) but measured slower:
+    // 6.96 vs 6.90 ms per step -- opt-in ("tapgemm_ksub" = 1)
     p.ksub = 2;
     p.stages = grow_staging(2 * stage2, 2 * p.NT * 4 + 2 * Cos * 4, 8);
-    if (p.stages < 4 && options().tapgemm_ksub != 2) {
+    if (options().tapgemm_ksub == 1) {
       p.ksub = 1;
       p.stages = grow_staging(stage2, 2 * p.NT * 4 + 2 * Cos * 4, 8);
     }

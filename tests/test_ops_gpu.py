@@ -182,7 +182,7 @@ def test_tapgemm_fused_epilogues(dtype, backend, case):
 TAPGEMM_VARIANTS = {
     "pair_halo": dict(tapgemm_pair_min_items=1),                              # tc_tapgemm2h_kernel for k > 1
     "pair_plain": dict(tapgemm_pair_min_items=1, tapgemm_pair_halo=0),        # tc_tapgemm2_kernel for every k
-    "pair_plain_ksub2": dict(tapgemm_pair_min_items=1, tapgemm_pair_halo=0, tapgemm_ksub=2),   # two k chunks per stage
+    "pair_plain_ksub1": dict(tapgemm_pair_min_items=1, tapgemm_pair_halo=0, tapgemm_ksub=1),   # one k chunk per stage
     "single": dict(tapgemm_force_1cta=1),                                     # tc_tapgemm_kernel even above the threshold
     "single_halo": dict(tapgemm_force_1cta=1, tapgemm_halo=1),                # tc_tapgemm_halo_kernel
     "single_direct_epi": dict(tapgemm_force_1cta=1, tapgemm_direct_epi=1),    # per-thread global stores
