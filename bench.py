@@ -597,6 +597,45 @@ def run_megb200(args):
                       "X f32 (B,C,T) + Y f32 (B,F,T) + int32 subject indices (the reference collator's tensors)"),
            "h2d_bytes_per_step_f32_dense_targets": Xh.numel() * 4 + Yh.numel() * 4 + subj_h.numel() * 4}
 
+    # ---- optional extra leg (--e2e-resident): the label side of the dataset resident in HBM (megb200.data.DeviceTargetStore:
+    # the precomputed targets of every segment, packed), a batch's targets are a row gather by segment id; per step the
+    # host sends the brain data, the segment ids and the subject indices.  Reported as e2e["resident_targets"], never as e2e.value.
+    if args.e2e_resident and packed_ok and gstep_ok:
+        try:
+            from megb200.data import DeviceTargetStore
+            nseg = 4 * B
+            store = DeviceTargetStore(PackedTargets(Ypd.rows.repeat(4, 1), Ypd.sumsq.repeat(4), Yph.feature_shape), dev)
+            ids_h = [torch.randint(0, nseg, (B,), generator=torch.Generator().manual_seed(100 + i)).pin_memory()
+                     for i in range(8)]
+            pre2 = DevicePrefetcher(iter(()), dev, keep_on_host=(2,))
+
+            def batches2(n):
+                for i in range(n):
+                    yield (Xh, ids_h[i % len(ids_h)], subj_h)
+
+            def run_resident():
+                n = PRIME + args.steps + PRIME
+                reader = AsyncScalarReader(dev, lag=1)
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                barrier()
+                for i, (X, ids, subj) in enumerate(pre2.reset(batches2(n))):
+                    if i == PRIME:
+                        g0.record()
+                    reader.push(gstep(X, store.gather(ids), subj))
+                    if i == PRIME + args.steps - 1:
+                        g1.record()
+                reader.drain()
+                barrier()
+                return max_over_ranks(g0.elapsed_time(g1) / args.steps)
+            run_resident()
+            r_ms = statistics.median([run_resident() for _ in range(reps)])
+            e2e["resident_targets"] = {"ms_per_step": r_ms, "value": B * world / (r_ms / 1e3), "unit": UNIT,
+                                       "h2d_bytes_per_step": Xh.numel() * 4 + B * 8 + subj_h.numel() * 4,
+                                       "store": f"{nseg} segments x {Ypd.rows.shape[1] * 2} B packed bf16 in HBM"}
+            del store
+        except Exception as e:
+            e2e["resident_targets"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+
     flops_step = B * synth.encoder_flops_per_sample(cfg) + synth.clip_flops(cfg, B, B * world)
     line = {
         "metric": METRIC, "value": B * world / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -672,6 +711,8 @@ def main():
     ap.add_argument("--targets", default="packed", choices=["packed", "dense"],
                     help="target format of the CUDA-graph step and the end-to-end leg: PackedTargets (bf16) or dense f32")
     ap.add_argument("--ncu-step", action="store_true", help="run one step inside cudaProfilerStart/Stop and exit")
+    ap.add_argument("--e2e-resident", action="store_true",
+                    help="extra end-to-end leg with the targets resident in HBM (DeviceTargetStore); reported beside e2e")
     ap.add_argument("--timeline", default="", help="rank 0 writes a per-kernel timeline of one replayed step to this JSON file")
     args = ap.parse_args()
     if args.max_seconds > 0:

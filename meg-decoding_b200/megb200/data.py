@@ -61,6 +61,42 @@ class PackedTargets:
         return self
 
 
+class DeviceTargetStore:
+    """The dataset's precomputed targets resident in HBM, in the form the loss contracts (``PackedTargets``: position-major
+    rows in the activation dtype + f32 norms): the companion of ``DeviceSegmentStore`` for the label side.  The reference
+    keeps ``self.Y`` (one (F, T) wav2vec2 block per speech segment, gwilliams2022.py:415-422) on the host and collates it
+    per batch; here a batch is ``store.gather(segment_ids)`` -- one row gather on the device -- so that a training step's
+    host->device traffic is the brain data (or, with ``DeviceSegmentStore``, indices only).  A Gwilliams-sized label set
+    (a few thousand segments x 737 KB in bf16) is a few GB of the 180 GB."""
+
+    def __init__(self, Y_all, device="cuda", dtype=torch.bfloat16, chunk: int = 256):
+        self.device = torch.device(device)
+        if hasattr(Y_all, "rows"):
+            self.packed = Y_all.to(self.device)
+        else:                                    # dense (N, F, T) | (N, F): packed chunk by chunk to bound peak memory
+            parts = [PackedTargets.from_dense(torch.as_tensor(Y_all[i:i + chunk]), dtype).to(self.device)
+                     for i in range(0, len(Y_all), chunk)]
+            self.packed = PackedTargets(torch.cat([p.rows for p in parts]), torch.cat([p.sumsq for p in parts]),
+                                        parts[0].feature_shape)
+        self.n = int(self.packed.rows.shape[0])
+
+    def __len__(self):
+        return self.n
+
+    def gather(self, seg_ids) -> "PackedTargets":
+        """Targets of the batch's segments (ids on the host or the device; IndexError outside [0, n) like the reference's
+        list indexing).  Returns device-resident PackedTargets accepted by ``CLIPLoss.forward`` in place of ``Y``."""
+        ids = torch.as_tensor(seg_ids)
+        if ids.numel():
+            lo, hi = int(ids.min()), int(ids.max())
+            if lo < -self.n or hi >= self.n:
+                raise IndexError("segment id {} is out of range".format(hi if hi >= self.n else lo))
+        ids = ids.to(self.device, dtype=torch.int64, non_blocking=True)
+        ids = torch.where(ids < 0, ids + self.n, ids)
+        return PackedTargets(self.packed.rows.index_select(0, ids), self.packed.sumsq.index_select(0, ids),
+                             self.packed.feature_shape)
+
+
 class DevicePrefetcher:
     """Wraps an iterable of host batches (tuples of tensors; non-tensors and CPU index tensors listed in ``keep_on_host``
     pass through) and yields the same tuples with the tensors resident on ``device``.

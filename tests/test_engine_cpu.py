@@ -189,3 +189,19 @@ def test_packed_and_bf16_targets_equal_dense_f32(torch_ops):
     with torch.no_grad():
         Z2 = enc2(X2, subj2)
         assert torch.equal(lossf2(Y2, Z2), lossf2(PackedTargets.from_dense(Y2, dtype=torch.float32), Z2))
+
+
+def test_device_target_store_gathers_packed_rows():
+    """megb200.data.DeviceTargetStore (the label-side companion of DeviceSegmentStore): a batch is a row gather out of the
+    resident packed targets; same loss as the dense collated batch."""
+    from megb200.data import DeviceTargetStore, PackedTargets
+    g = torch.Generator().manual_seed(3)
+    Yall = torch.randn(10, 16, 5, generator=g)
+    store = DeviceTargetStore(Yall, device="cpu", dtype=torch.float32, chunk=4)
+    assert len(store) == 10
+    ids = torch.tensor([7, 0, 3, -1])
+    got = store.gather(ids)
+    ref = PackedTargets.from_dense(Yall[[7, 0, 3, 9]], torch.float32)
+    assert torch.equal(got.rows, ref.rows) and torch.allclose(got.sumsq, ref.sumsq) and got.shape == (4, 16, 5)
+    with pytest.raises(IndexError):
+        store.gather([10])
