@@ -607,7 +607,7 @@ def run_megb200(args):
             store = DeviceTargetStore(PackedTargets(Ypd.rows.repeat(4, 1), Ypd.sumsq.repeat(4), Yph.feature_shape), dev)
             ids_h = [torch.randint(0, nseg, (B,), generator=torch.Generator().manual_seed(100 + i)).pin_memory()
                      for i in range(8)]
-            pre2 = DevicePrefetcher(iter(()), dev, keep_on_host=(2,))
+            pre2 = DevicePrefetcher(iter(()), dev, keep_on_host=(1, 2))      # ids stay on the host: range-checked there, copied by gather()
 
             def batches2(n):
                 for i in range(n):
