@@ -69,11 +69,14 @@ class SpatialAttention(nn.Module):
                               error_msgs):
         """A checkpoint the reference wrote while running on CUDA has no ``z`` key: there ``nn.Parameter(...).to(device)``
         turns z into a plain tensor that is neither trained nor saved (models.py:186-188).  Such a checkpoint loads
-        here (strict or not) with z left at its current value and a warning, instead of a missing-key error."""
+        here with z left at its current value and a warning, instead of a missing-key error.  torch hands this hook only
+        the keys under its own prefix, so whether the dict is a checkpoint of the subject block at all (rather than a
+        partial non-strict load of other keys, which stays silent) is noted by ``BrainEncoder.load_state_dict``."""
         if prefix + "z" not in state_dict:
-            import warnings
-            warnings.warn("megb200: checkpoint has no '{}z' (written by the reference on CUDA, where z is not a "
-                          "registered parameter); keeping the current z".format(prefix))
+            if getattr(self, "_warn_missing_z", True):
+                import warnings
+                warnings.warn("megb200: checkpoint has no '{}z' (written by the reference on CUDA, where z is not a "
+                              "registered parameter); keeping the current z".format(prefix))
             state_dict = dict(state_dict)
             state_dict[prefix + "z"] = self.z.detach()
         super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
@@ -318,6 +321,15 @@ class BrainEncoder(nn.Module):
         if self.seq2seq:
             return Zi.permute(0, 2, 1)
         return Zi[:, 0, : self.F]
+
+    def load_state_dict(self, state_dict, strict=True, assign=False):
+        # see SpatialAttention._load_from_state_dict: warn about an absent z only for dicts that cover the subject block
+        sa = self.subject_block.spatial_attention
+        sa._warn_missing_z = any(k.startswith("subject_block.") for k in state_dict)
+        try:
+            return super().load_state_dict(state_dict, strict=strict, assign=assign)
+        finally:
+            sa._warn_missing_z = True
 
 
 class BrainEncoderSeq2Static(BrainEncoder):
