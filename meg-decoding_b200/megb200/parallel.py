@@ -43,26 +43,54 @@ class PeerGather:
         self.buf = torch.empty(self.world, self.slab_elems, dtype=dtype, device=device)
         self.slab_bytes = self.slab_elems * self.buf.element_size()
         self._fence = torch.zeros(1, dtype=torch.float32, device=device)
-        handle = (C.c_ubyte * 64)()
-        off = C.c_longlong(0)
-        torch.cuda.synchronize(device)
-        lib.call("megb200_ipc_export", self.buf.data_ptr(), C.addressof(handle), C.addressof(off))
-        mine = (bytes(handle), int(off.value), self.slab_bytes)
+        self._bases, self.peer_ptr = {}, {}
+        # Every rank runs the SAME sequence of collectives whatever fails locally (a rank that raised half-way would
+        # leave its peers waiting in a collective it never joins): export -> all-gather of the handles -> import ->
+        # agreement; only then does the constructor raise, on every rank or on none.
+        err, mine = None, None
+        try:
+            handle = (C.c_ubyte * 64)()
+            off = C.c_longlong(0)
+            if device.type == "cuda":
+                torch.cuda.synchronize(device)
+            lib.call("megb200_ipc_export", self.buf.data_ptr(), C.addressof(handle), C.addressof(off))
+            mine = (bytes(handle), int(off.value), self.slab_bytes)
+        except Exception as e:              # e.g. memory from a VMM-backed (expandable segments) pool has no IPC handle
+            err = e
         everyone = [None] * self.world
         dist.all_gather_object(everyone, mine, group=ctx.group)
-        self._bases, self.peer_ptr = {}, {}
-        with torch.cuda.device(device):
+        if err is None:
+            try:
+                failed = [p for p, x in enumerate(everyone) if x is None]
+                if failed:
+                    raise RuntimeError("IPC export failed on rank(s) %s" % failed)
+                self._import_peers(everyone)
+            except Exception as e:
+                err = e
+        ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=ctx.group)
+        if int(ok.item()) == 0:
+            self.close()
+            raise RuntimeError("PeerGather: " + ("%s: %s" % (type(err).__name__, err) if err is not None
+                                                 else "peer mapping failed on another rank"))
+        self.copies_per_gather = self.world - 1
+
+    def _import_peers(self, everyone):
+        import contextlib
+        import ctypes as C
+
+        from . import lib
+        with (torch.cuda.device(self.device) if self.device.type == "cuda" else contextlib.nullcontext()):
             for p, (h, o, nb) in enumerate(everyone):
                 if p == self.rank:
                     continue
                 if nb != self.slab_bytes:
-                    raise RuntimeError("PeerGather: ranks disagree on the slab size")
+                    raise RuntimeError("ranks disagree on the slab size")
                 hb = (C.c_ubyte * 64).from_buffer_copy(h)
                 base = C.c_void_p(0)
                 lib.call("megb200_ipc_import", C.addressof(hb), C.addressof(base))
                 self._bases[p] = int(base.value)
                 self.peer_ptr[p] = int(base.value) + o
-        self.copies_per_gather = self.world - 1
 
     def slot(self, r=None) -> torch.Tensor:
         return self.buf[self.rank if r is None else r]
@@ -115,19 +143,15 @@ class DistContext:
         pair = None
         want = os.environ.get("MEGB200_DP_GATHER", "peer")
         if device.type == "cuda" and want != "nccl" and dist.get_backend(self.group) == "nccl":
-            ok = 1
+            # PeerGather's constructor raises on every rank or on none, so all ranks take the same branch here
+            first = None
             try:
-                pair = (PeerGather(self, B * D, dtype, device), PeerGather(self, B, torch.float32, device))
-            except Exception as e:          # no peer access / IPC refused: fall back to NCCL, on EVERY rank
+                first = PeerGather(self, B * D, dtype, device)
+                pair = (first, PeerGather(self, B, torch.float32, device))
+            except Exception as e:          # no peer access / IPC refused: the NCCL all-gather, on EVERY rank
                 self.gather_note = f"peer mapping failed: {type(e).__name__}: {e}"[:200]
-                pair, ok = None, 0
-            flag = torch.tensor([ok], dtype=torch.int32, device=device)
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
-            if int(flag.item()) == 0:
-                if pair is not None:
-                    for g in pair:
-                        g.close()
-                    self.gather_note = "peer mapping failed on another rank"
+                if first is not None:
+                    first.close()
                 pair = None
         self.gather_mode = "peer_copy_engine" if pair is not None else "nccl"
         self._gathers[key] = pair
