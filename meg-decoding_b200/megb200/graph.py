@@ -14,10 +14,11 @@ What makes the step capturable (nothing in it may depend on host values that cha
   * tensor maps, packed-weight tables and shared-memory attributes are created by the warm-up steps, so the captured
     region contains kernel launches and memsets only.
 
-Data parallel (``megb200.parallel.init()`` done): the recording includes the hot path's collectives -- the all-gather
-of the packed targets on a forked side stream (it overlaps the encoder forward inside the graph), the two all-reduces
-of the softmax partials and the SUM all-reduce of the gradients -- captured in ``thread_local`` error mode because the
-NCCL watchdog thread polls events while the stream captures.  Every rank must build the step at the same point of the
+Data parallel (``megb200.parallel.init()`` done): the recording includes the hot path's exchange step -- the gather of
+the packed targets on a forked side stream (copy-engine pulls from peer-mapped slabs between two 4-byte fences, or an
+NCCL all-gather; either overlaps the encoder forward inside the graph), ONE all-gather of the softmax partials and
+the in-place SUM all-reduce of the flat gradient pool -- captured in ``thread_local`` error mode because the NCCL
+watchdog thread polls events while the stream captures.  Every rank must build the step at the same point of the
 program (the warm-up steps run real collectives).
 """
 from __future__ import annotations
